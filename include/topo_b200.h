@@ -1,0 +1,182 @@
+/*
+ * topo_b200.h -- C ABI of libtopo_b200.so: the B200 (sm_100a) implementation of the per-iteration
+ * topology-optimisation hot path of SolidsPy-Opt (SIMP / BESO / ESO on structured quad4 meshes).
+ *
+ * The reference has no FFI layer: it is pure Python (numpy/scipy) and its boundary is the four
+ * functions of src/solidspy_opt/optimize.py (SIMP :360, BESO :215, ESO_stiff :116, ESO_stress :16).
+ * Each entry point below replaces the reference statement(s) cited next to it; the Python package
+ * solidspy-opt_b200/solidspy_opt re-creates the four functions on top of this ABI through ctypes
+ * (see INTEGRATION.md for the binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TOPO_E* code on failure; topo_last_error()
+ *     returns a human-readable message for the calling thread's last failure;
+ *   - all host arrays are caller-owned, C-contiguous; doubles are IEEE fp64, ids are int64/int32
+ *     as declared; nothing is retained after the call returns;
+ *   - a handle owns all device memory for one mesh on one GPU; handles are not re-entrant;
+ *   - mesh numbering is the reference's (solidspy rect_grid): node id = row*(nx+1)+col, x fastest,
+ *     y upwards; element id = row*nx+col; connectivity [n, n+1, n+nx+2, n+nx+1], n = e + row;
+ *     element DOF order [ux0,uy0,ux1,uy1,ux2,uy2,ux3,uy3];
+ *   - nodal vectors live in "full DOF space": 2*(nx+1)*(ny+1) doubles, (ux,uy) interleaved per node
+ *     -- exactly the (N_n,2) array solidspy.postprocesor.complete_disp returns (optimize.py:438);
+ *     constrained DOFs hold 0.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     TOPO_ENODEV.
+ */
+#ifndef TOPO_B200_H
+#define TOPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOPO_ABI_VERSION 1
+
+enum {
+  TOPO_OK = 0,
+  TOPO_EINVAL = -1,    /* bad argument */
+  TOPO_ENODEV = -2,    /* no usable CUDA device */
+  TOPO_ECUDA = -3,     /* CUDA runtime error (message in topo_last_error) */
+  TOPO_ENOCONV = -4,   /* linear solve hit maxit before reaching rtol (results still readable) */
+  TOPO_ESTATE = -5     /* call order violated (e.g. solve before loads were set) */
+};
+
+/* preconditioners for topo_solve */
+enum { TOPO_PRECOND_JACOBI = 0, TOPO_PRECOND_GMG = 1 };
+
+/* device fields readable/writable through topo_get / topo_set */
+enum {
+  TOPO_F_U = 0,        /* displacement, 2*N_n doubles                      (optimize.py:438 UC)     */
+  TOPO_F_LOAD = 1,     /* load vector in full DOF space, 2*N_n doubles     (optimize.py:434)         */
+  TOPO_F_RHO = 2,      /* density, N_e doubles                             (optimize.py:399,449)     */
+  TOPO_F_DC = 3,       /* (filtered) sensitivity, N_e doubles              (optimize.py:444-445)     */
+  TOPO_F_SCALE = 4,    /* element stiffness scale E_e, N_e doubles         (optimize.py:430 mats[:,2]) */
+  TOPO_F_CONS = 5,     /* BC flags, 2*N_n int8: -1 constrained, 0 free     (nodes[:,3:5])            */
+  TOPO_F_SENS = 6,     /* BESO/ESO sensitivity number, N_e doubles         (optimize.py:188,304-311) */
+  TOPO_F_KEEP = 7,     /* element mask, N_e uint8: 1 = present             (optimize.py:273,328)     */
+  TOPO_F_RESID = 8,    /* last residual f - K u, 2*N_n doubles                                       */
+  TOPO_F_SENS_PREV = 9,/* BESO history sensitivity (optimize.py:344 sensi_I), N_e doubles            */
+  TOPO_F_NODAL = 10    /* BESO nodal sensitivity (optimize.py:305 sensi_nodes), N_n doubles          */
+};
+
+typedef struct topo_handle topo_t;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+int topo_abi_version(void);
+const char *topo_last_error(void);
+int topo_device_count(int *count);
+
+/* Mesh of nx*ny quad4 elements sharing one 8x8 element matrix ke (row-major).  Replaces the arrays
+ * built by beam()/rect_grid (Utils/beams.py:73-90) + DME (optimize.py:417): connectivity and DOF
+ * numbering are implicit in (nx, ny).  `device` is the CUDA ordinal. */
+int topo_create(topo_t **out, int nx, int ny, const double ke[64], int device);
+int topo_destroy(topo_t *h);
+
+/* ---- model state --------------------------------------------------------------------------- */
+/* BC flags as in nodes[:,3:5] (-1 constrained / 0 free), 2*N_n int8.  Replaces the `cons` argument of
+ * ass.DME (optimize.py:56,79,156,176,255,293,417). */
+int topo_set_cons(topo_t *h, const int8_t *cons);
+/* Point loads with ass.loadasem semantics (optimize.py:58,81,158,178,257,295,434): value ASSIGNED to
+ * free DOFs in row order (later rows win), constrained DOFs skipped.  The (node,fx,fy) rows are kept
+ * and re-applied whenever the BC flags change. */
+int topo_set_loads(topo_t *h, const int64_t *node, const double *fx, const double *fy, int n_loads);
+int topo_set(topo_t *h, int field, const void *host, size_t bytes);
+int topo_get(topo_t *h, int field, void *host, size_t bytes);
+/* scalar fill of an element field (TOPO_F_RHO / TOPO_F_SCALE / TOPO_F_KEEP) */
+int topo_fill(topo_t *h, int field, double value);
+
+/* ---- stage 1: matrix-free stiffness application --------------------------------------------- */
+/* y = K(scale) u restricted to free DOFs (rows/cols of constrained DOFs removed, y = 0 there):
+ * the product stiff_mat.dot(disp) of optimize.py:455 without sparse_assem (solver.py:364-410). */
+int topo_matvec(topo_t *h, const double *u_host, double *y_host);
+/* same, device-resident operands: y(field_y) = K u(field_u); used by bench for kernel timing */
+int topo_matvec_device(topo_t *h, int repeats, float *ms_per_launch);
+
+/* ---- stage 2: linear solve (replaces spsolve, optimize.py:61,84,161,181,260,298,437) -------- */
+/* Preconditioned CG on K u = f.  warm != 0 starts from the current TOPO_F_U.  Stops when
+ * ||f - K u||_2 <= rtol * ||f||_2.  Returns TOPO_ENOCONV if maxit is reached. */
+int topo_solve(topo_t *h, int precond, double rtol, int maxit, int warm, int *iters, double *relres);
+/* compliance f.u (optimize.py:440) */
+int topo_compliance(topo_t *h, double *c);
+/* The reference's guard np.allclose(K u / K.max(), f / K.max()) (optimize.py:72,172,286,455). */
+int topo_equilibrium_check(topo_t *h, int *ok);
+
+/* ---- stages 3+4 for SIMP ------------------------------------------------------------------- */
+/* scale_e = emin + rho_e^penal (emax - emin)                                   (optimize.py:430) */
+int topo_simp_scale(topo_t *h, double penal, double emin, double emax);
+/* dc_e = -penal rho_e^(penal-1) (emax-emin) u_e^T ke u_e                       (optimize.py:443-444);
+ * *objective receives sum_e scale_e u_e^T ke u_e (= u^T K u, the energy form of f.u) */
+int topo_simp_sensitivity(topo_t *h, double penal, double emin, double emax, double *objective);
+/* dc <- sum_j H_ij rho_j dc_j / (max(1e-3,rho_i) sum_j H_ij), H = max(0, rmin - dist)
+ * (density_filter, solver.py:452-477; call optimize.py:445).  dx, dy: element size. */
+int topo_filter_sensitivity(topo_t *h, double rmin, double dx, double dy);
+/* optimality_criteria (solver.py:412-448; call optimize.py:449) + the change norm (optimize.py:452):
+ * rho <- OC(rho, dc, *g); *g <- gt; *change <- max|rho_new - rho_old|; *nsteps bisection steps. */
+int topo_oc_update(topo_t *h, double move, double *g, double *change, int *nsteps);
+/* One whole SIMP design iteration on device-resident state (optimize.py:430-455). */
+typedef struct {
+  double penal, emin, emax, rmin, dx, dy, move;
+  double rtol;
+  int precond, maxit, warm;
+} topo_simp_params;
+typedef struct {
+  double compliance, objective, g, change, relres;
+  int cg_iters, oc_steps, equilibrium_ok, status;
+} topo_simp_result;
+int topo_simp_step(topo_t *h, const topo_simp_params *p, double *g_inout, topo_simp_result *res);
+/* Same iteration through HOST buffers: uploads rho_in (N_e), runs the step, downloads rho_out (N_e). */
+int topo_simp_step_host(topo_t *h, const topo_simp_params *p, const double *rho_in, double *rho_out,
+                        double *g_inout, topo_simp_result *res);
+
+/* ---- stages 3+4 for BESO / ESO -------------------------------------------------------------- */
+/* sens_e = (1/2 u_e^T ke u_e) * keep_e, divided by its max     (sensitivity_elsBESO solver.py:90-129,
+ * sensitivity_elsESO :245-279).  use_keep = 0 ignores the mask (ESO: absent elements have scale 0
+ * and are excluded from max/threshold through keep anyway). */
+int topo_energy_sensitivity(topo_t *h, int use_keep);
+/* BESO smoothing: element -> node (sensitivity_nodes, solver.py:177-210) -> element
+ * (sensitivity_filter, :212-243; r_min selecting the 4 corner nodes), / max; then, if
+ * average_with_prev, (s + s_prev)/2 (optimize.py:310); / max (optimize.py:311).
+ * w4/w2x/w2y/we: the reference's floating-point weights (computed by the host wrapper with the
+ * reference's formula). */
+int topo_beso_filter(topo_t *h, const double w4[4], const double w2x[2], const double w2y[2],
+                     const double we[4], int average_with_prev);
+/* The two halves of topo_beso_filter as separate calls (the reference's helper-level API):
+ * nodal <- sensitivity_nodes(sens)   (solver.py:177-210)   and
+ * sens  <- sensitivity_filter(nodal) (solver.py:212-243, including its division by the max). */
+int topo_beso_nodes(topo_t *h, const double w4[4], const double w2x[2], const double w2y[2]);
+int topo_beso_elements(topo_t *h, const double we[4]);
+/* alpha = sort(sens)[::-1][k] over ALL N_e values (optimize.py:323-325): device radix select. */
+int topo_rank_select(topo_t *h, int64_t k, double *alpha);
+/* BESO: keep = sens > alpha; keep |= protect_els(removed) ; del_node  (optimize.py:328-331,
+ * solver.py:6-58).  protect: node ids (loads + BC).  Outputs kept count and #re-added elements. */
+int topo_beso_apply(topo_t *h, double alpha, const int64_t *protect_nodes, int n_protect,
+                    int64_t *n_kept, int64_t *n_protected);
+/* ESO: delete present elements with sens < rr unless protected; scale_e <- 0, keep_e <- 0;
+ * del_nodeESO (optimize.py:189-196, solver.py:318-362). */
+int topo_eso_apply(topo_t *h, double rr, const int64_t *protect_nodes, int n_protect, int64_t *n_kept);
+/* sens_prev <- sens (optimize.py:344) */
+int topo_beso_save_history(topo_t *h);
+/* ESO_stress criterion: nodal stress averaging over present elements + element average + von Mises,
+ * divided by max (strain_nodes contract; strain_els solver.py:281-316; optimize.py:86-92).
+ * E, nu: material; dx, dy: element size. */
+int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double dx, double dy);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* CUDA-event time (ms) of the most recent call of each stage on this handle. */
+typedef struct {
+  float solve_ms, matvec_ms, sens_ms, filter_ms, oc_ms, setup_ms, total_ms;
+  long long kernel_launches; /* cumulative count of kernels launched by this handle */
+} topo_timing;
+int topo_get_timing(topo_t *h, topo_timing *t);
+/* GMG hierarchy description: number of levels and the (nx, ny) of each (up to 32). */
+int topo_gmg_info(topo_t *h, int *n_levels, int *nx_levels, int *ny_levels);
+/* Solver knobs: omega = Jacobi damping of the V-cycle smoother, nu = sweeps pre/post. */
+int topo_set_gmg(topo_t *h, double omega, int nu_pre, int nu_post);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPO_B200_H */

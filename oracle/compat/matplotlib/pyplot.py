@@ -1,0 +1,1 @@
+"""Stub: the oracle never plots (reference ``plot=False`` paths only)."""

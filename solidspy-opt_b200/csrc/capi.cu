@@ -1,0 +1,384 @@
+// extern "C" glue of libtopo_b200.so: life cycle, state transfer, the fused SIMP step and timing.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "topo_internal.cuh"
+
+int topo_mask_vector(topo_handle *h, double2 *v);
+int topo_dot(topo_handle *h, const double2 *a, const double2 *b, double *host_out);
+
+static thread_local char g_err[512] = "";
+
+void topo_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *topo_last_error(void) { return g_err; }
+extern "C" int topo_abi_version(void) { return TOPO_ABI_VERSION; }
+
+extern "C" int topo_device_count(int *count) {
+  if (!count) return TOPO_EINVAL;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    *count = 0;
+    topo_set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return TOPO_ENODEV;
+  }
+  *count = n;
+  return TOPO_OK;
+}
+
+namespace {
+
+__global__ void k_fill(double *p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill8(uint8_t *p, int64_t n, uint8_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// reference BC flags (-1 constrained / 0 free, two per node) <-> device bitmask
+__global__ void k_cons_to_fixed(const int8_t *cons, uint8_t *fixed, int64_t nn) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x)
+    fixed[n] = (cons[2 * n] != 0 ? 1u : 0u) | (cons[2 * n + 1] != 0 ? 2u : 0u);
+}
+__global__ void k_fixed_to_cons(const uint8_t *fixed, int8_t *cons, int64_t nn) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned m = fixed[n];
+    cons[2 * n] = (m & 1u) ? -1 : 0;
+    cons[2 * n + 1] = (m & 2u) ? -1 : 0;
+  }
+}
+
+inline int nblk(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 8); }
+
+struct FieldRef {
+  void *ptr;
+  size_t bytes;
+};
+
+int field_ref(topo_handle *h, int field, FieldRef *out) {
+  const size_t nv = sizeof(double2) * (size_t)h->nn, ev = sizeof(double) * (size_t)h->ne;
+  switch (field) {
+    case TOPO_F_U: *out = {h->u, nv}; return TOPO_OK;
+    case TOPO_F_LOAD: *out = {h->f, nv}; return TOPO_OK;
+    case TOPO_F_RESID: *out = {h->tmp, nv}; return TOPO_OK;
+    case TOPO_F_RHO: *out = {h->rho, ev}; return TOPO_OK;
+    case TOPO_F_DC: *out = {h->dc, ev}; return TOPO_OK;
+    case TOPO_F_SCALE: *out = {h->scale, ev}; return TOPO_OK;
+    case TOPO_F_SENS: *out = {h->sens, ev}; return TOPO_OK;
+    case TOPO_F_SENS_PREV: *out = {h->sens_prev, ev}; return TOPO_OK;
+    case TOPO_F_KEEP: *out = {h->keep, (size_t)h->ne}; return TOPO_OK;
+    case TOPO_F_NODAL: *out = {h->nodal, sizeof(double) * (size_t)h->nn}; return TOPO_OK;
+    case TOPO_F_CONS: *out = {nullptr, 2 * (size_t)h->nn}; return TOPO_OK;
+    default:
+      topo_set_error("unknown field id %d", field);
+      return TOPO_EINVAL;
+  }
+}
+
+}  // namespace
+
+extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], int device) {
+  if (!out || !ke || nx < 1 || ny < 1) {
+    topo_set_error("topo_create: bad arguments (nx=%d, ny=%d)", nx, ny);
+    return TOPO_EINVAL;
+  }
+  if ((int64_t)(nx + 1) * (ny + 1) * 2 >= (int64_t)1 << 31) {
+    topo_set_error("topo_create: mesh too large for 32-bit DOF indices on one GPU");
+    return TOPO_EINVAL;
+  }
+  int ndev = 0;
+  TOPO_TRY(topo_device_count(&ndev));
+  if (device < 0 || device >= ndev) {
+    topo_set_error("topo_create: device %d not in [0,%d)", device, ndev);
+    return TOPO_ENODEV;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  topo_handle *h = new (std::nothrow) topo_handle();
+  if (!h) return TOPO_EINVAL;
+  h->device = device;
+  h->nx = nx;
+  h->ny = ny;
+  h->nn = (int64_t)(nx + 1) * (ny + 1);
+  h->ne = (int64_t)nx * ny;
+  std::memcpy(h->ke.k, ke, sizeof(double) * 64);
+  h->omega = 0.7;
+  h->nu_pre = 1;
+  h->nu_post = 1;
+  h->n_loads = 0;
+  h->loads_set = h->cons_set = h->diag_valid = h->gmg_valid = false;
+  h->d_load_node = nullptr;
+  h->d_load_fx = h->d_load_fy = nullptr;
+  std::memset(&h->timing, 0, sizeof(h->timing));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&h->evs[i]));
+
+  // nodal vectors in one slab (z and p adjacent: ESO_stress borrows them as 3 planes of nn doubles)
+  const size_t nvec = 9;
+  double2 *slab = nullptr;
+  CUDA_TRY(cudaMalloc(&slab, sizeof(double2) * (size_t)h->nn * nvec));
+  CUDA_TRY(cudaMemsetAsync(slab, 0, sizeof(double2) * (size_t)h->nn * nvec, h->stream));
+  h->slab_nodal = slab;
+  double2 **vecs[nvec] = {&h->u, &h->f, &h->r, &h->z, &h->p, &h->Ap, &h->dinv, &h->tmp, &h->tmp2};
+  for (size_t i = 0; i < nvec; ++i) *vecs[i] = slab + i * (size_t)h->nn;
+  double *eslab = nullptr;
+  const size_t nev = 7;
+  CUDA_TRY(cudaMalloc(&eslab, sizeof(double) * (size_t)h->ne * nev));
+  CUDA_TRY(cudaMemsetAsync(eslab, 0, sizeof(double) * (size_t)h->ne * nev, h->stream));
+  h->slab_elem = eslab;
+  double **evs[nev] = {&h->rho, &h->rho_new, &h->dc, &h->dc2, &h->scale, &h->sens, &h->sens_prev};
+  for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * (size_t)h->ne;
+  CUDA_TRY(cudaMalloc(&h->nodal, sizeof(double) * (size_t)h->nn));
+  CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn));
+  CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn, h->stream));
+  CUDA_TRY(cudaMalloc(&h->keep, (size_t)h->ne));
+  CUDA_TRY(cudaMemsetAsync(h->keep, 1, (size_t)h->ne, h->stream));
+  CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * TOPO_RED_SLOTS * TOPO_MAX_PARTIAL_BLOCKS));
+  CUDA_TRY(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream));
+  CUDA_TRY(cudaMalloc(&h->red_out, sizeof(double) * 16));
+  CUDA_TRY(cudaMemsetAsync(h->red_out, 0, sizeof(double) * 16, h->stream));
+  CUDA_TRY(cudaMalloc(&h->sc, sizeof(SolverScalars)));
+  CUDA_TRY(cudaMemsetAsync(h->sc, 0, sizeof(SolverScalars), h->stream));
+  CUDA_TRY(cudaMallocHost(&h->sc_host, sizeof(SolverScalars)));
+  CUDA_TRY(cudaMalloc(&h->oc, sizeof(OcState)));
+  CUDA_TRY(cudaMallocHost(&h->oc_host, sizeof(OcState)));
+  CUDA_TRY(cudaMalloc(&h->kmax, sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->sel, sizeof(unsigned long long) * 260));
+  k_fill<<<nblk(h->ne), 256, 0, h->stream>>>(h->scale, h->ne, 1.0);
+  CUDA_TRY(cudaGetLastError());
+
+  // matvec chunking: aim at ~4 resident blocks per SM in a single wave
+  {
+    const int bx = div_up(nx + 1, 128);
+    int chunks = std::max(1, (148 * 4) / bx);
+    int rows = std::max(8, div_up(ny + 1, chunks));
+    h->matvec_rows_per_chunk = rows;
+  }
+  int s = topo_gmg_plan(h);
+  if (s != TOPO_OK) return s;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return TOPO_OK;
+}
+
+extern "C" int topo_destroy(topo_t *h) {
+  if (!h) return TOPO_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->slab_nodal);
+  cudaFree(h->slab_elem);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(h->evs[i]);
+  cudaFree(h->nodal);
+  cudaFree(h->fixed);
+  cudaFree(h->keep);
+  cudaFree(h->partials);
+  cudaFree(h->ticket);
+  cudaFree(h->red_out);
+  cudaFree(h->sc);
+  cudaFreeHost(h->sc_host);
+  cudaFree(h->oc);
+  cudaFreeHost(h->oc_host);
+  cudaFree(h->kmax);
+  cudaFree(h->sel);
+  cudaFree(h->d_load_node);
+  cudaFree(h->d_load_fx);
+  cudaFree(h->d_load_fy);
+  for (size_t l = 1; l < h->levels.size(); ++l) {
+    GmgLevel &L = h->levels[l];
+    cudaFree(L.cell); cudaFree(L.st); cudaFree(L.dinv);
+    cudaFree(L.x); cudaFree(L.x2); cudaFree(L.b); cudaFree(L.r);
+  }
+  cudaFree(h->coarse_inv);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+  return TOPO_OK;
+}
+
+extern "C" int topo_set_cons(topo_t *h, const int8_t *cons) {
+  if (!h || !cons) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int8_t *d = reinterpret_cast<int8_t *>(h->tmp);
+  CUDA_TRY(cudaMemcpyAsync(d, cons, 2 * (size_t)h->nn, cudaMemcpyHostToDevice, h->stream));
+  k_cons_to_fixed<<<nblk(h->nn), 256, 0, h->stream>>>(d, h->fixed, h->nn);
+  CUDA_TRY(cudaGetLastError());
+  h->cons_set = true;
+  h->diag_valid = h->gmg_valid = false;
+  if (h->loads_set) TOPO_TRY(topo_apply_loads(h));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_set_loads(topo_t *h, const int64_t *node, const double *fx, const double *fy, int n_loads) {
+  if (!h || n_loads < 0 || (n_loads > 0 && (!node || !fx || !fy))) return TOPO_EINVAL;
+  for (int i = 0; i < n_loads; ++i)
+    if (node[i] < 0 || node[i] >= h->nn) {
+      topo_set_error("load %d: node id %lld out of range [0,%lld)", i, (long long)node[i], (long long)h->nn);
+      return TOPO_EINVAL;
+    }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaFree(h->d_load_node); cudaFree(h->d_load_fx); cudaFree(h->d_load_fy);
+  h->d_load_node = nullptr; h->d_load_fx = h->d_load_fy = nullptr;
+  h->n_loads = n_loads;
+  if (n_loads > 0) {
+    CUDA_TRY(cudaMalloc(&h->d_load_node, sizeof(int64_t) * n_loads));
+    CUDA_TRY(cudaMalloc(&h->d_load_fx, sizeof(double) * n_loads));
+    CUDA_TRY(cudaMalloc(&h->d_load_fy, sizeof(double) * n_loads));
+    CUDA_TRY(cudaMemcpyAsync(h->d_load_node, node, sizeof(int64_t) * n_loads, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_load_fx, fx, sizeof(double) * n_loads, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_load_fy, fy, sizeof(double) * n_loads, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->loads_set = true;
+  TOPO_TRY(topo_apply_loads(h));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_set(topo_t *h, int field, const void *host, size_t bytes) {
+  if (!h || !host) return TOPO_EINVAL;
+  if (field == TOPO_F_CONS) {
+    if (bytes != 2 * (size_t)h->nn) { topo_set_error("topo_set(CONS): expected %zu bytes", 2 * (size_t)h->nn); return TOPO_EINVAL; }
+    return topo_set_cons(h, static_cast<const int8_t *>(host));
+  }
+  FieldRef f;
+  TOPO_TRY(field_ref(h, field, &f));
+  if (bytes != f.bytes) {
+    topo_set_error("topo_set(field %d): got %zu bytes, expected %zu", field, bytes, f.bytes);
+    return TOPO_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(f.ptr, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (field == TOPO_F_SCALE || field == TOPO_F_RHO) h->diag_valid = h->gmg_valid = false;
+  if (field == TOPO_F_LOAD) h->loads_set = true;
+  return TOPO_OK;
+}
+
+extern "C" int topo_get(topo_t *h, int field, void *host, size_t bytes) {
+  if (!h || !host) return TOPO_EINVAL;
+  FieldRef f;
+  TOPO_TRY(field_ref(h, field, &f));
+  if (bytes != f.bytes) {
+    topo_set_error("topo_get(field %d): got %zu bytes, expected %zu", field, bytes, f.bytes);
+    return TOPO_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (field == TOPO_F_CONS) {
+    int8_t *d = reinterpret_cast<int8_t *>(h->tmp);
+    k_fixed_to_cons<<<nblk(h->nn), 256, 0, h->stream>>>(h->fixed, d, h->nn);
+    CUDA_TRY(cudaGetLastError());
+    f.ptr = d;
+  }
+  CUDA_TRY(cudaMemcpyAsync(host, f.ptr, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_fill(topo_t *h, int field, double value) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (field == TOPO_F_KEEP) {
+    k_fill8<<<nblk(h->ne), 256, 0, h->stream>>>(h->keep, h->ne, value != 0.0 ? 1 : 0);
+  } else if (field == TOPO_F_RHO || field == TOPO_F_SCALE || field == TOPO_F_SENS || field == TOPO_F_SENS_PREV ||
+             field == TOPO_F_DC) {
+    FieldRef f;
+    TOPO_TRY(field_ref(h, field, &f));
+    k_fill<<<nblk(h->ne), 256, 0, h->stream>>>(static_cast<double *>(f.ptr), h->ne, value);
+    h->diag_valid = h->gmg_valid = false;
+  } else {
+    topo_set_error("topo_fill: field %d is not an element field", field);
+    return TOPO_EINVAL;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_matvec(topo_t *h, const double *u_host, double *y_host) {
+  if (!h || !u_host || !y_host) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t nv = sizeof(double2) * (size_t)h->nn;
+  CUDA_TRY(cudaMemcpyAsync(h->p, u_host, nv, cudaMemcpyHostToDevice, h->stream));
+  TOPO_TRY(topo_mask_vector(h, h->p));
+  TOPO_TRY(topo_fine_matvec(h, h->p, h->Ap));
+  CUDA_TRY(cudaMemcpyAsync(y_host, h->Ap, nv, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_matvec_device(topo_t *h, int repeats, float *ms_per_launch) {
+  if (!h || repeats < 1) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < repeats; ++i) TOPO_TRY(topo_fine_matvec(h, h->p, h->Ap));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->timing.matvec_ms = ms / repeats;
+  if (ms_per_launch) *ms_per_launch = ms / repeats;
+  return TOPO_OK;
+}
+
+extern "C" int topo_simp_step(topo_t *h, const topo_simp_params *p, double *g_inout, topo_simp_result *res) {
+  if (!h || !p || !g_inout || !res) return TOPO_EINVAL;
+  std::memset(res, 0, sizeof(*res));
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaEventRecord(h->evs[0], st));
+  TOPO_TRY(topo_simp_scale(h, p->penal, p->emin, p->emax));
+  CUDA_TRY(cudaEventRecord(h->evs[1], st));
+  int s = topo_solve(h, p->precond, p->rtol, p->maxit, p->warm, &res->cg_iters, &res->relres);
+  res->status = s;
+  if (s != TOPO_OK && s != TOPO_ENOCONV) return s;
+  CUDA_TRY(cudaEventRecord(h->evs[2], st));
+  TOPO_TRY(topo_compliance(h, &res->compliance));
+  TOPO_TRY(topo_simp_sensitivity(h, p->penal, p->emin, p->emax, &res->objective));
+  CUDA_TRY(cudaEventRecord(h->evs[3], st));
+  TOPO_TRY(topo_filter_sensitivity(h, p->rmin, p->dx, p->dy));
+  CUDA_TRY(cudaEventRecord(h->evs[4], st));
+  double g = *g_inout;
+  TOPO_TRY(topo_oc_update(h, p->move, &g, &res->change, &res->oc_steps));
+  *g_inout = g;
+  res->g = g;
+  CUDA_TRY(cudaEventRecord(h->evs[5], st));
+  TOPO_TRY(topo_equilibrium_check(h, &res->equilibrium_ok));
+  CUDA_TRY(cudaEventRecord(h->evs[6], st));
+  CUDA_TRY(cudaEventSynchronize(h->evs[6]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.setup_ms, h->evs[0], h->evs[1]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.solve_ms, h->evs[1], h->evs[2]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.sens_ms, h->evs[2], h->evs[3]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.filter_ms, h->evs[3], h->evs[4]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.oc_ms, h->evs[4], h->evs[5]));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.total_ms, h->evs[0], h->evs[6]));
+  return s;
+}
+
+extern "C" int topo_simp_step_host(topo_t *h, const topo_simp_params *p, const double *rho_in, double *rho_out,
+                                   double *g_inout, topo_simp_result *res) {
+  if (!h || !rho_in || !rho_out) return TOPO_EINVAL;
+  const size_t ev = sizeof(double) * (size_t)h->ne;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(h->rho, rho_in, ev, cudaMemcpyHostToDevice, h->stream));
+  int s = topo_simp_step(h, p, g_inout, res);
+  if (s != TOPO_OK && s != TOPO_ENOCONV) return s;
+  CUDA_TRY(cudaMemcpyAsync(rho_out, h->rho, ev, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return s;
+}
+
+extern "C" int topo_get_timing(topo_t *h, topo_timing *t) {
+  if (!h || !t) return TOPO_EINVAL;
+  *t = h->timing;
+  return TOPO_OK;
+}

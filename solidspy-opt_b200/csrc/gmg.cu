@@ -1,0 +1,579 @@
+// Geometric multigrid V-cycle used as the PCG preconditioner (stage 2; no counterpart in the
+// reference, which calls SuperLU at optimize.py:437).
+//
+// Hierarchy: level 0 is the matrix-free fine grid; level l+1 halves level l in both directions
+// (ceil, so any nx, ny coarsens down to <= 2x2 cells: a trailing single child is allowed).  Coarse
+// operators are exact Galerkin products of the CONSTRAINED fine operator, A_{l+1} = P^T A_l P with
+// bilinear P, built cell by cell: K_C = sum_children P_c^T K_c P_c (bilinear spaces nest, so the sum
+// over the <=4 children is the whole product).  Level 1 is built straight from the element scales
+// (K_c = scale_c * ke; children touching constrained DOFs get their rows/cols masked).  Cell matrices
+// are then gathered into 3x3-block node stencils (36 doubles per node, SoA planes) which is what the
+// smoother / residual kernels stream.  Smoother: damped Jacobi.  Coarsest level: dense inverse.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "topo_internal.cuh"
+
+int topo_fine_smooth(topo_handle *h, const double2 *x, const double2 *b, double2 *x_out, double omega,
+                     const int *done);
+
+namespace {
+
+#define LAUNCHED(h) ((h)->timing.kernel_launches++)
+
+// ---- child geometry ---------------------------------------------------------------------------
+// 1-D child type t: 0 = first child of a 2-cell parent, 1 = second child, 2 = only child (parent == child)
+__host__ __device__ inline double l1d(int t, int fine_local, int coarse_local) {
+  // weight of coarse local node (0 left, 1 right) at fine local node (0 left, 1 right)
+  if (t == 2) return fine_local == coarse_local ? 1.0 : 0.0;
+  if (t == 0) return fine_local == 0 ? (coarse_local == 0 ? 1.0 : 0.0) : 0.5;
+  return fine_local == 1 ? (coarse_local == 1 ? 1.0 : 0.0) : 0.5;
+}
+// local node a (CCW from lower-left) -> (ix, iy)
+__host__ __device__ inline int lx(int a) { return (a == 1 || a == 2) ? 1 : 0; }
+__host__ __device__ inline int ly(int a) { return (a >= 2) ? 1 : 0; }
+
+struct PwTable {
+  double w[9][4][4];   // [variant = 3*ty+tx][fine local a][coarse local A]
+};
+struct GTable {
+  double g[9][64];     // P_v^T ke P_v
+};
+
+__constant__ PwTable c_pw;
+__constant__ GTable c_g;
+
+// ---- level-1 cells straight from element scales -------------------------------------------------
+__device__ __noinline__ void masked_child(const KeParam &ke, int v, double s, unsigned freebits, double *acc) {
+  // acc = s * (m o P)^T ke (m o P): freebits bit (2a+d) set = fine DOF free (acc is a scratch array)
+  for (int i = 0; i < 8; ++i) {
+    const int A = i >> 1, d = i & 1;
+    for (int j = 0; j < 8; ++j) {
+      const int B = j >> 1, e = j & 1;
+      double t = 0.0;
+      for (int a = 0; a < 4; ++a) {
+        const double wa = c_pw.w[v][a][A];
+        if (wa == 0.0 || !((freebits >> (2 * a + d)) & 1u)) continue;
+        for (int b = 0; b < 4; ++b) {
+          const double wb = c_pw.w[v][b][B];
+          if (wb == 0.0 || !((freebits >> (2 * b + e)) & 1u)) continue;
+          t = fma(wa * wb, ke.k[(2 * a + d) * 8 + 2 * b + e], t);
+        }
+      }
+      acc[i * 8 + j] = s * t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_cells_level1(const __grid_constant__ KeParam ke,
+                                                      const double *__restrict__ scale,
+                                                      const uint8_t *__restrict__ fixed, double *__restrict__ cell,
+                                                      int nxf, int nyf, int nxc, int nyc) {
+  const int64_t ncell = (int64_t)nxc * nyc;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncell) return;
+  const int J = (int)(t / nxc), I = (int)(t - (int64_t)J * nxc);
+  double acc[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) acc[k] = 0.0;
+  const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
+  for (int cy = 0; cy < sy; ++cy) {
+    for (int cx = 0; cx < sx; ++cx) {
+      const int ex = 2 * I + cx, ey = 2 * J + cy;
+      const int v = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
+      const double s = scale[(size_t)ey * nxf + ex];
+      const size_t n0 = (size_t)ey * (nxf + 1) + ex;
+      const unsigned f0 = fixed[n0], f1 = fixed[n0 + 1], f2 = fixed[n0 + nxf + 2], f3 = fixed[n0 + nxf + 1];
+      const unsigned fixedbits = (f0 & 3u) | ((f1 & 3u) << 2) | ((f2 & 3u) << 4) | ((f3 & 3u) << 6);
+      if (fixedbits == 0u) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[k] = fma(s, c_g.g[v][k], acc[k]);
+      } else if (fixedbits != 0xffu) {
+        double tmpm[64];                       // rare path (children touching constrained DOFs)
+        masked_child(ke, v, s, (~fixedbits) & 0xffu, tmpm);
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[k] += tmpm[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 64; ++k) cell[(size_t)k * ncell + t] = acc[k];
+}
+
+// ---- generic Galerkin coarsening of cell matrices ---------------------------------------------------
+// thread = (coarse cell, coarse local node pair (A,B)); produces the 2x2 block K_C[2A+d][2B+e]
+__global__ void __launch_bounds__(128) k_cells_coarsen(const double *__restrict__ fcell, double *__restrict__ ccell,
+                                                       int nxf, int nyf, int nxc, int nyc) {
+  const int64_t ncc = (int64_t)nxc * nyc, ncf = (int64_t)nxf * nyf;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncc) return;
+  const int A = blockIdx.y >> 2, B = blockIdx.y & 3;
+  const int J = (int)(t / nxc), I = (int)(t - (int64_t)J * nxc);
+  const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
+  double k00 = 0.0, k01 = 0.0, k10 = 0.0, k11 = 0.0;
+  for (int cy = 0; cy < sy; ++cy) {
+    for (int cx = 0; cx < sx; ++cx) {
+      const int v = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
+      const size_t fc = (size_t)(2 * J + cy) * nxf + (2 * I + cx);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double wa = c_pw.w[v][a][A];
+        if (wa == 0.0) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double w = wa * c_pw.w[v][b][B];
+          if (w == 0.0) continue;
+          const double *base = fcell + fc;
+          k00 = fma(w, __ldg(base + (size_t)((2 * a) * 8 + 2 * b) * ncf), k00);
+          k01 = fma(w, __ldg(base + (size_t)((2 * a) * 8 + 2 * b + 1) * ncf), k01);
+          k10 = fma(w, __ldg(base + (size_t)((2 * a + 1) * 8 + 2 * b) * ncf), k10);
+          k11 = fma(w, __ldg(base + (size_t)((2 * a + 1) * 8 + 2 * b + 1) * ncf), k11);
+        }
+      }
+    }
+  }
+  ccell[(size_t)((2 * A) * 8 + 2 * B) * ncc + t] = k00;
+  ccell[(size_t)((2 * A) * 8 + 2 * B + 1) * ncc + t] = k01;
+  ccell[(size_t)((2 * A + 1) * 8 + 2 * B) * ncc + t] = k10;
+  ccell[(size_t)((2 * A + 1) * 8 + 2 * B + 1) * ncc + t] = k11;
+}
+
+// ---- cells -> node stencils ---------------------------------------------------------------------------
+// stencil plane index: 4*nb + 2*i + j with nb = 3*(dr+1) + (dc+1)
+__global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restrict__ cell, double *__restrict__ st,
+                                                          double2 *__restrict__ dinv, int nx, int ny) {
+  const int npr = nx + 1;
+  const int64_t nn = (int64_t)npr * (ny + 1), ncell = (int64_t)nx * ny;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double s[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) s[k] = 0.0;
+  // adjacent cells: (cell row offset, cell col offset, local index of this node in that cell)
+  const int cro[4] = {0, 0, -1, -1}, cco[4] = {0, -1, -1, 0}, me[4] = {0, 1, 2, 3};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cr = r + cro[q], cc = c + cco[q];
+    if (cr < 0 || cr >= ny || cc < 0 || cc >= nx) continue;
+    const size_t ci = (size_t)cr * nx + cc;
+    const int a = me[q];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      // node b of that cell sits at (cr + ly(b), cc + lx(b)); offset from (r, c):
+      const int dr = cr + ly(b) - r, dc = cc + lx(b) - c;
+      const int nb = 3 * (dr + 1) + (dc + 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          s[4 * nb + 2 * i + j] += __ldg(cell + (size_t)((2 * a + i) * 8 + 2 * b + j) * ncell + ci);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k) st[(size_t)k * nn + n] = s[k];
+  const double dx = s[4 * 4 + 0], dy = s[4 * 4 + 3];
+  dinv[n] = make_double2(dx > 0.0 ? 1.0 / dx : 0.0, dy > 0.0 ? 1.0 / dy : 0.0);
+}
+
+// ---- stencil application on coarse levels ---------------------------------------------------------------
+enum { ST_RESID = 0, ST_SMOOTH = 1 };
+template <int MODE>
+__global__ void __launch_bounds__(128) k_stencil_apply(const double *__restrict__ st, const double2 *__restrict__ x,
+                                                       const double2 *__restrict__ b,
+                                                       const double2 *__restrict__ dinv, double2 *__restrict__ out,
+                                                       int nx, int ny, double omega) {
+  const int npr = nx + 1;
+  const int64_t nn = (int64_t)npr * (ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double ax = 0.0, ay = 0.0;
+#pragma unroll
+  for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int rr = r + dr, cc = c + dc;
+      if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
+      const int nb = 3 * (dr + 1) + (dc + 1);
+      const double2 xv = __ldg(x + (size_t)rr * npr + cc);
+      const double *sp = st + (size_t)(4 * nb) * nn + n;
+      ax = fma(__ldg(sp), xv.x, ax);
+      ax = fma(__ldg(sp + nn), xv.y, ax);
+      ay = fma(__ldg(sp + 2 * nn), xv.x, ay);
+      ay = fma(__ldg(sp + 3 * nn), xv.y, ay);
+    }
+  }
+  const double2 bv = b[n];
+  const double2 dv = dinv[n];
+  if (MODE == ST_RESID) {
+    out[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
+  } else {
+    const double2 xv = x[n];
+    out[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
+  }
+}
+
+// x = omega * dinv * b   (first pre-smoothing sweep from a zero initial guess)
+__global__ void k_smooth0(const double2 *__restrict__ b, const double2 *__restrict__ dinv, double2 *__restrict__ x,
+                          int64_t nn, double omega) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 bv = b[n], dv = dinv[n];
+    x[n] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
+  }
+}
+
+// ---- transfers --------------------------------------------------------------------------------------------------
+// 1-D: coarse node I sits at fine index X = min(2I, nf).  Fine node i is a coarse node if i is even or
+// i == nf; otherwise it interpolates (1/2, 1/2) between coarse (i-1)/2 and (i+1)/2.
+__device__ __forceinline__ void restrict_taps(int I, int nf, int &X, double &wl, double &wr) {
+  X = min(2 * I, nf);
+  const bool even = (X == 2 * I);
+  wl = (even && I >= 1) ? 0.5 : 0.0;              // fine X-1 is odd (interpolated) iff X is even and > 0
+  wr = (even && X + 1 < nf) ? 0.5 : 0.0;          // fine X+1 interpolated iff it exists and is not the last node
+}
+
+// b_c = P^T r  (r is already zero at constrained DOFs); thread per coarse node
+__global__ void __launch_bounds__(128) k_restrict(const double2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
+                                                  int nyf, int nxc, int nyc) {
+  const int nprc = nxc + 1, nprf = nxf + 1;
+  const int64_t nnc = (int64_t)nprc * (nyc + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnc) return;
+  const int J = (int)(n / nprc), I = (int)(n - (int64_t)J * nprc);
+  int X, Y;
+  double wxl, wxr, wyl, wyr;
+  restrict_taps(I, nxf, X, wxl, wxr);
+  restrict_taps(J, nyf, Y, wyl, wyr);
+  const double wx[3] = {wxl, 1.0, wxr}, wy[3] = {wyl, 1.0, wyr};
+  double sx = 0.0, sy = 0.0;
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj) {
+    if (wy[dj + 1] == 0.0) continue;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+      const double w = wy[dj + 1] * wx[di + 1];
+      if (w == 0.0) continue;
+      const double2 v = __ldg(rf + (size_t)(Y + dj) * nprf + (X + di));
+      sx = fma(w, v.x, sx);
+      sy = fma(w, v.y, sy);
+    }
+  }
+  bc[n] = make_double2(sx, sy);
+}
+
+__device__ __forceinline__ void prolong_taps(int i, int nf, int &I0, int &I1, double &w0, double &w1) {
+  if ((i & 1) == 0) {
+    I0 = I1 = i >> 1; w0 = 1.0; w1 = 0.0;
+  } else if (i == nf) {
+    I0 = I1 = (i + 1) >> 1; w0 = 1.0; w1 = 0.0;
+  } else {
+    I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w0 = 0.5; w1 = 0.5;
+  }
+}
+
+// x_f += P x_c, zeroed where the fine DOF is constrained/dead.  MASKMODE 0: fixed flags (level 0);
+// 1: dinv == 0 (coarse levels)
+template <int MASKMODE>
+__global__ void __launch_bounds__(128) k_prolong_add(const double2 *__restrict__ xc, double2 *__restrict__ xf,
+                                                     const uint8_t *__restrict__ fixed,
+                                                     const double2 *__restrict__ dinv, int nxf, int nyf, int nxc) {
+  const int nprf = nxf + 1, nprc = nxc + 1;
+  const int64_t nnf = (int64_t)nprf * (nyf + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnf) return;
+  const int j = (int)(n / nprf), i = (int)(n - (int64_t)j * nprf);
+  int I0, I1, J0, J1;
+  double wx0, wx1, wy0, wy1;
+  prolong_taps(i, nxf, I0, I1, wx0, wx1);
+  prolong_taps(j, nyf, J0, J1, wy0, wy1);
+  double2 acc = xf[n];
+  double px = 0.0, py = 0.0;
+  {
+    const double2 v = __ldg(xc + (size_t)J0 * nprc + I0);
+    px = wy0 * wx0 * v.x; py = wy0 * wx0 * v.y;
+  }
+  if (wx1 != 0.0) {
+    const double2 v = __ldg(xc + (size_t)J0 * nprc + I1);
+    px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
+  }
+  if (wy1 != 0.0) {
+    const double2 v = __ldg(xc + (size_t)J1 * nprc + I0);
+    px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
+    if (wx1 != 0.0) {
+      const double2 u = __ldg(xc + (size_t)J1 * nprc + I1);
+      px = fma(wy1 * wx1, u.x, px); py = fma(wy1 * wx1, u.y, py);
+    }
+  }
+  if (MASKMODE == 0) {
+    const unsigned m = fixed[n];
+    if (m & 1u) px = 0.0;
+    if (m & 2u) py = 0.0;
+  } else {
+    const double2 d = dinv[n];
+    if (d.x == 0.0) px = 0.0;
+    if (d.y == 0.0) py = 0.0;
+  }
+  xf[n] = make_double2(acc.x + px, acc.y + py);
+}
+
+// ---- coarsest level: dense inverse --------------------------------------------------------------------------------
+// One block.  Builds the dense operator from the node stencil, replaces dead rows/cols (zero diagonal)
+// by identity, inverts by Gauss-Jordan (SPD => no pivoting) in shared memory, stores the inverse.
+__global__ void k_coarse_invert(const double *__restrict__ st, int nx, int ny, double *__restrict__ inv) {
+  extern __shared__ double sm[];   // N x 2N augmented
+  const int npr = nx + 1, nn = npr * (ny + 1), N = 2 * nn, W = 2 * N;
+  for (int t = threadIdx.x; t < N * W; t += blockDim.x) sm[t] = 0.0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < nn * 9; t += blockDim.x) {
+    const int n = t / 9, nb = t % 9;
+    const int r = n / npr, c = n % npr;
+    const int rr = r + nb / 3 - 1, cc = c + nb % 3 - 1;
+    if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
+    const int m = rr * npr + cc;
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) sm[(2 * n + i) * W + 2 * m + j] = st[(size_t)(4 * nb + 2 * i + j) * nn + n];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    if (!(sm[t * W + t] > 0.0)) {
+      for (int j = 0; j < N; ++j) { sm[t * W + j] = 0.0; sm[j * W + t] = 0.0; }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    if (!(sm[t * W + t] > 0.0)) sm[t * W + t] = 1.0;
+    sm[t * W + N + t] = 1.0;
+  }
+  __syncthreads();
+  __shared__ double colk[64];
+  for (int k = 0; k < N; ++k) {
+    const double piv = sm[k * W + k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < W; j += blockDim.x) sm[k * W + j] /= piv;
+    // column k is read by every thread of a row while being zeroed: snapshot it first
+    for (int i = threadIdx.x; i < N; i += blockDim.x) colk[i] = sm[i * W + k];
+    __syncthreads();
+    for (int t = threadIdx.x; t < N * W; t += blockDim.x) {
+      const int i = t / W, j = t % W;
+      if (i != k) sm[i * W + j] = fma(-colk[i], sm[k * W + j], sm[i * W + j]);
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = sm[(t / N) * W + N + (t % N)];
+}
+
+__global__ void k_coarse_apply(const double *__restrict__ inv, const double2 *__restrict__ b,
+                               const double2 *__restrict__ dinv, double2 *__restrict__ x, int N) {
+  const double *bb = reinterpret_cast<const double *>(b);
+  const double *dd = reinterpret_cast<const double *>(dinv);
+  double *xx = reinterpret_cast<double *>(x);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < N; ++j) s = fma(inv[i * N + j], bb[j], s);
+    xx[i] = dd[i] != 0.0 ? s : 0.0;
+  }
+}
+
+inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+int topo_gmg_plan(topo_handle *h) {
+  h->n_levels = 1;
+  h->lvl_nx[0] = h->nx;
+  h->lvl_ny[0] = h->ny;
+  int nx = h->nx, ny = h->ny;
+  while (std::max(nx, ny) > 2 && h->n_levels < TOPO_MAX_LEVELS) {
+    nx = (nx + 1) / 2;
+    ny = (ny + 1) / 2;
+    h->lvl_nx[h->n_levels] = nx;
+    h->lvl_ny[h->n_levels] = ny;
+    h->n_levels++;
+  }
+  h->levels.assign(h->n_levels, GmgLevel{});
+  for (int l = 1; l < h->n_levels; ++l) {
+    GmgLevel &L = h->levels[l];
+    L.nx = h->lvl_nx[l];
+    L.ny = h->lvl_ny[l];
+    L.nn = (L.nx + 1) * (L.ny + 1);
+    L.ncell = L.nx * L.ny;
+    CUDA_TRY(cudaMalloc(&L.cell, sizeof(double) * 64 * (size_t)L.ncell));
+    CUDA_TRY(cudaMalloc(&L.st, sizeof(double) * 36 * (size_t)L.nn));
+    CUDA_TRY(cudaMalloc(&L.dinv, sizeof(double2) * (size_t)L.nn));
+    CUDA_TRY(cudaMalloc(&L.x, sizeof(double2) * (size_t)L.nn));
+    CUDA_TRY(cudaMalloc(&L.x2, sizeof(double2) * (size_t)L.nn));
+    CUDA_TRY(cudaMalloc(&L.b, sizeof(double2) * (size_t)L.nn));
+    CUDA_TRY(cudaMalloc(&L.r, sizeof(double2) * (size_t)L.nn));
+  }
+  h->coarse_n = 0;
+  h->coarse_inv = nullptr;
+  if (h->n_levels > 1) {
+    h->coarse_n = 2 * h->levels[h->n_levels - 1].nn;
+    CUDA_TRY(cudaMalloc(&h->coarse_inv, sizeof(double) * (size_t)h->coarse_n * h->coarse_n));
+  }
+  // constant tables (per-process; identical for every handle except G, which depends on ke)
+  PwTable pw;
+  for (int ty = 0; ty < 3; ++ty)
+    for (int tx = 0; tx < 3; ++tx)
+      for (int a = 0; a < 4; ++a)
+        for (int A = 0; A < 4; ++A) pw.w[3 * ty + tx][a][A] = l1d(tx, lx(a), lx(A)) * l1d(ty, ly(a), ly(A));
+  CUDA_TRY(cudaMemcpyToSymbol(c_pw, &pw, sizeof(pw)));
+  return TOPO_OK;
+}
+
+static int upload_gtable(topo_handle *h) {
+  // G_v = P_v^T ke P_v (host, once per setup: ke is per handle but the symbol is per process)
+  GTable g;
+  for (int v = 0; v < 9; ++v) {
+    const int tx = v % 3, ty = v / 3;
+    double P[8][8];
+    std::memset(P, 0, sizeof(P));
+    for (int a = 0; a < 4; ++a)
+      for (int A = 0; A < 4; ++A) {
+        const double w = l1d(tx, lx(a), lx(A)) * l1d(ty, ly(a), ly(A));
+        P[2 * a][2 * A] = w;
+        P[2 * a + 1][2 * A + 1] = w;
+      }
+    for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 8; ++j) {
+        double s = 0.0;
+        for (int a = 0; a < 8; ++a)
+          for (int b = 0; b < 8; ++b) s += P[a][i] * h->ke.k[a * 8 + b] * P[b][j];
+        g.g[v][i * 8 + j] = s;
+      }
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_g, &g, sizeof(g), 0, cudaMemcpyHostToDevice, h->stream));
+  return TOPO_OK;
+}
+
+int topo_gmg_setup(topo_handle *h) {
+  if (h->n_levels < 2) return TOPO_OK;
+  cudaStream_t st = h->stream;
+  TOPO_TRY(upload_gtable(h));
+  {
+    GmgLevel &L = h->levels[1];
+    k_cells_level1<<<blocks_for(L.ncell), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.cell, h->nx, h->ny, L.nx, L.ny);
+    LAUNCHED(h);
+  }
+  for (int l = 2; l < h->n_levels; ++l) {
+    GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
+    dim3 grid(blocks_for(C.ncell), 16);
+    k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny);
+    LAUNCHED(h);
+  }
+  for (int l = 1; l < h->n_levels; ++l) {
+    GmgLevel &L = h->levels[l];
+    k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny);
+    LAUNCHED(h);
+  }
+  {
+    GmgLevel &L = h->levels[h->n_levels - 1];
+    const int N = h->coarse_n;
+    if (N > 48) {
+      topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
+      return TOPO_EINVAL;
+    }
+    k_coarse_invert<<<1, 256, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv);
+    LAUNCHED(h);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->gmg_valid = true;
+  return TOPO_OK;
+}
+
+// z = V(r): one V-cycle with zero initial guess.  `r` is not modified.  Uses h->tmp (fine residual)
+// and h->tmp2 (fine ping-pong buffer).
+int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z) {
+  cudaStream_t st = h->stream;
+  const double om = h->omega;
+  const int L = h->n_levels;
+  if (L < 2) {   // degenerate hierarchy: plain Jacobi
+    k_smooth0<<<std::min(blocks_for(h->nn, 256), 1184), 256, 0, st>>>(r, h->dinv, z, h->nn, 1.0);
+    LAUNCHED(h);
+    return TOPO_OK;
+  }
+  // ---- down ----
+  // level 0: pre-smooth into xa
+  double2 *xa = h->tmp2, *xb = z;
+  k_smooth0<<<std::min(blocks_for(h->nn, 256), 1184), 256, 0, st>>>(r, h->dinv, xa, h->nn, om);
+  LAUNCHED(h);
+  for (int s = 1; s < h->nu_pre; ++s) {
+    TOPO_TRY(topo_fine_smooth(h, xa, r, xb, om, nullptr));
+    std::swap(xa, xb);
+  }
+  TOPO_TRY(topo_fine_residual(h, xa, r, h->tmp));
+  {
+    GmgLevel &C = h->levels[1];
+    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(h->tmp, C.b, h->nx, h->ny, C.nx, C.ny);
+    LAUNCHED(h);
+  }
+  for (int l = 1; l < L - 1; ++l) {
+    GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
+    k_smooth0<<<std::min(blocks_for(F.nn, 256), 1184), 256, 0, st>>>(F.b, F.dinv, F.x, F.nn, om);
+    LAUNCHED(h);
+    for (int s = 1; s < h->nu_pre; ++s) {
+      k_stencil_apply<ST_SMOOTH><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.x2, F.nx, F.ny, om);
+      LAUNCHED(h);
+      std::swap(F.x, F.x2);
+    }
+    k_stencil_apply<ST_RESID><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.r, F.nx, F.ny, om);
+    LAUNCHED(h);
+    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny);
+    LAUNCHED(h);
+  }
+  // ---- coarsest ----
+  {
+    GmgLevel &C = h->levels[L - 1];
+    k_coarse_apply<<<1, 64, 0, st>>>(h->coarse_inv, C.b, C.dinv, C.x, h->coarse_n);
+    LAUNCHED(h);
+  }
+  // ---- up ----
+  for (int l = L - 2; l >= 1; --l) {
+    GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
+    k_prolong_add<1><<<blocks_for(F.nn), 128, 0, st>>>(C.x, F.x, nullptr, F.dinv, F.nx, F.ny, C.nx);
+    LAUNCHED(h);
+    for (int s = 0; s < h->nu_post; ++s) {
+      k_stencil_apply<ST_SMOOTH><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.x2, F.nx, F.ny, om);
+      LAUNCHED(h);
+      std::swap(F.x, F.x2);
+    }
+  }
+  {
+    GmgLevel &C = h->levels[1];
+    k_prolong_add<0><<<blocks_for(h->nn), 128, 0, st>>>(C.x, xa, h->fixed, nullptr, h->nx, h->ny, C.nx);
+    LAUNCHED(h);
+  }
+  for (int s = 0; s < h->nu_post; ++s) {
+    TOPO_TRY(topo_fine_smooth(h, xa, r, xb, om, nullptr));
+    std::swap(xa, xb);
+  }
+  if (xa != z) {
+    CUDA_TRY(cudaMemcpyAsync(z, xa, sizeof(double2) * (size_t)h->nn, cudaMemcpyDeviceToDevice, st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_gmg_info(topo_t *h, int *n_levels, int *nx_levels, int *ny_levels) {
+  if (!h || !n_levels) return TOPO_EINVAL;
+  *n_levels = h->n_levels;
+  for (int l = 0; l < h->n_levels; ++l) {
+    if (nx_levels) nx_levels[l] = h->lvl_nx[l];
+    if (ny_levels) ny_levels[l] = h->lvl_ny[l];
+  }
+  return TOPO_OK;
+}
+
+extern "C" int topo_set_gmg(topo_t *h, double omega, int nu_pre, int nu_post) {
+  if (!h || !(omega > 0.0) || nu_pre < 1 || nu_post < 1) {
+    topo_set_error("topo_set_gmg: omega > 0 and nu_pre, nu_post >= 1 required");
+    return TOPO_EINVAL;
+  }
+  h->omega = omega;
+  h->nu_pre = nu_pre;
+  h->nu_post = nu_post;
+  return TOPO_OK;
+}

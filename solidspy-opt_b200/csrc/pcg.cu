@@ -1,0 +1,320 @@
+// Stage 2: preconditioned conjugate gradients on K u = f in full DOF space (replaces
+// scipy.sparse.linalg.spsolve, reference optimize.py:61,84,161,181,260,298,437).
+//
+// All PCG scalars (alpha, beta, residual norms, the convergence flag) stay in device memory
+// (SolverScalars); kernels read them directly, so the host only launches batches of iterations and
+// polls the `done` flag between batches.  Dot products are warp-shuffle + block + ordered grid
+// reductions (deterministic).
+#include <algorithm>
+#include <cmath>
+
+#include "topo_internal.cuh"
+
+int topo_fine_matvec_dot(topo_handle *h, const double2 *u, double2 *y, double *dot_out, const int *done);
+
+namespace {
+
+constexpr int VEC_THREADS = 256;
+inline int vec_blocks(int64_t n) { return (int)std::min<int64_t>(div_up(n, VEC_THREADS), 148 * 8); }
+
+// r = f - A u was computed by the residual kernel; this sets z = dinv*r (Jacobi) or takes z as given
+// (GMG), p = z, and reduces rz, rr, bb.  Also resets iteration state.
+__global__ void k_pcg_init(const double2 *__restrict__ r, const double2 *__restrict__ f,
+                           const double2 *__restrict__ dinv, double2 *__restrict__ z, double2 *__restrict__ p,
+                           int64_t nn, int jacobi, double *partials, unsigned int *ticket, SolverScalars *sc) {
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 rv = r[n], fv = f[n];
+    double2 zv;
+    if (jacobi) {
+      const double2 d = dinv[n];
+      zv = make_double2(d.x * rv.x, d.y * rv.y);
+      z[n] = zv;
+    } else {
+      zv = z[n];
+    }
+    p[n] = zv;
+    v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
+    v[1] = fma(rv.x, rv.x, fma(rv.y, rv.y, v[1]));
+    v[2] = fma(fv.x, fv.x, fma(fv.y, fv.y, v[2]));
+  }
+  if (grid_reduce<3>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
+    sc->rz[0] = v[0];
+    sc->rr = v[1];
+    sc->bb = v[2];
+    sc->iters = 0;
+    sc->done = (v[1] <= sc->tol2 * v[2]) ? 1 : 0;
+  }
+}
+
+// x += alpha p ; r -= alpha Ap ; [Jacobi: z = dinv r ; rz_new = r.z] ; rr = r.r ; convergence flag.
+__global__ void k_pcg_update(double2 *__restrict__ x, double2 *__restrict__ r, double2 *__restrict__ z,
+                             const double2 *__restrict__ p, const double2 *__restrict__ Ap,
+                             const double2 *__restrict__ dinv, int64_t nn, int jacobi, double *partials,
+                             unsigned int *ticket, SolverScalars *sc) {
+  if (sc->done) return;
+  const int par = sc->iters & 1;
+  const double alpha = sc->rz[par] / sc->pAp;
+  double v[2] = {0.0, 0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pv = p[n], av = Ap[n];
+    double2 xv = x[n], rv = r[n];
+    xv.x = fma(alpha, pv.x, xv.x);
+    xv.y = fma(alpha, pv.y, xv.y);
+    rv.x = fma(-alpha, av.x, rv.x);
+    rv.y = fma(-alpha, av.y, rv.y);
+    x[n] = xv;
+    r[n] = rv;
+    v[1] = fma(rv.x, rv.x, fma(rv.y, rv.y, v[1]));
+    if (jacobi) {
+      const double2 d = dinv[n];
+      const double2 zv = make_double2(d.x * rv.x, d.y * rv.y);
+      z[n] = zv;
+      v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
+    }
+  }
+  if (grid_reduce<2>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
+    sc->rr = v[1];
+    if (jacobi) sc->rz[par ^ 1] = v[0];
+    const int it = sc->iters + 1;
+    if (v[1] <= sc->tol2 * sc->bb || !(v[1] == v[1])) {   // converged (or NaN: stop, host reports)
+      sc->done = 1;
+      sc->iters = it;
+    } else if (jacobi) {
+      sc->iters = it;     // GMG: iteration counter advances in k_pcg_dir after rz_new is known
+      if (it >= sc->maxit) sc->done = 2;
+    }
+  }
+}
+
+// GMG path: rz_new = r.z after the V-cycle, then p = z + beta p in the same kernel is impossible
+// (beta needs the full dot), so: k_dot_rz reduces, k_pcg_dir updates p.
+__global__ void k_dot_rz(const double2 *__restrict__ r, const double2 *__restrict__ z, int64_t nn,
+                         double *partials, unsigned int *ticket, SolverScalars *sc) {
+  if (sc->done) return;
+  double v[1] = {0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 rv = r[n], zv = z[n];
+    v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
+  }
+  if (grid_reduce<1>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
+    const int par = sc->iters & 1;
+    sc->rz[par ^ 1] = v[0];
+    sc->iters = sc->iters + 1;
+    if (sc->iters >= sc->maxit) sc->done = 2;
+  }
+}
+
+// p = z + beta p with beta = rz_new / rz_old.  `iters` was already advanced, so new = parity(iters).
+__global__ void k_pcg_dir(double2 *__restrict__ p, const double2 *__restrict__ z, int64_t nn,
+                          const SolverScalars *sc) {
+  if (sc->done == 1) return;
+  const int par = sc->iters & 1;
+  const double beta = sc->rz[par] / sc->rz[par ^ 1];
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 zv = z[n];
+    double2 pv = p[n];
+    pv.x = fma(beta, pv.x, zv.x);
+    pv.y = fma(beta, pv.y, zv.y);
+    p[n] = pv;
+  }
+}
+
+__global__ void k_store_pAp(SolverScalars *sc, const double *dot) {
+  if (sc->done) return;
+  sc->pAp = *dot;
+}
+
+__global__ void k_dot(const double2 *__restrict__ a, const double2 *__restrict__ b, int64_t nn,
+                      double *partials, unsigned int *ticket, double *out) {
+  double v[1] = {0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 x = a[n], y = b[n];
+    v[0] = fma(x.x, y.x, fma(x.y, y.y, v[0]));
+  }
+  grid_reduce<1>(v, partials, ticket, out);
+}
+
+// Equilibrium guard of the reference: all(|Ku - f|/kmax <= atol + rtol*|f|/kmax), atol=1e-8, rtol=1e-5
+// (np.allclose defaults; optimize.py:455).  `r` holds f - K u on free DOFs.  Reduces the count of
+// violating DOFs (NaN counts as a violation, like np.allclose).
+__global__ void k_equilibrium(const double2 *__restrict__ r, const double2 *__restrict__ f, int64_t nn,
+                              const double *kmax, double *partials, unsigned int *ticket, double *out) {
+  const double km = *kmax;
+  double v[1] = {0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 rv = r[n], fv = f[n];
+    const bool okx = fabs(rv.x / km) <= 1e-8 + 1e-5 * fabs(fv.x / km);
+    const bool oky = fabs(rv.y / km) <= 1e-8 + 1e-5 * fabs(fv.y / km);
+    v[0] += (okx ? 0.0 : 1.0) + (oky ? 0.0 : 1.0);
+  }
+  grid_reduce<1>(v, partials, ticket, out);
+}
+
+__global__ void k_zero2(double2 *p, int64_t nn) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x)
+    p[n] = make_double2(0.0, 0.0);
+}
+
+// loadasem semantics (assignment in row order; constrained DOFs skipped): one thread walks the rows.
+__global__ void k_apply_loads(double2 *f, const uint8_t *fixed, const int64_t *node, const double *fx,
+                              const double *fy, int n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int i = 0; i < n; ++i) {
+      const int64_t nd = node[i];
+      const unsigned m = fixed[nd];
+      double2 v = f[nd];
+      if (!(m & 1u)) v.x = fx[i];
+      if (!(m & 2u)) v.y = fy[i];
+      f[nd] = v;
+    }
+  }
+}
+
+__global__ void k_mask2(double2 *v, const uint8_t *fixed, int64_t nn) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned m = fixed[n];
+    double2 x = v[n];
+    if (m & 1u) x.x = 0.0;
+    if (m & 2u) x.y = 0.0;
+    v[n] = x;
+  }
+}
+
+}  // namespace
+
+#define LAUNCHED(h) ((h)->timing.kernel_launches++)
+
+int topo_apply_loads(topo_handle *h) {
+  const int64_t nn = h->nn;
+  k_zero2<<<vec_blocks(nn), VEC_THREADS, 0, h->stream>>>(h->f, nn);
+  LAUNCHED(h);
+  if (h->n_loads > 0) {
+    k_apply_loads<<<1, 32, 0, h->stream>>>(h->f, h->fixed, h->d_load_node, h->d_load_fx, h->d_load_fy,
+                                           h->n_loads);
+    LAUNCHED(h);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+int topo_mask_vector(topo_handle *h, double2 *v) {
+  k_mask2<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(v, h->fixed, h->nn);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+int topo_dot(topo_handle *h, const double2 *a, const double2 *b, double *host_out) {
+  k_dot<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(a, b, h->nn, h->partials, h->ticket, h->red_out);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(host_out, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int warm, int *iters, double *relres) {
+  if (!h) return TOPO_EINVAL;
+  if (!h->loads_set || !h->cons_set) {
+    topo_set_error("topo_solve: set BC flags and loads first");
+    return TOPO_ESTATE;
+  }
+  if (precond != TOPO_PRECOND_JACOBI && precond != TOPO_PRECOND_GMG) {
+    topo_set_error("topo_solve: unknown preconditioner %d", precond);
+    return TOPO_EINVAL;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t nn = h->nn;
+  const int nb = vec_blocks(nn);
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaEventRecord(h->ev0, st));
+
+  TOPO_TRY(topo_build_diag(h));
+  const bool jacobi = precond == TOPO_PRECOND_JACOBI;
+  if (!jacobi) TOPO_TRY(topo_gmg_setup(h));
+
+  if (!warm) {
+    k_zero2<<<nb, VEC_THREADS, 0, st>>>(h->u, nn);
+    LAUNCHED(h);
+  } else {
+    TOPO_TRY(topo_mask_vector(h, h->u));   // BC flags may have changed since the last solve
+  }
+  SolverScalars init = {};
+  init.tol2 = rtol * rtol;
+  init.maxit = maxit;
+  CUDA_TRY(cudaMemcpyAsync(h->sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+
+  TOPO_TRY(topo_fine_residual(h, h->u, h->f, h->r));
+  if (!jacobi) TOPO_TRY(topo_gmg_vcycle(h, h->r, h->z));
+  k_pcg_init<<<nb, VEC_THREADS, 0, st>>>(h->r, h->f, h->dinv, h->z, h->p, nn, jacobi ? 1 : 0, h->partials,
+                                         h->ticket, h->sc);
+  LAUNCHED(h);
+
+  const int batch = jacobi ? 50 : 4;
+  int launched = 0;
+  SolverScalars *hs = h->sc_host;
+  hs->done = 0;
+  hs->iters = 0;
+  while (true) {
+    CUDA_TRY(cudaMemcpyAsync(hs, h->sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (hs->done || launched >= maxit) break;
+    const int nrun = std::min(batch, maxit - launched);
+    for (int i = 0; i < nrun; ++i) {
+      TOPO_TRY(topo_fine_matvec_dot(h, h->p, h->Ap, h->red_out, &h->sc->done));
+      k_store_pAp<<<1, 1, 0, st>>>(h->sc, h->red_out);
+      LAUNCHED(h);
+      k_pcg_update<<<nb, VEC_THREADS, 0, st>>>(h->u, h->r, h->z, h->p, h->Ap, h->dinv, nn, jacobi ? 1 : 0,
+                                               h->partials, h->ticket, h->sc);
+      LAUNCHED(h);
+      if (!jacobi) {
+        TOPO_TRY(topo_gmg_vcycle(h, h->r, h->z));
+        k_dot_rz<<<nb, VEC_THREADS, 0, st>>>(h->r, h->z, nn, h->partials, h->ticket, h->sc);
+        LAUNCHED(h);
+      }
+      k_pcg_dir<<<nb, VEC_THREADS, 0, st>>>(h->p, h->z, nn, h->sc);
+      LAUNCHED(h);
+    }
+    launched += nrun;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, st));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.solve_ms, h->ev0, h->ev1));
+  if (iters) *iters = hs->iters;
+  const double rel = (hs->bb > 0.0) ? std::sqrt(hs->rr / hs->bb) : (hs->rr == 0.0 ? 0.0 : INFINITY);
+  if (relres) *relres = rel;
+  if (hs->done != 1) {
+    topo_set_error("PCG did not converge: %d iterations, relative residual %.3e (rtol %.1e)", hs->iters, rel,
+                   rtol);
+    return TOPO_ENOCONV;
+  }
+  if (!(hs->rr == hs->rr)) {
+    topo_set_error("PCG produced NaN (singular system?)");
+    return TOPO_ENOCONV;
+  }
+  return TOPO_OK;
+}
+
+extern "C" int topo_compliance(topo_t *h, double *c) {
+  if (!h || !c) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return topo_dot(h, h->f, h->u, c);
+}
+
+extern "C" int topo_equilibrium_check(topo_t *h, int *ok) {
+  if (!h || !ok) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->diag_valid) TOPO_TRY(topo_build_diag(h));
+  TOPO_TRY(topo_fine_residual(h, h->u, h->f, h->tmp));
+  k_equilibrium<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(h->tmp, h->f, h->nn, h->kmax, h->partials,
+                                                                  h->ticket, h->red_out);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  double bad = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *ok = (bad == 0.0) ? 1 : 0;
+  return TOPO_OK;
+}

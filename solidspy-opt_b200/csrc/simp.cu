@@ -1,0 +1,254 @@
+// Stages 3+4 of the SIMP iteration: SIMP interpolation, element sensitivity fused with the objective
+// reduction, radius filter as a shared-memory-tiled stencil, optimality-criteria update with a
+// device-side bisection.  Reference: optimize.py:430,443-452; solver.py:412-477.
+#include <algorithm>
+#include <cmath>
+
+#include "topo_internal.cuh"
+
+namespace {
+
+#define LAUNCHED(h) ((h)->timing.kernel_launches++)
+constexpr int ET = 256;
+inline int el_blocks(int64_t n) { return (int)std::min<int64_t>(div_up(n, ET), 148 * 8); }
+
+// numpy minimum/maximum propagate NaN (CUDA fmin/fmax do not)
+__device__ __forceinline__ double np_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ double np_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+__device__ __forceinline__ double powp(double x, double p) {
+  if (p == 2.0) return x * x;            // numpy's fast path for ** 2 (rho**(penal-1), optimize.py:444)
+  if (p == 1.0) return x;
+  return pow(x, p);
+}
+
+// scale_e = emin + rho^penal (emax - emin)                               (optimize.py:430)
+__global__ void k_simp_scale(const double *__restrict__ rho, double *__restrict__ scale, int64_t ne, double penal,
+                             double emin, double emax) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x)
+    scale[e] = emin + pow(rho[e], penal) * (emax - emin);
+}
+
+// s_e = u_e^T ke u_e ; dc_e = (-penal rho^(penal-1) (emax-emin)) s_e ; objective += scale_e s_e
+__global__ void __launch_bounds__(ET) k_simp_sens(const __grid_constant__ KeParam ke, const double2 *__restrict__ u,
+                                                  const double *__restrict__ rho, const double *__restrict__ scale,
+                                                  double *__restrict__ dc, int nx, int ny, double penal, double emin,
+                                                  double emax, double *partials, unsigned int *ticket, double *out) {
+  const int64_t ne = (int64_t)nx * ny;
+  const int npr = nx + 1;
+  double v[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / nx), c = (int)(e - (int64_t)r * nx);
+    const double2 *p = u + (size_t)r * npr + c;
+    const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + npr + 1), q3 = __ldg(p + npr);
+    const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {      // (u^T ke)[j] * u[j], summed over j (same contraction order as :443)
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fma(w[i], ke.k[i * 8 + j], t);
+      s = fma(t, w[j], s);
+    }
+    const double rh = rho[e];
+    dc[e] = (-penal * powp(rh, penal - 1.0) * (emax - emin)) * s;
+    v[0] = fma(scale[e], s, v[0]);
+  }
+  grid_reduce<1>(v, partials, ticket, out);
+}
+
+// ---- filter ----------------------------------------------------------------------------------------
+constexpr int FH_MAX = 8;               // stencil half width (elements)
+struct FilterTaps {
+  int hx, hy;
+  double w[(2 * FH_MAX + 1) * (2 * FH_MAX + 1)];   // row-major [dj+hy][di+hx], <=0 entries are skipped
+};
+
+constexpr int FT = 32;                  // tile edge (elements)
+// out_i = sum_j w_ij rho_j dc_j / (sum_j w_ij * max(1e-3, rho_i)); taps in (dj, di) row-major order
+__global__ void __launch_bounds__(256) k_filter(const __grid_constant__ FilterTaps taps, const double *__restrict__ rho,
+                                                const double *__restrict__ dc, double *__restrict__ out, int nx,
+                                                int ny) {
+  extern __shared__ double tile[];      // (FT+2hy) x (FT+2hx)
+  const int hx = taps.hx, hy = taps.hy;
+  const int tw = FT + 2 * hx, th = FT + 2 * hy;
+  const int x0 = blockIdx.x * FT, y0 = blockIdx.y * FT;
+  for (int t = threadIdx.y * 32 + threadIdx.x; t < tw * th; t += 256) {
+    const int ty = t / tw, tx = t - ty * tw;
+    const int gx = x0 + tx - hx, gy = y0 + ty - hy;
+    double q = 0.0;
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) {
+      const size_t e = (size_t)gy * nx + gx;
+      q = rho[e] * dc[e];
+    }
+    tile[t] = q;
+  }
+  __syncthreads();
+  const int gx = x0 + threadIdx.x;
+  if (gx >= nx) return;
+  const int wrow = 2 * hx + 1;
+#pragma unroll 1
+  for (int k = 0; k < FT / 8; ++k) {
+    const int ly = threadIdx.y + 8 * k;
+    const int gy = y0 + ly;
+    if (gy >= ny) break;
+    double num = 0.0, den = 0.0;
+    for (int dj = -hy; dj <= hy; ++dj) {
+      const bool rowok = (gy + dj >= 0) && (gy + dj < ny);
+      const double *trow = tile + (ly + hy + dj) * tw + threadIdx.x + hx;
+      for (int di = -hx; di <= hx; ++di) {
+        const double w = taps.w[(dj + hy) * wrow + di + hx];
+        if (w > 0.0) {
+          num = fma(w, trow[di], num);
+          if (rowok && gx + di >= 0 && gx + di < nx) den += w;
+        }
+      }
+    }
+    const size_t e = (size_t)gy * nx + gx;
+    out[e] = num / (den * np_max(0.001, rho[e]));
+  }
+}
+
+// ---- optimality criteria ---------------------------------------------------------------------------
+__device__ __forceinline__ double oc_candidate(double rho, double dc, double lmid, double move) {
+  // np.maximum(0, np.maximum(rho-move, np.minimum(1, np.minimum(rho+move, rho*np.sqrt(-dc/lmid)))))
+  const double b = rho * sqrt(-dc / lmid);
+  return np_max(0.0, np_max(rho - move, np_min(1.0, np_min(rho + move, b))));
+}
+
+__global__ void k_oc_init(OcState *oc, double g) {
+  oc->l1 = 0.0;
+  oc->l2 = 1e9;
+  oc->g = g;
+  oc->gt = g;
+  oc->lmid = 0.0;
+  oc->steps = 0;
+  oc->change = 0.0;
+  oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
+}
+
+// one bisection step: gt = g + sum(rho_new(lmid) - rho); gt > 0 ? l1 = lmid : l2 = lmid
+__global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, const double *__restrict__ dc,
+                                                int64_t ne, double move, double *partials, unsigned int *ticket,
+                                                double *out, OcState *oc) {
+  if (oc->done) return;
+  const double lmid = 0.5 * (oc->l2 + oc->l1);
+  double v[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const double rh = rho[e];
+    v[0] += oc_candidate(rh, dc[e], lmid, move) - rh;
+  }
+  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0) {
+    const double gt = oc->g + v[0];
+    if (gt > 0.0) oc->l1 = lmid; else oc->l2 = lmid;
+    oc->gt = gt;
+    oc->lmid = lmid;
+    oc->steps += 1;
+    oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
+  }
+}
+
+// rho_new at the LAST evaluated multiplier (what the reference returns) + change = max|rho_new - rho|
+__global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho, const double *__restrict__ dc,
+                                                 double *__restrict__ rho_new, int64_t ne, double move,
+                                                 double *partials, unsigned int *ticket, double *out, OcState *oc) {
+  const double lmid = oc->lmid;
+  const int steps = oc->steps;
+  double v[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const double rh = rho[e];
+    // zero bisection steps: the reference returns its zero-initialised rho_new (solver.py:439)
+    const double rn = steps > 0 ? oc_candidate(rh, dc[e], lmid, move) : 0.0;
+    rho_new[e] = rn;
+    const double d = fabs(rn - rh);
+    v[0] = (d > v[0] || d != d) ? d : v[0];
+  }
+  if (grid_reduce<1, true>(v, partials, ticket, out) && threadIdx.x == 0) oc->change = v[0];
+}
+
+}  // namespace
+
+extern "C" int topo_simp_scale(topo_t *h, double penal, double emin, double emax) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_simp_scale<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->rho, h->scale, h->ne, penal, emin, emax);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  h->diag_valid = false;
+  h->gmg_valid = false;
+  return TOPO_OK;
+}
+
+extern "C" int topo_simp_sensitivity(topo_t *h, double penal, double emin, double emax, double *objective) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
+                                                      emax, h->partials, h->ticket, h->red_out);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  if (objective) {
+    CUDA_TRY(cudaMemcpyAsync(objective, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return TOPO_OK;
+}
+
+extern "C" int topo_filter_sensitivity(topo_t *h, double rmin, double dx, double dy) {
+  if (!h || !(rmin > 0.0) || !(dx > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  FilterTaps taps;
+  taps.hx = taps.hy = 0;                        // largest offsets that still carry a positive weight
+  while (taps.hx <= FH_MAX && rmin - (taps.hx + 1) * dx > 0.0) taps.hx++;
+  while (taps.hy <= FH_MAX && rmin - (taps.hy + 1) * dy > 0.0) taps.hy++;
+  if (taps.hx > FH_MAX || taps.hy > FH_MAX) {
+    topo_set_error("filter radius %.3g spans more than %d elements", rmin, FH_MAX);
+    return TOPO_EINVAL;
+  }
+  const int wrow = 2 * taps.hx + 1;
+  for (int dj = -taps.hy; dj <= taps.hy; ++dj)
+    for (int di = -taps.hx; di <= taps.hx; ++di)
+      taps.w[(dj + taps.hy) * wrow + di + taps.hx] = rmin - std::sqrt((di * dx) * (di * dx) + (dj * dy) * (dj * dy));
+  dim3 grid(div_up(h->nx, FT), div_up(h->ny, FT)), block(32, 8);
+  const size_t smem = sizeof(double) * (FT + 2 * taps.hx) * (FT + 2 * taps.hy);
+  k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  std::swap(h->dc, h->dc2);
+  return TOPO_OK;
+}
+
+extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change, int *nsteps) {
+  if (!h || !g) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int nb = el_blocks(h->ne);
+  CUDA_TRY(cudaEventRecord(h->ev0, st));
+  k_oc_init<<<1, 1, 0, st>>>(h->oc, *g);
+  LAUNCHED(h);
+  OcState *hs = h->oc_host;
+  hs->done = 0;
+  int launched = 0;
+  const int batch = 48, hard_cap = 2400;   // the bracket [0,1e9] underflows after ~1100 halvings
+  while (launched < hard_cap) {
+    for (int i = 0; i < batch; ++i) {
+      k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc);
+      LAUNCHED(h);
+    }
+    launched += batch;
+    CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (hs->done) break;
+  }
+  k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out, h->oc);
+  LAUNCHED(h);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(h->ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaEventElapsedTime(&h->timing.oc_ms, h->ev0, h->ev1));
+  std::swap(h->rho, h->rho_new);          // rho_new now holds the previous design
+  *g = hs->gt;
+  if (change) *change = hs->change;
+  if (nsteps) *nsteps = hs->steps;
+  return TOPO_OK;
+}

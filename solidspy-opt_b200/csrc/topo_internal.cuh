@@ -1,0 +1,221 @@
+// Internal declarations shared by the translation units of libtopo_b200.so (sm_100a only).
+// Public ABI: include/topo_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/topo_b200.h"
+
+#define TOPO_MAX_LEVELS 32
+#define TOPO_RED_SLOTS 8          // scalars reduced per kernel (max)
+#define TOPO_MAX_PARTIAL_BLOCKS 8192
+
+void topo_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      topo_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                 \
+                     cudaGetErrorString(e__));                                             \
+      return TOPO_ECUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define TOPO_TRY(expr)                                                                     \
+  do {                                                                                     \
+    int s__ = (expr);                                                                      \
+    if (s__ != TOPO_OK) return s__;                                                        \
+  } while (0)
+
+// 8x8 element matrix passed by value as a kernel parameter: lives in the constant bank, so DFMA can
+// take its entries as c[][] operands without occupying registers.
+struct KeParam {
+  double k[64];
+};
+
+// Device-resident scalars shared between the solver kernels (no host round trip inside the PCG loop).
+struct SolverScalars {
+  double rz[2];      // r.z of the current / next iteration (indexed by parity)
+  double pAp;
+  double rr;         // ||r||^2
+  double bb;         // ||f||^2
+  double tol2;       // rtol^2
+  double aux[4];
+  int iters;         // PCG iterations completed
+  int done;          // 1 once rr <= tol2*bb (kernels become no-ops)
+  int maxit;
+  int pad;
+};
+
+struct OcState {
+  double l1, l2, lmid, gt, g, change;
+  int steps, done;
+};
+
+// one coarse level of the multigrid hierarchy (level 0 = the matrix-free fine grid, not stored here)
+struct GmgLevel {
+  int nx, ny;          // cells
+  int nn;              // nodes
+  int ncell;
+  double *cell;        // 64 planes x ncell : per-cell 8x8 Galerkin matrix (SoA, plane = 8*i+j)
+  double *st;          // 36 planes x nn : node stencil, plane = 4*nb + 2*i + j, nb = 3*(dr+1)+(dc+1)
+  double2 *dinv;       // 1/diag (0 at constrained DOFs)
+  double2 *x, *x2, *b, *r;
+  uint8_t *fixed;
+};
+
+struct topo_handle {
+  int device;
+  int nx, ny;
+  int64_t nn, ne;
+  KeParam ke;
+  cudaStream_t stream;
+
+  // fine-grid fields
+  double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2;
+  double *rho, *rho_new, *dc, *dc2, *scale, *sens, *sens_prev, *nodal;
+  uint8_t *fixed, *keep;
+  int8_t *cons_host_shadow;
+
+  // loads (kept to re-apply when BC flags change)
+  std::vector<int64_t> load_node;
+  std::vector<double> load_fx, load_fy;
+  int64_t *d_load_node;
+  double *d_load_fx, *d_load_fy;
+  int n_loads;
+  bool loads_set, cons_set, diag_valid, gmg_valid;
+
+  // reductions
+  double *partials;        // TOPO_RED_SLOTS x TOPO_MAX_PARTIAL_BLOCKS
+  unsigned int *ticket;
+  double *red_out;         // TOPO_RED_SLOTS results of the most recent reduction
+  SolverScalars *sc;       // device
+  SolverScalars *sc_host;  // pinned
+  OcState *oc;             // device
+  OcState *oc_host;        // pinned
+  double *kmax;            // device scalar: max diagonal of K over free DOFs
+  unsigned long long *sel; // radix-select scratch
+
+  // multigrid
+  int n_levels;            // including the fine level
+  int lvl_nx[TOPO_MAX_LEVELS], lvl_ny[TOPO_MAX_LEVELS];
+  std::vector<GmgLevel> levels;   // levels[0] unused placeholder; levels[l] for l>=1
+  double *gtab;            // 9 x 64 level-1 Galerkin tables (device)
+  double *ptab;            // 9 x 64 child interpolation matrices (device)
+  double *coarse_inv;      // dense inverse of the coarsest operator
+  int coarse_n;            // its dimension (2*nn of last level)
+  double omega;
+  int nu_pre, nu_post;
+
+  void *slab_nodal, *slab_elem;   // allocation bases (field pointers get swapped)
+
+  // timing
+  cudaEvent_t ev0, ev1;
+  cudaEvent_t evs[8];             // stage boundaries of topo_simp_step
+  topo_timing timing;
+  int matvec_rows_per_chunk;
+};
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels / drivers implemented across translation units ----
+int topo_fine_matvec(topo_handle *h, const double2 *u, double2 *y);                  // y = A u
+int topo_fine_residual(topo_handle *h, const double2 *u, const double2 *b, double2 *r); // r = b - A u
+int topo_build_diag(topo_handle *h);
+int topo_gmg_plan(topo_handle *h);
+int topo_gmg_setup(topo_handle *h);
+int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z);
+int topo_apply_loads(topo_handle *h);
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// Deterministic two-stage grid reduction.  Every block reduces its values in a fixed order and stores
+// one partial per slot; the block that draws the last ticket folds the partials in index order, so
+// the result does not depend on block scheduling (needed for reproducible OC bisection decisions,
+// reference solver.py:443-447).
+// ------------------------------------------------------------------------------------------
+template <int NV, bool IS_MAX = false>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem /* NV*32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double t = __shfl_down_sync(0xffffffffu, v[k], o);
+      v[k] = IS_MAX ? fmax(v[k], t) : v[k] + t;
+    }
+    if (lane == 0) smem[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = (lane < nwarp) ? smem[k * 32 + lane] : (IS_MAX ? -1.0 / 0.0 : 0.0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double s = __shfl_down_sync(0xffffffffu, t, o);
+        t = IS_MAX ? fmax(t, s) : t + s;
+      }
+      v[k] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// Returns true in ALL threads of the last block after `out[k]` holds the final values (thread 0 of
+// that block wrote them); other blocks return false.  blockDim must be 1-D here (x only) with <=1024.
+template <int NV, bool IS_MAX = false>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned int *ticket,
+                                            double *out) {
+  __shared__ double s_red[NV * 32];
+  __shared__ bool s_last;
+  const int nblk = gridDim.x * gridDim.y;
+  const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+  block_reduce<NV, IS_MAX>(v, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[k * TOPO_MAX_PARTIAL_BLOCKS + bid] = v[k];
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == (unsigned int)(nblk - 1));
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double w[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double acc = IS_MAX ? -1.0 / 0.0 : 0.0;
+    // fixed assignment of partials to threads, fixed order inside a thread
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+      double t = __ldcg(&partials[k * TOPO_MAX_PARTIAL_BLOCKS + i]);
+      acc = IS_MAX ? fmax(acc, t) : acc + t;
+    }
+    w[k] = acc;
+  }
+  block_reduce<NV, IS_MAX>(w, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = w[k];
+    *ticket = 0u;
+    __threadfence();
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = w[k];
+  __syncthreads();
+  return true;
+}
+
+__device__ __forceinline__ double2 shfl_up2(double2 v, int d) {
+  return make_double2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ double2 shfl_down2(double2 v, int d) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+#endif  // __CUDACC__

@@ -1,0 +1,273 @@
+"""The four optimisers of SolidsPy-Opt with the reference's signatures, driven on a B200.
+
+Entry points (argument order identical to reference ``src/solidspy_opt/optimize.py``):
+
+    SIMP      (length, height, nx, ny, dirs, positions, niter, penal, plot=False)            :360
+    BESO      (length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=False)   :215
+    ESO_stiff (length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False)  :116
+    ESO_stress(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False)  :16
+
+The host loop stays in Python; every numerical stage of an iteration is a call into
+``libtopo_b200.so`` (matrix-free K(rho)u, GMG-preconditioned CG instead of ``spsolve``, sensitivity,
+filter, OC / rank-select removal).  Keyword-only extras (``precond``, ``rtol``, ``device``,
+``history`` ...) default to the reference's behaviour; ``*_from_model`` variants take the
+``{"nodes","cons","elements","mats","loads"}`` dict of the SolidsPy README (reference README.rst:134-141).
+"""
+import numpy as np
+
+from solidspy_opt import _capi
+from solidspy_opt.Utils.beams import beam
+from solidspy_opt.Utils.solver import (beso_weights, grid_shape_from_els, grid_shape_from_nodes, ke_quad4,
+                                       kloc_simp, volume)
+
+np.seterr(divide='ignore', invalid='ignore')      # reference optimize.py:12
+
+_PRECOND = {"jacobi": _capi.PRECOND_JACOBI, "gmg": _capi.PRECOND_GMG}
+DEFAULT_RTOL_SIMP = 1e-10     # 1e-8 is the loosest tolerance that keeps the 1e-6 trajectory bar
+DEFAULT_RTOL_ESO = 1e-12      # removal sets come from strict comparisons: solve tighter
+DEFAULT_MAXIT = 100000
+
+
+def _els_rows(nx, ids):
+    """Rows ``[id, 1, 0, n, n+1, n+nx+2, n+nx+1]`` of the given element ids (rect_grid numbering)."""
+    ids = np.asarray(ids, dtype=np.int64)
+    n = ids + ids//nx
+    out = np.empty((ids.size, 7), dtype=np.int64)
+    out[:, 0], out[:, 1], out[:, 2] = ids, 1, 0
+    out[:, 3], out[:, 4], out[:, 5], out[:, 6] = n, n + 1, n + nx + 2, n + nx + 1
+    return out
+
+
+def _plot_density(rho, nx, ny):
+    import matplotlib.pyplot as plt                       # optional dependency, only for plot=True
+    from matplotlib import colors
+    plt.ion()
+    fig, ax = plt.subplots()
+    ax.imshow(-rho.reshape(nx, ny), cmap='gray', interpolation='none', norm=colors.Normalize(vmin=-1, vmax=0))
+    ax.set_title('Predicted')
+    fig.show()
+
+
+def _simp_loop(topo, nx, ny, dx, dy, r_min, niter, penal, precond, rtol, maxit, history, verbose, rho0=None):
+    """Body of reference optimize.py:419-456 on device-resident state."""
+    Emin, Emax = 1e-9, 1.0                                  # :391-392
+    change, g = 10.0, 0.0                                   # :397-398
+    if rho0 is None:
+        topo.fill(_capi.F_RHO, 0.5)                         # :399
+    else:
+        topo.set(_capi.F_RHO, rho0)
+    params = _capi.SimpParams(penal=float(penal), emin=Emin, emax=Emax, rmin=float(r_min), dx=float(dx),
+                              dy=float(dy), move=0.2, rtol=float(rtol), precond=_PRECOND[precond],
+                              maxit=int(maxit), warm=1)
+    for _ in range(niter):
+        if change < 0.01:                                   # :424
+            if verbose:
+                print('Convergence reached')
+            break
+        g, res = topo.simp_step(params, g)
+        change = res.change
+        if history is not None:
+            history.setdefault("compliance", []).append(res.compliance)
+            history.setdefault("objective", []).append(res.objective)
+            history.setdefault("g", []).append(g)
+            history.setdefault("change", []).append(res.change)
+            history.setdefault("cg_iters", []).append(res.cg_iters)
+            history.setdefault("relres", []).append(res.relres)
+            history.setdefault("oc_steps", []).append(res.oc_steps)
+            if history.get("keep_rho", False):
+                history.setdefault("rho", []).append(topo.get(_capi.F_RHO))
+            if history.get("keep_dc", False):
+                history.setdefault("dc", []).append(topo.get(_capi.F_DC))
+        if res.status == _capi.ENOCONV or not res.equilibrium_ok:    # :455 (PCG failure = no equilibrium)
+            break
+    return topo.get(_capi.F_RHO)
+
+
+def SIMP(length, height, nx, ny, dirs, positions, niter, penal, plot=False, *, n=1, r_min=None, r_factor=4,
+         precond="gmg", rtol=DEFAULT_RTOL_SIMP, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+    """SIMP compliance minimisation of a rectangular beam (reference optimize.py:360-465).
+
+    Returns ``rho`` (nx*ny,) float64.  Keyword-only extras: ``n`` support selector of ``beam``
+    (reference hard-codes 1, :394), ``r_min``/``r_factor`` filter radius (reference: 4 element
+    widths, :404), solver controls, ``history`` dict to collect per-iteration scalars.
+    """
+    nodes, mats, els, loads, _ = beam(L=length, H=height, nx=nx, ny=ny, dirs=dirs, positions=positions, n=n)
+    if r_min is None:
+        r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*r_factor             # :404
+    kloc = kloc_simp(mats[0, 0], mats[0, 1])                                        # :406-416
+    with _capi.Topo(nx, ny, kloc, device=device) as topo:
+        topo.set_cons(nodes[:, 3:5])
+        topo.set_loads(loads)
+        rho = _simp_loop(topo, nx, ny, length/nx, height/ny, r_min, niter, penal, precond, rtol, maxit,
+                         history, verbose)
+    if plot:
+        _plot_density(rho, nx, ny)
+    return rho
+
+
+def _model_grid(data):
+    nodes = np.asarray(data["nodes"], dtype=float)
+    els = np.asarray(data["elements"]).astype(np.int64)
+    nx, ny = grid_shape_from_els(els)
+    nx2, ny2, dx, dy = grid_shape_from_nodes(nodes)
+    if (nx, ny) != (nx2, ny2):
+        raise ValueError("nodes and elements describe different grids")
+    return nodes, els, nx, ny, dx, dy
+
+
+def SIMP_from_model(data, niter, penal, *, r_min=None, r_factor=4, precond="gmg", rtol=DEFAULT_RTOL_SIMP,
+                    maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, rho0=None):
+    """SIMP on a model given as the SolidsPy dict ``{"nodes","cons","elements","mats","loads"}``
+    (reference README.rst:134-141), restricted to structured quad4 grids with square elements.
+    ``mats[0] = (E, nu)``; ``loads`` rows ``[node, fx, fy]``; ``cons`` (N_n, 2) with -1 = constrained."""
+    nodes, els, nx, ny, dx, dy = _model_grid(data)
+    mats = np.asarray(data["mats"], dtype=float)
+    if not np.isclose(dx, dy):
+        raise ValueError("SIMP's closed-form element matrix needs square elements (dx=%g, dy=%g)" % (dx, dy))
+    if r_min is None:
+        r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*r_factor
+    kloc = kloc_simp(mats[0, 0], mats[0, 1])
+    with _capi.Topo(nx, ny, kloc, device=device) as topo:
+        topo.set_cons(np.asarray(data["cons"]))
+        topo.set_loads(np.asarray(data["loads"], dtype=float))
+        return _simp_loop(topo, nx, ny, dx, dy, r_min, niter, penal, precond, rtol, maxit, history, verbose,
+                          rho0=rho0)
+
+
+# ------------------------------------------------------------------------------------------------
+def _setup_eso(length, height, nx, ny, dirs, positions, device):
+    nodes, mats, els, loads, BC = beam(L=length, H=height, nx=nx, ny=ny, dirs=dirs, positions=positions, n=1)
+    ke = ke_quad4(nodes[els[0, 3:7], 1:3], mats[0, 0], mats[0, 1])
+    topo = _capi.Topo(nx, ny, ke, device=device)
+    topo.set_cons(nodes[:, 3:5])
+    topo.set_loads(loads)
+    protect = np.hstack((loads[:, 0], BC)).astype(np.int64)
+    return nodes, mats, els, loads, BC, topo, protect
+
+
+def _solve(topo, precond, rtol, maxit, stats):
+    it, rel, code = topo.solve(_PRECOND[precond], rtol, maxit, warm=True, raise_on_noconv=False)
+    if stats is not None:
+        stats.setdefault("cg_iters", []).append(it)
+        stats.setdefault("relres", []).append(rel)
+    ok = (code == _capi.OK) and topo.equilibrium_ok()        # the guard of :72,:172,:286 for the NEXT pass
+    return ok
+
+
+def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=False, *, precond="gmg",
+         rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+    """Bi-directional ESO (reference optimize.py:215-356), quirks included: the full
+    mesh is solved every iteration and removal acts by pinning the DOFs of orphaned nodes.
+    Returns ``(ELS, nodes)``."""
+    if plot:
+        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
+    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device)
+    with topo:
+        eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :255-261
+        r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*1                    # :264
+        w4, w2x, w2y, we = beso_weights(nodes, els, nx, ny, r_min)
+        vol_el = volume(els[:1], length, height, nx, ny)[0]
+        nels = els.shape[0]
+        V_opt = volume(els, length, height, nx, ny).sum()*volfrac                  # :268-269
+        V_full = volume(els, length, height, nx, ny).sum()
+        ELS_mask = None
+        mask = np.ones(nels, dtype=bool)                                           # :273
+        C_h = np.zeros(niter)
+        error = 1000
+        for i in range(niter):
+            if verbose:
+                print("Number of elements: {}".format(nels))                       # :279
+            n_kept = int(np.count_nonzero(mask))
+            V = np.full(n_kept, vol_el).sum()                                      # Vi[mask].sum(), :283
+            if not eq_ok or V_full < V_opt:                                        # :286
+                break
+            ELS_mask = mask                                                        # :290
+            eq_ok = _solve(topo, precond, rtol, maxit, history)                    # :293-299
+            C = 0.5*topo.compliance()                                              # :334 (same f, u)
+            topo.energy_sensitivity()                                              # :304
+            topo.beso_filter(w4, w2x, w2y, we, average_with_prev=(i > 0))          # :305-311
+            V_r = False
+            if V <= V_opt:                                                         # :315
+                break
+            V_k = V*(1 + ER) if V < V_opt else V*(1 - ER)                          # :320
+            els_k = n_kept*V_k/V                                                   # :324
+            alpha_del = topo.rank_select(int(els_k))                               # :323,:325
+            n_new, n_prot = topo.beso_apply(alpha_del, protect)                    # :328-331
+            mask = topo.get(_capi.F_KEEP).astype(bool)
+            C_h[i] = C
+            if history is not None:
+                history.setdefault("kept_ids", []).append(np.flatnonzero(mask))
+                history.setdefault("alpha", []).append(alpha_del)
+                history.setdefault("C", []).append(C)
+                history.setdefault("n_protected", []).append(n_prot)
+                history.setdefault("cons", []).append(topo.get_cons())
+                if history.get("keep_sens", False):
+                    history.setdefault("sens", []).append(topo.get(_capi.F_SENS))
+            if i > 10:
+                error = C_h[i - 5:].sum() - C_h[i - 10:-5].sum()/C_h[i - 5:].sum()   # :336, as written
+            if error <= t and V_r:                                                 # :339 (unreachable)
+                if verbose:
+                    print("convergence")
+                break
+            topo.beso_save_history()                                               # :344
+        nodes[:, 3:5] = topo.get_cons()
+    ELS = None if ELS_mask is None else _els_rows(nx, np.flatnonzero(ELS_mask))
+    return ELS, nodes
+
+
+def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit, device,
+         history, verbose):
+    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device)
+    with topo:
+        eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :56-61 / :156-161
+        if kind == "stiff":
+            niter, RR, ER = 200, 0.005, 0.05                                       # :165-167 overrides the caller
+        vol_el = volume(els[:1], length, height, nx, ny)[0]
+        V_opt = volume(els, length, height, nx, ny).sum()*volfrac
+        mask = np.ones(els.shape[0], dtype=bool)
+        ELS_mask = None
+        for _ in range(niter):
+            n_present = int(np.count_nonzero(mask))
+            if kind == "stress" and verbose:
+                print("Number of elements: {}".format(n_present))                  # :69
+            if not eq_ok or np.full(n_present, vol_el).sum() < V_opt:              # :72 / :172
+                if kind == "stress" and verbose:
+                    print('hollaa')                                                # :73
+                break
+            ELS_mask = mask                                                        # :76 / :192
+            eq_ok = _solve(topo, precond, rtol, maxit, history)
+            if kind == "stiff":
+                if verbose:
+                    print("Number of elements: {}".format(n_present))              # :185
+                topo.energy_sensitivity()                                          # :188
+            else:
+                topo.vonmises_sensitivity(mats[0, 0], mats[0, 1], length/nx, height/ny)   # :86-92
+            topo.eso_apply(RR, protect)                                            # :93-97 / :189-196
+            mask = topo.get(_capi.F_KEEP).astype(bool)
+            if history is not None:
+                history.setdefault("els_ids", []).append(np.flatnonzero(mask))
+                history.setdefault("cons", []).append(topo.get_cons())
+            RR += ER                                                               # :99 / :198
+        nodes[:, 3:5] = topo.get_cons()
+    ELS = None if ELS_mask is None else _els_rows(nx, np.flatnonzero(ELS_mask))
+    return ELS, nodes
+
+
+def ESO_stiff(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False, *, precond="gmg",
+              rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+    """Stiffness-based ESO (reference optimize.py:116-210).  As in the reference, ``niter``, ``RR`` and
+    ``ER`` are overridden by 200, 0.005, 0.05 (:165-167).  Returns ``(ELS, nodes)``."""
+    if plot:
+        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
+    return _eso("stiff", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
+                device, history, verbose)
+
+
+def ESO_stress(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False, *, precond="gmg",
+               rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+    """Stress-based ESO (reference optimize.py:16-111): von Mises of element-averaged nodal stresses.
+    Returns ``(ELS, nodes)``."""
+    if plot:
+        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
+    return _eso("stress", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
+                device, history, verbose)
