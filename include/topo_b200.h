@@ -171,6 +171,13 @@ typedef struct {
   long long kernel_launches; /* cumulative count of kernels launched by this handle */
 } topo_timing;
 int topo_get_timing(topo_t *h, topo_timing *t);
+/* Device-side stopwatch on the handle's stream (CUDA events): bench.py brackets its timed region. */
+int topo_timer_start(topo_t *h);
+int topo_timer_stop(topo_t *h, float *ms);
+/* Per-launch CUDA-event timing of the stage-1 kernel (all variants of the fine-grid K application)
+ * while enabled; read returns the number of launches recorded and their summed duration. */
+int topo_profile_matvec(topo_t *h, int enable);
+int topo_profile_read(topo_t *h, int *launches, float *total_ms);
 /* GMG hierarchy description: number of levels and the (nx, ny) of each (up to 32). */
 int topo_gmg_info(topo_t *h, int *n_levels, int *nx_levels, int *ny_levels);
 /* Solver knobs: omega = Jacobi damping of the V-cycle smoother, nu = sweeps pre/post. */

@@ -120,6 +120,10 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&h->evs[i]));
+  CUDA_TRY(cudaEventCreate(&h->ev_t0));
+  CUDA_TRY(cudaEventCreate(&h->ev_t1));
+  h->prof_on = false;
+  h->prof_n = 0;
 
   // nodal vectors in one slab (z and p adjacent: ESO_stress borrows them as 3 planes of nn doubles)
   const size_t nvec = 9;
@@ -177,6 +181,9 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaFree(h->slab_nodal);
   cudaFree(h->slab_elem);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(h->evs[i]);
+  cudaEventDestroy(h->ev_t0);
+  cudaEventDestroy(h->ev_t1);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   cudaFree(h->nodal);
   cudaFree(h->fixed);
   cudaFree(h->keep);
@@ -380,5 +387,48 @@ extern "C" int topo_simp_step_host(topo_t *h, const topo_simp_params *p, const d
 extern "C" int topo_get_timing(topo_t *h, topo_timing *t) {
   if (!h || !t) return TOPO_EINVAL;
   *t = h->timing;
+  return TOPO_OK;
+}
+
+extern "C" int topo_timer_start(topo_t *h) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev_t0, h->stream));
+  return TOPO_OK;
+}
+
+extern "C" int topo_timer_stop(topo_t *h, float *ms) {
+  if (!h || !ms) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev_t1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev_t1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return TOPO_OK;
+}
+
+extern "C" int topo_profile_matvec(topo_t *h, int enable) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && h->prof_ev.empty()) {
+    h->prof_ev.resize(2 * 8192);
+    for (auto &e : h->prof_ev) CUDA_TRY(cudaEventCreate(&e));
+  }
+  h->prof_on = enable != 0;
+  if (enable) h->prof_n = 0;
+  return TOPO_OK;
+}
+
+extern "C" int topo_profile_read(topo_t *h, int *launches, float *total_ms) {
+  if (!h || !launches || !total_ms) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float tot = 0.f;
+  for (int i = 0; i < h->prof_n; ++i) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    tot += ms;
+  }
+  *launches = h->prof_n;
+  *total_ms = tot;
   return TOPO_OK;
 }

@@ -222,7 +222,10 @@ int launch_apply(topo_handle *h, MvArgs &a) {
     topo_set_error("matvec grid too large for the reduction buffer");
     return TOPO_EINVAL;
   }
+  const bool prof = h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size();
+  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
   k_fine_apply<MODE><<<grid, 128, 0, h->stream>>>(h->ke, a);
+  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n++ + 1], h->stream);
   h->timing.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;

@@ -117,6 +117,10 @@ struct topo_handle {
   // timing
   cudaEvent_t ev0, ev1;
   cudaEvent_t evs[8];             // stage boundaries of topo_simp_step
+  cudaEvent_t ev_t0, ev_t1;       // topo_timer_start/stop
+  bool prof_on;
+  int prof_n;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
   topo_timing timing;
   int matvec_rows_per_chunk;
 };

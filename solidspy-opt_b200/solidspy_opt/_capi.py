@@ -25,7 +25,8 @@ SYMBOLS = [
     "topo_simp_sensitivity", "topo_filter_sensitivity", "topo_oc_update", "topo_simp_step",
     "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_rank_select",
     "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity",
-    "topo_get_timing", "topo_gmg_info", "topo_set_gmg",
+    "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
+    "topo_profile_matvec", "topo_profile_read",
 ]
 
 
@@ -102,6 +103,10 @@ def load_library():
         "topo_get_timing": [vp, C.POINTER(Timing)],
         "topo_gmg_info": [vp, ip, ip, ip],
         "topo_set_gmg": [vp, C.c_double, C.c_int, C.c_int],
+        "topo_timer_start": [vp],
+        "topo_timer_stop": [vp, C.POINTER(C.c_float)],
+        "topo_profile_matvec": [vp, C.c_int],
+        "topo_profile_read": [vp, ip, C.POINTER(C.c_float)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -311,3 +316,19 @@ class Topo:
 
     def set_gmg(self, omega=0.7, nu_pre=1, nu_post=1):
         _check(self.lib.topo_set_gmg(self.h, omega, nu_pre, nu_post))
+
+    def timer_start(self):
+        _check(self.lib.topo_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        _check(self.lib.topo_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_matvec(self, enable):
+        _check(self.lib.topo_profile_matvec(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        n, ms = C.c_int(0), C.c_float(0)
+        _check(self.lib.topo_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value

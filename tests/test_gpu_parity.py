@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in package) against the oracle and the goldens.
+
+All tests here need a B200 (``-m gpu``).  Tolerances: integer / index / mask results are bit-exact;
+floating-point results use the tolerance BASELINE.json's north_star states (1e-6 relative on compliance
+and density per iteration), tighter where the stage is a pure kernel (1e-12..1e-13).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.linalg import spsolve
+
+import gmg_proto
+import t1
+from conftest import golden, unpack_ragged
+
+pytestmark = pytest.mark.gpu
+
+E0, NU = 206.8e9, 0.28
+
+
+@pytest.fixture(scope="module")
+def capi(lib_built):
+    from solidspy_opt import _capi
+    _capi.device_count()
+    return _capi
+
+
+def _cons(nx, ny, kind, rng=None):
+    nn = (nx + 1)*(ny + 1)
+    cons = np.zeros((nn, 2), dtype=np.int8)
+    col = np.arange(nn) % (nx + 1)
+    row = np.arange(nn)//(nx + 1)
+    if kind == "cantilever":
+        cons[col == 0] = -1
+    elif kind == "mbb":                      # symmetry rollers on the left edge + one vertical support
+        cons[col == 0, 0] = -1
+        cons[nx, 1] = -1
+    elif kind == "right_partial":            # beam_2 style
+        cons[(col == nx) & ((row > 3*ny//4) | (row < ny//4))] = -1
+    elif kind == "scattered":
+        cons[col == 0] = -1
+        pick = rng.choice(nn, size=max(1, nn//15), replace=False)
+        cons[pick, rng.integers(0, 2, pick.size)] = -1
+    return cons
+
+
+def _assembled(nx, ny, scale, ke, cons):
+    K = gmg_proto.full_K(nx, ny, scale, ke)
+    free = (cons.reshape(-1) == 0).astype(float)
+    M = sp.diags(free)
+    return (M @ K @ M).tocsr(), free
+
+
+@pytest.mark.parametrize("nx,ny,kind", [(60, 60, "cantilever"), (31, 5, "mbb"), (32, 9, "right_partial"),
+                                        (33, 17, "scattered"), (129, 40, "cantilever"), (1, 1, "mbb"),
+                                        (300, 2, "cantilever"), (2, 200, "scattered")])
+def test_matvec_matches_assembled_matrix(capi, nx, ny, kind):
+    rng = np.random.default_rng(nx*1000 + ny)
+    ke = t1.kloc_closed_form(E0, NU)
+    cons = _cons(nx, ny, kind, rng)
+    scale = 1e-9 + rng.uniform(0, 1, nx*ny)**3
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        y = t.matvec(u).reshape(-1)
+    K, free = _assembled(nx, ny, scale, ke, cons)
+    ref = K @ (u*free)
+    assert np.abs(y - ref).max() <= 1e-13*np.abs(ref).max()
+    assert np.all(y[free == 0] == 0.0)
+
+
+def test_matvec_general_rectangular_ke(capi):
+    rng = np.random.default_rng(5)
+    nx, ny = 45, 14
+    ke = t1.ke_gauss(np.array([[0, 0], [2.0, 0], [2.0, 0.7], [0, 0.7]]), 3.0, 0.31)
+    cons = _cons(nx, ny, "cantilever")
+    scale = rng.uniform(0.1, 1, nx*ny)
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        y = t.matvec(u).reshape(-1)
+    K, free = _assembled(nx, ny, scale, ke, cons)
+    ref = K @ (u*free)
+    assert np.abs(y - ref).max() <= 1e-13*np.abs(ref).max()
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+@pytest.mark.parametrize("nx,ny,kind", [(60, 60, "cantilever"), (37, 23, "mbb"), (64, 20, "right_partial"),
+                                        (50, 30, "scattered")])
+def test_solve_matches_direct(capi, precond, nx, ny, kind):
+    rng = np.random.default_rng(nx + ny)
+    ke = t1.kloc_closed_form(E0, NU)
+    cons = _cons(nx, ny, kind, rng)
+    rho = rng.uniform(0.05, 1, nx*ny)
+    scale = 1e-9 + rho**3
+    loads = np.array([[(nx + 1)*(ny//3) + nx, 0.0, -1.0], [(nx + 1)*ny + nx//2, 2.0, 0.5]])
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        t.set_loads(loads)
+        it, rel, _ = t.solve(capi.PRECOND_JACOBI if precond == "jacobi" else capi.PRECOND_GMG, 1e-11, 50000, warm=False)
+        u = t.get(capi.F_U).reshape(-1)
+        f = t.get(capi.F_LOAD).reshape(-1)
+        c = t.compliance()
+        assert t.equilibrium_ok()
+    K, free = _assembled(nx, ny, scale, ke, cons)
+    idx = np.flatnonzero(free)
+    uref = np.zeros_like(u)
+    uref[idx] = spsolve(K[idx][:, idx].tocsc(), f[idx])
+    assert rel <= 1e-11
+    assert np.abs(u - uref).max() <= 1e-7*np.abs(uref).max()
+    assert abs(c - f @ uref) <= 1e-9*abs(f @ uref)
+    assert np.all(u[free == 0] == 0.0)
+    if precond == "gmg":
+        assert it < 80, "GMG-PCG took %d iterations" % it
+
+
+def test_simp_stage_kernels_match_oracle(capi):
+    rng = np.random.default_rng(11)
+    nx, ny = 70, 33
+    ke = t1.kloc_closed_form(E0, NU)
+    rho = rng.uniform(0, 1, nx*ny)
+    rho[rng.integers(0, nx*ny, 40)] = 0.0
+    UC = rng.standard_normal(((nx + 1)*(ny + 1), 2))*1e-11
+    _, _, els = t1.rect_grid(nx, ny, nx, ny)
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(_cons(nx, ny, "cantilever"))
+        t.set(capi.F_RHO, rho)
+        t.set(capi.F_U, UC)
+        t.simp_scale(3.0, 1e-9, 1.0)
+        assert np.allclose(t.get(capi.F_SCALE), 1e-9 + rho**3*(1 - 1e-9), rtol=1e-15, atol=0)
+        obj = t.simp_sensitivity(3.0, 1e-9, 1.0)
+        s = t1.element_energy(UC, els, ke)
+        dc_ref = (-3*rho**2*(1 - 1e-9))*s
+        dc = t.get(capi.F_DC)
+        assert np.allclose(dc, dc_ref, rtol=1e-13, atol=1e-13*np.abs(dc_ref).max())
+        assert np.isclose(obj, ((1e-9 + rho**3*(1 - 1e-9))*s).sum(), rtol=1e-12)
+        for rmin in (4.0, 2.5, 1.5):
+            t.set(capi.F_DC, dc_ref)
+            t.filter_sensitivity(rmin, 1.0, 1.0)
+            ref = t1.sensitivity_filter_simp(nx, ny, 1.0, 1.0, rmin, rho, dc_ref)
+            got = t.get(capi.F_DC)
+            assert np.allclose(got, ref, rtol=1e-13, atol=1e-300), rmin
+        # optimality criteria: same bisection path, same result
+        dcf = t1.sensitivity_filter_simp(nx, ny, 1.0, 1.0, 4.0, rho, dc_ref)
+        t.set(capi.F_DC, dcf)
+        g, change, nsteps = t.oc_update(0.37)
+        rho_ref, g_ref, n_ref = t1.optimality_criteria(rho, dcf, 0.37)
+        assert nsteps == n_ref
+        assert np.allclose(t.get(capi.F_RHO), rho_ref, rtol=1e-14, atol=0)
+        assert np.isclose(g, g_ref, rtol=0, atol=1e-9)
+        assert np.isclose(change, np.abs(rho_ref - rho).max(), rtol=1e-14)
+
+
+@pytest.mark.parametrize("case", ["c1", "c2"])
+@pytest.mark.parametrize("precond", ["gmg", "jacobi"])
+def test_simp_trajectory_matches_reference(capi, case, precond):
+    """Config 1 of BASELINE.json (reference tests/test_optimize.py:13-42) + a second case."""
+    from solidspy_opt.optimize import SIMP
+    g = golden("simp_" + case)
+    hist = {"keep_rho": True}
+    rho = SIMP(float(g["length"]), float(g["height"]), int(g["nx"]), int(g["ny"]), g["dirs"], g["positions"],
+               int(g["niter"]), int(g["penal"]), precond=precond, history=hist, verbose=False)
+    assert isinstance(rho, np.ndarray) and rho.size == int(g["nx"])*int(g["ny"])     # the reference's own asserts
+    n = len(g["compliance"])
+    assert len(hist["compliance"]) == n
+    assert np.allclose(hist["compliance"], g["compliance"], rtol=1e-6, atol=0)
+    assert np.allclose(hist["objective"], g["compliance"], rtol=1e-6, atol=0)       # u^T K u == f.u
+    for k in range(n):
+        assert np.abs(hist["rho"][k] - g["rho"][k]).max() <= 1e-6, "iteration %d" % k
+    assert np.abs(rho - g["rho_final"]).max() <= 1e-6
+    assert np.allclose(hist["g"], g["g"], rtol=0, atol=1e-5)
+
+
+def _first_singular(g, n):
+    C = g["C"]
+    return n if np.all(np.isfinite(C)) else int(np.argmax(~np.isfinite(C))) - 1
+
+
+@pytest.mark.parametrize("case", ["c1", "c2"])
+def test_beso_removal_sets_match_reference(capi, case):
+    from solidspy_opt.optimize import BESO
+    g = golden("beso_" + case)
+    hist = {}
+    ELS, nodes = BESO(float(g["length"]), float(g["height"]), int(g["nx"]), int(g["ny"]), g["dirs"], g["positions"],
+                      int(g["niter"]), float(g["t"]), float(g["ER"]), float(g["volfrac"]), history=hist, verbose=False)
+    kept = unpack_ragged(g["kept_flat"], g["kept_off"])
+    assert len(hist["kept_ids"]) == len(kept)
+    for k, (a, b) in enumerate(zip(hist["kept_ids"], kept)):
+        assert np.array_equal(a, b), "removal %d: %d vs %d kept" % (k, a.size, b.size)
+    assert ELS.dtype == g["ELS"].dtype and np.array_equal(ELS, g["ELS"])
+    assert np.array_equal(nodes, g["nodes"])
+    assert np.array_equal(np.array(hist["cons"]), g["cons"])
+    assert np.array_equal(hist["n_protected"], g["n_protected"])
+    assert np.allclose(hist["C"], g["C"][1:1 + len(hist["C"])], rtol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["c1", "c2"])
+@pytest.mark.parametrize("kind", ["eso_stiff", "eso_stress"])
+def test_eso_removal_sets_match_reference(capi, kind, case):
+    import solidspy_opt.optimize as opt
+    g = golden("%s_%s" % (kind, case))
+    fn = opt.ESO_stiff if kind == "eso_stiff" else opt.ESO_stress
+    hist = {}
+    ELS, nodes = fn(float(g["length"]), float(g["height"]), int(g["nx"]), int(g["ny"]), g["dirs"], g["positions"],
+                    int(g["niter"]), float(g["RR"]), float(g["ER"]), float(g["volfrac"]), history=hist, verbose=False)
+    ids = unpack_ragged(g["ids_flat"], g["ids_off"])
+    n_ok = _first_singular(g, len(ids))
+    assert len(hist["els_ids"]) >= n_ok
+    for k, (a, b) in enumerate(zip(hist["els_ids"][:n_ok], ids[:n_ok])):
+        assert np.array_equal(a, b), "removal %d: %d vs %d present" % (k, a.size, b.size)
+    if n_ok == len(ids):
+        assert np.array_equal(ELS, g["ELS"])
+        assert np.array_equal(nodes, g["nodes"])
+
+
+def test_rank_select_matches_sort(capi):
+    rng = np.random.default_rng(2)
+    nx, ny = 97, 41
+    n = nx*ny
+    vals = rng.uniform(0, 1, n)
+    vals[rng.integers(0, n, 300)] = 0.0
+    vals[rng.integers(0, n, 200)] = vals[7]            # duplicates around a common value
+    vals[rng.integers(0, n, 50)] = 1.0
+    vals[5] = -0.25
+    vals[6] = 5e-324
+    srt = np.sort(vals)[::-1]
+    with capi.Topo(nx, ny, np.eye(8)) as t:
+        t.set(capi.F_SENS, vals)
+        for k in (0, 1, 49, 50, 51, n//2, int(n*0.95), n - 302, n - 2, n - 1):
+            assert t.rank_select(k) == srt[k], k
+
+
+def test_helper_level_api(capi):
+    """Secondary boundary: reference Utils helper names on small inputs."""
+    from solidspy_opt.Utils import (beam, center_els, density_filter, optimality_criteria, sparse_assem,
+                                    sensitivity_elsESO, sensitivity_elsBESO, sensitivity_nodes, sensitivity_filter)
+    rng = np.random.default_rng(4)
+    nx, ny = 24, 10
+    nodes, mats, els, loads, BC = beam(L=nx, H=ny, nx=nx, ny=ny, dirs=np.array([[0, -1]]), positions=np.array([[3, 1]]))
+    centers = center_els(nodes, els)
+    rho = rng.uniform(0, 1, nx*ny)
+    dc = -rng.uniform(0, 1, nx*ny)
+    assert np.allclose(density_filter(centers, 4.0, rho, dc), t1.sensitivity_filter_simp(nx, ny, 1.0, 1.0, 4.0, rho, dc), rtol=1e-13)
+    r_new, gt = optimality_criteria(nx, ny, rho, dc, 0.1)
+    r_ref, g_ref, _ = t1.optimality_criteria(rho, dc, 0.1)
+    assert np.allclose(r_new, r_ref, rtol=1e-14) and np.isclose(gt, g_ref, atol=1e-10)
+    assem_op, bc, neq = t1.dme(nodes[:, -2:], els)
+    kloc = t1.kloc_closed_form(mats[0, 0], mats[0, 1])
+    mats[:, 2] = 1e-9 + rho**3
+    K = sparse_assem(els, mats, neq, assem_op, kloc)
+    Kref = t1.assemble(mats[:, 2], kloc, assem_op, neq)
+    v = rng.standard_normal(neq)
+    assert np.allclose(K.dot(v), Kref.dot(v), rtol=1e-12, atol=1e-12*np.abs(Kref.dot(v)).max())
+    assert np.isclose(K.max(), Kref.max(), rtol=1e-14)
+    UC = rng.standard_normal((nodes.shape[0], 2))
+    mats[:, 2] = 1
+    ke = t1.ke_gauss(nodes[els[0, 3:7], 1:3], mats[0, 0], mats[0, 1])
+    a = t1.strain_energy_els(UC, els, ke)
+    assert np.allclose(sensitivity_elsESO(nodes, mats, els, UC), a/a.max(), rtol=1e-12)
+    mask = rng.uniform(0, 1, nx*ny) > 0.3
+    am = np.where(mask, a, 0.0)
+    assert np.allclose(sensitivity_elsBESO(nodes, mats, els, mask, UC), am/am.max(), rtol=1e-12)
+    w4, w2x, w2y, we = t1.beso_weights(nodes, els, nx, ny, 1.0)
+    s = rng.uniform(0, 1, nx*ny)
+    sn = sensitivity_nodes(nodes, None, centers, s)
+    assert np.array_equal(sn, t1.sensitivity_nodes(nx, ny, s, w4, w2x, w2y))      # bit-exact operation order
+    assert np.array_equal(sensitivity_filter(nodes, centers, sn, 1.0), t1.sensitivity_filter_beso(nx, ny, sn, we))
+
+
+# ---- full-size properties (BASELINE configs 3/4) ------------------------------------------------------
+def test_fullsize_matvec_properties(capi):
+    nx, ny = 2048, 1024
+    rng = np.random.default_rng(0)
+    ke = t1.kloc_closed_form(E0, NU)
+    nn = (nx + 1)*(ny + 1)
+    u, v = rng.standard_normal(2*nn), rng.standard_normal(2*nn)
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(_cons(nx, ny, "cantilever"))
+        t.set(capi.F_SCALE, 1e-9 + rng.uniform(0, 1, nx*ny)**3)
+        Ku, Kv = t.matvec(u).reshape(-1), t.matvec(v).reshape(-1)
+        Kuv = t.matvec(2.0*u - 3.0*v).reshape(-1)
+        # linearity, symmetry, positive definiteness, rigid translation in the null space of the free-free K
+        assert np.abs(Kuv - (2*Ku - 3*Kv)).max() <= 1e-12*np.abs(Ku).max()
+        assert abs(v @ Ku - u @ Kv) <= 1e-11*abs(v @ Ku)
+        assert u @ Ku > 0
+        t.set_cons(np.zeros((nn, 2), dtype=np.int8))
+        ones = np.tile([1.0, 0.0], nn)
+        assert np.abs(t.matvec(ones)).max() <= 1e-9*np.abs(Ku).max()
+
+
+def test_fullsize_simp_iteration(capi):
+    """2048x1024 headline mesh: two design iterations run, PCG converges, volume is conserved by OC and
+    the energy form of the objective equals f.u."""
+    from solidspy_opt.optimize import SIMP
+    hist = {}
+    nx, ny = 2048, 1024
+    rho = SIMP(nx, ny, nx, ny, np.array([[0, -1]]), np.array([[ny//4, 1]]), 2, 3, history=hist, verbose=False)
+    assert rho.shape == (nx*ny,) and np.all((rho >= 0) & (rho <= 1))
+    assert max(hist["relres"]) <= 1e-10
+    assert np.allclose(hist["objective"], hist["compliance"], rtol=1e-8)
+    assert abs(rho.mean() - 0.5) < 2e-3
+    assert hist["compliance"][1] < hist["compliance"][0]
