@@ -1,4 +1,5 @@
 // extern "C" glue of libtopo_b200.so: life cycle, state transfer, the fused SIMP step and timing.
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <new>
@@ -93,6 +94,31 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
     topo_set_error("topo_create: mesh too large for 32-bit DOF indices on one GPU");
     return TOPO_EINVAL;
   }
+  {
+    // The stage-1 kernel derives the row blocks of local nodes 1..3 from that of node 0 through the
+    // mirror symmetries of a rectangular, isotropic element (x-mirror: nodes [1,0,3,2], ux -> -ux;
+    // y-mirror: nodes [3,2,1,0], uy -> -uy).  Every matrix the reference builds on rect_grid meshes has
+    // them (closed form optimize.py:408-416; Gauss elast_quad4 on rectangles); anything else is refused.
+    const int px[4] = {1, 0, 3, 2}, py[4] = {3, 2, 1, 0};
+    double kmax = 0.0, dev = 0.0;
+    for (int i = 0; i < 64; ++i) kmax = fmax(kmax, fabs(ke[i]));
+    for (int a = 0; a < 4; ++a)
+      for (int d = 0; d < 2; ++d)
+        for (int b = 0; b < 4; ++b)
+          for (int e = 0; e < 2; ++e) {
+            const double v = ke[(2 * a + d) * 8 + 2 * b + e];
+            const double sx = ((d == 0) ? -1.0 : 1.0) * ((e == 0) ? -1.0 : 1.0);
+            const double sy = ((d == 1) ? -1.0 : 1.0) * ((e == 1) ? -1.0 : 1.0);
+            dev = fmax(dev, fabs(ke[(2 * px[a] + d) * 8 + 2 * px[b] + e] - sx * v));
+            dev = fmax(dev, fabs(ke[(2 * py[a] + d) * 8 + 2 * py[b] + e] - sy * v));
+            dev = fmax(dev, fabs(ke[(2 * b + e) * 8 + 2 * a + d] - v));
+          }
+    if (!(kmax > 0.0) || dev > 1e-9 * kmax) {
+      topo_set_error("topo_create: element matrix is not that of a rectangular isotropic quad4 "
+                     "(symmetry defect %.3e of max entry %.3e)", dev, kmax);
+      return TOPO_EINVAL;
+    }
+  }
   int ndev = 0;
   TOPO_TRY(topo_device_count(&ndev));
   if (device < 0 || device >= ndev) {
@@ -126,12 +152,12 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->prof_n = 0;
 
   // nodal vectors in one slab (z and p adjacent: ESO_stress borrows them as 3 planes of nn doubles)
-  const size_t nvec = 9;
+  const size_t nvec = 12;
   double2 *slab = nullptr;
   CUDA_TRY(cudaMalloc(&slab, sizeof(double2) * (size_t)h->nn * nvec));
   CUDA_TRY(cudaMemsetAsync(slab, 0, sizeof(double2) * (size_t)h->nn * nvec, h->stream));
   h->slab_nodal = slab;
-  double2 **vecs[nvec] = {&h->u, &h->f, &h->r, &h->z, &h->p, &h->Ap, &h->dinv, &h->tmp, &h->tmp2};
+  double2 **vecs[nvec] = {&h->u, &h->f, &h->r, &h->z, &h->p, &h->Ap, &h->dinv, &h->tmp, &h->tmp2, &h->u2, &h->r2, &h->p2};
   for (size_t i = 0; i < nvec; ++i) *vecs[i] = slab + i * (size_t)h->nn;
   double *eslab = nullptr;
   const size_t nev = 7;

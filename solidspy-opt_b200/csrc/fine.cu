@@ -1,0 +1,539 @@
+// Stage 1 + the fine-grid half of stage 2: matrix-free application of K(scale) on the structured
+// quad4 mesh, fused with the PCG / multigrid vector work that surrounds it.
+//
+// Replaces reference solver.py:364-410 (sparse_assem) and the CSR products inside spsolve /
+// stiff_mat.dot (optimize.py:437,455): K is never formed.
+//
+// Kernel shape ("staged marching"):
+//   * a CTA of 128 threads owns 128 node columns (+1 halo column each side) and marches over a
+//     chunk of node rows;
+//   * every raw input vector (1..5 per kernel) is streamed row by row into a shared-memory ring with
+//     cp.async (LDGSTS) D rows ahead of use, so the bytes in flight per SM are set by the ring depth,
+//     not by registers or occupancy: that is what makes the kernel HBM-bound instead of
+//     latency-bound;  element scales ride in the same ring;
+//   * stage B ("derive"): each thread turns the raw values of ITS node of the newest row into the
+//     vector the stencil is applied to (e.g. p = z + beta p, or x~ = x^ + P x_coarse), stores side
+//     outputs, and publishes the value in a 2-slot shared row;
+//   * stage C: each thread gathers the 4 element contributions of ITS node from a 3x3 register window
+//     (new row read from shared memory: 3 LDS.128), so there are no atomics and no scatter; the 8x8
+//     element matrix is a kernel parameter, i.e. constant-bank operands of the DFMAs;
+//   * epilogue: fused axpy / smoothing / masking and warp+block+ordered-grid dot products.
+// Inputs that are also outputs (p, u, r) are written to a second buffer: neighbouring CTAs still read
+// the old halo rows/columns.
+// Algorithmic traffic of the plain product: 16 B (u) + 16 B (y) per node + 8 B per element.
+#include "topo_internal.cuh"
+
+namespace {
+
+constexpr int BW = 128;        // own columns per CTA
+constexpr int SW = BW + 2;     // staged node columns
+constexpr int EW = BW + 1;     // staged element columns (c0-1 .. c0+BW-1)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+enum {
+  FK_APPLY = 0,        // y = mask(A u)                                  raw: u
+  FK_RESID = 1,        // y = mask(b - A u)                              raw: u, b
+  FK_PCG_MATVEC = 2,   // p' = z + beta p ; Ap = A p' ; pAp              raw: z, p
+  FK_PCG_MATVEC_J = 3, // p' = dinv*r + beta p ; Ap ; pAp  (Jacobi)      raw: r, p, dinv
+  FK_UPDATE_RESID0 = 4,// u' = u + alpha p ; r' = r - alpha Ap ; rr ;    raw: p, Ap, u, r, dinv
+                       // x^ = omega dinv r' ; res = r' - A x^
+  FK_PROLONG_SMOOTH = 5,// x~ = x^ + P xc ; z = x~ + omega dinv (r - A x~) ; rz   raw: x^, r, dinv
+  FK_SMOOTH = 6        // y = u + omega dinv (b - A u)                   raw: u, b, dinv
+};
+
+// ring depth: S = 6 slots for every kind (4 rows in flight per CTA); the row loop is unrolled by 6 so
+// that ring slots AND the 3-row register window are compile-time (no index arithmetic, no moves)
+constexpr int S = 6, D = S - 2;
+template <int K> struct FK;
+template <> struct FK<FK_APPLY> { static constexpr int NIN = 1; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_RESID> { static constexpr int NIN = 2; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_SMOOTH> { static constexpr int NIN = 3; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_PCG_MATVEC> { static constexpr int NIN = 2; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PCG_MATVEC_J> { static constexpr int NIN = 3; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_UPDATE_RESID0> { static constexpr int NIN = 5; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PROLONG_SMOOTH> { static constexpr int NIN = 3; static constexpr bool DERIVE = true; };
+
+struct FineArgs {
+  const double2 *in[5];
+  double2 *out[4];
+  const double *scale;
+  const uint8_t *fixed;
+  const double2 *coarse;     // FK_PROLONG_SMOOTH: level-1 correction (nullptr: already added)
+  int cnx;                   // its cells per row
+  double omega;
+  double *partials;
+  unsigned int *ticket;
+  double *dot_out;           // FK_APPLY with want_dot
+  SolverScalars *sc;
+  int nx, ny, rows_per_chunk;
+  int want_dot;              // FK_APPLY: reduce u.y into dot_out
+  int check_done;            // early exit when sc->done
+  int init;                  // FK_UPDATE_RESID0 / FK_PROLONG_SMOOTH: first pass (alpha = 0, beta = 0)
+};
+
+// Rows 0 and 1 of the element matrix (the row block of local node 0).  For a rectangular element of an
+// isotropic material the row blocks of the other three local nodes follow from it by the element's
+// mirror symmetries (node permutation + sign flips, checked on the host in topo_create), so the 72
+// DFMAs of a node use 16 constants that live in ordinary registers.  (On sm_100a DFMA cannot take a
+// constant-bank operand: with all 64 entries as kernel-parameter constants ptxas spends two R2UR per
+// DFMA and 128 registers on them.)
+struct KeRow {
+  double r0[8], r1[8];
+};
+
+// FLIP = false: t = R0 . q      (NE element, node is local 0; SW element with nodes permuted [2,3,0,1])
+// FLIP = true : mirrored once   (NW element: x-mirror; SE element: y-mirror) -- same sign pattern
+template <bool FLIP>
+__device__ __forceinline__ void row_terms(const KeRow &k, const double2 &q0, const double2 &q1, const double2 &q2,
+                                          const double2 &q3, double &tx, double &ty) {
+  if (!FLIP) {
+    tx = k.r0[0] * q0.x;            ty = k.r1[0] * q0.x;
+    tx = fma(k.r0[1], q0.y, tx);    ty = fma(k.r1[1], q0.y, ty);
+    tx = fma(k.r0[2], q1.x, tx);    ty = fma(k.r1[2], q1.x, ty);
+    tx = fma(k.r0[3], q1.y, tx);    ty = fma(k.r1[3], q1.y, ty);
+    tx = fma(k.r0[4], q2.x, tx);    ty = fma(k.r1[4], q2.x, ty);
+    tx = fma(k.r0[5], q2.y, tx);    ty = fma(k.r1[5], q2.y, ty);
+    tx = fma(k.r0[6], q3.x, tx);    ty = fma(k.r1[6], q3.x, ty);
+    tx = fma(k.r0[7], q3.y, tx);    ty = fma(k.r1[7], q3.y, ty);
+  } else {
+    tx = k.r0[0] * q0.x;            ty = k.r1[1] * q0.y;
+    tx = fma(-k.r0[1], q0.y, tx);   ty = fma(-k.r1[0], q0.x, ty);
+    tx = fma(k.r0[2], q1.x, tx);    ty = fma(-k.r1[2], q1.x, ty);
+    tx = fma(-k.r0[3], q1.y, tx);   ty = fma(k.r1[3], q1.y, ty);
+    tx = fma(k.r0[4], q2.x, tx);    ty = fma(-k.r1[4], q2.x, ty);
+    tx = fma(-k.r0[5], q2.y, tx);   ty = fma(k.r1[5], q2.y, ty);
+    tx = fma(k.r0[6], q3.x, tx);    ty = fma(-k.r1[6], q3.x, ty);
+    tx = fma(-k.r0[7], q3.y, tx);   ty = fma(k.r1[7], q3.y, ty);
+  }
+}
+
+__device__ __forceinline__ void prolong_taps1(int i, int nf, int &I0, int &I1, double &w1) {
+  if ((i & 1) == 0) { I0 = I1 = i >> 1; w1 = 0.0; }
+  else if (i == nf) { I0 = I1 = (i + 1) >> 1; w1 = 0.0; }
+  else { I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w1 = 0.5; }
+}
+
+// register image of one node row as seen by a thread: stencil input at columns c-1, c, c+1 and the
+// scales of the two elements BELOW the row (element row q-1, columns c-1 and c)
+struct RowWin {
+  double2 u[3];
+  double el, er;
+};
+
+template <int V> struct IC { static constexpr int value = V; };
+
+template <int KIND>
+__global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kparam, const __grid_constant__ FineArgs a) {
+  const KeRow ke = kparam;                                // 16 constants -> registers
+  constexpr int NIN = FK<KIND>::NIN;
+  constexpr bool DERIVE = FK<KIND>::DERIVE;
+  constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID || KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J);
+  if (a.check_done && a.sc->done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *raw = reinterpret_cast<double2 *>(smem_raw);                 // [S][NIN][SW]
+  double2 *der = raw + S * NIN * SW;                                     // [2][SW] (DERIVE kinds)
+  double *ering = reinterpret_cast<double *>(der + 2 * SW);              // [S][EW]
+
+  const int t = threadIdx.x;
+  const int npr = a.nx + 1;
+  const int c0 = blockIdx.x * BW;
+  const int c = c0 + t;                                  // own node column (staged column t+1)
+  const int r0 = blockIdx.y * a.rows_per_chunk;
+  const int r1 = min(r0 + a.rows_per_chunk, a.ny + 1);
+  const bool col_ok = c < npr;
+  const bool ecol_ok = c < a.nx;
+  // halo duty: thread 0 -> staged col 0 (node col c0-1), thread 1 -> staged col SW-1 (node col c0+BW)
+  const int hs = (t == 0) ? 0 : SW - 1;
+  const int hc = (t == 0) ? c0 - 1 : c0 + BW;
+  const bool has_halo = t < 2;
+  const bool hcol_ok = has_halo && hc >= 0 && hc < npr;
+  const bool ehalo_ok = (t == 0) && c0 > 0;
+  // column offsets clamped into the row so that masked (zero-fill) copies still carry a valid address
+  const int coff = col_ok ? c : 0, hoff = hcol_ok ? hc : 0;
+  const int eoff = ecol_ok ? c : 0, ehoff = ehalo_ok ? c0 - 1 : 0;
+
+  double alpha = 0.0, beta = 0.0;
+  if (KIND == FK_UPDATE_RESID0 && !a.init) alpha = a.sc->rz[0] / a.sc->pAp;
+  if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) beta = a.sc->rz[1];     // rz[1] holds beta (pcg.cu)
+  const double omega = a.omega;
+
+  // ---- copies of group G_q = {raw row q, element row q-1} into ring slot SL = (q - (r0-1)) mod S ----
+  int q_issue = r0 - 1;
+  auto issue = [&](auto slc) {
+    constexpr int SL = decltype(slc)::value;
+    const int q = q_issue++;
+    const bool row_ok = q >= 0 && q <= a.ny;
+    const size_t rowoff = (size_t)(row_ok ? q : 0) * npr;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+      double2 *dst = raw + (SL * NIN + k) * SW;
+      const double2 *src = a.in[k] + rowoff;
+      cp_async16(dst + t + 1, src + coff, row_ok && col_ok);
+      if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
+    }
+    const bool erow_ok = q >= 1 && q <= a.ny;
+    const double *esrc = a.scale + (size_t)(erow_ok ? q - 1 : 0) * a.nx;
+    double *edst = ering + SL * EW;
+    cp_async8(edst + t + 1, esrc + eoff, erow_ok && ecol_ok);
+    if (t == 0) cp_async8(edst, esrc + ehoff, erow_ok && ehalo_ok);
+    cp_async_commit();
+  };
+
+  double dots[1] = {0.0};
+
+  // ---- stage B (DERIVE kinds): stencil input of (row, staged column) from this thread's raw copies ----
+  auto derive_at = [&](const double2 *rw, int row, int ncol, bool own) -> double2 {
+    const bool in_dom = row >= 0 && row <= a.ny && ncol >= 0 && ncol < npr;
+    const size_t n = (size_t)(in_dom ? row : 0) * npr + (in_dom ? ncol : 0);
+    const bool store = own && in_dom && row >= r0 && row < r1;
+    if (KIND == FK_PCG_MATVEC) {
+      const double2 z = rw[0], p = rw[SW];
+      const double2 v = make_double2(fma(beta, p.x, z.x), fma(beta, p.y, z.y));
+      if (store) a.out[0][n] = v;
+      return v;
+    } else if (KIND == FK_PCG_MATVEC_J) {
+      const double2 r = rw[0], p = rw[SW], d = rw[2 * SW];
+      const double2 v = make_double2(fma(beta, p.x, d.x * r.x), fma(beta, p.y, d.y * r.y));
+      if (store) a.out[0][n] = v;
+      return v;
+    } else if (KIND == FK_UPDATE_RESID0) {
+      const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = rw[4 * SW];
+      const double2 rn = make_double2(fma(-alpha, ap.x, r.x), fma(-alpha, ap.y, r.y));
+      const double2 xh = make_double2(omega * d.x * rn.x, omega * d.y * rn.y);
+      if (store) {
+        a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
+        a.out[1][n] = rn;
+        a.out[2][n] = xh;
+        dots[0] = fma(rn.x, rn.x, fma(rn.y, rn.y, dots[0]));
+      }
+      return xh;
+    } else {  // FK_PROLONG_SMOOTH
+      const double2 xh = rw[0], d = rw[2 * SW];
+      double px = 0.0, py = 0.0;
+      if (in_dom && a.coarse != nullptr) {
+        int I0, I1, J0, J1;
+        double wx1, wy1;
+        prolong_taps1(ncol, a.nx, I0, I1, wx1);
+        prolong_taps1(row, a.ny, J0, J1, wy1);
+        const double wx0 = 1.0 - wx1, wy0 = 1.0 - wy1;
+        const int nprc = a.cnx + 1;
+        const double2 v00 = __ldg(a.coarse + (size_t)J0 * nprc + I0);
+        px = wy0 * wx0 * v00.x;
+        py = wy0 * wx0 * v00.y;
+        if (wx1 != 0.0) {
+          const double2 v = __ldg(a.coarse + (size_t)J0 * nprc + I1);
+          px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
+        }
+        if (wy1 != 0.0) {
+          const double2 v = __ldg(a.coarse + (size_t)J1 * nprc + I0);
+          px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
+          if (wx1 != 0.0) {
+            const double2 w = __ldg(a.coarse + (size_t)J1 * nprc + I1);
+            px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
+          }
+        }
+      }
+      return make_double2(d.x != 0.0 ? xh.x + px : 0.0, d.y != 0.0 ? xh.y + py : 0.0);
+    }
+  };
+  // SL = ring slot of `row`; derived rows alternate between the two `der` slots
+  auto stage_b = [&](auto slc, int row) {
+    constexpr int SL = decltype(slc)::value;
+    if (DERIVE) {
+      double2 *dr = der + (SL & 1) * SW;
+      const double2 *rw = raw + SL * NIN * SW;
+      dr[t + 1] = derive_at(rw + t + 1, row, c, true);
+      if (has_halo) dr[hs] = derive_at(rw + hs, row, hc, false);
+    }
+  };
+  // register image of the node row held in ring slot SL (after the barrier that publishes it)
+  auto fill = [&](auto slc, RowWin &w) {
+    constexpr int SL = decltype(slc)::value;
+    const double2 *src = DERIVE ? (der + (SL & 1) * SW + t) : (raw + SL * NIN * SW + t);
+    w.u[0] = src[0]; w.u[1] = src[1]; w.u[2] = src[2];
+    const double *e = ering + SL * EW + t;
+    w.el = e[0]; w.er = e[1];
+  };
+
+  // ---- prologue: S groups in flight (rows r0-1 .. r0+D), rows r0-1 and r0 resident ----
+  issue(IC<0>()); issue(IC<1>()); issue(IC<2>()); issue(IC<3>()); issue(IC<4>()); issue(IC<5>());
+  cp_async_wait<D>();
+  RowWin Wa, Wb, Wc;
+  if (DERIVE) {
+    stage_b(IC<0>(), r0 - 1);
+    stage_b(IC<1>(), r0);
+  }
+  __syncthreads();
+  fill(IC<0>(), Wa);
+  fill(IC<1>(), Wb);
+  unsigned fx_next = 0;
+  if (NEEDS_FIXED && col_ok && r0 < r1) fx_next = a.fixed[(size_t)r0 * npr + c];
+  size_t n_out = (size_t)r0 * npr + c;
+
+  // one node row r held in slot K+1: Wm = row r-1, W0 = row r, Wp receives row r+1 (slot K+2);
+  // the slot of row r-1 (K) is refilled with row r-1+S
+  auto step = [&](auto kc, int r, const RowWin &Wm, const RowWin &W0, RowWin &Wp) {
+    constexpr int K = decltype(kc)::value;
+    constexpr int S_prev = K % S, S_cur = (K + 1) % S, S_next = (K + 2) % S;
+    cp_async_wait<D - 1>();                                // group G_{r+1} has landed (this thread's part)
+    stage_b(IC<S_next>(), r + 1);
+    __syncthreads();                                       // row r+1 visible; everyone is done with row r-1's slot
+    issue(IC<S_prev>());
+    fill(IC<S_next>(), Wp);
+    const unsigned fx = fx_next;
+    if (NEEDS_FIXED && col_ok && r + 1 < r1) fx_next = a.fixed[n_out + npr];
+    double yx, yy, tx, ty;
+    row_terms<false>(ke, W0.u[1], W0.u[2], Wp.u[2], Wp.u[1], tx, ty);   // NE element (r, c): node is local 0
+    yx = Wp.er * tx; yy = Wp.er * ty;
+    row_terms<true>(ke, W0.u[1], W0.u[0], Wp.u[0], Wp.u[1], tx, ty);    // NW (r, c-1): x-mirror image
+    yx = fma(Wp.el, tx, yx); yy = fma(Wp.el, ty, yy);
+    row_terms<false>(ke, W0.u[1], W0.u[0], Wm.u[0], Wm.u[1], tx, ty);   // SW (r-1, c-1): point-mirror image
+    yx = fma(W0.el, tx, yx); yy = fma(W0.el, ty, yy);
+    row_terms<true>(ke, W0.u[1], W0.u[2], Wm.u[2], Wm.u[1], tx, ty);    // SE (r-1, c): y-mirror image
+    yx = fma(W0.er, tx, yx); yy = fma(W0.er, ty, yy);
+    if (col_ok) {
+      const size_t n = n_out;
+      const double2 *rw = raw + S_cur * NIN * SW + t + 1;            // raw inputs of this node
+      const double2 v = W0.u[1];
+      if (KIND == FK_APPLY) {
+        if (fx & 1u) yx = 0.0;
+        if (fx & 2u) yy = 0.0;
+        a.out[0][n] = make_double2(yx, yy);
+        if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+      } else if (KIND == FK_RESID) {
+        const double2 b = rw[SW];
+        a.out[0][n] = make_double2((fx & 1u) ? 0.0 : b.x - yx, (fx & 2u) ? 0.0 : b.y - yy);
+      } else if (KIND == FK_SMOOTH) {
+        const double2 b = rw[SW], d = rw[2 * SW];
+        a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
+      } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
+        if (fx & 1u) yx = 0.0;
+        if (fx & 2u) yy = 0.0;
+        a.out[1][n] = make_double2(yx, yy);
+        dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+      } else if (KIND == FK_UPDATE_RESID0) {
+        const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
+        const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
+        a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
+      } else {  // FK_PROLONG_SMOOTH
+        const double2 rr = rw[SW], d = rw[2 * SW];
+        const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
+        a.out[0][n] = make_double2(zx, zy);
+        dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+      }
+    }
+    n_out += npr;
+  };
+  // six rows per trip: ring slots and the 3-row register window are compile-time
+  for (int r = r0; r < r1; r += 6) {
+    step(IC<0>(), r, Wa, Wb, Wc);
+    if (r + 1 < r1) step(IC<1>(), r + 1, Wb, Wc, Wa);
+    if (r + 2 < r1) step(IC<2>(), r + 2, Wc, Wa, Wb);
+    if (r + 3 < r1) step(IC<3>(), r + 3, Wa, Wb, Wc);
+    if (r + 4 < r1) step(IC<4>(), r + 4, Wb, Wc, Wa);
+    if (r + 5 < r1) step(IC<5>(), r + 5, Wc, Wa, Wb);
+  }
+  cp_async_wait<0>();
+
+  // ---- reductions + scalar bookkeeping (last block) ----
+  if (KIND == FK_APPLY) {
+    if (a.want_dot) grid_reduce<1>(dots, a.partials, a.ticket, a.dot_out);
+  } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) a.sc->pAp = dots[0];
+  } else if (KIND == FK_UPDATE_RESID0) {
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) {
+      SolverScalars *sc = a.sc;
+      sc->rr = dots[0];
+      if (!a.init) sc->iters += 1;
+      if (dots[0] <= sc->tol2 * sc->bb || !(dots[0] == dots[0])) sc->done = 1;
+      else if (sc->iters >= sc->maxit) sc->done = 2;
+    }
+  } else if (KIND == FK_PROLONG_SMOOTH) {
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) {
+      SolverScalars *sc = a.sc;
+      sc->rz[1] = a.init ? 0.0 : dots[0] / sc->rz[0];      // beta for the next direction update
+      sc->rz[0] = dots[0];
+    }
+  }
+}
+
+template <int KIND>
+size_t fine_smem() {
+  constexpr int NIN = FK<KIND>::NIN;
+  return sizeof(double2) * (S * NIN * SW + 2 * SW) + sizeof(double) * S * EW;
+}
+
+template <int KIND>
+int launch_fine(topo_handle *h, FineArgs &a) {
+  a.scale = h->scale;
+  a.fixed = h->fixed;
+  a.nx = h->nx;
+  a.ny = h->ny;
+  a.rows_per_chunk = h->matvec_rows_per_chunk;
+  a.partials = h->partials;
+  a.ticket = h->ticket;
+  a.sc = h->sc;
+  dim3 grid(div_up(h->nx + 1, BW), div_up(h->ny + 1, a.rows_per_chunk));
+  if ((int64_t)grid.x * grid.y > TOPO_MAX_PARTIAL_BLOCKS) {
+    topo_set_error("fine-grid launch too large for the reduction buffer");
+    return TOPO_EINVAL;
+  }
+  static bool attr_set = false;
+  const size_t smem = fine_smem<KIND>();
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const bool prof = h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size();
+  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
+  KeRow kr;
+  for (int j = 0; j < 8; ++j) { kr.r0[j] = h->ke.k[j]; kr.r1[j] = h->ke.k[8 + j]; }
+  k_fine<KIND><<<grid, BW, smem, h->stream>>>(kr, a);
+  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n++ + 1], h->stream);
+  h->timing.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// diag(K) per node from the 4 adjacent element scales; stores 1/diag (0 at constrained DOFs) and the
+// max diagonal over free DOFs (= K.max() of the reference's equilibrium guard, optimize.py:455: the
+// largest entry of an SPD matrix sits on its diagonal).
+__global__ void k_build_diag(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
+                             const uint8_t *__restrict__ fixed, double2 *__restrict__ dinv, int nx, int ny,
+                             double *partials, unsigned int *ticket, double *kmax_out) {
+  const int64_t nn = (int64_t)(nx + 1) * (ny + 1);
+  double mx = 0.0;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(n / (nx + 1)), c = (int)(n - (int64_t)r * (nx + 1));
+    const double ne = (r < ny && c < nx) ? scale[(size_t)r * nx + c] : 0.0;
+    const double nw = (r < ny && c > 0) ? scale[(size_t)r * nx + c - 1] : 0.0;
+    const double sw = (r > 0 && c > 0) ? scale[(size_t)(r - 1) * nx + c - 1] : 0.0;
+    const double se = (r > 0 && c < nx) ? scale[(size_t)(r - 1) * nx + c] : 0.0;
+    const double dx = ne * ke.k[0 * 8 + 0] + nw * ke.k[2 * 8 + 2] + sw * ke.k[4 * 8 + 4] + se * ke.k[6 * 8 + 6];
+    const double dy = ne * ke.k[1 * 8 + 1] + nw * ke.k[3 * 8 + 3] + sw * ke.k[5 * 8 + 5] + se * ke.k[7 * 8 + 7];
+    const unsigned fx = fixed[n];
+    double ix = 0.0, iy = 0.0;
+    if (!(fx & 1u)) {
+      mx = fmax(mx, dx);
+      ix = dx > 0.0 ? 1.0 / dx : 0.0;
+    }
+    if (!(fx & 2u)) {
+      mx = fmax(mx, dy);
+      iy = dy > 0.0 ? 1.0 / dy : 0.0;
+    }
+    dinv[n] = make_double2(ix, iy);
+  }
+  double v[1] = {mx};
+  grid_reduce<1, true>(v, partials, ticket, kmax_out);
+}
+
+}  // namespace
+
+// ---- drivers -------------------------------------------------------------------------------------------
+int topo_fine_matvec(topo_handle *h, const double2 *u, double2 *y) {
+  FineArgs a = {};
+  a.in[0] = u;
+  a.out[0] = y;
+  return launch_fine<FK_APPLY>(h, a);
+}
+
+int topo_fine_residual(topo_handle *h, const double2 *u, const double2 *b, double2 *r) {
+  FineArgs a = {};
+  a.in[0] = u;
+  a.in[1] = b;
+  a.out[0] = r;
+  return launch_fine<FK_RESID>(h, a);
+}
+
+int topo_fine_smooth(topo_handle *h, const double2 *x, const double2 *b, double2 *x_out, double omega) {
+  FineArgs a = {};
+  a.in[0] = x;
+  a.in[1] = b;
+  a.in[2] = h->dinv;
+  a.out[0] = x_out;
+  a.omega = omega;
+  return launch_fine<FK_SMOOTH>(h, a);
+}
+
+// p_out = z + beta p_in (beta from sc) ; Ap = A p_out ; sc->pAp
+int topo_fine_pcg_matvec(topo_handle *h, const double2 *z, const double2 *p_in, double2 *p_out, double2 *Ap) {
+  FineArgs a = {};
+  a.in[0] = z;
+  a.in[1] = p_in;
+  a.out[0] = p_out;
+  a.out[1] = Ap;
+  a.check_done = 1;
+  return launch_fine<FK_PCG_MATVEC>(h, a);
+}
+
+// Jacobi flavour: p_out = dinv*r + beta p_in
+int topo_fine_pcg_matvec_jacobi(topo_handle *h, const double2 *r, const double2 *p_in, double2 *p_out, double2 *Ap) {
+  FineArgs a = {};
+  a.in[0] = r;
+  a.in[1] = p_in;
+  a.in[2] = h->dinv;
+  a.out[0] = p_out;
+  a.out[1] = Ap;
+  a.check_done = 1;
+  return launch_fine<FK_PCG_MATVEC_J>(h, a);
+}
+
+// u_out = u_in + alpha p ; r_out = r_in - alpha Ap ; rr, convergence flag ; xhat = omega dinv r_out ;
+// res = r_out - A xhat
+int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap, const double2 *u_in,
+                            const double2 *r_in, double2 *u_out, double2 *r_out, double2 *xhat, double2 *res,
+                            double omega, int init) {
+  FineArgs a = {};
+  a.in[0] = p;
+  a.in[1] = Ap;
+  a.in[2] = u_in;
+  a.in[3] = r_in;
+  a.in[4] = h->dinv;
+  a.out[0] = u_out;
+  a.out[1] = r_out;
+  a.out[2] = xhat;
+  a.out[3] = res;
+  a.omega = omega;
+  a.init = init;
+  a.check_done = init ? 0 : 1;
+  return launch_fine<FK_UPDATE_RESID0>(h, a);
+}
+
+// z = x~ + omega dinv (r - A x~), x~ = xhat + P xc ; sc->rz, beta
+int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 *r, const double2 *xc, int cnx,
+                             double2 *z, double omega, int init) {
+  FineArgs a = {};
+  a.in[0] = xhat;
+  a.in[1] = r;
+  a.in[2] = h->dinv;
+  a.out[0] = z;
+  a.coarse = xc;
+  a.cnx = cnx;
+  a.omega = omega;
+  a.init = init;
+  a.check_done = init ? 0 : 1;
+  return launch_fine<FK_PROLONG_SMOOTH>(h, a);
+}
+
+int topo_build_diag(topo_handle *h) {
+  const int blocks = (int)std::min<int64_t>(div_up(h->nn, 256), 1184);
+  k_build_diag<<<blocks, 256, 0, h->stream>>>(h->ke, h->scale, h->fixed, h->dinv, h->nx, h->ny, h->partials,
+                                              h->ticket, h->kmax);
+  h->timing.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  h->diag_valid = true;
+  return TOPO_OK;
+}

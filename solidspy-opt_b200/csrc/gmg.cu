@@ -15,9 +15,6 @@
 
 #include "topo_internal.cuh"
 
-int topo_fine_smooth(topo_handle *h, const double2 *x, const double2 *b, double2 *x_out, double omega,
-                     const int *done);
-
 namespace {
 
 #define LAUNCHED(h) ((h)->timing.kernel_launches++)
@@ -484,30 +481,18 @@ int topo_gmg_setup(topo_handle *h) {
   return TOPO_OK;
 }
 
-// z = V(r): one V-cycle with zero initial guess.  `r` is not modified.  Uses h->tmp (fine residual)
-// and h->tmp2 (fine ping-pong buffer).
-int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z) {
+// Coarse part of the V-cycle.  Input: the fine-grid residual after the first smoothing step
+// (res = r - A x^, computed by the fused fine kernel).  Restricts it, runs levels 1..L-1 with a zero
+// initial guess on each (damped-Jacobi pre/post smoothing, dense solve on the coarsest level) and adds
+// the prolongated level-1 correction into the fine-grid iterate x^ (constrained DOFs stay zero).
+int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine) {
   cudaStream_t st = h->stream;
   const double om = h->omega;
   const int L = h->n_levels;
-  if (L < 2) {   // degenerate hierarchy: plain Jacobi
-    k_smooth0<<<std::min(blocks_for(h->nn, 256), 1184), 256, 0, st>>>(r, h->dinv, z, h->nn, 1.0);
-    LAUNCHED(h);
-    return TOPO_OK;
-  }
-  // ---- down ----
-  // level 0: pre-smooth into xa
-  double2 *xa = h->tmp2, *xb = z;
-  k_smooth0<<<std::min(blocks_for(h->nn, 256), 1184), 256, 0, st>>>(r, h->dinv, xa, h->nn, om);
-  LAUNCHED(h);
-  for (int s = 1; s < h->nu_pre; ++s) {
-    TOPO_TRY(topo_fine_smooth(h, xa, r, xb, om, nullptr));
-    std::swap(xa, xb);
-  }
-  TOPO_TRY(topo_fine_residual(h, xa, r, h->tmp));
+  if (L < 2) return TOPO_OK;
   {
     GmgLevel &C = h->levels[1];
-    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(h->tmp, C.b, h->nx, h->ny, C.nx, C.ny);
+    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(res_fine, C.b, h->nx, h->ny, C.nx, C.ny);
     LAUNCHED(h);
   }
   for (int l = 1; l < L - 1; ++l) {
@@ -524,13 +509,11 @@ int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z) {
     k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny);
     LAUNCHED(h);
   }
-  // ---- coarsest ----
   {
     GmgLevel &C = h->levels[L - 1];
     k_coarse_apply<<<1, 64, 0, st>>>(h->coarse_inv, C.b, C.dinv, C.x, h->coarse_n);
     LAUNCHED(h);
   }
-  // ---- up ----
   for (int l = L - 2; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
     k_prolong_add<1><<<blocks_for(F.nn), 128, 0, st>>>(C.x, F.x, nullptr, F.dinv, F.nx, F.ny, C.nx);
@@ -543,15 +526,8 @@ int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z) {
   }
   {
     GmgLevel &C = h->levels[1];
-    k_prolong_add<0><<<blocks_for(h->nn), 128, 0, st>>>(C.x, xa, h->fixed, nullptr, h->nx, h->ny, C.nx);
+    k_prolong_add<0><<<blocks_for(h->nn), 128, 0, st>>>(C.x, xhat_fine, h->fixed, nullptr, h->nx, h->ny, C.nx);
     LAUNCHED(h);
-  }
-  for (int s = 0; s < h->nu_post; ++s) {
-    TOPO_TRY(topo_fine_smooth(h, xa, r, xb, om, nullptr));
-    std::swap(xa, xb);
-  }
-  if (xa != z) {
-    CUDA_TRY(cudaMemcpyAsync(z, xa, sizeof(double2) * (size_t)h->nn, cudaMemcpyDeviceToDevice, st));
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;

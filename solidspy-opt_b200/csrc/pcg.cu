@@ -1,45 +1,49 @@
 // Stage 2: preconditioned conjugate gradients on K u = f in full DOF space (replaces
 // scipy.sparse.linalg.spsolve, reference optimize.py:61,84,161,181,260,298,437).
 //
-// All PCG scalars (alpha, beta, residual norms, the convergence flag) stay in device memory
-// (SolverScalars); kernels read them directly, so the host only launches batches of iterations and
-// polls the `done` flag between batches.  Dot products are warp-shuffle + block + ordered grid
-// reductions (deterministic).
+// One PCG iteration with the multigrid preconditioner is
+//   K2  u' = u + alpha p ; r' = r - alpha Ap ; ||r'||^2 ; x^ = omega D^-1 r' ; res = r' - A x^   (fine.cu)
+//       restrict res, coarse levels of the V-cycle, prolongate into x^                                (gmg.cu)
+//   K4  z = x^ + omega D^-1 (r' - A x^) ; r'.z ; beta                                                 (fine.cu)
+//   K1  p' = z + beta p ; Ap = A p' ; p'.Ap                                                           (fine.cu)
+// i.e. three passes over the fine grid, every vector update and dot product fused into them.  All PCG
+// scalars (alpha, beta, norms, iteration count, convergence flag) live in device memory
+// (SolverScalars); the host only enqueues batches of iterations and polls the flag between batches.
+// Dot products are warp-shuffle + block + ordered grid reductions (deterministic).
 #include <algorithm>
 #include <cmath>
 
 #include "topo_internal.cuh"
 
-int topo_fine_matvec_dot(topo_handle *h, const double2 *u, double2 *y, double *dot_out, const int *done);
+int topo_fine_smooth(topo_handle *h, const double2 *x, const double2 *b, double2 *x_out, double omega);
+int topo_fine_pcg_matvec(topo_handle *h, const double2 *z, const double2 *p_in, double2 *p_out, double2 *Ap);
+int topo_fine_pcg_matvec_jacobi(topo_handle *h, const double2 *r, const double2 *p_in, double2 *p_out, double2 *Ap);
+int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap, const double2 *u_in,
+                            const double2 *r_in, double2 *u_out, double2 *r_out, double2 *xhat, double2 *res,
+                            double omega, int init);
+int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 *r, const double2 *xc, int cnx,
+                             double2 *z, double omega, int init);
+int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine);
 
 namespace {
 
 constexpr int VEC_THREADS = 256;
 inline int vec_blocks(int64_t n) { return (int)std::min<int64_t>(div_up(n, VEC_THREADS), 148 * 8); }
 
-// r = f - A u was computed by the residual kernel; this sets z = dinv*r (Jacobi) or takes z as given
-// (GMG), p = z, and reduces rz, rr, bb.  Also resets iteration state.
-__global__ void k_pcg_init(const double2 *__restrict__ r, const double2 *__restrict__ f,
-                           const double2 *__restrict__ dinv, double2 *__restrict__ z, double2 *__restrict__ p,
-                           int64_t nn, int jacobi, double *partials, unsigned int *ticket, SolverScalars *sc) {
+// Jacobi path: rz = r.(dinv r), rr, bb ; beta = 0
+__global__ void k_pcg_init_jacobi(const double2 *__restrict__ r, const double2 *__restrict__ f,
+                                  const double2 *__restrict__ dinv, int64_t nn, double *partials,
+                                  unsigned int *ticket, SolverScalars *sc) {
   double v[3] = {0.0, 0.0, 0.0};
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
-    const double2 rv = r[n], fv = f[n];
-    double2 zv;
-    if (jacobi) {
-      const double2 d = dinv[n];
-      zv = make_double2(d.x * rv.x, d.y * rv.y);
-      z[n] = zv;
-    } else {
-      zv = z[n];
-    }
-    p[n] = zv;
-    v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
+    const double2 rv = r[n], fv = f[n], d = dinv[n];
+    v[0] = fma(rv.x, d.x * rv.x, fma(rv.y, d.y * rv.y, v[0]));
     v[1] = fma(rv.x, rv.x, fma(rv.y, rv.y, v[1]));
     v[2] = fma(fv.x, fv.x, fma(fv.y, fv.y, v[2]));
   }
   if (grid_reduce<3>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
     sc->rz[0] = v[0];
+    sc->rz[1] = 0.0;
     sc->rr = v[1];
     sc->bb = v[2];
     sc->iters = 0;
@@ -47,17 +51,16 @@ __global__ void k_pcg_init(const double2 *__restrict__ r, const double2 *__restr
   }
 }
 
-// x += alpha p ; r -= alpha Ap ; [Jacobi: z = dinv r ; rz_new = r.z] ; rr = r.r ; convergence flag.
-__global__ void k_pcg_update(double2 *__restrict__ x, double2 *__restrict__ r, double2 *__restrict__ z,
-                             const double2 *__restrict__ p, const double2 *__restrict__ Ap,
-                             const double2 *__restrict__ dinv, int64_t nn, int jacobi, double *partials,
-                             unsigned int *ticket, SolverScalars *sc) {
+// Jacobi path: x += alpha p ; r -= alpha Ap ; rz_new = r.(dinv r) ; rr ; beta ; convergence flag
+__global__ void k_pcg_update_jacobi(double2 *__restrict__ x, double2 *__restrict__ r,
+                                    const double2 *__restrict__ p, const double2 *__restrict__ Ap,
+                                    const double2 *__restrict__ dinv, int64_t nn, double *partials,
+                                    unsigned int *ticket, SolverScalars *sc) {
   if (sc->done) return;
-  const int par = sc->iters & 1;
-  const double alpha = sc->rz[par] / sc->pAp;
+  const double alpha = sc->rz[0] / sc->pAp;
   double v[2] = {0.0, 0.0};
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
-    const double2 pv = p[n], av = Ap[n];
+    const double2 pv = p[n], av = Ap[n], d = dinv[n];
     double2 xv = x[n], rv = r[n];
     xv.x = fma(alpha, pv.x, xv.x);
     xv.y = fma(alpha, pv.y, xv.y);
@@ -65,64 +68,17 @@ __global__ void k_pcg_update(double2 *__restrict__ x, double2 *__restrict__ r, d
     rv.y = fma(-alpha, av.y, rv.y);
     x[n] = xv;
     r[n] = rv;
+    v[0] = fma(rv.x, d.x * rv.x, fma(rv.y, d.y * rv.y, v[0]));
     v[1] = fma(rv.x, rv.x, fma(rv.y, rv.y, v[1]));
-    if (jacobi) {
-      const double2 d = dinv[n];
-      const double2 zv = make_double2(d.x * rv.x, d.y * rv.y);
-      z[n] = zv;
-      v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
-    }
   }
   if (grid_reduce<2>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
+    sc->rz[1] = v[0] / sc->rz[0];
+    sc->rz[0] = v[0];
     sc->rr = v[1];
-    if (jacobi) sc->rz[par ^ 1] = v[0];
-    const int it = sc->iters + 1;
-    if (v[1] <= sc->tol2 * sc->bb || !(v[1] == v[1])) {   // converged (or NaN: stop, host reports)
-      sc->done = 1;
-      sc->iters = it;
-    } else if (jacobi) {
-      sc->iters = it;     // GMG: iteration counter advances in k_pcg_dir after rz_new is known
-      if (it >= sc->maxit) sc->done = 2;
-    }
+    sc->iters += 1;
+    if (v[1] <= sc->tol2 * sc->bb || !(v[1] == v[1])) sc->done = 1;
+    else if (sc->iters >= sc->maxit) sc->done = 2;
   }
-}
-
-// GMG path: rz_new = r.z after the V-cycle, then p = z + beta p in the same kernel is impossible
-// (beta needs the full dot), so: k_dot_rz reduces, k_pcg_dir updates p.
-__global__ void k_dot_rz(const double2 *__restrict__ r, const double2 *__restrict__ z, int64_t nn,
-                         double *partials, unsigned int *ticket, SolverScalars *sc) {
-  if (sc->done) return;
-  double v[1] = {0.0};
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
-    const double2 rv = r[n], zv = z[n];
-    v[0] = fma(rv.x, zv.x, fma(rv.y, zv.y, v[0]));
-  }
-  if (grid_reduce<1>(v, partials, ticket, sc->aux) && threadIdx.x == 0) {
-    const int par = sc->iters & 1;
-    sc->rz[par ^ 1] = v[0];
-    sc->iters = sc->iters + 1;
-    if (sc->iters >= sc->maxit) sc->done = 2;
-  }
-}
-
-// p = z + beta p with beta = rz_new / rz_old.  `iters` was already advanced, so new = parity(iters).
-__global__ void k_pcg_dir(double2 *__restrict__ p, const double2 *__restrict__ z, int64_t nn,
-                          const SolverScalars *sc) {
-  if (sc->done == 1) return;
-  const int par = sc->iters & 1;
-  const double beta = sc->rz[par] / sc->rz[par ^ 1];
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
-    const double2 zv = z[n];
-    double2 pv = p[n];
-    pv.x = fma(beta, pv.x, zv.x);
-    pv.y = fma(beta, pv.y, zv.y);
-    p[n] = pv;
-  }
-}
-
-__global__ void k_store_pAp(SolverScalars *sc, const double *dot) {
-  if (sc->done) return;
-  sc->pAp = *dot;
 }
 
 __global__ void k_dot(const double2 *__restrict__ a, const double2 *__restrict__ b, int64_t nn,
@@ -181,6 +137,10 @@ __global__ void k_mask2(double2 *v, const uint8_t *fixed, int64_t nn) {
   }
 }
 
+__global__ void k_set_bb(SolverScalars *sc, const double *bb) {
+  sc->bb = *bb;
+}
+
 }  // namespace
 
 #define LAUNCHED(h) ((h)->timing.kernel_launches++)
@@ -227,11 +187,12 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   CUDA_TRY(cudaSetDevice(h->device));
   const int64_t nn = h->nn;
   const int nb = vec_blocks(nn);
+  const size_t vbytes = sizeof(double2) * (size_t)nn;
   cudaStream_t st = h->stream;
   CUDA_TRY(cudaEventRecord(h->ev0, st));
 
   TOPO_TRY(topo_build_diag(h));
-  const bool jacobi = precond == TOPO_PRECOND_JACOBI;
+  const bool jacobi = (precond == TOPO_PRECOND_JACOBI) || h->n_levels < 2;
   if (!jacobi) TOPO_TRY(topo_gmg_setup(h));
 
   if (!warm) {
@@ -245,13 +206,31 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   init.maxit = maxit;
   CUDA_TRY(cudaMemcpyAsync(h->sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
 
-  TOPO_TRY(topo_fine_residual(h, h->u, h->f, h->r));
-  if (!jacobi) TOPO_TRY(topo_gmg_vcycle(h, h->r, h->z));
-  k_pcg_init<<<nb, VEC_THREADS, 0, st>>>(h->r, h->f, h->dinv, h->z, h->p, nn, jacobi ? 1 : 0, h->partials,
-                                         h->ticket, h->sc);
-  LAUNCHED(h);
+  // ping-pong pairs: index 0 = current, 1 = other
+  double2 *ub[2] = {h->u, h->u2}, *rb[2] = {h->r, h->r2}, *pb[2] = {h->p, h->p2};
+  double2 *xhat = h->tmp2, *res = h->tmp;
+  TOPO_TRY(topo_fine_residual(h, ub[0], h->f, rb[0]));
+  CUDA_TRY(cudaMemsetAsync(pb[0], 0, vbytes, st));
+  int cur = 0;                                 // buffers holding the current u / r
+  int pcur = 0;                                // buffer holding the current p
 
-  const int batch = jacobi ? 50 : 4;
+  if (jacobi) {
+    k_pcg_init_jacobi<<<nb, VEC_THREADS, 0, st>>>(rb[0], h->f, h->dinv, nn, h->partials, h->ticket, h->sc);
+    LAUNCHED(h);
+  } else {
+    CUDA_TRY(cudaMemsetAsync(h->Ap, 0, vbytes, st));
+    k_dot<<<nb, VEC_THREADS, 0, st>>>(h->f, h->f, nn, h->partials, h->ticket, h->red_out);
+    LAUNCHED(h);
+    k_set_bb<<<1, 1, 0, st>>>(h->sc, h->red_out);
+    LAUNCHED(h);
+    // z0 = V(r0): the update kernel with alpha = 0 copies u, r into the other buffers
+    TOPO_TRY(topo_fine_update_resid0(h, pb[0], h->Ap, ub[0], rb[0], ub[1], rb[1], xhat, res, h->omega, 1));
+    cur = 1;
+    TOPO_TRY(topo_gmg_coarse(h, res, xhat));
+    TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[cur], nullptr, 0, h->z, h->omega, 1));
+  }
+
+  const int batch = jacobi ? 64 : 6;
   int launched = 0;
   SolverScalars *hs = h->sc_host;
   hs->done = 0;
@@ -262,22 +241,33 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
     if (hs->done || launched >= maxit) break;
     const int nrun = std::min(batch, maxit - launched);
     for (int i = 0; i < nrun; ++i) {
-      TOPO_TRY(topo_fine_matvec_dot(h, h->p, h->Ap, h->red_out, &h->sc->done));
-      k_store_pAp<<<1, 1, 0, st>>>(h->sc, h->red_out);
-      LAUNCHED(h);
-      k_pcg_update<<<nb, VEC_THREADS, 0, st>>>(h->u, h->r, h->z, h->p, h->Ap, h->dinv, nn, jacobi ? 1 : 0,
-                                               h->partials, h->ticket, h->sc);
-      LAUNCHED(h);
-      if (!jacobi) {
-        TOPO_TRY(topo_gmg_vcycle(h, h->r, h->z));
-        k_dot_rz<<<nb, VEC_THREADS, 0, st>>>(h->r, h->z, nn, h->partials, h->ticket, h->sc);
+      if (jacobi) {
+        TOPO_TRY(topo_fine_pcg_matvec_jacobi(h, rb[0], pb[pcur], pb[pcur ^ 1], h->Ap));
+        pcur ^= 1;
+        k_pcg_update_jacobi<<<nb, VEC_THREADS, 0, st>>>(ub[0], rb[0], pb[pcur], h->Ap, h->dinv, nn, h->partials,
+                                                        h->ticket, h->sc);
         LAUNCHED(h);
+      } else {
+        TOPO_TRY(topo_fine_pcg_matvec(h, h->z, pb[pcur], pb[pcur ^ 1], h->Ap));
+        pcur ^= 1;
+        TOPO_TRY(topo_fine_update_resid0(h, pb[pcur], h->Ap, ub[cur], rb[cur], ub[cur ^ 1], rb[cur ^ 1], xhat, res,
+                                         h->omega, 0));
+        cur ^= 1;
+        TOPO_TRY(topo_gmg_coarse(h, res, xhat));
+        TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[cur], nullptr, 0, h->z, h->omega, 0));
       }
-      k_pcg_dir<<<nb, VEC_THREADS, 0, st>>>(h->p, h->z, nn, h->sc);
-      LAUNCHED(h);
     }
     launched += nrun;
     CUDA_TRY(cudaGetLastError());
+  }
+  // The device executed hs->iters real iterations; later launches were no-ops.  GMG: the update of
+  // iteration k wrote buffer (k+1)&1 (the alpha=0 pass wrote buffer 1).
+  if (!jacobi) {
+    const int fin = (hs->iters + 1) & 1;
+    if (fin == 1) {
+      std::swap(h->u, h->u2);
+      std::swap(h->r, h->r2);
+    }
   }
   CUDA_TRY(cudaEventRecord(h->ev1, st));
   CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -285,13 +275,13 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   if (iters) *iters = hs->iters;
   const double rel = (hs->bb > 0.0) ? std::sqrt(hs->rr / hs->bb) : (hs->rr == 0.0 ? 0.0 : INFINITY);
   if (relres) *relres = rel;
+  if (!(hs->rr == hs->rr)) {
+    topo_set_error("PCG produced NaN (singular system?)");
+    return TOPO_ENOCONV;
+  }
   if (hs->done != 1) {
     topo_set_error("PCG did not converge: %d iterations, relative residual %.3e (rtol %.1e)", hs->iters, rel,
                    rtol);
-    return TOPO_ENOCONV;
-  }
-  if (!(hs->rr == hs->rr)) {
-    topo_set_error("PCG produced NaN (singular system?)");
     return TOPO_ENOCONV;
   }
   return TOPO_OK;

@@ -77,7 +77,7 @@ struct topo_handle {
   cudaStream_t stream;
 
   // fine-grid fields
-  double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2;
+  double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
   double *rho, *rho_new, *dc, *dc2, *scale, *sens, *sens_prev, *nodal;
   uint8_t *fixed, *keep;
   int8_t *cons_host_shadow;
@@ -133,7 +133,6 @@ int topo_fine_residual(topo_handle *h, const double2 *u, const double2 *b, doubl
 int topo_build_diag(topo_handle *h);
 int topo_gmg_plan(topo_handle *h);
 int topo_gmg_setup(topo_handle *h);
-int topo_gmg_vcycle(topo_handle *h, const double2 *r, double2 *z);
 int topo_apply_loads(topo_handle *h);
 
 #ifdef __CUDACC__
