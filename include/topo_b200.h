@@ -178,6 +178,9 @@ int topo_timer_stop(topo_t *h, float *ms);
  * while enabled; read returns the number of launches recorded and their summed duration. */
 int topo_profile_matvec(topo_t *h, int enable);
 int topo_profile_read(topo_t *h, int *launches, float *total_ms);
+/* While profiling is enabled EVERY kernel launch of the handle is bracketed by events; the report is a
+ * text table "kernel count total_ms" (one line per kernel, sorted by time) written into buf. */
+int topo_profile_report(topo_t *h, char *buf, size_t buflen);
 /* GMG hierarchy description: number of levels and the (nx, ny) of each (up to 32). */
 int topo_gmg_info(topo_t *h, int *n_levels, int *nx_levels, int *ny_levels);
 /* Solver knobs: omega = Jacobi damping of the V-cycle smoother, nu = sweeps pre/post. */

@@ -115,12 +115,19 @@ def p_big():
                              precond=_capi.PRECOND_GMG, maxit=2000, warm=1)
         g = 0.0
         for i in range(6):
+            if i == 5:
+                t.profile_matvec(True)
             t0 = time.time()
             g, res = t.simp_step(p, g)
             tm = t.timing()
             print("it %d: %.1f ms wall | cg %d relres %.1e | oc %d | compliance %.6e change %.3f | solve %.1f sens %.2f filt %.2f oc %.2f setup %.2f total %.1f ms | launches %d"
                   % (i, (time.time()-t0)*1e3, res.cg_iters, res.relres, res.oc_steps, res.compliance, res.change,
                      tm.solve_ms, tm.sens_ms, tm.filter_ms, tm.oc_ms, tm.setup_ms, tm.total_ms, tm.kernel_launches), flush=True)
+        rep = t.profile_report()
+        tot = sum(r[2] for r in rep)
+        print("in-situ kernel profile of the last iteration (sum %.2f ms):" % tot)
+        for name, n, ms in rep:
+            print("  %-28s n=%5d total=%8.3f ms avg=%8.2f us %5.1f%%" % (name, n, ms, ms/n*1e3, 100*ms/tot))
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["matvec", "solve", "simp", "beso", "big"]

@@ -11,5 +11,6 @@ t = _capi.Topo(nx, ny, kloc_simp(206.8e9, 0.28))
 cons = np.zeros((t.nn, 2), np.int8); cons[::nx + 1] = -1
 t.set_cons(cons); t.fill(_capi.F_RHO, 0.5); t.simp_scale(3.0, 1e-9, 1.0)
 t.set(_capi.F_U, np.random.default_rng(0).standard_normal(2*t.nn))
+t.matvec_device(5)
 ms = t.matvec_device(reps)
 print("matvec %.2f us  %.0f GB/s algorithmic" % (ms*1e3, (32*t.nn + 8*t.ne)/ms/1e6))

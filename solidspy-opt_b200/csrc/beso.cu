@@ -327,8 +327,7 @@ int build_prot(topo_handle *h, const int64_t *protect_nodes, int n_protect, uint
     int64_t *d_ids = reinterpret_cast<int64_t *>(h->tmp);
     if ((size_t)n_protect * sizeof(int64_t) > (size_t)h->nn * sizeof(double2)) return TOPO_EINVAL;
     CUDA_TRY(cudaMemcpyAsync(d_ids, protect_nodes, sizeof(int64_t) * n_protect, cudaMemcpyHostToDevice, h->stream));
-    k_mark_nodes<<<div_up(n_protect, 256), 256, 0, h->stream>>>(prot, d_ids, n_protect);
-    LAUNCHED(h);
+    KL(h, "k_mark_nodes", k_mark_nodes<<<div_up(n_protect, 256), 256, 0, h->stream>>>(prot, d_ids, n_protect));
   }
   *prot_out = prot;
   return TOPO_OK;
@@ -340,11 +339,9 @@ extern "C" int topo_energy_sensitivity(topo_t *h, int use_keep) {
   if (!h) return TOPO_EINVAL;
   (void)use_keep;
   CUDA_TRY(cudaSetDevice(h->device));
-  k_energy<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->keep, h->sens, h->nx, h->ny, h->partials, h->ticket,
-                                                   h->red_out);
-  LAUNCHED(h);
-  k_div_scalar<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->sens, h->red_out, h->ne);
-  LAUNCHED(h);
+  KL(h, "k_energy", k_energy<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->keep, h->sens, h->nx, h->ny, h->partials, h->ticket,
+                                                   h->red_out));
+  KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->sens, h->red_out, h->ne));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -361,15 +358,11 @@ extern "C" int topo_beso_filter(topo_t *h, const double w4[4], const double w2x[
   // h->sens holds a/amax already (topo_energy_sensitivity); nodes read it with divisor 1
   double one = 1.0;
   CUDA_TRY(cudaMemcpyAsync(h->red_out + 4, &one, sizeof(double), cudaMemcpyHostToDevice, st));
-  k_beso_nodes<<<el_blocks(h->nn), ET, 0, st>>>(W, h->sens, h->red_out + 4, h->nodal, h->nx, h->ny);
-  LAUNCHED(h);
-  k_beso_els<<<el_blocks(h->ne), ET, 0, st>>>(W, h->nodal, h->sens, h->nx, h->ny, h->partials, h->ticket, h->red_out);
-  LAUNCHED(h);
-  k_beso_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->sens_prev, h->red_out, average_with_prev ? 1 : 0, h->ne,
-                                               h->partials, h->ticket, h->red_out + 1);
-  LAUNCHED(h);
-  k_div_scalar<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out + 1, h->ne);
-  LAUNCHED(h);
+  KL(h, "k_beso_nodes", k_beso_nodes<<<el_blocks(h->nn), ET, 0, st>>>(W, h->sens, h->red_out + 4, h->nodal, h->nx, h->ny));
+  KL(h, "k_beso_els", k_beso_els<<<el_blocks(h->ne), ET, 0, st>>>(W, h->nodal, h->sens, h->nx, h->ny, h->partials, h->ticket, h->red_out));
+  KL(h, "k_beso_hist", k_beso_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->sens_prev, h->red_out, average_with_prev ? 1 : 0, h->ne,
+                                               h->partials, h->ticket, h->red_out + 1));
+  KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out + 1, h->ne));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -382,8 +375,7 @@ extern "C" int topo_beso_nodes(topo_t *h, const double w4[4], const double w2x[2
   for (int i = 0; i < 2; ++i) { W.w2x[i] = w2x[i]; W.w2y[i] = w2y[i]; }
   double one = 1.0;
   CUDA_TRY(cudaMemcpyAsync(h->red_out + 4, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  k_beso_nodes<<<el_blocks(h->nn), ET, 0, h->stream>>>(W, h->sens, h->red_out + 4, h->nodal, h->nx, h->ny);
-  LAUNCHED(h);
+  KL(h, "k_beso_nodes", k_beso_nodes<<<el_blocks(h->nn), ET, 0, h->stream>>>(W, h->sens, h->red_out + 4, h->nodal, h->nx, h->ny));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -394,11 +386,9 @@ extern "C" int topo_beso_elements(topo_t *h, const double we[4]) {
   BesoW W = {};
   for (int i = 0; i < 4; ++i) W.we[i] = we[i];
   W.wesum = ((we[0] + we[1]) + we[2]) + we[3];
-  k_beso_els<<<el_blocks(h->ne), ET, 0, h->stream>>>(W, h->nodal, h->sens, h->nx, h->ny, h->partials, h->ticket,
-                                                     h->red_out);
-  LAUNCHED(h);
-  k_div_scalar<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->sens, h->red_out, h->ne);
-  LAUNCHED(h);
+  KL(h, "k_beso_els", k_beso_els<<<el_blocks(h->ne), ET, 0, h->stream>>>(W, h->nodal, h->sens, h->nx, h->ny, h->partials, h->ticket,
+                                                     h->red_out));
+  KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->sens, h->red_out, h->ne));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -410,13 +400,10 @@ extern "C" int topo_rank_select(topo_t *h, int64_t k, double *alpha) {
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  k_sel_init<<<1, 256, 0, st>>>(h->sel, (unsigned long long)k);
-  LAUNCHED(h);
+  KL(h, "k_sel_init", k_sel_init<<<1, 256, 0, st>>>(h->sel, (unsigned long long)k));
   for (int pass = 0; pass < 8; ++pass) {
-    k_sel_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->ne, h->sel);
-    k_sel_scan<<<1, 256, 0, st>>>(h->sel, h->red_out + 2);
-    LAUNCHED(h);
-    LAUNCHED(h);
+    KL(h, "k_sel_hist", k_sel_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->ne, h->sel));
+    KL(h, "k_sel_scan", k_sel_scan<<<1, 256, 0, st>>>(h->sel, h->red_out + 2));
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(alpha, h->red_out + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -440,11 +427,9 @@ extern "C" int topo_beso_apply(topo_t *h, double alpha, const int64_t *protect_n
   uint8_t *prot = nullptr;
   TOPO_TRY(build_prot(h, protect_nodes, n_protect, &prot));
   CUDA_TRY(cudaMemcpyAsync(h->red_out + 2, &alpha, sizeof(double), cudaMemcpyHostToDevice, st));
-  k_beso_mask<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out + 2, prot, h->keep, h->nx, h->ny, h->partials,
-                                               h->ticket, h->red_out + 4);
-  LAUNCHED(h);
-  k_del_node<<<el_blocks(h->nn), ET, 0, st>>>(h->keep, prot, h->fixed, h->nx, h->ny, 1);
-  LAUNCHED(h);
+  KL(h, "k_beso_mask", k_beso_mask<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out + 2, prot, h->keep, h->nx, h->ny, h->partials,
+                                               h->ticket, h->red_out + 4));
+  KL(h, "k_del_node", k_del_node<<<el_blocks(h->nn), ET, 0, st>>>(h->keep, prot, h->fixed, h->nx, h->ny, 1));
   CUDA_TRY(cudaGetLastError());
   double cnt[2];
   CUDA_TRY(cudaMemcpyAsync(cnt, h->red_out + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -460,11 +445,9 @@ extern "C" int topo_eso_apply(topo_t *h, double rr, const int64_t *protect_nodes
   cudaStream_t st = h->stream;
   uint8_t *prot = nullptr;
   TOPO_TRY(build_prot(h, protect_nodes, n_protect, &prot));
-  k_eso_mask<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, rr, prot, h->keep, h->scale, h->nx, h->ny, h->partials,
-                                              h->ticket, h->red_out + 4);
-  LAUNCHED(h);
-  k_del_node<<<el_blocks(h->nn), ET, 0, st>>>(h->keep, prot, h->fixed, h->nx, h->ny, 0);
-  LAUNCHED(h);
+  KL(h, "k_eso_mask", k_eso_mask<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, rr, prot, h->keep, h->scale, h->nx, h->ny, h->partials,
+                                              h->ticket, h->red_out + 4));
+  KL(h, "k_del_node", k_del_node<<<el_blocks(h->nn), ET, 0, st>>>(h->keep, prot, h->fixed, h->nx, h->ny, 0));
   CUDA_TRY(cudaGetLastError());
   double cnt = 0.0;
   CUDA_TRY(cudaMemcpyAsync(&cnt, h->red_out + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -503,12 +486,9 @@ extern "C" int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double 
   cudaStream_t st = h->stream;
   double *sn = reinterpret_cast<double *>(h->tmp);       // 3*nn doubles fit in tmp (2*nn) + tmp2? no: use z,p
   sn = reinterpret_cast<double *>(h->z);                 // z and p are contiguous scratch outside a solve
-  k_stress_nodes<<<el_blocks(h->nn), ET, 0, st>>>(T, h->u, h->keep, sn, h->nx, h->ny);
-  LAUNCHED(h);
-  k_vonmises<<<el_blocks(h->ne), ET, 0, st>>>(sn, h->keep, h->sens, h->nx, h->ny, h->partials, h->ticket, h->red_out);
-  LAUNCHED(h);
-  k_div_scalar<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out, h->ne);
-  LAUNCHED(h);
+  KL(h, "k_stress_nodes", k_stress_nodes<<<el_blocks(h->nn), ET, 0, st>>>(T, h->u, h->keep, sn, h->nx, h->ny));
+  KL(h, "k_vonmises", k_vonmises<<<el_blocks(h->ne), ET, 0, st>>>(sn, h->keep, h->sens, h->nx, h->ny, h->partials, h->ticket, h->red_out));
+  KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out, h->ne));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }

@@ -1,6 +1,8 @@
 // extern "C" glue of libtopo_b200.so: life cycle, state transfer, the fused SIMP step and timing.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -137,6 +139,12 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->omega = 0.7;
   h->nu_pre = 1;
   h->nu_post = 1;
+  h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
+  h->tail_dbg = nullptr;
+  h->use_graph = true;
+  h->pcg_graph_valid = false;
+  h->pcg_graph_exec = nullptr;
+  h->pcg_graph_launches = 0;
   h->n_loads = 0;
   h->loads_set = h->cons_set = h->diag_valid = h->gmg_valid = false;
   h->d_load_node = nullptr;
@@ -227,10 +235,11 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaFree(h->d_load_fy);
   for (size_t l = 1; l < h->levels.size(); ++l) {
     GmgLevel &L = h->levels[l];
-    cudaFree(L.cell); cudaFree(L.st); cudaFree(L.dinv);
-    cudaFree(L.x); cudaFree(L.x2); cudaFree(L.b); cudaFree(L.r);
+    cudaFree(L.cell);
   }
-  cudaFree(h->coarse_inv);
+  cudaFree(h->lvl1_slab);
+  cudaFree(h->coarse_slab);
+  if (h->pcg_graph_exec) cudaGraphExecDestroy(h->pcg_graph_exec);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -436,7 +445,8 @@ extern "C" int topo_profile_matvec(topo_t *h, int enable) {
   if (!h) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
   if (enable && h->prof_ev.empty()) {
-    h->prof_ev.resize(2 * 8192);
+    h->prof_ev.resize(2 * 32768);
+    h->prof_name.assign(32768, nullptr);
     for (auto &e : h->prof_ev) CUDA_TRY(cudaEventCreate(&e));
   }
   h->prof_on = enable != 0;
@@ -445,16 +455,67 @@ extern "C" int topo_profile_matvec(topo_t *h, int enable) {
 }
 
 extern "C" int topo_profile_read(topo_t *h, int *launches, float *total_ms) {
+  // stage-1 kernel only: every variant of the fine-grid K application
   if (!h || !launches || !total_ms) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   float tot = 0.f;
+  int cnt = 0;
   for (int i = 0; i < h->prof_n; ++i) {
+    if (!h->prof_name[i] || strncmp(h->prof_name[i], "k_fine", 6) != 0) continue;
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
     tot += ms;
+    ++cnt;
   }
-  *launches = h->prof_n;
+  *launches = cnt;
   *total_ms = tot;
+  return TOPO_OK;
+}
+
+extern "C" int topo_profile_report(topo_t *h, char *buf, size_t buflen) {
+  // text table "name count total_ms" per kernel, sorted by total time
+  if (!h || !buf || buflen == 0) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  struct Row { const char *name; int n; double ms; };
+  std::vector<Row> rows;
+  for (int i = 0; i < h->prof_n; ++i) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    const char *nm = h->prof_name[i] ? h->prof_name[i] : "?";
+    bool found = false;
+    for (auto &r : rows)
+      if (strcmp(r.name, nm) == 0) { r.n++; r.ms += ms; found = true; break; }
+    if (!found) rows.push_back({nm, 1, (double)ms});
+  }
+  std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.ms > b.ms; });
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto &r : rows) {
+    int w = snprintf(buf + off, buflen - off, "%s %d %.6f\n", r.name, r.n, r.ms);
+    if (w < 0 || (size_t)w >= buflen - off) break;
+    off += (size_t)w;
+  }
+  return TOPO_OK;
+}
+
+// development aid: stage-boundary time stamps (ns) of the most recent k_tail launch
+extern "C" int topo_debug_tail_stamps(topo_t *h, unsigned long long *out, int max_out, int *n) {
+  if (!h || !out || !n) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->tail_dbg) {
+    CUDA_TRY(cudaMalloc(&h->tail_dbg, sizeof(unsigned long long) * 512));
+    CUDA_TRY(cudaMemset(h->tail_dbg, 0, sizeof(unsigned long long) * 512));
+    h->pcg_graph_valid = false;
+    *n = 0;
+    return TOPO_OK;
+  }
+  unsigned long long buf[512];
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(buf, h->tail_dbg, sizeof(buf), cudaMemcpyDeviceToHost));
+  int cnt = (int)std::min<unsigned long long>(buf[0], (unsigned long long)std::min(max_out, 511));
+  for (int i = 0; i < cnt; ++i) out[i] = buf[1 + i];
+  *n = cnt;
   return TOPO_OK;
 }

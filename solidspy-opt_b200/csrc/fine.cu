@@ -4,30 +4,31 @@
 // Replaces reference solver.py:364-410 (sparse_assem) and the CSR products inside spsolve /
 // stiff_mat.dot (optimize.py:437,455): K is never formed.
 //
-// Kernel shape ("staged marching"):
-//   * a CTA of 128 threads owns 128 node columns (+1 halo column each side) and marches over a
-//     chunk of node rows;
-//   * every raw input vector (1..5 per kernel) is streamed row by row into a shared-memory ring with
-//     cp.async (LDGSTS) D rows ahead of use, so the bytes in flight per SM are set by the ring depth,
-//     not by registers or occupancy: that is what makes the kernel HBM-bound instead of
-//     latency-bound;  element scales ride in the same ring;
-//   * stage B ("derive"): each thread turns the raw values of ITS node of the newest row into the
-//     vector the stencil is applied to (e.g. p = z + beta p, or x~ = x^ + P x_coarse), stores side
-//     outputs, and publishes the value in a 2-slot shared row;
-//   * stage C: each thread gathers the 4 element contributions of ITS node from a 3x3 register window
-//     (new row read from shared memory: 3 LDS.128), so there are no atomics and no scatter; the 8x8
-//     element matrix is a kernel parameter, i.e. constant-bank operands of the DFMAs;
+// Kernel shape ("staged marching", warp-private):
+//   * a WARP owns 32 node columns (+1 halo column each side) and marches over a chunk of node rows; the
+//     four warps of a CTA are independent (no block barrier anywhere in the row loop);
+//   * every raw input vector (1..5 per kernel) is streamed row by row into the warp's shared-memory ring
+//     with cp.async (LDGSTS) several rows ahead of use, so the bytes in flight per SM are set by the ring
+//     depth, not by registers or occupancy; element scales ride in the same ring;
+//   * stage B ("derive"): each lane turns the raw values of ITS node of the newest row into the vector the
+//     stencil is applied to (e.g. p = z + beta p), stores side outputs, and publishes the value in a
+//     2-slot shared row (__syncwarp);
+//   * stage C: each lane gathers the 4 element contributions of ITS node from a 3x3 register window
+//     (new row: 3 LDS.128), so there are no atomics and no scatter; the element matrix is 16 constants
+//     in registers (mirror symmetry of the rectangle);
 //   * epilogue: fused axpy / smoothing / masking and warp+block+ordered-grid dot products.
-// Inputs that are also outputs (p, u, r) are written to a second buffer: neighbouring CTAs still read
+// Ring slots and the register window are compile-time (row loop unrolled by the ring depth).
+// Inputs that are also outputs (p, u, r) are written to a second buffer: neighbouring warps still read
 // the old halo rows/columns.
 // Algorithmic traffic of the plain product: 16 B (u) + 16 B (y) per node + 8 B per element.
 #include "topo_internal.cuh"
 
 namespace {
 
-constexpr int BW = 128;        // own columns per CTA
-constexpr int SW = BW + 2;     // staged node columns
-constexpr int EW = BW + 1;     // staged element columns (c0-1 .. c0+BW-1)
+constexpr int BW = 128;        // threads per CTA = 4 warps = 4 independent strips of 32 columns
+constexpr int WC = 32;         // own columns per warp
+constexpr int SW = WC + 2;     // staged node columns per warp
+constexpr int EW = WC + 2;     // staged element columns per warp (c0-1 .. c0+31, padded to even)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -54,17 +55,16 @@ enum {
   FK_SMOOTH = 6        // y = u + omega dinv (b - A u)                   raw: u, b, dinv
 };
 
-// ring depth: S = 6 slots for every kind (4 rows in flight per CTA); the row loop is unrolled by 6 so
-// that ring slots AND the 3-row register window are compile-time (no index arithmetic, no moves)
-constexpr int S = 6, D = S - 2;
+// ring depth per kind (S slots, S-2 rows in flight per warp); the row loop is unrolled by S and the
+// register window cycles through 4 row images, so slots and window roles are compile-time
 template <int K> struct FK;
-template <> struct FK<FK_APPLY> { static constexpr int NIN = 1; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_RESID> { static constexpr int NIN = 2; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_SMOOTH> { static constexpr int NIN = 3; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_PCG_MATVEC> { static constexpr int NIN = 2; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_PCG_MATVEC_J> { static constexpr int NIN = 3; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_UPDATE_RESID0> { static constexpr int NIN = 5; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_PROLONG_SMOOTH> { static constexpr int NIN = 3; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_APPLY> { static constexpr int NIN = 1, S = 8; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_RESID> { static constexpr int NIN = 2, S = 8; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_SMOOTH> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_PCG_MATVEC> { static constexpr int NIN = 2, S = 8; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PCG_MATVEC_J> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_UPDATE_RESID0> { static constexpr int NIN = 5, S = 4; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PROLONG_SMOOTH> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = true; };
 
 struct FineArgs {
   const double2 *in[5];
@@ -136,31 +136,38 @@ struct RowWin {
 template <int V> struct IC { static constexpr int value = V; };
 
 template <int KIND>
+__host__ __device__ constexpr int warp_smem_bytes() {
+  return (int)(sizeof(double2) * (FK<KIND>::S * FK<KIND>::NIN * SW + 2 * SW) + sizeof(double) * FK<KIND>::S * EW);
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kparam, const __grid_constant__ FineArgs a) {
-  const KeRow ke = kparam;                                // 16 constants -> registers
-  constexpr int NIN = FK<KIND>::NIN;
+  constexpr int NIN = FK<KIND>::NIN, S = FK<KIND>::S, D = S - 2;
   constexpr bool DERIVE = FK<KIND>::DERIVE;
   constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID || KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J);
   if (a.check_done && a.sc->done) return;
+  const KeRow ke = kparam;                                // 16 constants -> registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2 *raw = reinterpret_cast<double2 *>(smem_raw);                 // [S][NIN][SW]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + warp * warp_smem_bytes<KIND>();
+  double2 *raw = reinterpret_cast<double2 *>(wbase);                     // [S][NIN][SW]
   double2 *der = raw + S * NIN * SW;                                     // [2][SW] (DERIVE kinds)
   double *ering = reinterpret_cast<double *>(der + 2 * SW);              // [S][EW]
 
-  const int t = threadIdx.x;
   const int npr = a.nx + 1;
-  const int c0 = blockIdx.x * BW;
-  const int c = c0 + t;                                  // own node column (staged column t+1)
+  const int c0 = (blockIdx.x * 4 + warp) * WC;            // first own node column of this warp
+  const int c = c0 + lane;                                // own node column (staged column lane+1)
   const int r0 = blockIdx.y * a.rows_per_chunk;
   const int r1 = min(r0 + a.rows_per_chunk, a.ny + 1);
+  const bool active = c0 < npr;                           // warp-uniform
   const bool col_ok = c < npr;
   const bool ecol_ok = c < a.nx;
-  // halo duty: thread 0 -> staged col 0 (node col c0-1), thread 1 -> staged col SW-1 (node col c0+BW)
-  const int hs = (t == 0) ? 0 : SW - 1;
-  const int hc = (t == 0) ? c0 - 1 : c0 + BW;
-  const bool has_halo = t < 2;
+  // halo duty: lane 0 -> staged col 0 (node col c0-1), lane 1 -> staged col SW-1 (node col c0+WC)
+  const int hs = (lane == 0) ? 0 : SW - 1;
+  const int hc = (lane == 0) ? c0 - 1 : c0 + WC;
+  const bool has_halo = lane < 2;
   const bool hcol_ok = has_halo && hc >= 0 && hc < npr;
-  const bool ehalo_ok = (t == 0) && c0 > 0;
+  const bool ehalo_ok = (lane == 0) && c0 > 0;
   // column offsets clamped into the row so that masked (zero-fill) copies still carry a valid address
   const int coff = col_ok ? c : 0, hoff = hcol_ok ? hc : 0;
   const int eoff = ecol_ok ? c : 0, ehoff = ehalo_ok ? c0 - 1 : 0;
@@ -169,186 +176,192 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
   if (KIND == FK_UPDATE_RESID0 && !a.init) alpha = a.sc->rz[0] / a.sc->pAp;
   if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) beta = a.sc->rz[1];     // rz[1] holds beta (pcg.cu)
   const double omega = a.omega;
-
-  // ---- copies of group G_q = {raw row q, element row q-1} into ring slot SL = (q - (r0-1)) mod S ----
-  int q_issue = r0 - 1;
-  auto issue = [&](auto slc) {
-    constexpr int SL = decltype(slc)::value;
-    const int q = q_issue++;
-    const bool row_ok = q >= 0 && q <= a.ny;
-    const size_t rowoff = (size_t)(row_ok ? q : 0) * npr;
-#pragma unroll
-    for (int k = 0; k < NIN; ++k) {
-      double2 *dst = raw + (SL * NIN + k) * SW;
-      const double2 *src = a.in[k] + rowoff;
-      cp_async16(dst + t + 1, src + coff, row_ok && col_ok);
-      if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
-    }
-    const bool erow_ok = q >= 1 && q <= a.ny;
-    const double *esrc = a.scale + (size_t)(erow_ok ? q - 1 : 0) * a.nx;
-    double *edst = ering + SL * EW;
-    cp_async8(edst + t + 1, esrc + eoff, erow_ok && ecol_ok);
-    if (t == 0) cp_async8(edst, esrc + ehoff, erow_ok && ehalo_ok);
-    cp_async_commit();
-  };
-
   double dots[1] = {0.0};
 
-  // ---- stage B (DERIVE kinds): stencil input of (row, staged column) from this thread's raw copies ----
-  auto derive_at = [&](const double2 *rw, int row, int ncol, bool own) -> double2 {
-    const bool in_dom = row >= 0 && row <= a.ny && ncol >= 0 && ncol < npr;
-    const size_t n = (size_t)(in_dom ? row : 0) * npr + (in_dom ? ncol : 0);
-    const bool store = own && in_dom && row >= r0 && row < r1;
-    if (KIND == FK_PCG_MATVEC) {
-      const double2 z = rw[0], p = rw[SW];
-      const double2 v = make_double2(fma(beta, p.x, z.x), fma(beta, p.y, z.y));
-      if (store) a.out[0][n] = v;
-      return v;
-    } else if (KIND == FK_PCG_MATVEC_J) {
-      const double2 r = rw[0], p = rw[SW], d = rw[2 * SW];
-      const double2 v = make_double2(fma(beta, p.x, d.x * r.x), fma(beta, p.y, d.y * r.y));
-      if (store) a.out[0][n] = v;
-      return v;
-    } else if (KIND == FK_UPDATE_RESID0) {
-      const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = rw[4 * SW];
-      const double2 rn = make_double2(fma(-alpha, ap.x, r.x), fma(-alpha, ap.y, r.y));
-      const double2 xh = make_double2(omega * d.x * rn.x, omega * d.y * rn.y);
-      if (store) {
-        a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
-        a.out[1][n] = rn;
-        a.out[2][n] = xh;
-        dots[0] = fma(rn.x, rn.x, fma(rn.y, rn.y, dots[0]));
+  if (active) {
+    // ---- copies of group G_q = {raw row q, element row q-1} into ring slot SL = (q - (r0-1)) mod S ----
+    int q_issue = r0 - 1;
+    auto issue = [&](auto slc) {
+      constexpr int SL = decltype(slc)::value;
+      const int q = q_issue++;
+      const bool row_ok = q >= 0 && q <= a.ny;
+      const size_t rowoff = (size_t)(row_ok ? q : 0) * npr;
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) {
+        double2 *dst = raw + (SL * NIN + k) * SW;
+        const double2 *src = a.in[k] + rowoff;
+        cp_async16(dst + lane + 1, src + coff, row_ok && col_ok);
+        if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
       }
-      return xh;
-    } else {  // FK_PROLONG_SMOOTH
-      const double2 xh = rw[0], d = rw[2 * SW];
-      double px = 0.0, py = 0.0;
-      if (in_dom && a.coarse != nullptr) {
-        int I0, I1, J0, J1;
-        double wx1, wy1;
-        prolong_taps1(ncol, a.nx, I0, I1, wx1);
-        prolong_taps1(row, a.ny, J0, J1, wy1);
-        const double wx0 = 1.0 - wx1, wy0 = 1.0 - wy1;
-        const int nprc = a.cnx + 1;
-        const double2 v00 = __ldg(a.coarse + (size_t)J0 * nprc + I0);
-        px = wy0 * wx0 * v00.x;
-        py = wy0 * wx0 * v00.y;
-        if (wx1 != 0.0) {
-          const double2 v = __ldg(a.coarse + (size_t)J0 * nprc + I1);
-          px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
+      const bool erow_ok = q >= 1 && q <= a.ny;
+      const double *esrc = a.scale + (size_t)(erow_ok ? q - 1 : 0) * a.nx;
+      double *edst = ering + SL * EW;
+      cp_async8(edst + lane + 1, esrc + eoff, erow_ok && ecol_ok);
+      if (lane == 0) cp_async8(edst, esrc + ehoff, erow_ok && ehalo_ok);
+      cp_async_commit();
+    };
+
+    // ---- stage B (DERIVE kinds): stencil input of (row, column) from this lane's own raw copies ----
+    auto derive_at = [&](const double2 *rw, int row, int ncol, bool own) -> double2 {
+      const bool in_dom = row >= 0 && row <= a.ny && ncol >= 0 && ncol < npr;
+      const size_t n = (size_t)(in_dom ? row : 0) * npr + (in_dom ? ncol : 0);
+      const bool store = own && in_dom && row >= r0 && row < r1;
+      if (KIND == FK_PCG_MATVEC) {
+        const double2 z = rw[0], p = rw[SW];
+        const double2 v = make_double2(fma(beta, p.x, z.x), fma(beta, p.y, z.y));
+        if (store) a.out[0][n] = v;
+        return v;
+      } else if (KIND == FK_PCG_MATVEC_J) {
+        const double2 r = rw[0], p = rw[SW], d = rw[2 * SW];
+        const double2 v = make_double2(fma(beta, p.x, d.x * r.x), fma(beta, p.y, d.y * r.y));
+        if (store) a.out[0][n] = v;
+        return v;
+      } else if (KIND == FK_UPDATE_RESID0) {
+        const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = rw[4 * SW];
+        const double2 rn = make_double2(fma(-alpha, ap.x, r.x), fma(-alpha, ap.y, r.y));
+        const double2 xh = make_double2(omega * d.x * rn.x, omega * d.y * rn.y);
+        if (store) {
+          a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
+          a.out[1][n] = rn;
+          a.out[2][n] = xh;
+          dots[0] = fma(rn.x, rn.x, fma(rn.y, rn.y, dots[0]));
         }
-        if (wy1 != 0.0) {
-          const double2 v = __ldg(a.coarse + (size_t)J1 * nprc + I0);
-          px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
+        return xh;
+      } else {  // FK_PROLONG_SMOOTH
+        const double2 xh = rw[0], d = rw[2 * SW];
+        double px = 0.0, py = 0.0;
+        if (in_dom && a.coarse != nullptr) {
+          int I0, I1, J0, J1;
+          double wx1, wy1;
+          prolong_taps1(ncol, a.nx, I0, I1, wx1);
+          prolong_taps1(row, a.ny, J0, J1, wy1);
+          const double wx0 = 1.0 - wx1, wy0 = 1.0 - wy1;
+          const int nprc = a.cnx + 1;
+          const double2 v00 = __ldg(a.coarse + (size_t)J0 * nprc + I0);
+          px = wy0 * wx0 * v00.x;
+          py = wy0 * wx0 * v00.y;
           if (wx1 != 0.0) {
-            const double2 w = __ldg(a.coarse + (size_t)J1 * nprc + I1);
-            px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
+            const double2 v = __ldg(a.coarse + (size_t)J0 * nprc + I1);
+            px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
+          }
+          if (wy1 != 0.0) {
+            const double2 v = __ldg(a.coarse + (size_t)J1 * nprc + I0);
+            px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
+            if (wx1 != 0.0) {
+              const double2 w = __ldg(a.coarse + (size_t)J1 * nprc + I1);
+              px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
+            }
           }
         }
+        return make_double2(d.x != 0.0 ? xh.x + px : 0.0, d.y != 0.0 ? xh.y + py : 0.0);
       }
-      return make_double2(d.x != 0.0 ? xh.x + px : 0.0, d.y != 0.0 ? xh.y + py : 0.0);
-    }
-  };
-  // SL = ring slot of `row`; derived rows alternate between the two `der` slots
-  auto stage_b = [&](auto slc, int row) {
-    constexpr int SL = decltype(slc)::value;
+    };
+    auto stage_b = [&](auto slc, int row) {
+      constexpr int SL = decltype(slc)::value;
+      if (DERIVE) {
+        double2 *dr = der + (SL & 1) * SW;
+        const double2 *rw = raw + SL * NIN * SW;
+        dr[lane + 1] = derive_at(rw + lane + 1, row, c, true);
+        if (has_halo) dr[hs] = derive_at(rw + hs, row, hc, false);
+      }
+    };
+    // register image of the node row held in ring slot SL (after the __syncwarp that publishes it)
+    auto fill = [&](auto slc, RowWin &w) {
+      constexpr int SL = decltype(slc)::value;
+      const double2 *src = DERIVE ? (der + (SL & 1) * SW + lane) : (raw + SL * NIN * SW + lane);
+      w.u[0] = src[0]; w.u[1] = src[1]; w.u[2] = src[2];
+      const double *e = ering + SL * EW + lane;
+      w.el = e[0]; w.er = e[1];
+    };
+
+    // ---- prologue: S groups in flight (rows r0-1 .. r0+D), rows r0-1 and r0 resident ----
+    issue(IC<0>()); issue(IC<1>()); issue(IC<2>()); issue(IC<3>());
+    if (S == 8) { issue(IC<4 % S>()); issue(IC<5 % S>()); issue(IC<6 % S>()); issue(IC<7 % S>()); }
+    cp_async_wait<D>();
+    RowWin W0, W1, W2, W3;
     if (DERIVE) {
-      double2 *dr = der + (SL & 1) * SW;
-      const double2 *rw = raw + SL * NIN * SW;
-      dr[t + 1] = derive_at(rw + t + 1, row, c, true);
-      if (has_halo) dr[hs] = derive_at(rw + hs, row, hc, false);
+      stage_b(IC<0>(), r0 - 1);
+      stage_b(IC<1>(), r0);
     }
-  };
-  // register image of the node row held in ring slot SL (after the barrier that publishes it)
-  auto fill = [&](auto slc, RowWin &w) {
-    constexpr int SL = decltype(slc)::value;
-    const double2 *src = DERIVE ? (der + (SL & 1) * SW + t) : (raw + SL * NIN * SW + t);
-    w.u[0] = src[0]; w.u[1] = src[1]; w.u[2] = src[2];
-    const double *e = ering + SL * EW + t;
-    w.el = e[0]; w.er = e[1];
-  };
+    __syncwarp();
+    fill(IC<0>(), W0);
+    fill(IC<1>(), W1);
+    unsigned fx_next = 0;
+    if (NEEDS_FIXED && col_ok && r0 < r1) fx_next = a.fixed[(size_t)r0 * npr + c];
+    size_t n_out = (size_t)r0 * npr + c;
 
-  // ---- prologue: S groups in flight (rows r0-1 .. r0+D), rows r0-1 and r0 resident ----
-  issue(IC<0>()); issue(IC<1>()); issue(IC<2>()); issue(IC<3>()); issue(IC<4>()); issue(IC<5>());
-  cp_async_wait<D>();
-  RowWin Wa, Wb, Wc;
-  if (DERIVE) {
-    stage_b(IC<0>(), r0 - 1);
-    stage_b(IC<1>(), r0);
-  }
-  __syncthreads();
-  fill(IC<0>(), Wa);
-  fill(IC<1>(), Wb);
-  unsigned fx_next = 0;
-  if (NEEDS_FIXED && col_ok && r0 < r1) fx_next = a.fixed[(size_t)r0 * npr + c];
-  size_t n_out = (size_t)r0 * npr + c;
-
-  // one node row r held in slot K+1: Wm = row r-1, W0 = row r, Wp receives row r+1 (slot K+2);
-  // the slot of row r-1 (K) is refilled with row r-1+S
-  auto step = [&](auto kc, int r, const RowWin &Wm, const RowWin &W0, RowWin &Wp) {
-    constexpr int K = decltype(kc)::value;
-    constexpr int S_prev = K % S, S_cur = (K + 1) % S, S_next = (K + 2) % S;
-    cp_async_wait<D - 1>();                                // group G_{r+1} has landed (this thread's part)
-    stage_b(IC<S_next>(), r + 1);
-    __syncthreads();                                       // row r+1 visible; everyone is done with row r-1's slot
-    issue(IC<S_prev>());
-    fill(IC<S_next>(), Wp);
-    const unsigned fx = fx_next;
-    if (NEEDS_FIXED && col_ok && r + 1 < r1) fx_next = a.fixed[n_out + npr];
-    double yx, yy, tx, ty;
-    row_terms<false>(ke, W0.u[1], W0.u[2], Wp.u[2], Wp.u[1], tx, ty);   // NE element (r, c): node is local 0
-    yx = Wp.er * tx; yy = Wp.er * ty;
-    row_terms<true>(ke, W0.u[1], W0.u[0], Wp.u[0], Wp.u[1], tx, ty);    // NW (r, c-1): x-mirror image
-    yx = fma(Wp.el, tx, yx); yy = fma(Wp.el, ty, yy);
-    row_terms<false>(ke, W0.u[1], W0.u[0], Wm.u[0], Wm.u[1], tx, ty);   // SW (r-1, c-1): point-mirror image
-    yx = fma(W0.el, tx, yx); yy = fma(W0.el, ty, yy);
-    row_terms<true>(ke, W0.u[1], W0.u[2], Wm.u[2], Wm.u[1], tx, ty);    // SE (r-1, c): y-mirror image
-    yx = fma(W0.er, tx, yx); yy = fma(W0.er, ty, yy);
-    if (col_ok) {
-      const size_t n = n_out;
-      const double2 *rw = raw + S_cur * NIN * SW + t + 1;            // raw inputs of this node
-      const double2 v = W0.u[1];
-      if (KIND == FK_APPLY) {
-        if (fx & 1u) yx = 0.0;
-        if (fx & 2u) yy = 0.0;
-        a.out[0][n] = make_double2(yx, yy);
-        if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
-      } else if (KIND == FK_RESID) {
-        const double2 b = rw[SW];
-        a.out[0][n] = make_double2((fx & 1u) ? 0.0 : b.x - yx, (fx & 2u) ? 0.0 : b.y - yy);
-      } else if (KIND == FK_SMOOTH) {
-        const double2 b = rw[SW], d = rw[2 * SW];
-        a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
-      } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
-        if (fx & 1u) yx = 0.0;
-        if (fx & 2u) yy = 0.0;
-        a.out[1][n] = make_double2(yx, yy);
-        dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
-      } else if (KIND == FK_UPDATE_RESID0) {
-        const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
-        const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
-        a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
-      } else {  // FK_PROLONG_SMOOTH
-        const double2 rr = rw[SW], d = rw[2 * SW];
-        const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
-        a.out[0][n] = make_double2(zx, zy);
-        dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+    // one node row r held in slot K+1: Wm = row r-1, Wc = row r, Wp receives row r+1 (slot K+2);
+    // the slot of row r-1 (K) is refilled with row r-1+S
+    auto step = [&](auto kc, int r, const RowWin &Wm, const RowWin &Wc, RowWin &Wp) {
+      constexpr int K = decltype(kc)::value;
+      constexpr int S_prev = K % S, S_cur = (K + 1) % S, S_next = (K + 2) % S;
+      cp_async_wait<D - 1>();                              // group G_{r+1} has landed (this lane's part)
+      stage_b(IC<S_next>(), r + 1);
+      __syncwarp();                                        // row r+1 visible; every lane is done with row r-1's slot
+      issue(IC<S_prev>());
+      fill(IC<S_next>(), Wp);
+      const unsigned fx = fx_next;
+      if (NEEDS_FIXED && col_ok && r + 1 < r1) fx_next = a.fixed[n_out + npr];
+      double yx, yy, tx, ty;
+      row_terms<false>(ke, Wc.u[1], Wc.u[2], Wp.u[2], Wp.u[1], tx, ty);   // NE element (r, c): node is local 0
+      yx = Wp.er * tx; yy = Wp.er * ty;
+      row_terms<true>(ke, Wc.u[1], Wc.u[0], Wp.u[0], Wp.u[1], tx, ty);    // NW (r, c-1): x-mirror image
+      yx = fma(Wp.el, tx, yx); yy = fma(Wp.el, ty, yy);
+      row_terms<false>(ke, Wc.u[1], Wc.u[0], Wm.u[0], Wm.u[1], tx, ty);   // SW (r-1, c-1): point-mirror image
+      yx = fma(Wc.el, tx, yx); yy = fma(Wc.el, ty, yy);
+      row_terms<true>(ke, Wc.u[1], Wc.u[2], Wm.u[2], Wm.u[1], tx, ty);    // SE (r-1, c): y-mirror image
+      yx = fma(Wc.er, tx, yx); yy = fma(Wc.er, ty, yy);
+      if (col_ok) {
+        const size_t n = n_out;
+        const double2 *rw = raw + S_cur * NIN * SW + lane + 1;         // raw inputs of this node
+        const double2 v = Wc.u[1];
+        if (KIND == FK_APPLY) {
+          if (fx & 1u) yx = 0.0;
+          if (fx & 2u) yy = 0.0;
+          a.out[0][n] = make_double2(yx, yy);
+          if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+        } else if (KIND == FK_RESID) {
+          const double2 b = rw[SW];
+          a.out[0][n] = make_double2((fx & 1u) ? 0.0 : b.x - yx, (fx & 2u) ? 0.0 : b.y - yy);
+        } else if (KIND == FK_SMOOTH) {
+          const double2 b = rw[SW], d = rw[2 * SW];
+          a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
+        } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
+          if (fx & 1u) yx = 0.0;
+          if (fx & 2u) yy = 0.0;
+          a.out[1][n] = make_double2(yx, yy);
+          dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+        } else if (KIND == FK_UPDATE_RESID0) {
+          const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
+          const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
+          a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
+        } else {  // FK_PROLONG_SMOOTH
+          const double2 rr = rw[SW], d = rw[2 * SW];
+          const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
+          a.out[0][n] = make_double2(zx, zy);
+          dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+        }
+      }
+      n_out += npr;
+    };
+    // S rows per trip; window roles cycle through the 4 row images (4 divides S)
+    for (int r = r0; r < r1; r += S) {
+      step(IC<0>(), r, W0, W1, W2);
+      if (r + 1 < r1) step(IC<1>(), r + 1, W1, W2, W3);
+      if (r + 2 < r1) step(IC<2>(), r + 2, W2, W3, W0);
+      if (r + 3 < r1) step(IC<3>(), r + 3, W3, W0, W1);
+      if (S == 8) {
+        if (r + 4 < r1) step(IC<4>(), r + 4, W0, W1, W2);
+        if (r + 5 < r1) step(IC<5>(), r + 5, W1, W2, W3);
+        if (r + 6 < r1) step(IC<6>(), r + 6, W2, W3, W0);
+        if (r + 7 < r1) step(IC<7>(), r + 7, W3, W0, W1);
       }
     }
-    n_out += npr;
-  };
-  // six rows per trip: ring slots and the 3-row register window are compile-time
-  for (int r = r0; r < r1; r += 6) {
-    step(IC<0>(), r, Wa, Wb, Wc);
-    if (r + 1 < r1) step(IC<1>(), r + 1, Wb, Wc, Wa);
-    if (r + 2 < r1) step(IC<2>(), r + 2, Wc, Wa, Wb);
-    if (r + 3 < r1) step(IC<3>(), r + 3, Wa, Wb, Wc);
-    if (r + 4 < r1) step(IC<4>(), r + 4, Wb, Wc, Wa);
-    if (r + 5 < r1) step(IC<5>(), r + 5, Wc, Wa, Wb);
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
 
   // ---- reductions + scalar bookkeeping (last block) ----
+  const int t = threadIdx.x;
   if (KIND == FK_APPLY) {
     if (a.want_dot) grid_reduce<1>(dots, a.partials, a.ticket, a.dot_out);
   } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
@@ -372,8 +385,7 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
 
 template <int KIND>
 size_t fine_smem() {
-  constexpr int NIN = FK<KIND>::NIN;
-  return sizeof(double2) * (S * NIN * SW + 2 * SW) + sizeof(double) * S * EW;
+  return 4 * (size_t)warp_smem_bytes<KIND>();
 }
 
 template <int KIND>
@@ -397,13 +409,11 @@ int launch_fine(topo_handle *h, FineArgs &a) {
     CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const bool prof = h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size();
-  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
   KeRow kr;
   for (int j = 0; j < 8; ++j) { kr.r0[j] = h->ke.k[j]; kr.r1[j] = h->ke.k[8 + j]; }
-  k_fine<KIND><<<grid, BW, smem, h->stream>>>(kr, a);
-  if (prof) cudaEventRecord(h->prof_ev[2 * h->prof_n++ + 1], h->stream);
-  h->timing.kernel_launches++;
+  static const char *const names[7] = {"k_fine<apply>", "k_fine<resid>", "k_fine<pcg_matvec>", "k_fine<pcg_matvec_jacobi>",
+                                       "k_fine<update_resid0>", "k_fine<smooth_dot>", "k_fine<smooth>"};
+  KL(h, names[KIND], k_fine<KIND><<<grid, BW, smem, h->stream>>>(kr, a));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -530,9 +540,8 @@ int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 
 
 int topo_build_diag(topo_handle *h) {
   const int blocks = (int)std::min<int64_t>(div_up(h->nn, 256), 1184);
-  k_build_diag<<<blocks, 256, 0, h->stream>>>(h->ke, h->scale, h->fixed, h->dinv, h->nx, h->ny, h->partials,
-                                              h->ticket, h->kmax);
-  h->timing.kernel_launches++;
+  KL(h, "k_build_diag", k_build_diag<<<blocks, 256, 0, h->stream>>>(h->ke, h->scale, h->fixed, h->dinv, h->nx, h->ny,
+                                                                      h->partials, h->ticket, h->kmax));
   CUDA_TRY(cudaGetLastError());
   h->diag_valid = true;
   return TOPO_OK;

@@ -11,6 +11,7 @@
 // smoother / residual kernels stream.  Smoother: damped Jacobi.  Coarsest level: dense inverse.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "topo_internal.cuh"
@@ -174,147 +175,6 @@ __global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restri
   dinv[n] = make_double2(dx > 0.0 ? 1.0 / dx : 0.0, dy > 0.0 ? 1.0 / dy : 0.0);
 }
 
-// ---- stencil application on coarse levels ---------------------------------------------------------------
-enum { ST_RESID = 0, ST_SMOOTH = 1 };
-template <int MODE>
-__global__ void __launch_bounds__(128) k_stencil_apply(const double *__restrict__ st, const double2 *__restrict__ x,
-                                                       const double2 *__restrict__ b,
-                                                       const double2 *__restrict__ dinv, double2 *__restrict__ out,
-                                                       int nx, int ny, double omega) {
-  const int npr = nx + 1;
-  const int64_t nn = (int64_t)npr * (ny + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nn) return;
-  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
-  double ax = 0.0, ay = 0.0;
-#pragma unroll
-  for (int dr = -1; dr <= 1; ++dr) {
-#pragma unroll
-    for (int dc = -1; dc <= 1; ++dc) {
-      const int rr = r + dr, cc = c + dc;
-      if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
-      const int nb = 3 * (dr + 1) + (dc + 1);
-      const double2 xv = __ldg(x + (size_t)rr * npr + cc);
-      const double *sp = st + (size_t)(4 * nb) * nn + n;
-      ax = fma(__ldg(sp), xv.x, ax);
-      ax = fma(__ldg(sp + nn), xv.y, ax);
-      ay = fma(__ldg(sp + 2 * nn), xv.x, ay);
-      ay = fma(__ldg(sp + 3 * nn), xv.y, ay);
-    }
-  }
-  const double2 bv = b[n];
-  const double2 dv = dinv[n];
-  if (MODE == ST_RESID) {
-    out[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
-  } else {
-    const double2 xv = x[n];
-    out[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
-  }
-}
-
-// x = omega * dinv * b   (first pre-smoothing sweep from a zero initial guess)
-__global__ void k_smooth0(const double2 *__restrict__ b, const double2 *__restrict__ dinv, double2 *__restrict__ x,
-                          int64_t nn, double omega) {
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
-    const double2 bv = b[n], dv = dinv[n];
-    x[n] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
-  }
-}
-
-// ---- transfers --------------------------------------------------------------------------------------------------
-// 1-D: coarse node I sits at fine index X = min(2I, nf).  Fine node i is a coarse node if i is even or
-// i == nf; otherwise it interpolates (1/2, 1/2) between coarse (i-1)/2 and (i+1)/2.
-__device__ __forceinline__ void restrict_taps(int I, int nf, int &X, double &wl, double &wr) {
-  X = min(2 * I, nf);
-  const bool even = (X == 2 * I);
-  wl = (even && I >= 1) ? 0.5 : 0.0;              // fine X-1 is odd (interpolated) iff X is even and > 0
-  wr = (even && X + 1 < nf) ? 0.5 : 0.0;          // fine X+1 interpolated iff it exists and is not the last node
-}
-
-// b_c = P^T r  (r is already zero at constrained DOFs); thread per coarse node
-__global__ void __launch_bounds__(128) k_restrict(const double2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
-                                                  int nyf, int nxc, int nyc) {
-  const int nprc = nxc + 1, nprf = nxf + 1;
-  const int64_t nnc = (int64_t)nprc * (nyc + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnc) return;
-  const int J = (int)(n / nprc), I = (int)(n - (int64_t)J * nprc);
-  int X, Y;
-  double wxl, wxr, wyl, wyr;
-  restrict_taps(I, nxf, X, wxl, wxr);
-  restrict_taps(J, nyf, Y, wyl, wyr);
-  const double wx[3] = {wxl, 1.0, wxr}, wy[3] = {wyl, 1.0, wyr};
-  double sx = 0.0, sy = 0.0;
-#pragma unroll
-  for (int dj = -1; dj <= 1; ++dj) {
-    if (wy[dj + 1] == 0.0) continue;
-#pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const double w = wy[dj + 1] * wx[di + 1];
-      if (w == 0.0) continue;
-      const double2 v = __ldg(rf + (size_t)(Y + dj) * nprf + (X + di));
-      sx = fma(w, v.x, sx);
-      sy = fma(w, v.y, sy);
-    }
-  }
-  bc[n] = make_double2(sx, sy);
-}
-
-__device__ __forceinline__ void prolong_taps(int i, int nf, int &I0, int &I1, double &w0, double &w1) {
-  if ((i & 1) == 0) {
-    I0 = I1 = i >> 1; w0 = 1.0; w1 = 0.0;
-  } else if (i == nf) {
-    I0 = I1 = (i + 1) >> 1; w0 = 1.0; w1 = 0.0;
-  } else {
-    I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w0 = 0.5; w1 = 0.5;
-  }
-}
-
-// x_f += P x_c, zeroed where the fine DOF is constrained/dead.  MASKMODE 0: fixed flags (level 0);
-// 1: dinv == 0 (coarse levels)
-template <int MASKMODE>
-__global__ void __launch_bounds__(128) k_prolong_add(const double2 *__restrict__ xc, double2 *__restrict__ xf,
-                                                     const uint8_t *__restrict__ fixed,
-                                                     const double2 *__restrict__ dinv, int nxf, int nyf, int nxc) {
-  const int nprf = nxf + 1, nprc = nxc + 1;
-  const int64_t nnf = (int64_t)nprf * (nyf + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnf) return;
-  const int j = (int)(n / nprf), i = (int)(n - (int64_t)j * nprf);
-  int I0, I1, J0, J1;
-  double wx0, wx1, wy0, wy1;
-  prolong_taps(i, nxf, I0, I1, wx0, wx1);
-  prolong_taps(j, nyf, J0, J1, wy0, wy1);
-  double2 acc = xf[n];
-  double px = 0.0, py = 0.0;
-  {
-    const double2 v = __ldg(xc + (size_t)J0 * nprc + I0);
-    px = wy0 * wx0 * v.x; py = wy0 * wx0 * v.y;
-  }
-  if (wx1 != 0.0) {
-    const double2 v = __ldg(xc + (size_t)J0 * nprc + I1);
-    px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
-  }
-  if (wy1 != 0.0) {
-    const double2 v = __ldg(xc + (size_t)J1 * nprc + I0);
-    px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
-    if (wx1 != 0.0) {
-      const double2 u = __ldg(xc + (size_t)J1 * nprc + I1);
-      px = fma(wy1 * wx1, u.x, px); py = fma(wy1 * wx1, u.y, py);
-    }
-  }
-  if (MASKMODE == 0) {
-    const unsigned m = fixed[n];
-    if (m & 1u) px = 0.0;
-    if (m & 2u) py = 0.0;
-  } else {
-    const double2 d = dinv[n];
-    if (d.x == 0.0) px = 0.0;
-    if (d.y == 0.0) py = 0.0;
-  }
-  xf[n] = make_double2(acc.x + px, acc.y + py);
-}
-
 // ---- coarsest level: dense inverse --------------------------------------------------------------------------------
 // One block.  Builds the dense operator from the node stencil, replaces dead rows/cols (zero diagonal)
 // by identity, inverts by Gauss-Jordan (SPD => no pivoting) in shared memory, stores the inverse.
@@ -361,18 +221,6 @@ __global__ void k_coarse_invert(const double *__restrict__ st, int nx, int ny, d
   for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = sm[(t / N) * W + N + (t % N)];
 }
 
-__global__ void k_coarse_apply(const double *__restrict__ inv, const double2 *__restrict__ b,
-                               const double2 *__restrict__ dinv, double2 *__restrict__ x, int N) {
-  const double *bb = reinterpret_cast<const double *>(b);
-  const double *dd = reinterpret_cast<const double *>(dinv);
-  double *xx = reinterpret_cast<double *>(x);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    double s = 0.0;
-    for (int j = 0; j < N; ++j) s = fma(inv[i * N + j], bb[j], s);
-    xx[i] = dd[i] != 0.0 ? s : 0.0;
-  }
-}
-
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -398,18 +246,64 @@ int topo_gmg_plan(topo_handle *h) {
     L.nn = (L.nx + 1) * (L.ny + 1);
     L.ncell = L.nx * L.ny;
     CUDA_TRY(cudaMalloc(&L.cell, sizeof(double) * 64 * (size_t)L.ncell));
-    CUDA_TRY(cudaMalloc(&L.st, sizeof(double) * 36 * (size_t)L.nn));
-    CUDA_TRY(cudaMalloc(&L.dinv, sizeof(double2) * (size_t)L.nn));
-    CUDA_TRY(cudaMalloc(&L.x, sizeof(double2) * (size_t)L.nn));
-    CUDA_TRY(cudaMalloc(&L.x2, sizeof(double2) * (size_t)L.nn));
-    CUDA_TRY(cudaMalloc(&L.b, sizeof(double2) * (size_t)L.nn));
-    CUDA_TRY(cudaMalloc(&L.r, sizeof(double2) * (size_t)L.nn));
   }
+  // Per-cycle data of the levels: level 1 gets its own allocation; levels >= 2 (and the coarsest dense
+  // inverse) share ONE slab so that a single L2 persisting access-policy window can cover them -- the
+  // fine grid streams ~1 GB per PCG iteration through the 126 MB L2 and would otherwise evict them,
+  // leaving the small, latency-bound kernels to pay DRAM latency on every load.
+  auto level_bytes = [](const GmgLevel &L) {
+    return (size_t)L.nn * (sizeof(double) * 36 + sizeof(double2) * 5);
+  };
+  auto carve = [](GmgLevel &L, char *base) {
+    size_t off = 0;
+    L.st = reinterpret_cast<double *>(base + off); off += sizeof(double) * 36 * (size_t)L.nn;
+    L.dinv = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
+    L.x = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
+    L.x2 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
+    L.b = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
+    L.r = reinterpret_cast<double2 *>(base + off);
+  };
+  h->lvl1_slab = nullptr;
+  h->coarse_slab = nullptr;
+  h->coarse_slab_bytes = 0;
   h->coarse_n = 0;
   h->coarse_inv = nullptr;
   if (h->n_levels > 1) {
+    char *p1 = nullptr;
+    CUDA_TRY(cudaMalloc(&p1, level_bytes(h->levels[1])));
+    h->lvl1_slab = p1;
+    carve(h->levels[1], p1);
     h->coarse_n = 2 * h->levels[h->n_levels - 1].nn;
-    CUDA_TRY(cudaMalloc(&h->coarse_inv, sizeof(double) * (size_t)h->coarse_n * h->coarse_n));
+    size_t tot = 256 + sizeof(double) * (size_t)h->coarse_n * h->coarse_n;
+    for (int l = 2; l < h->n_levels; ++l) tot += (level_bytes(h->levels[l]) + 255) & ~(size_t)255;
+    char *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, tot));
+    h->coarse_slab = p;
+    h->coarse_slab_bytes = tot;
+    size_t off = 0;
+    for (int l = 2; l < h->n_levels; ++l) {
+      carve(h->levels[l], p + off);
+      off += (level_bytes(h->levels[l]) + 255) & ~(size_t)255;
+    }
+    h->coarse_inv = reinterpret_cast<double *>(p + off);
+    if (h->n_levels == 2) {   // the only coarse level is level 1: its data is not in the slab
+    }
+    // L2 residency for the slab (best effort: ignored if the device refuses)
+    int dev_max_persist = 0, dev_max_window = 0;
+    cudaDeviceGetAttribute(&dev_max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&dev_max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    const size_t want = std::min<size_t>(tot, (size_t)std::max(dev_max_persist, 0));
+    if (want > 0 && dev_max_window > 0 && !getenv("TOPO_NO_L2PERSIST")) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr = {};
+      attr.accessPolicyWindow.base_ptr = p;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(tot, (size_t)dev_max_window);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
   }
   // constant tables (per-process; identical for every handle except G, which depends on ke)
   PwTable pw;
@@ -452,19 +346,16 @@ int topo_gmg_setup(topo_handle *h) {
   TOPO_TRY(upload_gtable(h));
   {
     GmgLevel &L = h->levels[1];
-    k_cells_level1<<<blocks_for(L.ncell), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.cell, h->nx, h->ny, L.nx, L.ny);
-    LAUNCHED(h);
+    KL(h, "k_cells_level1", k_cells_level1<<<blocks_for(L.ncell), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.cell, h->nx, h->ny, L.nx, L.ny));
   }
   for (int l = 2; l < h->n_levels; ++l) {
     GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
     dim3 grid(blocks_for(C.ncell), 16);
-    k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny);
-    LAUNCHED(h);
+    KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
   for (int l = 1; l < h->n_levels; ++l) {
     GmgLevel &L = h->levels[l];
-    k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny);
-    LAUNCHED(h);
+    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
   }
   {
     GmgLevel &L = h->levels[h->n_levels - 1];
@@ -473,63 +364,10 @@ int topo_gmg_setup(topo_handle *h) {
       topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
       return TOPO_EINVAL;
     }
-    k_coarse_invert<<<1, 256, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv);
-    LAUNCHED(h);
+    KL(h, "k_coarse_invert", k_coarse_invert<<<1, 256, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv));
   }
   CUDA_TRY(cudaGetLastError());
   h->gmg_valid = true;
-  return TOPO_OK;
-}
-
-// Coarse part of the V-cycle.  Input: the fine-grid residual after the first smoothing step
-// (res = r - A x^, computed by the fused fine kernel).  Restricts it, runs levels 1..L-1 with a zero
-// initial guess on each (damped-Jacobi pre/post smoothing, dense solve on the coarsest level) and adds
-// the prolongated level-1 correction into the fine-grid iterate x^ (constrained DOFs stay zero).
-int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine) {
-  cudaStream_t st = h->stream;
-  const double om = h->omega;
-  const int L = h->n_levels;
-  if (L < 2) return TOPO_OK;
-  {
-    GmgLevel &C = h->levels[1];
-    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(res_fine, C.b, h->nx, h->ny, C.nx, C.ny);
-    LAUNCHED(h);
-  }
-  for (int l = 1; l < L - 1; ++l) {
-    GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
-    k_smooth0<<<std::min(blocks_for(F.nn, 256), 1184), 256, 0, st>>>(F.b, F.dinv, F.x, F.nn, om);
-    LAUNCHED(h);
-    for (int s = 1; s < h->nu_pre; ++s) {
-      k_stencil_apply<ST_SMOOTH><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.x2, F.nx, F.ny, om);
-      LAUNCHED(h);
-      std::swap(F.x, F.x2);
-    }
-    k_stencil_apply<ST_RESID><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.r, F.nx, F.ny, om);
-    LAUNCHED(h);
-    k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny);
-    LAUNCHED(h);
-  }
-  {
-    GmgLevel &C = h->levels[L - 1];
-    k_coarse_apply<<<1, 64, 0, st>>>(h->coarse_inv, C.b, C.dinv, C.x, h->coarse_n);
-    LAUNCHED(h);
-  }
-  for (int l = L - 2; l >= 1; --l) {
-    GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
-    k_prolong_add<1><<<blocks_for(F.nn), 128, 0, st>>>(C.x, F.x, nullptr, F.dinv, F.nx, F.ny, C.nx);
-    LAUNCHED(h);
-    for (int s = 0; s < h->nu_post; ++s) {
-      k_stencil_apply<ST_SMOOTH><<<blocks_for(F.nn), 128, 0, st>>>(F.st, F.x, F.b, F.dinv, F.x2, F.nx, F.ny, om);
-      LAUNCHED(h);
-      std::swap(F.x, F.x2);
-    }
-  }
-  {
-    GmgLevel &C = h->levels[1];
-    k_prolong_add<0><<<blocks_for(h->nn), 128, 0, st>>>(C.x, xhat_fine, h->fixed, nullptr, h->nx, h->ny, C.nx);
-    LAUNCHED(h);
-  }
-  CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
 
@@ -551,5 +389,6 @@ extern "C" int topo_set_gmg(topo_t *h, double omega, int nu_pre, int nu_post) {
   h->omega = omega;
   h->nu_pre = nu_pre;
   h->nu_post = nu_post;
+  h->pcg_graph_valid = false;
   return TOPO_OK;
 }

@@ -1,0 +1,478 @@
+// Coarse part of the multigrid V-cycle (levels >= 1): node-stencil kernels, transfers, and the
+// single-CTA "tail" kernel that runs all small levels in one launch.  Set-up (Galerkin products) is in
+// gmg.cu.  No counterpart in the reference (it calls SuperLU, optimize.py:437).
+//
+// Per level with a zero initial guess and one damped-Jacobi sweep before / after the coarse correction:
+//   down:  x = w D^-1 b ; r = b - A x          (one kernel: x of the 9 neighbours is recomputed on the fly)
+//          b_coarse = P^T r                     (restrict)
+//   up:    x~ = x + P x_coarse ; x' = x~ + w D^-1 (b - A x~)   (one kernel, x~ of the neighbours on the fly)
+// Levels with few nodes are latency/launch bound, so every level from `tail_level` on is handled by ONE
+// CTA of 1024 threads that walks down and up with __syncthreads between stages.
+#include <algorithm>
+
+#include <cooperative_groups.h>
+
+#include "topo_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+#define LAUNCHED(h) ((h)->timing.kernel_launches++)
+inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
+
+// ---- transfers: 1-D rules --------------------------------------------------------------------------------------
+// Coarse node I sits at fine index X = min(2I, nf).  Fine node i is a coarse node if i is even or
+// i == nf; otherwise it interpolates (1/2, 1/2) between coarse (i-1)/2 and (i+1)/2.
+__device__ __forceinline__ void restrict_taps(int I, int nf, int &X, double &wl, double &wr) {
+  X = min(2 * I, nf);
+  const bool even = (X == 2 * I);
+  wl = (even && I >= 1) ? 0.5 : 0.0;
+  wr = (even && X + 1 < nf) ? 0.5 : 0.0;
+}
+__device__ __forceinline__ void prolong_taps(int i, int nf, int &I0, int &I1, double &w0, double &w1) {
+  if ((i & 1) == 0) { I0 = I1 = i >> 1; w0 = 1.0; w1 = 0.0; }
+  else if (i == nf) { I0 = I1 = (i + 1) >> 1; w0 = 1.0; w1 = 0.0; }
+  else { I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w0 = 0.5; w1 = 0.5; }
+}
+
+__device__ __forceinline__ double2 restrict_node(const double2 *__restrict__ rf, int I, int J, int nxf, int nyf) {
+  const int nprf = nxf + 1;
+  int X, Y;
+  double wxl, wxr, wyl, wyr;
+  restrict_taps(I, nxf, X, wxl, wxr);
+  restrict_taps(J, nyf, Y, wyl, wyr);
+  const double wx[3] = {wxl, 1.0, wxr}, wy[3] = {wyl, 1.0, wyr};
+  double sx = 0.0, sy = 0.0;
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj) {
+    if (wy[dj + 1] == 0.0) continue;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+      const double w = wy[dj + 1] * wx[di + 1];
+      if (w == 0.0) continue;
+      const double2 v = rf[(size_t)(Y + dj) * nprf + (X + di)];
+      sx = fma(w, v.x, sx);
+      sy = fma(w, v.y, sy);
+    }
+  }
+  return make_double2(sx, sy);
+}
+
+// (P xc) at fine node (i, j)
+__device__ __forceinline__ double2 prolong_node(const double2 *__restrict__ xc, int i, int j, int nxf, int nyf,
+                                                int nprc) {
+  int I0, I1, J0, J1;
+  double wx0, wx1, wy0, wy1;
+  prolong_taps(i, nxf, I0, I1, wx0, wx1);
+  prolong_taps(j, nyf, J0, J1, wy0, wy1);
+  const double2 v00 = xc[(size_t)J0 * nprc + I0];
+  double px = wy0 * wx0 * v00.x, py = wy0 * wx0 * v00.y;
+  if (wx1 != 0.0) {
+    const double2 v = xc[(size_t)J0 * nprc + I1];
+    px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
+  }
+  if (wy1 != 0.0) {
+    const double2 v = xc[(size_t)J1 * nprc + I0];
+    px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
+    if (wx1 != 0.0) {
+      const double2 w = xc[(size_t)J1 * nprc + I1];
+      px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
+    }
+  }
+  return make_double2(px, py);
+}
+
+// A x at node n of a stencil level, x of each neighbour supplied by `get(rr, cc)`
+template <class Get>
+__device__ __forceinline__ void stencil_row(const double *__restrict__ st, int64_t nn, int64_t n, int r, int c, int nx,
+                                            int ny, Get get, double &ax, double &ay) {
+  ax = 0.0;
+  ay = 0.0;
+#pragma unroll
+  for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int rr = r + dr, cc = c + dc;
+      if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
+      const int nb = 3 * (dr + 1) + (dc + 1);
+      const double2 xv = get(rr, cc);
+      const double *sp = st + (size_t)(4 * nb) * nn + n;
+      ax = fma(sp[0], xv.x, ax);
+      ax = fma(sp[nn], xv.y, ax);
+      ay = fma(sp[2 * nn], xv.x, ay);
+      ay = fma(sp[3 * nn], xv.y, ay);
+    }
+  }
+}
+
+struct LevelView {
+  const double *st;
+  const double2 *dinv;
+  double2 *x, *x2, *b, *r;
+  int nx, ny;
+};
+
+// ---- per-node bodies shared by the multi-block kernels and the tail kernel -------------------------------
+// down: x = w dinv b ; r = b - A x   (x at neighbours recomputed from b, dinv)
+__device__ __forceinline__ void node_down(const LevelView &L, int64_t n, double omega) {
+  const int npr = L.nx + 1;
+  const int64_t nn = (int64_t)npr * (L.ny + 1);
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double ax, ay;
+  stencil_row(L.st, nn, n, r, c, L.nx, L.ny,
+              [&](int rr, int cc) {
+                const size_t m = (size_t)rr * npr + cc;
+                const double2 bv = L.b[m], dv = L.dinv[m];
+                return make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
+              },
+              ax, ay);
+  const double2 bv = L.b[n], dv = L.dinv[n];
+  L.x[n] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
+  L.r[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
+}
+
+// up: x~ = x + mask(P xc) ; x2 = x~ + w dinv (b - A x~)
+__device__ __forceinline__ void node_up(const LevelView &L, const double2 *__restrict__ xc, int cnx, int64_t n,
+                                        double omega) {
+  const int npr = L.nx + 1, nprc = cnx + 1;
+  const int64_t nn = (int64_t)npr * (L.ny + 1);
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  auto xt = [&](int rr, int cc) {
+    const size_t m = (size_t)rr * npr + cc;
+    const double2 xv = L.x[m], dv = L.dinv[m];
+    const double2 p = prolong_node(xc, cc, rr, L.nx, L.ny, nprc);
+    return make_double2(dv.x != 0.0 ? xv.x + p.x : 0.0, dv.y != 0.0 ? xv.y + p.y : 0.0);
+  };
+  double ax, ay;
+  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, xt, ax, ay);
+  const double2 bv = L.b[n], dv = L.dinv[n], xv = xt(r, c);
+  L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
+}
+
+// plain extra smoothing sweep: x2 = x + w dinv (b - A x)
+__device__ __forceinline__ void node_smooth(const LevelView &L, int64_t n, double omega) {
+  const int npr = L.nx + 1;
+  const int64_t nn = (int64_t)npr * (L.ny + 1);
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double ax, ay;
+  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
+  const double2 bv = L.b[n], dv = L.dinv[n], xv = L.x[n];
+  L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
+}
+// residual of the current iterate (needed when nu_pre > 1): r = b - A x
+__device__ __forceinline__ void node_resid(const LevelView &L, int64_t n) {
+  const int npr = L.nx + 1;
+  const int64_t nn = (int64_t)npr * (L.ny + 1);
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double ax, ay;
+  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
+  const double2 bv = L.b[n], dv = L.dinv[n];
+  L.r[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
+}
+
+// unfused stages (used by the tail, where a barrier is cheap and independent loads matter more)
+__device__ __forceinline__ void node_smooth0(const LevelView &L, int64_t n, double omega) {
+  const double2 bv = L.b[n], dv = L.dinv[n];
+  L.x[n] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
+}
+__device__ __forceinline__ void node_prolong_add(const LevelView &L, const double2 *__restrict__ xc, int cnx, int64_t n) {
+  const int npr = L.nx + 1;
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  const double2 p = prolong_node(xc, c, r, L.nx, L.ny, cnx + 1);
+  const double2 dv = L.dinv[n];
+  double2 xv = L.x[n];
+  if (dv.x != 0.0) xv.x += p.x;
+  if (dv.y != 0.0) xv.y += p.y;
+  L.x[n] = xv;
+}
+
+// ---- multi-block kernels (large coarse levels) ------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omega, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) node_down(L, n, omega);
+}
+__global__ void __launch_bounds__(128) k_lvl_up(const LevelView L, const double2 *__restrict__ xc, int cnx,
+                                                double omega, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) node_up(L, xc, cnx, n, omega);
+}
+__global__ void __launch_bounds__(128) k_lvl_smooth(const LevelView L, double omega, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) node_smooth(L, n, omega);
+}
+__global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) node_resid(L, n);
+}
+__global__ void __launch_bounds__(128) k_restrict(const double2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
+                                                  int nyf, int nxc, int nyc, const int *done) {
+  if (done && *done) return;
+  const int nprc = nxc + 1;
+  const int64_t nnc = (int64_t)nprc * (nyc + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnc) return;
+  const int J = (int)(n / nprc), I = (int)(n - (int64_t)J * nprc);
+  bc[n] = restrict_node(rf, I, J, nxf, nyf);
+}
+// fine grid: x^ += mask(P x1)   (constrained DOFs stay zero)
+__global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, double2 *__restrict__ xf,
+                                                          const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
+                                                          const int *done) {
+  if (done && *done) return;
+  const int nprf = nxf + 1;
+  const int64_t nnf = (int64_t)nprf * (nyf + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnf) return;
+  const int j = (int)(n / nprf), i = (int)(n - (int64_t)j * nprf);
+  const double2 p = prolong_node(xc, i, j, nxf, nyf, nxc + 1);
+  const unsigned m = fixed[n];
+  double2 acc = xf[n];
+  if (!(m & 1u)) acc.x += p.x;
+  if (!(m & 2u)) acc.y += p.y;
+  xf[n] = acc;
+}
+
+// ---- tail: all levels >= first in ONE launch of a thread-block cluster ------------------------------------
+// Levels with more than TAIL_SMALL nodes are worked on by every CTA of the cluster with a hardware
+// cluster barrier (barrier.cluster, release/acquire: global writes of one CTA are visible to the others
+// after it) between stages; the smallest levels are finished by CTA 0 alone with __syncthreads.
+constexpr int TAIL_MAX = 16;
+constexpr int TAIL_SMALL = 1024;
+struct TailArgs {
+  LevelView lv[TAIL_MAX];
+  int n;                       // number of levels in the tail (the last one is the coarsest)
+  const double2 *r_parent;     // residual of the level above the tail
+  int pnx, pny;                // its size
+  const double *coarse_inv;
+  int coarse_n;
+  double omega;
+  int nu_pre, nu_post;
+  const int *done;
+  unsigned long long *dbg;     // optional: globaltimer stamps at stage boundaries (thread 0 of CTA 0)
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+#define STAMP() do { if (a.dbg && gt == 0) { a.dbg[1 + a.dbg[0]] = gtimer(); a.dbg[0] += 1; } } while (0)
+
+template <class Sync>
+__device__ __forceinline__ void tail_down(const TailArgs &a, int l, int gt, int GT, Sync sync) {
+  LevelView L = a.lv[l];
+  const int nn = (L.nx + 1) * (L.ny + 1);
+  for (int n = gt; n < nn; n += GT) node_down(L, n, a.omega);            // x = w dinv b ; r = b - A x
+  sync();
+  STAMP();
+  for (int s = 1; s < a.nu_pre; ++s) {                                   // extra sweeps keep the iterate in x
+    for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);
+    sync();
+    for (int n = gt; n < nn; n += GT) L.x[n] = L.x2[n];
+    sync();
+    for (int n = gt; n < nn; n += GT) node_resid(L, n);
+    sync();
+  }
+  const LevelView &C = a.lv[l + 1];
+  const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
+  for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(L.r, n % nprc, n / nprc, L.nx, L.ny);
+  sync();
+  STAMP();
+}
+
+// result of a level lives in x2 when nu_post is odd, in x otherwise (same rule as the multi-block levels)
+template <class Sync>
+__device__ __forceinline__ void tail_up(const TailArgs &a, int l, int gt, int GT, Sync sync) {
+  LevelView L = a.lv[l];
+  const LevelView &C = a.lv[l + 1];
+  const double2 *xc = (l + 1 == a.n - 1) ? C.x : ((a.nu_post & 1) ? C.x2 : C.x);
+  const int nn = (L.nx + 1) * (L.ny + 1);
+  for (int n = gt; n < nn; n += GT) node_prolong_add(L, xc, C.nx, n);
+  sync();
+  STAMP();
+  for (int s = 0; s < a.nu_post; ++s) {
+    for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);        // x -> x2
+    sync();
+    STAMP();
+    double2 *tmp = L.x; L.x = L.x2; L.x2 = tmp;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs a) {
+  if (a.done && *a.done) return;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int T = blockDim.x, t = threadIdx.x;
+  const int gt = rank * T + t, GT = CS * T;
+  auto csync = [&]() { cluster.sync(); };
+  auto bsync = [&]() { __syncthreads(); };
+  if (a.dbg && gt == 0) a.dbg[0] = 0;
+  STAMP();
+  {
+    const LevelView &C = a.lv[0];
+    const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
+    for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny);
+  }
+  csync();
+  STAMP();
+  int l = 0;
+  for (; l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL; ++l) tail_down(a, l, gt, GT, csync);
+  const int lsmall = l;
+  if (rank == 0) {
+    for (l = lsmall; l + 1 < a.n; ++l) tail_down(a, l, t, T, bsync);
+    {  // coarsest: dense inverse
+      const LevelView &C = a.lv[a.n - 1];
+      const double *bb = reinterpret_cast<const double *>(C.b);
+      const double *dd = reinterpret_cast<const double *>(C.dinv);
+      double *xx = reinterpret_cast<double *>(C.x);
+      const int N = a.coarse_n;
+      for (int i = t; i < N; i += T) {
+        double sacc = 0.0;
+        for (int j = 0; j < N; ++j) sacc = fma(a.coarse_inv[i * N + j], bb[j], sacc);
+        xx[i] = dd[i] != 0.0 ? sacc : 0.0;
+      }
+    }
+    __syncthreads();
+    STAMP();
+    for (l = a.n - 2; l >= lsmall; --l) tail_up(a, l, t, T, bsync);
+  }
+  csync();
+  STAMP();
+  for (l = lsmall - 1; l >= 0; --l) tail_up(a, l, gt, GT, csync);
+}
+
+const char *lvl_name(const char *what, int l) {
+  static char names[2][TOPO_MAX_LEVELS][24];
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < TOPO_MAX_LEVELS; ++i) {
+      snprintf(names[0][i], 24, "k_lvl_down L%d", i);
+      snprintf(names[1][i], 24, "k_lvl_up L%d", i);
+    }
+    init = true;
+  }
+  return names[what[0] == 'd' ? 0 : 1][l];
+}
+
+LevelView view_of(const GmgLevel &G) {
+  LevelView v;
+  v.st = G.st; v.dinv = G.dinv; v.x = G.x; v.x2 = G.x2; v.b = G.b; v.r = G.r; v.nx = G.nx; v.ny = G.ny;
+  return v;
+}
+
+}  // namespace
+
+// Restricts the fine residual, runs levels 1..L-1 and adds the prolongated level-1 correction into the
+// fine-grid iterate x^ (constrained DOFs stay zero).  No host-side state changes (pointers are never
+// swapped), so the launch sequence can be captured in a CUDA graph and replayed.
+// Result of a multi-block level lives in its x2 (nu_post odd) or x (nu_post even); tail levels leave it in x.
+int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine) {
+  cudaStream_t st = h->stream;
+  const double om = h->omega;
+  const int L = h->n_levels;
+  if (L < 2) return TOPO_OK;
+  const int *done = &h->sc->done;
+  // first level handled by the tail kernel
+  int tail = L - 1;
+  while (tail > 1 && h->levels[tail - 1].nn <= h->tail_max_nodes) --tail;
+  auto result_of = [&](int l) -> const double2 * {
+    if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
+    return (h->nu_post & 1) ? h->levels[l].x2 : h->levels[l].x;
+  };
+
+  if (tail > 1) {
+    GmgLevel &C = h->levels[1];
+    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(res_fine, C.b, h->nx, h->ny, C.nx, C.ny, done));
+  }
+  for (int l = 1; l < tail; ++l) {
+    GmgLevel &F = h->levels[l];
+    LevelView V = view_of(F);
+    KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+    for (int s = 1; s < h->nu_pre; ++s) {
+      KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+      CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
+      KL(h, "k_lvl_resid", k_lvl_resid<<<blocks_for(F.nn), 128, 0, st>>>(V, done));
+    }
+    if (l + 1 < tail) {
+      GmgLevel &C = h->levels[l + 1];
+      KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny, done));
+    }
+  }
+  {
+    TailArgs ta = {};
+    ta.n = L - tail;
+    if (ta.n > TAIL_MAX) {
+      topo_set_error("multigrid tail has %d levels (max %d)", ta.n, TAIL_MAX);
+      return TOPO_EINVAL;
+    }
+    for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h->levels[l]);
+    if (tail == 1) {
+      ta.r_parent = res_fine; ta.pnx = h->nx; ta.pny = h->ny;
+    } else {
+      ta.r_parent = h->levels[tail - 1].r; ta.pnx = h->levels[tail - 1].nx; ta.pny = h->levels[tail - 1].ny;
+    }
+    ta.coarse_inv = h->coarse_inv;
+    ta.coarse_n = h->coarse_n;
+    ta.omega = om;
+    ta.nu_pre = h->nu_pre;
+    ta.nu_post = h->nu_post;
+    ta.done = done;
+    ta.dbg = h->tail_dbg;
+    // one cluster; 16 CTAs needs the non-portable size, fall back to 8 (portable) or 1
+    static int cluster_size = 0;
+    if (cluster_size == 0) {
+      cluster_size = 1;
+      if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        for (int cs : {16, 8, 4, 2}) {
+          cudaLaunchConfig_t q = {};
+          q.gridDim = dim3(cs); q.blockDim = dim3(1024);
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          q.attrs = at; q.numAttrs = 1;
+          int ncl = 0;
+          if (cudaOccupancyMaxActiveClusters(&ncl, k_tail, &q) == cudaSuccess && ncl >= 1) { cluster_size = cs; break; }
+        }
+      }
+      cudaGetLastError();
+    }
+    const bool big_tail = h->levels[tail].nn > TAIL_SMALL;
+    const int cs = big_tail ? cluster_size : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
+  }
+  for (int l = tail - 1; l >= 1; --l) {
+    GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
+    LevelView V = view_of(F);
+    KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
+    for (int s = 1; s < h->nu_post; ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
+      LevelView W = V;
+      if (s & 1) { W.x = F.x2; W.x2 = F.x; }
+      KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(W, om, done));
+    }
+  }
+  {
+    GmgLevel &C = h->levels[1];
+    KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), xhat_fine, h->fixed, h->nx, h->ny,
+                                                                                       C.nx, done));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}

@@ -147,27 +147,23 @@ __global__ void k_set_bb(SolverScalars *sc, const double *bb) {
 
 int topo_apply_loads(topo_handle *h) {
   const int64_t nn = h->nn;
-  k_zero2<<<vec_blocks(nn), VEC_THREADS, 0, h->stream>>>(h->f, nn);
-  LAUNCHED(h);
+  KL(h, "k_zero2", k_zero2<<<vec_blocks(nn), VEC_THREADS, 0, h->stream>>>(h->f, nn));
   if (h->n_loads > 0) {
-    k_apply_loads<<<1, 32, 0, h->stream>>>(h->f, h->fixed, h->d_load_node, h->d_load_fx, h->d_load_fy,
-                                           h->n_loads);
-    LAUNCHED(h);
+    KL(h, "k_apply_loads", k_apply_loads<<<1, 32, 0, h->stream>>>(h->f, h->fixed, h->d_load_node, h->d_load_fx, h->d_load_fy,
+                                           h->n_loads));
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
 
 int topo_mask_vector(topo_handle *h, double2 *v) {
-  k_mask2<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(v, h->fixed, h->nn);
-  LAUNCHED(h);
+  KL(h, "k_mask2", k_mask2<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(v, h->fixed, h->nn));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
 
 int topo_dot(topo_handle *h, const double2 *a, const double2 *b, double *host_out) {
-  k_dot<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(a, b, h->nn, h->partials, h->ticket, h->red_out);
-  LAUNCHED(h);
+  KL(h, "k_dot", k_dot<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(a, b, h->nn, h->partials, h->ticket, h->red_out));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(host_out, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -196,8 +192,7 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   if (!jacobi) TOPO_TRY(topo_gmg_setup(h));
 
   if (!warm) {
-    k_zero2<<<nb, VEC_THREADS, 0, st>>>(h->u, nn);
-    LAUNCHED(h);
+    KL(h, "k_zero2", k_zero2<<<nb, VEC_THREADS, 0, st>>>(h->u, nn));
   } else {
     TOPO_TRY(topo_mask_vector(h, h->u));   // BC flags may have changed since the last solve
   }
@@ -206,68 +201,91 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   init.maxit = maxit;
   CUDA_TRY(cudaMemcpyAsync(h->sc, &init, sizeof(init), cudaMemcpyHostToDevice, st));
 
-  // ping-pong pairs: index 0 = current, 1 = other
+  // ping-pong pairs (inputs that are also outputs are written to the other buffer)
   double2 *ub[2] = {h->u, h->u2}, *rb[2] = {h->r, h->r2}, *pb[2] = {h->p, h->p2};
   double2 *xhat = h->tmp2, *res = h->tmp;
   TOPO_TRY(topo_fine_residual(h, ub[0], h->f, rb[0]));
-  CUDA_TRY(cudaMemsetAsync(pb[0], 0, vbytes, st));
-  int cur = 0;                                 // buffers holding the current u / r
-  int pcur = 0;                                // buffer holding the current p
-
-  if (jacobi) {
-    k_pcg_init_jacobi<<<nb, VEC_THREADS, 0, st>>>(rb[0], h->f, h->dinv, nn, h->partials, h->ticket, h->sc);
-    LAUNCHED(h);
-  } else {
-    CUDA_TRY(cudaMemsetAsync(h->Ap, 0, vbytes, st));
-    k_dot<<<nb, VEC_THREADS, 0, st>>>(h->f, h->f, nn, h->partials, h->ticket, h->red_out);
-    LAUNCHED(h);
-    k_set_bb<<<1, 1, 0, st>>>(h->sc, h->red_out);
-    LAUNCHED(h);
-    // z0 = V(r0): the update kernel with alpha = 0 copies u, r into the other buffers
-    TOPO_TRY(topo_fine_update_resid0(h, pb[0], h->Ap, ub[0], rb[0], ub[1], rb[1], xhat, res, h->omega, 1));
-    cur = 1;
-    TOPO_TRY(topo_gmg_coarse(h, res, xhat));
-    TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[cur], nullptr, 0, h->z, h->omega, 1));
-  }
-
-  const int batch = jacobi ? 64 : 6;
-  int launched = 0;
   SolverScalars *hs = h->sc_host;
   hs->done = 0;
   hs->iters = 0;
-  while (true) {
-    CUDA_TRY(cudaMemcpyAsync(hs, h->sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (hs->done || launched >= maxit) break;
-    const int nrun = std::min(batch, maxit - launched);
-    for (int i = 0; i < nrun; ++i) {
-      if (jacobi) {
+  int launched = 0;
+
+  if (jacobi) {
+    CUDA_TRY(cudaMemsetAsync(pb[0], 0, vbytes, st));
+    KL(h, "k_pcg_init_jacobi", k_pcg_init_jacobi<<<nb, VEC_THREADS, 0, st>>>(rb[0], h->f, h->dinv, nn, h->partials, h->ticket, h->sc));
+    int pcur = 0;
+    while (true) {
+      CUDA_TRY(cudaMemcpyAsync(hs, h->sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (hs->done || launched >= maxit) break;
+      const int nrun = std::min(64, maxit - launched);
+      for (int i = 0; i < nrun; ++i) {
         TOPO_TRY(topo_fine_pcg_matvec_jacobi(h, rb[0], pb[pcur], pb[pcur ^ 1], h->Ap));
         pcur ^= 1;
-        k_pcg_update_jacobi<<<nb, VEC_THREADS, 0, st>>>(ub[0], rb[0], pb[pcur], h->Ap, h->dinv, nn, h->partials,
-                                                        h->ticket, h->sc);
-        LAUNCHED(h);
-      } else {
-        TOPO_TRY(topo_fine_pcg_matvec(h, h->z, pb[pcur], pb[pcur ^ 1], h->Ap));
-        pcur ^= 1;
-        TOPO_TRY(topo_fine_update_resid0(h, pb[pcur], h->Ap, ub[cur], rb[cur], ub[cur ^ 1], rb[cur ^ 1], xhat, res,
-                                         h->omega, 0));
-        cur ^= 1;
-        TOPO_TRY(topo_gmg_coarse(h, res, xhat));
-        TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[cur], nullptr, 0, h->z, h->omega, 0));
+        KL(h, "k_pcg_update_jacobi", k_pcg_update_jacobi<<<nb, VEC_THREADS, 0, st>>>(ub[0], rb[0], pb[pcur], h->Ap, h->dinv, nn,
+                                                                                    h->partials, h->ticket, h->sc));
       }
+      launched += nrun;
+      CUDA_TRY(cudaGetLastError());
     }
-    launched += nrun;
-    CUDA_TRY(cudaGetLastError());
-  }
-  // The device executed hs->iters real iterations; later launches were no-ops.  GMG: the update of
-  // iteration k wrote buffer (k+1)&1 (the alpha=0 pass wrote buffer 1).
-  if (!jacobi) {
-    const int fin = (hs->iters + 1) & 1;
-    if (fin == 1) {
-      std::swap(h->u, h->u2);
-      std::swap(h->r, h->r2);
+  } else {
+    // one PCG iteration reading the buffers of parity `par` and writing those of parity par^1
+    auto iteration = [&](int par) -> int {
+      TOPO_TRY(topo_fine_pcg_matvec(h, h->z, pb[par], pb[par ^ 1], h->Ap));
+      TOPO_TRY(topo_fine_update_resid0(h, pb[par ^ 1], h->Ap, ub[par], rb[par], ub[par ^ 1], rb[par ^ 1], xhat, res,
+                                       h->omega, 0));
+      TOPO_TRY(topo_gmg_coarse(h, res, xhat));
+      TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[par ^ 1], nullptr, 0, h->z, h->omega, 0));
+      return TOPO_OK;
+    };
+    CUDA_TRY(cudaMemsetAsync(pb[1], 0, vbytes, st));
+    CUDA_TRY(cudaMemsetAsync(h->Ap, 0, vbytes, st));
+    KL(h, "k_dot", k_dot<<<nb, VEC_THREADS, 0, st>>>(h->f, h->f, nn, h->partials, h->ticket, h->red_out));
+    KL(h, "k_set_bb", k_set_bb<<<1, 1, 0, st>>>(h->sc, h->red_out));
+    // z0 = V(r0): the update kernel with alpha = 0 copies u, r into the parity-1 buffers
+    TOPO_TRY(topo_fine_update_resid0(h, pb[1], h->Ap, ub[0], rb[0], ub[1], rb[1], xhat, res, h->omega, 1));
+    TOPO_TRY(topo_gmg_coarse(h, res, xhat));
+    TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[1], nullptr, 0, h->z, h->omega, 1));
+
+    // Two iterations (parity 1 then 0) form a closed cycle of buffer roles: capture them once in a CUDA
+    // graph (per handle) and replay it; converged iterations turn into no-op kernels.
+    const bool use_graph = !h->prof_on && h->use_graph;
+    if (use_graph && !h->pcg_graph_valid) {
+      if (h->pcg_graph_exec) { cudaGraphExecDestroy(h->pcg_graph_exec); h->pcg_graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const long long l0 = h->timing.kernel_launches;
+      int s1 = iteration(1);
+      int s2 = (s1 == TOPO_OK) ? iteration(0) : s1;
+      h->pcg_graph_launches = (int)(h->timing.kernel_launches - l0);
+      h->timing.kernel_launches = l0;            // captured, not launched
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (s2 != TOPO_OK) { if (graph) cudaGraphDestroy(graph); return s2; }
+      CUDA_TRY(ce);
+      CUDA_TRY(cudaGraphInstantiate(&h->pcg_graph_exec, graph, 0));
+      CUDA_TRY(cudaGraphDestroy(graph));
+      h->pcg_graph_valid = true;
     }
+    while (true) {
+      CUDA_TRY(cudaMemcpyAsync(hs, h->sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (hs->done || launched >= maxit) break;
+      const int pairs = std::max(1, std::min(4, (maxit - launched + 1) / 2));
+      for (int i = 0; i < pairs; ++i) {
+        if (use_graph) {
+          CUDA_TRY(cudaGraphLaunch(h->pcg_graph_exec, st));
+          h->timing.kernel_launches += h->pcg_graph_launches;
+        } else {
+          TOPO_TRY(iteration(1));
+          TOPO_TRY(iteration(0));
+        }
+      }
+      launched += 2 * pairs;
+      CUDA_TRY(cudaGetLastError());
+    }
+    // iteration k wrote the buffers of parity (k+1)&1 (the alpha = 0 pass wrote parity 1)
+    if (((hs->iters + 1) & 1) == 1)
+      CUDA_TRY(cudaMemcpyAsync(h->u, h->u2, vbytes, cudaMemcpyDeviceToDevice, st));
   }
   CUDA_TRY(cudaEventRecord(h->ev1, st));
   CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -298,9 +316,8 @@ extern "C" int topo_equilibrium_check(topo_t *h, int *ok) {
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->diag_valid) TOPO_TRY(topo_build_diag(h));
   TOPO_TRY(topo_fine_residual(h, h->u, h->f, h->tmp));
-  k_equilibrium<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(h->tmp, h->f, h->nn, h->kmax, h->partials,
-                                                                  h->ticket, h->red_out);
-  LAUNCHED(h);
+  KL(h, "k_equilibrium", k_equilibrium<<<vec_blocks(h->nn), VEC_THREADS, 0, h->stream>>>(h->tmp, h->f, h->nn, h->kmax, h->partials,
+                                                                  h->ticket, h->red_out));
   CUDA_TRY(cudaGetLastError());
   double bad = 0.0;
   CUDA_TRY(cudaMemcpyAsync(&bad, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));

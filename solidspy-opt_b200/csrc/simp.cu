@@ -171,8 +171,7 @@ __global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho,
 extern "C" int topo_simp_scale(topo_t *h, double penal, double emin, double emax) {
   if (!h) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
-  k_simp_scale<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->rho, h->scale, h->ne, penal, emin, emax);
-  LAUNCHED(h);
+  KL(h, "k_simp_scale", k_simp_scale<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->rho, h->scale, h->ne, penal, emin, emax));
   CUDA_TRY(cudaGetLastError());
   h->diag_valid = false;
   h->gmg_valid = false;
@@ -182,9 +181,8 @@ extern "C" int topo_simp_scale(topo_t *h, double penal, double emin, double emax
 extern "C" int topo_simp_sensitivity(topo_t *h, double penal, double emin, double emax, double *objective) {
   if (!h) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
-  k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
-                                                      emax, h->partials, h->ticket, h->red_out);
-  LAUNCHED(h);
+  KL(h, "k_simp_sens", k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
+                                                      emax, h->partials, h->ticket, h->red_out));
   CUDA_TRY(cudaGetLastError());
   if (objective) {
     CUDA_TRY(cudaMemcpyAsync(objective, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -210,8 +208,7 @@ extern "C" int topo_filter_sensitivity(topo_t *h, double rmin, double dx, double
       taps.w[(dj + taps.hy) * wrow + di + taps.hx] = rmin - std::sqrt((di * dx) * (di * dx) + (dj * dy) * (dj * dy));
   dim3 grid(div_up(h->nx, FT), div_up(h->ny, FT)), block(32, 8);
   const size_t smem = sizeof(double) * (FT + 2 * taps.hx) * (FT + 2 * taps.hy);
-  k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny);
-  LAUNCHED(h);
+  KL(h, "k_filter", k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny));
   CUDA_TRY(cudaGetLastError());
   std::swap(h->dc, h->dc2);
   return TOPO_OK;
@@ -223,24 +220,21 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   cudaStream_t st = h->stream;
   const int nb = el_blocks(h->ne);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
-  k_oc_init<<<1, 1, 0, st>>>(h->oc, *g);
-  LAUNCHED(h);
+  KL(h, "k_oc_init", k_oc_init<<<1, 1, 0, st>>>(h->oc, *g));
   OcState *hs = h->oc_host;
   hs->done = 0;
   int launched = 0;
   const int batch = 48, hard_cap = 2400;   // the bracket [0,1e9] underflows after ~1100 halvings
   while (launched < hard_cap) {
     for (int i = 0; i < batch; ++i) {
-      k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc);
-      LAUNCHED(h);
+      KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc));
     }
     launched += batch;
     CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (hs->done) break;
   }
-  k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out, h->oc);
-  LAUNCHED(h);
+  KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out, h->oc));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(h->ev1, st));

@@ -107,10 +107,17 @@ struct topo_handle {
   std::vector<GmgLevel> levels;   // levels[0] unused placeholder; levels[l] for l>=1
   double *gtab;            // 9 x 64 level-1 Galerkin tables (device)
   double *ptab;            // 9 x 64 child interpolation matrices (device)
-  double *coarse_inv;      // dense inverse of the coarsest operator
+  void *lvl1_slab, *coarse_slab;   // allocations behind levels[1] and levels[>=2] (+ coarse_inv)
+  size_t coarse_slab_bytes;
+  double *coarse_inv;      // dense inverse of the coarsest operator (inside coarse_slab)
   int coarse_n;            // its dimension (2*nn of last level)
   double omega;
   int nu_pre, nu_post;
+  unsigned long long *tail_dbg;   // device buffer for k_tail stage stamps (nullptr = off)
+  int tail_max_nodes;
+  bool use_graph, pcg_graph_valid;
+  cudaGraphExec_t pcg_graph_exec;
+  int pcg_graph_launches;      // levels with at most this many nodes run inside the single-CTA tail kernel
 
   void *slab_nodal, *slab_elem;   // allocation bases (field pointers get swapped)
 
@@ -121,9 +128,32 @@ struct topo_handle {
   bool prof_on;
   int prof_n;
   std::vector<cudaEvent_t> prof_ev;   // pairs
+  std::vector<const char *> prof_name;
   topo_timing timing;
   int matvec_rows_per_chunk;
 };
+
+// Kernel launch wrapper: counts the launch and, in profile mode, brackets it with CUDA events on the
+// handle's stream (per-kernel in-situ durations; read back through topo_profile_report).
+static inline void topo_prof_pre(topo_handle *h, const char *name) {
+  if (h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size()) {
+    h->prof_name[h->prof_n] = name;
+    cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
+  }
+}
+static inline void topo_prof_post(topo_handle *h) {
+  if (h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size()) {
+    cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], h->stream);
+    h->prof_n++;
+  }
+  h->timing.kernel_launches++;
+}
+#define KL(h, name, ...)        \
+  do {                          \
+    topo_prof_pre((h), (name)); \
+    __VA_ARGS__;                \
+    topo_prof_post((h));        \
+  } while (0)
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

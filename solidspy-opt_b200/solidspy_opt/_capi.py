@@ -26,7 +26,7 @@ SYMBOLS = [
     "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_rank_select",
     "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity",
     "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
-    "topo_profile_matvec", "topo_profile_read",
+    "topo_profile_matvec", "topo_profile_read", "topo_profile_report",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library():
         "topo_timer_stop": [vp, C.POINTER(C.c_float)],
         "topo_profile_matvec": [vp, C.c_int],
         "topo_profile_read": [vp, ip, C.POINTER(C.c_float)],
+        "topo_profile_report": [vp, C.c_char_p, C.c_size_t],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -332,3 +333,13 @@ class Topo:
         n, ms = C.c_int(0), C.c_float(0)
         _check(self.lib.topo_profile_read(self.h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
+
+    def profile_report(self):
+        """[(kernel, launches, total_ms)] for everything launched since profile_matvec(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.lib.topo_profile_report(self.h, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out.append((name, int(n), float(ms)))
+        return out
