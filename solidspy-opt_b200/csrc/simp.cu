@@ -124,14 +124,24 @@ __global__ void k_oc_init(OcState *oc, double g) {
   oc->lmid = 0.0;
   oc->steps = 0;
   oc->change = 0.0;
+  oc->need_exact = 0;
   oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
 }
 
-// one bisection step: gt = g + sum(rho_new(lmid) - rho); gt > 0 ? l1 = lmid : l2 = lmid
+// A_e = rho sqrt(-dc): rho*sqrt(-dc/lmid) == A_e / sqrt(lmid) up to a few ulp
+__global__ void __launch_bounds__(ET) k_oc_prep(const double *__restrict__ rho, const double *__restrict__ dc,
+                                                double *__restrict__ amp, int64_t ne) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x)
+    amp[e] = rho[e] * sqrt(-dc[e]);
+}
+
+// EXACT bisection step with the reference's formula: gt = g + sum(rho_new(lmid) - rho);
+// gt > 0 ? l1 = lmid : l2 = lmid.  only_when_needed: run only if the fast pass asked for it.
 __global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, const double *__restrict__ dc,
-                                                int64_t ne, double move, double *partials, unsigned int *ticket,
-                                                double *out, OcState *oc) {
+                                                int64_t ne, double move, int only_when_needed, double *partials,
+                                                unsigned int *ticket, double *out, OcState *oc) {
   if (oc->done) return;
+  if (only_when_needed && !oc->need_exact) return;
   const double lmid = 0.5 * (oc->l2 + oc->l1);
   double v[1] = {0.0};
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
@@ -144,8 +154,106 @@ __global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, 
     oc->gt = gt;
     oc->lmid = lmid;
     oc->steps += 1;
+    oc->need_exact = 0;
     oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
   }
+}
+
+// FAST pass: the 15 multipliers of the next 4 bisection levels (heap order, generated with exactly the
+// reference's 0.5*(l2+l1) arithmetic) are evaluated together with the cheap form A_e/sqrt(lmid).  The
+// last block then walks the decision tree.  Each clamped term differs from the reference's by a few
+// ulp (<= 1e-15 absolute), so a sum further than `margin` from zero has the reference's sign; a sum
+// inside the margin stops the walk and requests one exact step (k_oc_step) for that decision.
+constexpr int OC_LEVELS = 4, OC_CAND = (1 << OC_LEVELS) - 1;
+__global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho, const double *__restrict__ amp,
+                                                 int64_t ne, double move, double margin, double *partials,
+                                                 unsigned int *ticket, double *out, OcState *oc) {
+  if (oc->done || oc->need_exact) return;
+  // candidate multipliers in heap order; each of the first 15 threads does ONE 1/sqrt and shares it
+  __shared__ double s_tinv[OC_CAND];
+  if (threadIdx.x < OC_CAND) {
+    double lo[OC_CAND], hi[OC_CAND], lmj = 0.0;
+    lo[0] = oc->l1;
+    hi[0] = oc->l2;
+#pragma unroll
+    for (int j = 0; j < OC_CAND; ++j) {
+      const double m = 0.5 * (hi[j] + lo[j]);
+      if (j == (int)threadIdx.x) lmj = m;
+      if (2 * j + 2 < OC_CAND) {
+        lo[2 * j + 1] = lo[j]; hi[2 * j + 1] = m;        // gt <= 0 : l2 = lmid
+        lo[2 * j + 2] = m; hi[2 * j + 2] = hi[j];        // gt  > 0 : l1 = lmid
+      }
+    }
+    s_tinv[threadIdx.x] = 1.0 / sqrt(lmj);
+  }
+  __syncthreads();
+  double tinv[OC_CAND];
+#pragma unroll
+  for (int j = 0; j < OC_CAND; ++j) tinv[j] = s_tinv[j];
+  double tmin = tinv[0], tmax = tinv[0];
+#pragma unroll
+  for (int j = 1; j < OC_CAND; ++j) { tmin = fmin(tmin, tinv[j]); tmax = fmax(tmax, tinv[j]); }
+  double v[OC_CAND + 1];                 // [OC_CAND]: contributions common to all candidates (+ NaN contamination)
+#pragma unroll
+  for (int j = 0; j <= OC_CAND; ++j) v[j] = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const double rh = rho[e], am = amp[e];
+    const double cl = fmax(0.0, rh - move), ch = fmin(1.0, rh + move);
+    // elements clamped the same way by ALL 15 multipliers of this pass contribute a common constant
+    // (exactly: a*t is monotone in t, so the clamp result is identical for every candidate)
+    const double bmin = am * tmin, bmax = am * tmax;
+    if (bmax <= cl) {
+      v[OC_CAND] += cl - rh;
+    } else if (bmin >= ch) {
+      v[OC_CAND] += ch - rh;
+    } else {
+      v[OC_CAND] += (am - am) + (rh - rh);   // numpy's minimum/maximum propagate NaN; fmin/fmax do not
+#pragma unroll
+      for (int j = 0; j < OC_CAND; ++j) v[j] += fmax(cl, fmin(ch, am * tinv[j])) - rh;
+    }
+  }
+  if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0) {
+    double l1 = oc->l1, l2 = oc->l2;
+    int j = 0, steps = 0;
+    bool done = false, need = false;
+    double gt_last = oc->gt, lmid_last = oc->lmid;
+    for (int d = 0; d < OC_LEVELS; ++d) {
+      if (!((l2 - l1) / (l1 + l2) > 1e-3)) { done = true; break; }
+      double vj = 0.0;
+#pragma unroll
+      for (int q = 0; q < OC_CAND; ++q) vj = (q == j) ? v[q] : vj;
+      const double gt = oc->g + vj + v[OC_CAND];
+      const bool is_nan = !(gt == gt);
+      if (!is_nan && !(fabs(gt) > margin)) { need = true; break; }    // too close to call: the exact step decides
+      const double lmid = 0.5 * (l2 + l1);                            // == the candidate evaluated at heap node j
+      if (gt > 0.0) { l1 = lmid; j = 2 * j + 2; } else { l2 = lmid; j = 2 * j + 1; }   // NaN -> else, like the reference
+      gt_last = gt;
+      lmid_last = lmid;
+      ++steps;
+    }
+    if (!done && !need && !((l2 - l1) / (l1 + l2) > 1e-3)) done = true;
+    oc->l1 = l1;
+    oc->l2 = l2;
+    oc->gt = gt_last;
+    oc->lmid = lmid_last;
+    oc->steps += steps;
+    oc->need_exact = need ? 1 : 0;
+    oc->done = done ? 1 : 0;
+  }
+}
+
+// exact gt at the last evaluated multiplier (what the reference returns as the new constraint value)
+__global__ void __launch_bounds__(ET) k_oc_final_gt(const double *__restrict__ rho, const double *__restrict__ dc,
+                                                    int64_t ne, double move, double *partials, unsigned int *ticket,
+                                                    double *out, OcState *oc) {
+  if (oc->steps == 0) return;
+  const double lmid = oc->lmid;
+  double v[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const double rh = rho[e];
+    v[0] += oc_candidate(rh, dc[e], lmid, move) - rh;
+  }
+  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0) oc->gt = oc->g + v[0];
 }
 
 // rho_new at the LAST evaluated multiplier (what the reference returns) + change = max|rho_new - rho|
@@ -221,20 +329,30 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   const int nb = el_blocks(h->ne);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
   KL(h, "k_oc_init", k_oc_init<<<1, 1, 0, st>>>(h->oc, *g));
+  double *amp = h->sens;                   // scratch: SIMP does not use the BESO sensitivity field
+  KL(h, "k_oc_prep", k_oc_prep<<<nb, ET, 0, st>>>(h->rho, h->dc, amp, h->ne));
+  // rounding margin of the fast pass: (#elements) x (a few ulp of a value <= 1) with head-room
+  const double margin = 64.0 * 2.220446049250313e-16 * (double)h->ne + 1e-12;
   OcState *hs = h->oc_host;
   hs->done = 0;
-  int launched = 0;
-  const int batch = 48, hard_cap = 2400;   // the bracket [0,1e9] underflows after ~1100 halvings
-  while (launched < hard_cap) {
+  int rounds = 0;
+  const int batch = 12, hard_cap = 700;    // the bracket [0,1e9] underflows after ~1100 halvings = 275 rounds
+  while (rounds < hard_cap) {
     for (int i = 0; i < batch; ++i) {
-      KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc));
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+                                                        h->red_out, h->oc));
+      KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket,
+                                                      h->red_out, h->oc));
     }
-    launched += batch;
+    rounds += batch;
     CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (hs->done) break;
   }
-  KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out, h->oc));
+  KL(h, "k_oc_final_gt", k_oc_final_gt<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket,
+                                                          h->red_out, h->oc));
+  KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket,
+                                                    h->red_out, h->oc));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(h->ev1, st));

@@ -11,7 +11,7 @@
 #include "../../include/topo_b200.h"
 
 #define TOPO_MAX_LEVELS 32
-#define TOPO_RED_SLOTS 8          // scalars reduced per kernel (max)
+#define TOPO_RED_SLOTS 16         // scalars reduced per kernel (max)
 #define TOPO_MAX_PARTIAL_BLOCKS 8192
 
 void topo_set_error(const char *fmt, ...);
@@ -55,6 +55,8 @@ struct SolverScalars {
 struct OcState {
   double l1, l2, lmid, gt, g, change;
   int steps, done;
+  int need_exact;   // the next bisection decision must come from the exact (reference-formula) pass
+  int pad;
 };
 
 // one coarse level of the multigrid hierarchy (level 0 = the matrix-free fine grid, not stored here)
