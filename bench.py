@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--ny", type=int, default=1024)
-    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--rtol", type=float, default=1e-9)
     ap.add_argument("--precond", default="gmg", choices=["gmg", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -179,7 +179,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def trajectory(n_steps, host_io):
+    def trajectory(n_steps, host_io, profile=False):
         """rho = 0.5, then n_steps consecutive design iterations; returns per-step results."""
         out = []
         g = 0.0
@@ -192,7 +192,7 @@ def main():
         for i in range(n_steps):
             if i == args.warmup:
                 barrier()
-                if not host_io:
+                if profile:
                     topo.profile_matvec(True)
                 l0 = topo.timing().kernel_launches
                 topo.timer_start()
@@ -214,9 +214,13 @@ def main():
     sampler.start()
     res_dev, ms_dev, wall_dev, launches = trajectory(total, host_io=False)
     clocks = sampler.stop()
-    n_mv, mv_ms = topo.profile_read()
-    topo.profile_matvec(False)
     res_e2e, ms_e2e, wall_e2e, _ = trajectory(total, host_io=True)
+    # third pass over the same steps with every kernel launch bracketed by CUDA events (this disables the
+    # CUDA-graph replay, so it is NOT the pass `value` comes from): per-kernel durations inside real steps
+    _, ms_prof, _, _ = trajectory(total, host_io=False, profile=True)
+    n_mv, mv_ms = topo.profile_read()
+    report = topo.profile_report()
+    topo.profile_matvec(False)
 
     def allmax(x):
         if world == 1:
@@ -252,12 +256,14 @@ def main():
                          "frac": (achieved/peak) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "avg_launch_us": mv_us, "launches_timed": n_mv,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "share_of_step": mv_ms/ms_dev if ms_dev else None,
+                         "share_of_step": mv_ms/ms_prof if ms_prof else None,
+                         "note": "durations from a separate event-instrumented pass over the same steps",
                          "frac_of_nominal_8TBs": (achieved/8000.0) if achieved else None},
             "detail": {"cg_iters": [r[2] for r in timed], "oc_steps": [r[3] for r in timed],
                        "compliance_first_last": [timed[0][0], timed[-1][0]],
                        "max_relres": max(r[4] for r in timed), "all_converged": all(r[5] == 0 for r in timed),
-                       "wall_ms_per_step": wall_dev/args.steps},
+                       "wall_ms_per_step": wall_dev/args.steps,
+                       "kernel_ms_per_step": {name: round(ms/args.steps, 4) for name, n, ms in report[:14]}},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_port_rate(nx, ny)

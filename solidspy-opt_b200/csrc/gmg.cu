@@ -100,46 +100,67 @@ __global__ void __launch_bounds__(128) k_cells_level1(const __grid_constant__ Ke
 }
 
 // ---- generic Galerkin coarsening of cell matrices ---------------------------------------------------
-// thread = (coarse cell, coarse local node pair (A,B)); produces the 2x2 block K_C[2A+d][2B+e]
+// K_C = sum_children P^T K_c P.  P couples equal displacement components only, so for each component pair
+// (d,e) the 4x4 node block M_c[a][b] = K_c[2a+d][2b+e] transforms independently: K_C^{de} += W^T M_c W with
+// the 4x4 node-weight matrix W of the child.  thread = (coarse cell, (d,e)): 16 accumulators in registers,
+// 16 coalesced plane loads per child.
 __global__ void __launch_bounds__(128) k_cells_coarsen(const double *__restrict__ fcell, double *__restrict__ ccell,
                                                        int nxf, int nyf, int nxc, int nyc) {
   const int64_t ncc = (int64_t)nxc * nyc, ncf = (int64_t)nxf * nyf;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ncc) return;
-  const int A = blockIdx.y >> 2, B = blockIdx.y & 3;
+  const int d = blockIdx.y >> 1, e = blockIdx.y & 1;
   const int J = (int)(t / nxc), I = (int)(t - (int64_t)J * nxc);
   const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
-  double k00 = 0.0, k01 = 0.0, k10 = 0.0, k11 = 0.0;
+  double acc[4][4];
+#pragma unroll
+  for (int A = 0; A < 4; ++A)
+#pragma unroll
+    for (int B = 0; B < 4; ++B) acc[A][B] = 0.0;
   for (int cy = 0; cy < sy; ++cy) {
     for (int cx = 0; cx < sx; ++cx) {
       const int v = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
-      const size_t fc = (size_t)(2 * J + cy) * nxf + (2 * I + cx);
+      const double *base = fcell + (size_t)(2 * J + cy) * nxf + (2 * I + cx);
+      double M[4][4], T[4][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double wa = c_pw.w[v][a][A];
-        if (wa == 0.0) continue;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double w = wa * c_pw.w[v][b][B];
-          if (w == 0.0) continue;
-          const double *base = fcell + fc;
-          k00 = fma(w, __ldg(base + (size_t)((2 * a) * 8 + 2 * b) * ncf), k00);
-          k01 = fma(w, __ldg(base + (size_t)((2 * a) * 8 + 2 * b + 1) * ncf), k01);
-          k10 = fma(w, __ldg(base + (size_t)((2 * a + 1) * 8 + 2 * b) * ncf), k10);
-          k11 = fma(w, __ldg(base + (size_t)((2 * a + 1) * 8 + 2 * b + 1) * ncf), k11);
+        for (int b = 0; b < 4; ++b) M[a][b] = __ldg(base + (size_t)((2 * a + d) * 8 + 2 * b + e) * ncf);
+      double W[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int A = 0; A < 4; ++A) W[a][A] = c_pw.w[v][a][A];
+      // T = M W ; acc += W^T T
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int B = 0; B < 4; ++B) {
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s = fma(M[a][b], W[b][B], s);
+          T[a][B] = s;
         }
-      }
+#pragma unroll
+      for (int A = 0; A < 4; ++A)
+#pragma unroll
+        for (int B = 0; B < 4; ++B) {
+          double s = acc[A][B];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) s = fma(W[a][A], T[a][B], s);
+          acc[A][B] = s;
+        }
     }
   }
-  ccell[(size_t)((2 * A) * 8 + 2 * B) * ncc + t] = k00;
-  ccell[(size_t)((2 * A) * 8 + 2 * B + 1) * ncc + t] = k01;
-  ccell[(size_t)((2 * A + 1) * 8 + 2 * B) * ncc + t] = k10;
-  ccell[(size_t)((2 * A + 1) * 8 + 2 * B + 1) * ncc + t] = k11;
+#pragma unroll
+  for (int A = 0; A < 4; ++A)
+#pragma unroll
+    for (int B = 0; B < 4; ++B) ccell[(size_t)((2 * A + d) * 8 + 2 * B + e) * ncc + t] = acc[A][B];
 }
 
 // ---- cells -> node stencils ---------------------------------------------------------------------------
 // stencil plane index: 4*nb + 2*i + j with nb = 3*(dr+1) + (dc+1)
-__global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restrict__ cell, double *__restrict__ st,
+__global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restrict__ cell, stencil_t *__restrict__ st,
                                                           double2 *__restrict__ dinv, int nx, int ny) {
   const int npr = nx + 1;
   const int64_t nn = (int64_t)npr * (ny + 1), ncell = (int64_t)nx * ny;
@@ -170,15 +191,15 @@ __global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restri
     }
   }
 #pragma unroll
-  for (int k = 0; k < 36; ++k) st[(size_t)k * nn + n] = s[k];
-  const double dx = s[4 * 4 + 0], dy = s[4 * 4 + 3];
+  for (int k = 0; k < 36; ++k) st[(size_t)k * nn + n] = (stencil_t)s[k];
+  const double dx = (double)(stencil_t)s[4 * 4 + 0], dy = (double)(stencil_t)s[4 * 4 + 3];
   dinv[n] = make_double2(dx > 0.0 ? 1.0 / dx : 0.0, dy > 0.0 ? 1.0 / dy : 0.0);
 }
 
 // ---- coarsest level: dense inverse --------------------------------------------------------------------------------
 // One block.  Builds the dense operator from the node stencil, replaces dead rows/cols (zero diagonal)
 // by identity, inverts by Gauss-Jordan (SPD => no pivoting) in shared memory, stores the inverse.
-__global__ void k_coarse_invert(const double *__restrict__ st, int nx, int ny, double *__restrict__ inv) {
+__global__ void k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny, double *__restrict__ inv) {
   extern __shared__ double sm[];   // N x 2N augmented
   const int npr = nx + 1, nn = npr * (ny + 1), N = 2 * nn, W = 2 * N;
   for (int t = threadIdx.x; t < N * W; t += blockDim.x) sm[t] = 0.0;
@@ -252,11 +273,11 @@ int topo_gmg_plan(topo_handle *h) {
   // fine grid streams ~1 GB per PCG iteration through the 126 MB L2 and would otherwise evict them,
   // leaving the small, latency-bound kernels to pay DRAM latency on every load.
   auto level_bytes = [](const GmgLevel &L) {
-    return (size_t)L.nn * (sizeof(double) * 36 + sizeof(double2) * 5);
+    return (size_t)L.nn * (sizeof(stencil_t) * 36 + sizeof(double2) * 5);
   };
   auto carve = [](GmgLevel &L, char *base) {
     size_t off = 0;
-    L.st = reinterpret_cast<double *>(base + off); off += sizeof(double) * 36 * (size_t)L.nn;
+    L.st = reinterpret_cast<stencil_t *>(base + off); off += sizeof(stencil_t) * 36 * (size_t)L.nn;
     L.dinv = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
     L.x = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
     L.x2 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * (size_t)L.nn;
@@ -350,7 +371,7 @@ int topo_gmg_setup(topo_handle *h) {
   }
   for (int l = 2; l < h->n_levels; ++l) {
     GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
-    dim3 grid(blocks_for(C.ncell), 16);
+    dim3 grid(blocks_for(C.ncell), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
   for (int l = 1; l < h->n_levels; ++l) {

@@ -85,7 +85,7 @@ __device__ __forceinline__ double2 prolong_node(const double2 *__restrict__ xc, 
 
 // A x at node n of a stencil level, x of each neighbour supplied by `get(rr, cc)`
 template <class Get>
-__device__ __forceinline__ void stencil_row(const double *__restrict__ st, int64_t nn, int64_t n, int r, int c, int nx,
+__device__ __forceinline__ void stencil_row(const stencil_t *__restrict__ st, int64_t nn, int64_t n, int r, int c, int nx,
                                             int ny, Get get, double &ax, double &ay) {
   ax = 0.0;
   ay = 0.0;
@@ -97,17 +97,17 @@ __device__ __forceinline__ void stencil_row(const double *__restrict__ st, int64
       if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
       const int nb = 3 * (dr + 1) + (dc + 1);
       const double2 xv = get(rr, cc);
-      const double *sp = st + (size_t)(4 * nb) * nn + n;
-      ax = fma(sp[0], xv.x, ax);
-      ax = fma(sp[nn], xv.y, ax);
-      ay = fma(sp[2 * nn], xv.x, ay);
-      ay = fma(sp[3 * nn], xv.y, ay);
+      const stencil_t *sp = st + (size_t)(4 * nb) * nn + n;
+      ax = fma((double)sp[0], xv.x, ax);
+      ax = fma((double)sp[nn], xv.y, ax);
+      ay = fma((double)sp[2 * nn], xv.x, ay);
+      ay = fma((double)sp[3 * nn], xv.y, ay);
     }
   }
 }
 
 struct LevelView {
-  const double *st;
+  const stencil_t *st;
   const double2 *dinv;
   double2 *x, *x2, *b, *r;
   int nx, ny;
@@ -200,6 +200,12 @@ __global__ void __launch_bounds__(128) k_lvl_up(const LevelView L, const double2
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_up(L, xc, cnx, n, omega);
+}
+__global__ void __launch_bounds__(128) k_lvl_prolong(const LevelView L, const double2 *__restrict__ xc, int cnx, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) node_prolong_add(L, xc, cnx, n);
 }
 __global__ void __launch_bounds__(128) k_lvl_smooth(const LevelView L, double omega, const int *done) {
   if (done && *done) return;
@@ -461,7 +467,14 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine)
   for (int l = tail - 1; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
     LevelView V = view_of(F);
-    KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
+    if (F.nn > 200000) {
+      // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
+      // P x_c for all 9 neighbours inside the smoothing kernel
+      KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, done));
+      KL(h, lvl_name("up", l), k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+    } else {
+      KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
+    }
     for (int s = 1; s < h->nu_post; ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }

@@ -59,13 +59,18 @@ struct OcState {
   int pad;
 };
 
+// Coarse-level stencil coefficients are stored in fp32: they only shape the PRECONDITIONER (the outer PCG
+// residual is formed with the exact fp64 fine operator), A(n,m) and A(m,n)^T round identically so symmetry
+// is kept, and the stencil stream is the dominant traffic of levels >= 1.  Vectors stay fp64.
+typedef float stencil_t;
+
 // one coarse level of the multigrid hierarchy (level 0 = the matrix-free fine grid, not stored here)
 struct GmgLevel {
   int nx, ny;          // cells
   int nn;              // nodes
   int ncell;
   double *cell;        // 64 planes x ncell : per-cell 8x8 Galerkin matrix (SoA, plane = 8*i+j)
-  double *st;          // 36 planes x nn : node stencil, plane = 4*nb + 2*i + j, nb = 3*(dr+1)+(dc+1)
+  stencil_t *st;        // 36 planes x nn : node stencil, plane = 4*nb + 2*i + j, nb = 3*(dr+1)+(dc+1)
   double2 *dinv;       // 1/diag (0 at constrained DOFs)
   double2 *x, *x2, *b, *r;
   uint8_t *fixed;

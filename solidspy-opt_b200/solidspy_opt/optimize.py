@@ -23,7 +23,7 @@ from solidspy_opt.Utils.solver import (beso_weights, grid_shape_from_els, grid_s
 np.seterr(divide='ignore', invalid='ignore')      # reference optimize.py:12
 
 _PRECOND = {"jacobi": _capi.PRECOND_JACOBI, "gmg": _capi.PRECOND_GMG}
-DEFAULT_RTOL_SIMP = 1e-10     # 1e-8 is the loosest tolerance that keeps the 1e-6 trajectory bar
+DEFAULT_RTOL_SIMP = 1e-9      # design point 1e-9..1e-10 (1e-8 is the loosest that keeps the 1e-6 trajectory bar)
 DEFAULT_RTOL_ESO = 1e-12      # removal sets come from strict comparisons: solve tighter
 DEFAULT_MAXIT = 100000
 
