@@ -141,7 +141,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->nu_post = 1;
   h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
   h->tail_dbg = nullptr;
-  h->use_graph = true;
+  h->use_graph = getenv("TOPO_NO_GRAPH") ? false : true;
   h->pcg_graph_valid = false;
   h->pcg_graph_exec = nullptr;
   h->pcg_graph_launches = 0;

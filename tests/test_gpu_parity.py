@@ -303,3 +303,62 @@ def test_fullsize_simp_iteration(capi):
     assert np.allclose(hist["objective"], hist["compliance"], rtol=1e-8)
     assert abs(rho.mean() - 0.5) < 2e-3
     assert hist["compliance"][1] < hist["compliance"][0]
+
+
+def test_simp_from_model_mbb_config2(capi):
+    """BASELINE config 2 shape (MBB half beam, density-filter radius 2.5 elements) through the dict entry point
+    (SolidsPy README.rst:134-141 model format), against the oracle at a size it finishes in seconds."""
+    from solidspy_opt.optimize import SIMP_from_model
+    nx, ny = 120, 40
+    nodes, mats, els, loads, _ = t1.beam(L=nx, H=ny, nx=nx, ny=ny, dirs=np.array([[0, -1]]), positions=np.array([[ny, 1]]))
+    cons = np.zeros((nodes.shape[0], 2))
+    col = np.arange(nodes.shape[0]) % (nx + 1)
+    cons[col == 0, 0] = -1                       # symmetry plane: ux = 0
+    cons[nx, 1] = -1                             # roller at the bottom-right corner: uy = 0
+    load_node = (nx + 1)*ny                      # top-left corner, pushing down
+    data = {"nodes": nodes[:, :3], "cons": cons, "elements": els, "mats": np.array([[206.8e9, 0.28]]),
+            "loads": np.array([[load_node, 0.0, -1.0]])}
+    hist = {"keep_rho": True}
+    rho = SIMP_from_model(data, 12, 3, r_min=2.5, history=hist, verbose=False)
+    nodes_o = nodes.copy()
+    nodes_o[:, 3:5] = cons
+    ref = {}
+    import unittest.mock as mock
+    loads_o = np.array([[load_node, 0, -1]])
+    with mock.patch.object(t1, "beam", lambda **k: (nodes_o, np.tile([206.8e9, 0.28, 1.0], (nx*ny, 1)), els, loads_o, None)):
+        rho_ref = t1.simp(nx, ny, nx, ny, None, None, 12, 3, r_min=2.5, history=ref)
+    assert len(hist["compliance"]) == len(ref["compliance"]) == 12
+    assert np.allclose(hist["compliance"], ref["compliance"], rtol=1e-6)
+    for k in range(12):
+        assert np.abs(hist["rho"][k] - ref["rho"][k]).max() <= 1e-6, k
+    assert np.abs(rho - rho_ref).max() <= 1e-6
+
+
+def test_fullsize_beso_config3(capi):
+    """BASELINE config 3 (BESO cantilever 1024x512, sensitivity filtering, device rank-select): properties that do
+    not need the CPU oracle at this size -- kept counts follow the evolution ratio exactly, protected elements
+    survive, removed nodes are pinned, the rank-select threshold splits the sensitivities at the requested rank."""
+    from solidspy_opt.optimize import BESO
+    nx, ny = 1024, 512
+    hist = {"keep_sens": True}
+    ELS, nodes = BESO(nx, ny, nx, ny, np.array([[0, -1]]), np.array([[ny//4, 1]]), 4, 1e-3, 0.05, 0.5, history=hist,
+                      verbose=False)
+    ne = nx*ny
+    n_prev = ne
+    for k, kept in enumerate(hist["kept_ids"]):
+        target = int(n_prev*(np.full(n_prev, 1.0).sum()*(1 - 0.05))/np.full(n_prev, 1.0).sum())
+        assert kept.size - hist["n_protected"][k] <= target <= kept.size, (k, kept.size, target)
+        s = hist["sens"][k]
+        assert np.count_nonzero(s > hist["alpha"][k]) == kept.size - hist["n_protected"][k]
+        assert np.sort(s)[::-1][target] == hist["alpha"][k]                 # device radix select == full sort
+        n_prev = kept.size
+    assert ELS.shape[1] == 7 and ELS.shape[0] == hist["kept_ids"][-2].size
+    used = np.zeros(nodes.shape[0], bool)
+    last = hist["kept_ids"][-1]
+    nrow = last + last//nx
+    for off in (0, 1, nx + 1, nx + 2):
+        used[nrow + off] = True
+    assert np.all(nodes[~used, 3:5] == -1)
+    load_node = (nx + 1)*(ny//4) - 1
+    assert np.all(nodes[load_node, 3:5] == 0) and np.all(nodes[::nx + 1, 3:5] == -1)
+    assert max(hist["relres"]) <= 1e-12
