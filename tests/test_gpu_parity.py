@@ -362,3 +362,28 @@ def test_fullsize_beso_config3(capi):
     load_node = (nx + 1)*(ny//4) - 1
     assert np.all(nodes[load_node, 3:5] == 0) and np.all(nodes[::nx + 1, 3:5] == -1)
     assert max(hist["relres"]) <= 1e-12
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 1), (3, 3), (4, 2), (5, 7), (16, 9), (33, 32)])
+def test_simp_tiny_and_odd_meshes(capi, nx, ny):
+    """Hierarchies with 1..6 levels, odd sizes (trailing single child), strips narrower than a warp."""
+    from solidspy_opt.optimize import SIMP
+    dirs, pos = np.array([[0, -1]]), np.array([[max(ny//4, 1), 1]])
+    hist, ref = {"keep_rho": True}, {}
+    rho = SIMP(nx, ny, nx, ny, dirs, pos, 4, 3, history=hist, verbose=False)
+    rho_ref = t1.simp(nx, ny, nx, ny, dirs, pos, 4, 3, history=ref)
+    assert len(hist["compliance"]) == len(ref["compliance"])
+    assert np.allclose(hist["compliance"], ref["compliance"], rtol=1e-6)
+    assert np.abs(rho - rho_ref).max() <= 1e-6
+
+
+def test_simp_beam2_supports(capi):
+    """`beam(..., n=2)` supports (reference beams.py:133-136): right edge clamped above H/4 and below -H/4."""
+    from solidspy_opt.optimize import SIMP
+    nx, ny = 48, 32
+    dirs, pos = np.array([[0, -1], [1, 0]]), np.array([[16, 40], [30, 20]])
+    hist, ref = {}, {}
+    rho = SIMP(nx, ny, nx, ny, dirs, pos, 6, 3, n=2, history=hist, verbose=False)
+    rho_ref = t1.simp(nx, ny, nx, ny, dirs, pos, 6, 3, n=2, history=ref)
+    assert np.allclose(hist["compliance"], ref["compliance"], rtol=1e-6)
+    assert np.abs(rho - rho_ref).max() <= 1e-6
