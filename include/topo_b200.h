@@ -164,6 +164,25 @@ int topo_beso_save_history(topo_t *h);
  * E, nu: material; dx, dy: element size. */
 int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double dx, double dy);
 
+/* ---- multi-GPU building blocks (row slabs) --------------------------------------------
+ * One process per GPU owns a slab of element rows as an ordinary handle (nx x ny_local); interface node
+ * rows are duplicated on both neighbours.  These entry points work on CALLER-OWNED DEVICE pointers
+ * (e.g. torch tensors) so that the host side can exchange / all-reduce them with NCCL on the same stream. */
+/* run all of the handle's work on this CUDA stream (cudaStream_t passed as void*); default: private stream */
+int topo_set_stream(topo_t *h, void *cuda_stream);
+/* y_dev = K(scale) u_dev restricted to free DOFs; on a slab the interface rows of y hold PARTIAL sums
+ * (local elements only) that the caller adds to the neighbour's partials (halo sum). */
+int topo_matvec_dev(topo_t *h, const double *u_dev, double *y_dev);
+/* diag_dev = diag(K(scale)) (2 per node, 0 at constrained DOFs); partial on interface rows, like topo_matvec_dev */
+int topo_diag_dev(topo_t *h, double *diag_dev);
+/* c = alpha*a + beta*b over n_nodes nodes (2 doubles each); a, b, c may alias */
+int topo_vec_axpby_dev(topo_t *h, long long n_nodes, double alpha, const double *a_dev, double beta,
+                       const double *b_dev, double *c_dev);
+/* c = a (*) b elementwise, or c = (b != 0 ? a / b : 0) when divide != 0 */
+int topo_vec_mul_dev(topo_t *h, long long n_nodes, const double *a_dev, const double *b_dev, double *c_dev, int divide);
+/* out_dev[0] = sum over node rows [row_lo, row_hi) of a.b  (ownership-restricted dot; deterministic) */
+int topo_vec_dot_dev(topo_t *h, const double *a_dev, const double *b_dev, int row_lo, int row_hi, double *out_dev);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* CUDA-event time (ms) of the most recent call of each stage on this handle. */
 typedef struct {

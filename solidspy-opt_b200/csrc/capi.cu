@@ -151,6 +151,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->d_load_fx = h->d_load_fy = nullptr;
   std::memset(&h->timing, 0, sizeof(h->timing));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->owns_stream = true;
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&h->evs[i]));
@@ -242,7 +243,7 @@ extern "C" int topo_destroy(topo_t *h) {
   if (h->pcg_graph_exec) cudaGraphExecDestroy(h->pcg_graph_exec);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
-  cudaStreamDestroy(h->stream);
+  if (h->owns_stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
   return TOPO_OK;
@@ -517,5 +518,99 @@ extern "C" int topo_debug_tail_stamps(topo_t *h, unsigned long long *out, int ma
   int cnt = (int)std::min<unsigned long long>(buf[0], (unsigned long long)std::min(max_out, 511));
   for (int i = 0; i < cnt; ++i) out[i] = buf[1 + i];
   *n = cnt;
+  return TOPO_OK;
+}
+
+// ---- multi-GPU building blocks: operate on caller-owned device pointers ------------------------------------
+namespace {
+__global__ void k_axpby(const double2 *__restrict__ a, const double2 *__restrict__ b, double2 *__restrict__ c, int64_t n,
+                        double alpha, double beta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 x = a[i], y = b[i];
+    c[i] = make_double2(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y);
+  }
+}
+__global__ void k_vmul(const double2 *__restrict__ a, const double2 *__restrict__ b, double2 *__restrict__ c, int64_t n,
+                       int divide) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 x = a[i], y = b[i];
+    c[i] = divide ? make_double2(y.x != 0.0 ? x.x / y.x : 0.0, y.y != 0.0 ? x.y / y.y : 0.0)
+                  : make_double2(x.x * y.x, x.y * y.y);
+  }
+}
+__global__ void k_dot_rows(const double2 *__restrict__ a, const double2 *__restrict__ b, int64_t n0, int64_t n1,
+                           double *partials, unsigned int *ticket, double *out) {
+  double v[1] = {0.0};
+  for (int64_t i = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 x = a[i], y = b[i];
+    v[0] = fma(x.x, y.x, fma(x.y, y.y, v[0]));
+  }
+  grid_reduce<1>(v, partials, ticket, out);
+}
+__global__ void k_diag_from_dinv(const double2 *__restrict__ dinv, double2 *__restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 v = dinv[i];
+    d[i] = make_double2(v.x != 0.0 ? 1.0 / v.x : 0.0, v.y != 0.0 ? 1.0 / v.y : 0.0);
+  }
+}
+}  // namespace
+
+extern "C" int topo_set_stream(topo_t *h, void *cuda_stream) {
+  if (!h) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->owns_stream) cudaStreamDestroy(h->stream);
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->owns_stream = false;
+  h->pcg_graph_valid = false;
+  return TOPO_OK;
+}
+
+extern "C" int topo_matvec_dev(topo_t *h, const double *u_dev, double *y_dev) {
+  if (!h || !u_dev || !y_dev) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return topo_fine_matvec(h, reinterpret_cast<const double2 *>(u_dev), reinterpret_cast<double2 *>(y_dev));
+}
+
+extern "C" int topo_diag_dev(topo_t *h, double *diag_dev) {
+  if (!h || !diag_dev) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  TOPO_TRY(topo_build_diag(h));
+  KL(h, "k_diag_from_dinv", k_diag_from_dinv<<<nblk(h->nn), 256, 0, h->stream>>>(h->dinv, reinterpret_cast<double2 *>(diag_dev), h->nn));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_vec_axpby_dev(topo_t *h, long long n_nodes, double alpha, const double *a_dev, double beta,
+                                  const double *b_dev, double *c_dev) {
+  if (!h || !a_dev || !b_dev || !c_dev || n_nodes < 0) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  KL(h, "k_axpby", k_axpby<<<nblk(n_nodes), 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(a_dev),
+                                                                 reinterpret_cast<const double2 *>(b_dev),
+                                                                 reinterpret_cast<double2 *>(c_dev), n_nodes, alpha, beta));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_vec_mul_dev(topo_t *h, long long n_nodes, const double *a_dev, const double *b_dev, double *c_dev,
+                                int divide) {
+  if (!h || !a_dev || !b_dev || !c_dev || n_nodes < 0) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  KL(h, "k_vmul", k_vmul<<<nblk(n_nodes), 256, 0, h->stream>>>(reinterpret_cast<const double2 *>(a_dev),
+                                                               reinterpret_cast<const double2 *>(b_dev),
+                                                               reinterpret_cast<double2 *>(c_dev), n_nodes, divide));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_vec_dot_dev(topo_t *h, const double *a_dev, const double *b_dev, int row_lo, int row_hi,
+                                double *out_dev) {
+  if (!h || !a_dev || !b_dev || !out_dev || row_lo < 0 || row_hi > h->ny + 1 || row_lo > row_hi) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t npr = h->nx + 1, n0 = (int64_t)row_lo * npr, n1 = (int64_t)row_hi * npr;
+  KL(h, "k_dot_rows", k_dot_rows<<<nblk(std::max<int64_t>(n1 - n0, 1)), 256, 0, h->stream>>>(
+         reinterpret_cast<const double2 *>(a_dev), reinterpret_cast<const double2 *>(b_dev), n0, n1, h->partials, h->ticket,
+         out_dev));
+  CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }

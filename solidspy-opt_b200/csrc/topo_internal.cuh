@@ -82,6 +82,7 @@ struct topo_handle {
   int64_t nn, ne;
   KeParam ke;
   cudaStream_t stream;
+  bool owns_stream;
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;

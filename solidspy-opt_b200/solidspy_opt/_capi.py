@@ -26,7 +26,8 @@ SYMBOLS = [
     "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_rank_select",
     "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity",
     "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
-    "topo_profile_matvec", "topo_profile_read", "topo_profile_report",
+    "topo_profile_matvec", "topo_profile_read", "topo_profile_report", "topo_set_stream", "topo_matvec_dev",
+    "topo_diag_dev", "topo_vec_axpby_dev", "topo_vec_mul_dev", "topo_vec_dot_dev",
 ]
 
 
@@ -108,6 +109,12 @@ def load_library():
         "topo_profile_matvec": [vp, C.c_int],
         "topo_profile_read": [vp, ip, C.POINTER(C.c_float)],
         "topo_profile_report": [vp, C.c_char_p, C.c_size_t],
+        "topo_set_stream": [vp, C.c_void_p],
+        "topo_matvec_dev": [vp, C.c_void_p, C.c_void_p],
+        "topo_diag_dev": [vp, C.c_void_p],
+        "topo_vec_axpby_dev": [vp, C.c_longlong, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p],
+        "topo_vec_mul_dev": [vp, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
+        "topo_vec_dot_dev": [vp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -343,3 +350,25 @@ class Topo:
             name, n, ms = line.rsplit(" ", 2)
             out.append((name, int(n), float(ms)))
         return out
+
+    # ---- device-pointer entry points (multi-GPU building blocks) ----
+    def set_stream(self, cuda_stream):
+        _check(self.lib.topo_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def matvec_dev(self, u_ptr, y_ptr):
+        _check(self.lib.topo_matvec_dev(self.h, C.c_void_p(int(u_ptr)), C.c_void_p(int(y_ptr))))
+
+    def diag_dev(self, d_ptr):
+        _check(self.lib.topo_diag_dev(self.h, C.c_void_p(int(d_ptr))))
+
+    def axpby_dev(self, n_nodes, alpha, a_ptr, beta, b_ptr, c_ptr):
+        _check(self.lib.topo_vec_axpby_dev(self.h, int(n_nodes), float(alpha), C.c_void_p(int(a_ptr)), float(beta),
+                                           C.c_void_p(int(b_ptr)), C.c_void_p(int(c_ptr))))
+
+    def mul_dev(self, n_nodes, a_ptr, b_ptr, c_ptr, divide=False):
+        _check(self.lib.topo_vec_mul_dev(self.h, int(n_nodes), C.c_void_p(int(a_ptr)), C.c_void_p(int(b_ptr)),
+                                         C.c_void_p(int(c_ptr)), 1 if divide else 0))
+
+    def dot_dev(self, a_ptr, b_ptr, row_lo, row_hi, out_ptr):
+        _check(self.lib.topo_vec_dot_dev(self.h, C.c_void_p(int(a_ptr)), C.c_void_p(int(b_ptr)), int(row_lo), int(row_hi),
+                                         C.c_void_p(int(out_ptr))))

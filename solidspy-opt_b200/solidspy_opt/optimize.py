@@ -135,14 +135,33 @@ def SIMP_from_model(data, niter, penal, *, r_min=None, r_factor=4, precond="gmg"
 
 
 # ------------------------------------------------------------------------------------------------
-def _setup_eso(length, height, nx, ny, dirs, positions, device):
-    nodes, mats, els, loads, BC = beam(L=length, H=height, nx=nx, ny=ny, dirs=dirs, positions=positions, n=1)
+def _setup_eso(length, height, nx, ny, dirs, positions, device, model=None):
+    """Arrays + device handle of the ESO/BESO set-up (reference optimize.py:52,152,251).  ``model`` = an already
+    built ``(nodes, mats, els, loads, BC)`` tuple (the ``*_from_model`` entry points)."""
+    if model is None:
+        nodes, mats, els, loads, BC = beam(L=length, H=height, nx=nx, ny=ny, dirs=dirs, positions=positions, n=1)
+    else:
+        nodes, mats, els, loads, BC = model
     ke = ke_quad4(nodes[els[0, 3:7], 1:3], mats[0, 0], mats[0, 1])
     topo = _capi.Topo(nx, ny, ke, device=device)
     topo.set_cons(nodes[:, 3:5])
     topo.set_loads(loads)
     protect = np.hstack((loads[:, 0], BC)).astype(np.int64)
     return nodes, mats, els, loads, BC, topo, protect
+
+
+def _model_arrays(data):
+    """(length, height, nx, ny, (nodes5, mats, els, loads, BC)) from the SolidsPy dict model."""
+    nodes3, els, nx, ny, dx, dy = _model_grid(data)
+    cons = np.asarray(data["cons"], dtype=float).reshape(-1, 2)
+    nodes = np.zeros((nodes3.shape[0], 5))
+    nodes[:, :3] = nodes3[:, :3]
+    nodes[:, 3:5] = cons
+    m = np.asarray(data["mats"], dtype=float).reshape(-1)
+    mats = np.tile([m[0], m[1], 1.0], (els.shape[0], 1))
+    loads = np.asarray(data["loads"])
+    BC = nodes[(cons == -1).all(axis=1), 0]          # what beam() returns: the fully clamped nodes
+    return nx*dx, ny*dy, nx, ny, (nodes, mats, els, loads, BC)
 
 
 def _solve(topo, precond, rtol, maxit, stats):
@@ -155,13 +174,13 @@ def _solve(topo, precond, rtol, maxit, stats):
 
 
 def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=False, *, precond="gmg",
-         rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+         rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, _model=None):
     """Bi-directional ESO (reference optimize.py:215-356), quirks included: the full
     mesh is solved every iteration and removal acts by pinning the DOFs of orphaned nodes.
     Returns ``(ELS, nodes)``."""
     if plot:
         raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
-    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device)
+    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device, _model)
     with topo:
         eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :255-261
         r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*1                    # :264
@@ -216,8 +235,8 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
 
 
 def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit, device,
-         history, verbose):
-    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device)
+         history, verbose, model=None):
+    nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device, model)
     with topo:
         eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :56-61 / :156-161
         if kind == "stiff":
@@ -271,3 +290,26 @@ def ESO_stress(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
         raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
     return _eso("stress", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
                 device, history, verbose)
+
+
+def BESO_from_model(data, niter, t, ER, volfrac, **kw):
+    """``BESO`` on a model given as the SolidsPy dict ``{"nodes","cons","elements","mats","loads"}`` (structured
+    quad4 grid).  Protected nodes are the loaded nodes and the fully clamped ones, as ``beam()`` defines ``BC``."""
+    L, H, nx, ny, model = _model_arrays(data)
+    return BESO(L, H, nx, ny, None, None, niter, t, ER, volfrac, _model=model, **kw)
+
+
+def ESO_stiff_from_model(data, niter, RR, ER, volfrac, *, precond="gmg", rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT,
+                         device=0, history=None, verbose=True):
+    """``ESO_stiff`` on a dict model (niter/RR/ER are overridden exactly as in the reference, :165-167)."""
+    L, H, nx, ny, model = _model_arrays(data)
+    return _eso("stiff", L, H, nx, ny, None, None, niter, RR, ER, volfrac, precond, rtol, maxit, device, history,
+                verbose, model)
+
+
+def ESO_stress_from_model(data, niter, RR, ER, volfrac, *, precond="gmg", rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT,
+                          device=0, history=None, verbose=True):
+    """``ESO_stress`` on a dict model."""
+    L, H, nx, ny, model = _model_arrays(data)
+    return _eso("stress", L, H, nx, ny, None, None, niter, RR, ER, volfrac, precond, rtol, maxit, device, history,
+                verbose, model)

@@ -387,3 +387,35 @@ def test_simp_beam2_supports(capi):
     rho_ref = t1.simp(nx, ny, nx, ny, dirs, pos, 6, 3, n=2, history=ref)
     assert np.allclose(hist["compliance"], ref["compliance"], rtol=1e-6)
     assert np.abs(rho - rho_ref).max() <= 1e-6
+
+
+def test_from_model_variants_match_signature_variants(capi):
+    """The dict entry points (SolidsPy README model format) give exactly what the positional entry points give."""
+    import solidspy_opt.optimize as opt
+    g = golden("beso_c2")
+    L, H, nx, ny = float(g["length"]), float(g["height"]), int(g["nx"]), int(g["ny"])
+    nodes, mats, els, loads, BC = t1.beam(L=L, H=H, nx=nx, ny=ny, dirs=g["dirs"], positions=g["positions"])
+    data = {"nodes": nodes[:, :3], "cons": nodes[:, 3:5], "elements": els, "mats": np.array([[206.8e9, 0.28]]), "loads": loads}
+    ELS, nd = opt.BESO_from_model(data, int(g["niter"]), float(g["t"]), float(g["ER"]), float(g["volfrac"]), verbose=False)
+    assert np.array_equal(ELS, g["ELS"]) and np.array_equal(nd, g["nodes"])
+    for kind, fn in (("eso_stiff", opt.ESO_stiff_from_model), ("eso_stress", opt.ESO_stress_from_model)):
+        gg = golden(kind + "_c1")
+        n1, m1, e1, l1, b1 = t1.beam(L=60, H=60, nx=60, ny=60, dirs=gg["dirs"], positions=gg["positions"])
+        d1 = {"nodes": n1[:, :3], "cons": n1[:, 3:5], "elements": e1, "mats": np.array([[206.8e9, 0.28]]), "loads": l1}
+        ELS, nd = fn(d1, 50, 0.005, 0.05, 0.5, verbose=False)
+        assert np.array_equal(ELS, gg["ELS"]) and np.array_equal(nd, gg["nodes"])
+
+
+def test_slab_matvec_and_pcg_on_two_gpus(capi):
+    """Row-slab building block over NCCL (needs >= 2 GPUs on the box; skipped on the single-GPU test run)."""
+    import subprocess, sys, os, json
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = dict(os.environ, DIST_BIG="0")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]
