@@ -222,6 +222,38 @@ def main():
     report = topo.profile_report()
     topo.profile_matvec(False)
 
+    def slab_matvec():
+        """Stage 1 on the 8192x4096 mesh (BASELINE configs[4]) split into row slabs over all ranks: halo exchange of
+        the interface node rows over NCCL after every product (solidspy_opt.distributed).  Strong scaling."""
+        from solidspy_opt.distributed import SlabSolver, TopoBackend, slab_rows
+        bx, by = 8192, 4096
+        e0, e1 = slab_rows(by, world, rank)
+        nyl = e1 - e0
+        cons_l = np.zeros(((bx + 1)*(nyl + 1), 2), dtype=np.int8)
+        cons_l[::bx + 1] = -1
+        be = TopoBackend(bx, nyl, kloc_simp(206.8e9, 0.28), cons_l, np.full(bx*nyl, 0.125), local_rank)
+        S = SlabSolver(be, rank, world, dist if world > 1 else None)
+        a, b = be.zeros(), be.empty()
+        a.normal_()
+        a[:, 0, :] = 0
+        for _ in range(5):
+            S.matvec(a, b)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        ev0.record()
+        for _ in range(reps):
+            S.matvec(a, b)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = allmax(ev0.elapsed_time(ev1)/reps)
+        be.topo.close()
+        bn, bne = (bx + 1)*(by + 1), bx*by
+        gbs = (32*bn + 8*bne)/(ms*1e-3)/1e9
+        return {"mesh": [bx, by], "ms_per_matvec": ms, "algorithmic_gbs_all_gpus": gbs, "per_gpu_gbs": gbs/world,
+                "halo_bytes_per_rank_per_matvec": S.halo_bytes_per_exchange, "scaling": "strong",
+                "note": "row slabs, one interface node row exchanged each way per product (NCCL P2P), host-driven"}
+
     def allmax(x):
         if world == 1:
             return x
@@ -230,6 +262,7 @@ def main():
         return float(t.item())
 
     ms_dev_max, ms_e2e_max = allmax(ms_dev), allmax(ms_e2e)
+    slab = slab_matvec()
     if rank == 0:
         peak, peak_src = measured_peak()
         # ALGORITHMIC bytes per launch of each variant of the stage-1 kernel (fp64):
@@ -260,6 +293,7 @@ def main():
             "e2e": {"value": world*args.steps/(ms_e2e_max*1e-3), "unit": UNIT, "h2d_bytes_per_step": 8*ne,
                     "d2h_bytes_per_step": 8*ne, "ms_per_step": ms_e2e_max/args.steps},
             "gpu_launches": int(launches),
+            "slab_matvec": slab,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"] if dom else None,
                          "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
