@@ -419,3 +419,40 @@ def test_slab_matvec_and_pcg_on_two_gpus(capi):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+def test_handle_lifecycle_and_errors(capi):
+    """Repeated create/destroy does not leak device memory; bad arguments return error codes, not crashes."""
+    import ctypes as C
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(20):
+        with capi.Topo(256, 128, t1.kloc_closed_form(E0, NU)) as t:
+            t.set_cons(_cons(256, 128, "cantilever"))
+            t.set_loads(np.array([[129*256 + 256, 0.0, -1.0]]))
+            t.fill(capi.F_RHO, 0.5)
+            t.simp_scale(3.0, 1e-9, 1.0)
+            t.solve(capi.PRECOND_GMG, 1e-8, 500, warm=False)
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20                      # nothing but allocator noise left behind
+    with capi.Topo(8, 4, t1.kloc_closed_form(E0, NU)) as t:
+        with pytest.raises(capi.TopoError) as ei:
+            t.solve()                                    # BC flags / loads not set
+        assert ei.value.code == capi.ESTATE
+        t.set_cons(_cons(8, 4, "cantilever"))
+        with pytest.raises(capi.TopoError):
+            t.set_loads(np.array([[10**6, 0.0, 1.0]]))  # node id out of range
+        with pytest.raises(capi.TopoError):
+            t.rank_select(8*4)                           # rank outside [0, N_e)
+        with pytest.raises(capi.TopoError):
+            t.filter_sensitivity(100.0, 1.0, 1.0)        # radius wider than the stencil table
+        # an unloaded structure: zero right-hand side converges immediately to u = 0
+        t.set_loads(np.zeros((0, 3)))
+        it, rel, code = t.solve(capi.PRECOND_GMG, 1e-10, 10, warm=False)
+        assert it == 0 and code == capi.OK and np.all(t.get(capi.F_U) == 0)
+    # maxit exhausted -> TOPO_ENOCONV, results still readable
+    with capi.Topo(64, 32, t1.kloc_closed_form(E0, NU)) as t:
+        t.set_cons(_cons(64, 32, "cantilever"))
+        t.set_loads(np.array([[33*8 + 32, 0.0, -1.0]]))
+        it, rel, code = t.solve(capi.PRECOND_JACOBI, 1e-12, 5, warm=False, raise_on_noconv=False)
+        assert code == capi.ENOCONV and it == 5 and rel > 1e-12
