@@ -429,7 +429,7 @@ def test_handle_lifecycle_and_errors(capi):
     for _ in range(20):
         with capi.Topo(256, 128, t1.kloc_closed_form(E0, NU)) as t:
             t.set_cons(_cons(256, 128, "cantilever"))
-            t.set_loads(np.array([[129*256 + 256, 0.0, -1.0]]))
+            t.set_loads(np.array([[257*32 + 256, 0.0, -1.0]]))
             t.fill(capi.F_RHO, 0.5)
             t.simp_scale(3.0, 1e-9, 1.0)
             t.solve(capi.PRECOND_GMG, 1e-8, 500, warm=False)
@@ -453,6 +453,6 @@ def test_handle_lifecycle_and_errors(capi):
     # maxit exhausted -> TOPO_ENOCONV, results still readable
     with capi.Topo(64, 32, t1.kloc_closed_form(E0, NU)) as t:
         t.set_cons(_cons(64, 32, "cantilever"))
-        t.set_loads(np.array([[33*8 + 32, 0.0, -1.0]]))
+        t.set_loads(np.array([[65*8 + 64, 0.0, -1.0]]))
         it, rel, code = t.solve(capi.PRECOND_JACOBI, 1e-12, 5, warm=False, raise_on_noconv=False)
         assert code == capi.ENOCONV and it == 5 and rel > 1e-12
