@@ -176,8 +176,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   double **evs[nev] = {&h->rho, &h->rho_new, &h->dc, &h->dc2, &h->scale, &h->sens, &h->sens_prev};
   for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * (size_t)h->ne;
   CUDA_TRY(cudaMalloc(&h->nodal, sizeof(double) * (size_t)h->nn));
-  CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn));
-  CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn, h->stream));
+  CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn + 64));          // + slack: the stage-1 kernel reads aligned words
+  CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn + 64, h->stream));
   CUDA_TRY(cudaMalloc(&h->keep, (size_t)h->ne));
   CUDA_TRY(cudaMemsetAsync(h->keep, 1, (size_t)h->ne, h->stream));
   CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * TOPO_RED_SLOTS * TOPO_MAX_PARTIAL_BLOCKS));
@@ -202,6 +202,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
     int rows = std::max(8, div_up(ny + 1, chunks));
     h->matvec_rows_per_chunk = rows;
   }
+  h->fine_nc = getenv("TOPO_FINE_NC") ? atoi(getenv("TOPO_FINE_NC")) : (nx + 1 >= 1024 ? 2 : 1);
+  if (h->fine_nc != 2) h->fine_nc = 1;
   int s = topo_gmg_plan(h);
   if (s != TOPO_OK) return s;
   CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -26,9 +26,12 @@
 namespace {
 
 constexpr int BW = 128;        // threads per CTA = 4 warps = 4 independent strips of 32 columns
-constexpr int WC = 32;         // own columns per warp
-constexpr int SW = WC + 2;     // staged node columns per warp
-constexpr int EW = WC + 2;     // staged element columns per warp (c0-1 .. c0+31, padded to even)
+// NC = node columns per lane: a warp owns 32*NC columns (+1 halo column each side)
+template <int NC> struct Geo {
+  static constexpr int WC = 32 * NC;     // own columns per warp
+  static constexpr int SW = WC + 2;      // staged node columns per warp
+  static constexpr int EW = WC + 2;      // staged element columns per warp (c0-1 .. c0+WC-1, padded to even)
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -128,40 +131,47 @@ __device__ __forceinline__ void prolong_taps1(int i, int nf, int &I0, int &I1, d
 
 // register image of one node row as seen by a thread: stencil input at columns c-1, c, c+1 and the
 // scales of the two elements BELOW the row (element row q-1, columns c-1 and c)
+template <int NC>
 struct RowWin {
-  double2 u[3];
-  double el, er;
+  double2 u[NC + 2];     // columns c-1 .. c+NC of this lane's NC own columns c .. c+NC-1
+  double e[NC + 1];      // scales of element columns c-1 .. c+NC-1 of the element row below
 };
 
 template <int V> struct IC { static constexpr int value = V; };
 
-template <int KIND>
+template <int KIND, int NC>
 __host__ __device__ constexpr int warp_smem_bytes() {
-  return (int)(sizeof(double2) * (FK<KIND>::S * FK<KIND>::NIN * SW + 2 * SW) + sizeof(double) * FK<KIND>::S * EW);
+  return (int)(sizeof(double2) * (FK<KIND>::S * FK<KIND>::NIN * Geo<NC>::SW + 2 * Geo<NC>::SW) +
+               sizeof(double) * FK<KIND>::S * Geo<NC>::EW + 16 * ((FK<KIND>::S * ((Geo<NC>::WC + 6) / 4) * 4 + 15) / 16));
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kparam, const __grid_constant__ FineArgs a) {
+template <int KIND, int NC>
+__global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_constant__ KeRow kparam,
+                                                              const __grid_constant__ FineArgs a) {
   constexpr int NIN = FK<KIND>::NIN, S = FK<KIND>::S, D = S - 2;
+  constexpr int WC = Geo<NC>::WC, SW = Geo<NC>::SW, EW = Geo<NC>::EW;
   constexpr bool DERIVE = FK<KIND>::DERIVE;
-  constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID || KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J);
+  // BC flags are needed only by the kinds whose output is defined as masked and that have no D^-1 input; they ride
+  // in the ring as aligned 4-byte words (a direct byte load prefetched one row ahead was the dominant stall)
+  constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID);
+  constexpr int FWORDS = (WC + 3 + 3) / 4;               // aligned words covering the warp's WC flag bytes
   if (a.check_done && a.sc->done) return;
-  const KeRow ke = kparam;                                // 16 constants -> registers
+  const KeRow ke = kparam;                                // 16 constants -> (uniform) registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wbase = smem_raw + warp * warp_smem_bytes<KIND>();
+  unsigned char *wbase = smem_raw + warp * warp_smem_bytes<KIND, NC>();
   double2 *raw = reinterpret_cast<double2 *>(wbase);                     // [S][NIN][SW]
   double2 *der = raw + S * NIN * SW;                                     // [2][SW] (DERIVE kinds)
   double *ering = reinterpret_cast<double *>(der + 2 * SW);              // [S][EW]
+  unsigned *fring = reinterpret_cast<unsigned *>(ering + S * EW);        // [S][FWORDS] (NEEDS_FIXED kinds)
 
   const int npr = a.nx + 1;
   const int c0 = (blockIdx.x * 4 + warp) * WC;            // first own node column of this warp
-  const int c = c0 + lane;                                // own node column (staged column lane+1)
+  const int cl = c0 + NC * lane;                          // first own node column of this lane (staged NC*lane+1)
+  const int sl = NC * lane + 1;
   const int r0 = blockIdx.y * a.rows_per_chunk;
   const int r1 = min(r0 + a.rows_per_chunk, a.ny + 1);
   const bool active = c0 < npr;                           // warp-uniform
-  const bool col_ok = c < npr;
-  const bool ecol_ok = c < a.nx;
   // halo duty: lane 0 -> staged col 0 (node col c0-1), lane 1 -> staged col SW-1 (node col c0+WC)
   const int hs = (lane == 0) ? 0 : SW - 1;
   const int hc = (lane == 0) ? c0 - 1 : c0 + WC;
@@ -169,8 +179,7 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
   const bool hcol_ok = has_halo && hc >= 0 && hc < npr;
   const bool ehalo_ok = (lane == 0) && c0 > 0;
   // column offsets clamped into the row so that masked (zero-fill) copies still carry a valid address
-  const int coff = col_ok ? c : 0, hoff = hcol_ok ? hc : 0;
-  const int eoff = ecol_ok ? c : 0, ehoff = ehalo_ok ? c0 - 1 : 0;
+  const int hoff = hcol_ok ? hc : 0, ehoff = ehalo_ok ? c0 - 1 : 0;
 
   double alpha = 0.0, beta = 0.0;
   if (KIND == FK_UPDATE_RESID0 && !a.init) alpha = a.sc->rz[0] / a.sc->pAp;
@@ -190,14 +199,28 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
       for (int k = 0; k < NIN; ++k) {
         double2 *dst = raw + (SL * NIN + k) * SW;
         const double2 *src = a.in[k] + rowoff;
-        cp_async16(dst + lane + 1, src + coff, row_ok && col_ok);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const bool ok = cl + j < npr;
+          cp_async16(dst + sl + j, src + (ok ? cl + j : 0), row_ok && ok);
+        }
         if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
       }
       const bool erow_ok = q >= 1 && q <= a.ny;
       const double *esrc = a.scale + (size_t)(erow_ok ? q - 1 : 0) * a.nx;
       double *edst = ering + SL * EW;
-      cp_async8(edst + lane + 1, esrc + eoff, erow_ok && ecol_ok);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const bool ok = cl + j < a.nx;
+        cp_async8(edst + sl + j, esrc + (ok ? cl + j : 0), erow_ok && ok);
+      }
       if (lane == 0) cp_async8(edst, esrc + ehoff, erow_ok && ehalo_ok);
+      if (NEEDS_FIXED && lane < FWORDS) {
+        const size_t a0 = ((size_t)(row_ok ? q : 0) * npr + c0) & ~(size_t)3;
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(fring + SL * FWORDS + lane);
+        const int sz = row_ok ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sdst), "l"(a.fixed + a0 + 4 * lane), "r"(sz) : "memory");
+      }
       cp_async_commit();
     };
 
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
         return v;
       } else if (KIND == FK_UPDATE_RESID0) {
         const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = rw[4 * SW];
-        const double2 rn = make_double2(fma(-alpha, ap.x, r.x), fma(-alpha, ap.y, r.y));
+        const double2 rn = make_double2(d.x != 0.0 ? fma(-alpha, ap.x, r.x) : 0.0, d.y != 0.0 ? fma(-alpha, ap.y, r.y) : 0.0);
         const double2 xh = make_double2(omega * d.x * rn.x, omega * d.y * rn.y);
         if (store) {
           a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
@@ -261,24 +284,27 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
       if (DERIVE) {
         double2 *dr = der + (SL & 1) * SW;
         const double2 *rw = raw + SL * NIN * SW;
-        dr[lane + 1] = derive_at(rw + lane + 1, row, c, true);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) dr[sl + j] = derive_at(rw + sl + j, row, cl + j, true);
         if (has_halo) dr[hs] = derive_at(rw + hs, row, hc, false);
       }
     };
     // register image of the node row held in ring slot SL (after the __syncwarp that publishes it)
-    auto fill = [&](auto slc, RowWin &w) {
+    auto fill = [&](auto slc, RowWin<NC> &w) {
       constexpr int SL = decltype(slc)::value;
-      const double2 *src = DERIVE ? (der + (SL & 1) * SW + lane) : (raw + SL * NIN * SW + lane);
-      w.u[0] = src[0]; w.u[1] = src[1]; w.u[2] = src[2];
-      const double *e = ering + SL * EW + lane;
-      w.el = e[0]; w.er = e[1];
+      const double2 *src = DERIVE ? (der + (SL & 1) * SW + sl - 1) : (raw + SL * NIN * SW + sl - 1);
+#pragma unroll
+      for (int i = 0; i < NC + 2; ++i) w.u[i] = src[i];
+      const double *e = ering + SL * EW + sl - 1;
+#pragma unroll
+      for (int i = 0; i < NC + 1; ++i) w.e[i] = e[i];
     };
 
     // ---- prologue: S groups in flight (rows r0-1 .. r0+D), rows r0-1 and r0 resident ----
     issue(IC<0>()); issue(IC<1>()); issue(IC<2>()); issue(IC<3>());
     if (S == 8) { issue(IC<4 % S>()); issue(IC<5 % S>()); issue(IC<6 % S>()); issue(IC<7 % S>()); }
     cp_async_wait<D>();
-    RowWin W0, W1, W2, W3;
+    RowWin<NC> W0, W1, W2, W3;
     if (DERIVE) {
       stage_b(IC<0>(), r0 - 1);
       stage_b(IC<1>(), r0);
@@ -286,13 +312,11 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
     __syncwarp();
     fill(IC<0>(), W0);
     fill(IC<1>(), W1);
-    unsigned fx_next = 0;
-    if (NEEDS_FIXED && col_ok && r0 < r1) fx_next = a.fixed[(size_t)r0 * npr + c];
-    size_t n_out = (size_t)r0 * npr + c;
+    size_t n_out = (size_t)r0 * npr + cl;
 
     // one node row r held in slot K+1: Wm = row r-1, Wc = row r, Wp receives row r+1 (slot K+2);
     // the slot of row r-1 (K) is refilled with row r-1+S
-    auto step = [&](auto kc, int r, const RowWin &Wm, const RowWin &Wc, RowWin &Wp) {
+    auto step = [&](auto kc, int r, const RowWin<NC> &Wm, const RowWin<NC> &Wc, RowWin<NC> &Wp) {
       constexpr int K = decltype(kc)::value;
       constexpr int S_prev = K % S, S_cur = (K + 1) % S, S_next = (K + 2) % S;
       cp_async_wait<D - 1>();                              // group G_{r+1} has landed (this lane's part)
@@ -300,46 +324,61 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
       __syncwarp();                                        // row r+1 visible; every lane is done with row r-1's slot
       issue(IC<S_prev>());
       fill(IC<S_next>(), Wp);
-      const unsigned fx = fx_next;
-      if (NEEDS_FIXED && col_ok && r + 1 < r1) fx_next = a.fixed[n_out + npr];
-      double yx, yy, tx, ty;
-      row_terms<false>(ke, Wc.u[1], Wc.u[2], Wp.u[2], Wp.u[1], tx, ty);   // NE element (r, c): node is local 0
-      yx = Wp.er * tx; yy = Wp.er * ty;
-      row_terms<true>(ke, Wc.u[1], Wc.u[0], Wp.u[0], Wp.u[1], tx, ty);    // NW (r, c-1): x-mirror image
-      yx = fma(Wp.el, tx, yx); yy = fma(Wp.el, ty, yy);
-      row_terms<false>(ke, Wc.u[1], Wc.u[0], Wm.u[0], Wm.u[1], tx, ty);   // SW (r-1, c-1): point-mirror image
-      yx = fma(Wc.el, tx, yx); yy = fma(Wc.el, ty, yy);
-      row_terms<true>(ke, Wc.u[1], Wc.u[2], Wm.u[2], Wm.u[1], tx, ty);    // SE (r-1, c): y-mirror image
-      yx = fma(Wc.er, tx, yx); yy = fma(Wc.er, ty, yy);
-      if (col_ok) {
-        const size_t n = n_out;
-        const double2 *rw = raw + S_cur * NIN * SW + lane + 1;         // raw inputs of this node
-        const double2 v = Wc.u[1];
-        if (KIND == FK_APPLY) {
-          if (fx & 1u) yx = 0.0;
-          if (fx & 2u) yy = 0.0;
-          a.out[0][n] = make_double2(yx, yy);
-          if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
-        } else if (KIND == FK_RESID) {
-          const double2 b = rw[SW];
-          a.out[0][n] = make_double2((fx & 1u) ? 0.0 : b.x - yx, (fx & 2u) ? 0.0 : b.y - yy);
-        } else if (KIND == FK_SMOOTH) {
-          const double2 b = rw[SW], d = rw[2 * SW];
-          a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
-        } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
-          if (fx & 1u) yx = 0.0;
-          if (fx & 2u) yy = 0.0;
-          a.out[1][n] = make_double2(yx, yy);
-          dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
-        } else if (KIND == FK_UPDATE_RESID0) {
-          const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
-          const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
-          a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
-        } else {  // FK_PROLONG_SMOOTH
-          const double2 rr = rw[SW], d = rw[2 * SW];
-          const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
-          a.out[0][n] = make_double2(zx, zy);
-          dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+      unsigned fx[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) fx[j] = 0u;
+      if (NEEDS_FIXED) {
+        const unsigned char *fb = reinterpret_cast<const unsigned char *>(fring + S_cur * FWORDS);
+        const unsigned off = (unsigned)((n_out - (size_t)(NC * lane)) & 3);      // (r*npr + c0) mod 4
+#pragma unroll
+        for (int j = 0; j < NC; ++j) fx[j] = fb[off + NC * lane + j];
+      }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        double yx, yy, tx, ty;
+        row_terms<false>(ke, Wc.u[j + 1], Wc.u[j + 2], Wp.u[j + 2], Wp.u[j + 1], tx, ty);   // NE element (r, c): node is local 0
+        yx = Wp.e[j + 1] * tx; yy = Wp.e[j + 1] * ty;
+        row_terms<true>(ke, Wc.u[j + 1], Wc.u[j], Wp.u[j], Wp.u[j + 1], tx, ty);            // NW (r, c-1): x-mirror image
+        yx = fma(Wp.e[j], tx, yx); yy = fma(Wp.e[j], ty, yy);
+        row_terms<false>(ke, Wc.u[j + 1], Wc.u[j], Wm.u[j], Wm.u[j + 1], tx, ty);           // SW (r-1, c-1): point-mirror image
+        yx = fma(Wc.e[j], tx, yx); yy = fma(Wc.e[j], ty, yy);
+        row_terms<true>(ke, Wc.u[j + 1], Wc.u[j + 2], Wm.u[j + 2], Wm.u[j + 1], tx, ty);    // SE (r-1, c): y-mirror image
+        yx = fma(Wc.e[j + 1], tx, yx); yy = fma(Wc.e[j + 1], ty, yy);
+        if (cl + j < npr) {
+          const size_t n = n_out + j;
+          const double2 *rw = raw + S_cur * NIN * SW + sl + j;             // raw inputs of this node
+          const double2 v = Wc.u[j + 1];
+          if (KIND == FK_APPLY) {
+            if (fx[j] & 1u) yx = 0.0;
+            if (fx[j] & 2u) yy = 0.0;
+            a.out[0][n] = make_double2(yx, yy);
+            if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+          } else if (KIND == FK_RESID) {
+            const double2 b = rw[SW];
+            a.out[0][n] = make_double2((fx[j] & 1u) ? 0.0 : b.x - yx, (fx[j] & 2u) ? 0.0 : b.y - yy);
+          } else if (KIND == FK_SMOOTH) {
+            const double2 b = rw[SW], d = rw[2 * SW];
+            a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
+          } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
+            // Ap is NOT masked here: p vanishes at constrained DOFs (so p.Ap is unaffected) and the update
+            // kernel masks r' = r - alpha Ap through D^-1 == 0
+            if (KIND == FK_PCG_MATVEC_J) {
+              const double2 d = rw[2 * SW];
+              if (d.x == 0.0) yx = 0.0;
+              if (d.y == 0.0) yy = 0.0;
+            }
+            a.out[1][n] = make_double2(yx, yy);
+            dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
+          } else if (KIND == FK_UPDATE_RESID0) {
+            const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
+            const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
+            a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
+          } else {  // FK_PROLONG_SMOOTH
+            const double2 rr = rw[SW], d = rw[2 * SW];
+            const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
+            a.out[0][n] = make_double2(zx, zy);
+            dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+          }
         }
       }
       n_out += npr;
@@ -383,9 +422,26 @@ __global__ void __launch_bounds__(BW, 4) k_fine(const __grid_constant__ KeRow kp
   }
 }
 
-template <int KIND>
-size_t fine_smem() {
-  return 4 * (size_t)warp_smem_bytes<KIND>();
+template <int KIND, int NC>
+int launch_fine_nc(topo_handle *h, FineArgs &a) {
+  dim3 grid(div_up(h->nx + 1, 4 * Geo<NC>::WC), div_up(h->ny + 1, a.rows_per_chunk));
+  if ((int64_t)grid.x * grid.y > TOPO_MAX_PARTIAL_BLOCKS) {
+    topo_set_error("fine-grid launch too large for the reduction buffer");
+    return TOPO_EINVAL;
+  }
+  static bool attr_set = false;
+  const size_t smem = 4 * (size_t)warp_smem_bytes<KIND, NC>();
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  KeRow kr;
+  for (int j = 0; j < 8; ++j) { kr.r0[j] = h->ke.k[j]; kr.r1[j] = h->ke.k[8 + j]; }
+  static const char *const names[7] = {"k_fine<apply>", "k_fine<resid>", "k_fine<pcg_matvec>", "k_fine<pcg_matvec_jacobi>",
+                                       "k_fine<update_resid0>", "k_fine<smooth_dot>", "k_fine<smooth>"};
+  KL(h, names[KIND], k_fine<KIND, NC><<<grid, BW, smem, h->stream>>>(kr, a));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
 }
 
 template <int KIND>
@@ -394,28 +450,17 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   a.fixed = h->fixed;
   a.nx = h->nx;
   a.ny = h->ny;
-  a.rows_per_chunk = h->matvec_rows_per_chunk;
   a.partials = h->partials;
   a.ticket = h->ticket;
   a.sc = h->sc;
-  dim3 grid(div_up(h->nx + 1, BW), div_up(h->ny + 1, a.rows_per_chunk));
-  if ((int64_t)grid.x * grid.y > TOPO_MAX_PARTIAL_BLOCKS) {
-    topo_set_error("fine-grid launch too large for the reduction buffer");
-    return TOPO_EINVAL;
-  }
-  static bool attr_set = false;
-  const size_t smem = fine_smem<KIND>();
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  KeRow kr;
-  for (int j = 0; j < 8; ++j) { kr.r0[j] = h->ke.k[j]; kr.r1[j] = h->ke.k[8 + j]; }
-  static const char *const names[7] = {"k_fine<apply>", "k_fine<resid>", "k_fine<pcg_matvec>", "k_fine<pcg_matvec_jacobi>",
-                                       "k_fine<update_resid0>", "k_fine<smooth_dot>", "k_fine<smooth>"};
-  KL(h, names[KIND], k_fine<KIND><<<grid, BW, smem, h->stream>>>(kr, a));
-  CUDA_TRY(cudaGetLastError());
-  return TOPO_OK;
+  // node columns per lane: 2 on wide meshes (overhead instructions amortised over two nodes), 1 otherwise
+  const int nc = h->fine_nc;
+  // chunk rows so that one wave of CTAs covers the mesh (~4 resident CTAs per SM)
+  const int bx = div_up(h->nx + 1, 128 * nc);
+  const int chunks = std::max(1, (148 * (nc == 1 ? 4 : 3)) / bx);
+  a.rows_per_chunk = std::max(8, div_up(h->ny + 1, chunks));
+  if (nc == 2) return launch_fine_nc<KIND, 2>(h, a);
+  return launch_fine_nc<KIND, 1>(h, a);
 }
 
 // diag(K) per node from the 4 adjacent element scales; stores 1/diag (0 at constrained DOFs) and the

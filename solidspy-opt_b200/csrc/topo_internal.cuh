@@ -139,6 +139,7 @@ struct topo_handle {
   std::vector<const char *> prof_name;
   topo_timing timing;
   int matvec_rows_per_chunk;
+  int fine_nc;                    // node columns per lane of the stage-1 kernel (1 or 2)
 };
 
 // Kernel launch wrapper: counts the launch and, in profile mode, brackets it with CUDA events on the
