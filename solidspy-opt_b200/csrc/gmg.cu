@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restri
     }
   }
 #pragma unroll
-  for (int k = 0; k < 36; ++k) st[(size_t)k * nn + n] = (stencil_t)s[k];
+  // layout: 9 planes of float4 (one 2x2 block per neighbour), plane nb, node n
+#pragma unroll
+  for (int nb = 0; nb < 9; ++nb)
+    reinterpret_cast<float4 *>(st)[(size_t)nb * nn + n] =
+        make_float4((float)s[4 * nb], (float)s[4 * nb + 1], (float)s[4 * nb + 2], (float)s[4 * nb + 3]);
   const double dx = (double)(stencil_t)s[4 * 4 + 0], dy = (double)(stencil_t)s[4 * 4 + 3];
   dinv[n] = make_double2(dx > 0.0 ? 1.0 / dx : 0.0, dy > 0.0 ? 1.0 / dy : 0.0);
 }
@@ -211,7 +215,7 @@ __global__ void k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny
     if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
     const int m = rr * npr + cc;
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 2; ++j) sm[(2 * n + i) * W + 2 * m + j] = st[(size_t)(4 * nb + 2 * i + j) * nn + n];
+      for (int j = 0; j < 2; ++j) sm[(2 * n + i) * W + 2 * m + j] = st[((size_t)nb * nn + n) * 4 + 2 * i + j];
   }
   __syncthreads();
   for (int t = threadIdx.x; t < N; t += blockDim.x) {

@@ -97,11 +97,12 @@ __device__ __forceinline__ void stencil_row(const stencil_t *__restrict__ st, in
       if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
       const int nb = 3 * (dr + 1) + (dc + 1);
       const double2 xv = get(rr, cc);
-      const stencil_t *sp = st + (size_t)(4 * nb) * nn + n;
-      ax = fma((double)sp[0], xv.x, ax);
-      ax = fma((double)sp[nn], xv.y, ax);
-      ay = fma((double)sp[2 * nn], xv.x, ay);
-      ay = fma((double)sp[3 * nn], xv.y, ay);
+      // one float4 per neighbour block: (a00, a01, a10, a11), plane nb, consecutive nodes contiguous
+      const float4 cf = reinterpret_cast<const float4 *>(st)[(size_t)nb * nn + n];
+      ax = fma((double)cf.x, xv.x, ax);
+      ax = fma((double)cf.y, xv.y, ax);
+      ay = fma((double)cf.z, xv.x, ay);
+      ay = fma((double)cf.w, xv.y, ay);
     }
   }
 }

@@ -70,7 +70,7 @@ struct GmgLevel {
   int nn;              // nodes
   int ncell;
   double *cell;        // 64 planes x ncell : per-cell 8x8 Galerkin matrix (SoA, plane = 8*i+j)
-  stencil_t *st;        // 36 planes x nn : node stencil, plane = 4*nb + 2*i + j, nb = 3*(dr+1)+(dc+1)
+  stencil_t *st;        // 9 planes x nn x float4: node stencil, plane nb = 3*(dr+1)+(dc+1), entry (a00,a01,a10,a11)
   double2 *dinv;       // 1/diag (0 at constrained DOFs)
   double2 *x, *x2, *b, *r;
   uint8_t *fixed;
