@@ -262,7 +262,7 @@ struct TailArgs {
   const double *coarse_inv;
   int coarse_n;
   double omega;
-  int nu_pre, nu_post;
+  int nu[TAIL_MAX];            // smoothing sweeps (pre = post) per tail level
   const int *done;
   unsigned long long *dbg;     // optional: globaltimer stamps at stage boundaries (thread 0 of CTA 0)
 };
@@ -274,21 +274,31 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define STAMP() do { if (a.dbg && gt == 0) { a.dbg[1 + a.dbg[0]] = gtimer(); a.dbg[0] += 1; } } while (0)
 
+// nu pre-smoothing sweeps from a zero guess, then the residual, then its restriction.  Sweep 1 is pointwise
+// (x = w D^-1 b); for nu == 1 it is fused with the residual (node_down).  Sweeps ping-pong x <-> x2 through local
+// pointer swaps; the iterate ends in x for odd nu and in x2 for even nu -- recorded in cur[l].
 template <class Sync>
-__device__ __forceinline__ void tail_down(const TailArgs &a, int l, int gt, int GT, Sync sync) {
+__device__ __forceinline__ void tail_down(const TailArgs &a, int l, double2 **cur, int gt, int GT, Sync sync) {
   LevelView L = a.lv[l];
   const int nn = (L.nx + 1) * (L.ny + 1);
-  for (int n = gt; n < nn; n += GT) node_down(L, n, a.omega);            // x = w dinv b ; r = b - A x
-  sync();
-  STAMP();
-  for (int s = 1; s < a.nu_pre; ++s) {                                   // extra sweeps keep the iterate in x
-    for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);
+  const int nu = a.nu[l];
+  if (nu == 1) {
+    for (int n = gt; n < nn; n += GT) node_down(L, n, a.omega);          // x = w dinv b ; r = b - A x
     sync();
-    for (int n = gt; n < nn; n += GT) L.x[n] = L.x2[n];
+    STAMP();
+  } else {
+    for (int n = gt; n < nn; n += GT) node_smooth0(L, n, a.omega);
     sync();
-    for (int n = gt; n < nn; n += GT) node_resid(L, n);
+    for (int s = 1; s < nu; ++s) {
+      for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);      // L.x -> L.x2
+      sync();
+      double2 *t = L.x; L.x = L.x2; L.x2 = t;
+    }
+    for (int n = gt; n < nn; n += GT) node_resid(L, n);                  // r = b - A (current iterate)
     sync();
+    STAMP();
   }
+  cur[l] = L.x;
   const LevelView &C = a.lv[l + 1];
   const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
   for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(L.r, n % nprc, n / nprc, L.nx, L.ny);
@@ -296,22 +306,23 @@ __device__ __forceinline__ void tail_down(const TailArgs &a, int l, int gt, int 
   STAMP();
 }
 
-// result of a level lives in x2 when nu_post is odd, in x otherwise (same rule as the multi-block levels)
+// coarse correction + nu post-smoothing sweeps; the final iterate pointer is left in cur[l]
 template <class Sync>
-__device__ __forceinline__ void tail_up(const TailArgs &a, int l, int gt, int GT, Sync sync) {
+__device__ __forceinline__ void tail_up(const TailArgs &a, int l, double2 **cur, int gt, int GT, Sync sync) {
   LevelView L = a.lv[l];
   const LevelView &C = a.lv[l + 1];
-  const double2 *xc = (l + 1 == a.n - 1) ? C.x : ((a.nu_post & 1) ? C.x2 : C.x);
+  if (cur[l] != L.x) { L.x2 = L.x; L.x = cur[l]; }                       // iterate left by tail_down
   const int nn = (L.nx + 1) * (L.ny + 1);
-  for (int n = gt; n < nn; n += GT) node_prolong_add(L, xc, C.nx, n);
+  for (int n = gt; n < nn; n += GT) node_prolong_add(L, cur[l + 1], C.nx, n);
   sync();
   STAMP();
-  for (int s = 0; s < a.nu_post; ++s) {
+  for (int s = 0; s < a.nu[l]; ++s) {
     for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);        // x -> x2
     sync();
     STAMP();
-    double2 *tmp = L.x; L.x = L.x2; L.x2 = tmp;
+    double2 *t = L.x; L.x = L.x2; L.x2 = t;
   }
+  cur[l] = L.x;
 }
 
 __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs a) {
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
   auto bsync = [&]() { __syncthreads(); };
   if (a.dbg && gt == 0) a.dbg[0] = 0;
   STAMP();
+  double2 *cur[TAIL_MAX];                       // where each level's current iterate lives (x or x2)
   {
     const LevelView &C = a.lv[0];
     const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
@@ -332,10 +344,12 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
   csync();
   STAMP();
   int l = 0;
-  for (; l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL; ++l) tail_down(a, l, gt, GT, csync);
+  for (; l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL; ++l) tail_down(a, l, cur, gt, GT, csync);
   const int lsmall = l;
+  // every rank must know where the iterates of the big levels ended (same arithmetic on all ranks: cur[] is
+  // computed identically); the small levels are finished by CTA 0, which publishes cur[lsmall] via the rule below
   if (rank == 0) {
-    for (l = lsmall; l + 1 < a.n; ++l) tail_down(a, l, t, T, bsync);
+    for (l = lsmall; l + 1 < a.n; ++l) tail_down(a, l, cur, t, T, bsync);
     {  // coarsest: dense inverse
       const LevelView &C = a.lv[a.n - 1];
       const double *bb = reinterpret_cast<const double *>(C.b);
@@ -347,14 +361,26 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
         for (int j = 0; j < N; ++j) sacc = fma(a.coarse_inv[i * N + j], bb[j], sacc);
         xx[i] = dd[i] != 0.0 ? sacc : 0.0;
       }
+      cur[a.n - 1] = C.x;
     }
     __syncthreads();
     STAMP();
-    for (l = a.n - 2; l >= lsmall; --l) tail_up(a, l, t, T, bsync);
+    for (l = a.n - 2; l >= lsmall; --l) tail_up(a, l, cur, t, T, bsync);
+  }
+  // the final iterate of a level lives in x for an even number of pointer swaps, in x2 otherwise; that parity
+  // depends only on nu[l], so the other ranks can compute it without communication
+  if (lsmall < a.n) {
+    const LevelView &C = a.lv[lsmall];
+    if (lsmall == a.n - 1) cur[lsmall] = C.x;
+    else {
+      const int nu = a.nu[lsmall];
+      const int swaps = (nu > 1 ? nu - 1 : 0) + nu;           // pre-smoothing swaps + post-smoothing swaps
+      cur[lsmall] = (swaps & 1) ? C.x2 : C.x;
+    }
   }
   csync();
   STAMP();
-  for (l = lsmall - 1; l >= 0; --l) tail_up(a, l, gt, GT, csync);
+  for (l = lsmall - 1; l >= 0; --l) tail_up(a, l, cur, gt, GT, csync);
 }
 
 const char *lvl_name(const char *what, int l) {
@@ -382,18 +408,34 @@ LevelView view_of(const GmgLevel &G) {
 // fine-grid iterate x^ (constrained DOFs stay zero).  No host-side state changes (pointers are never
 // swapped), so the launch sequence can be captured in a CUDA graph and replayed.
 // Result of a multi-block level lives in its x2 (nu_post odd) or x (nu_post even); tail levels leave it in x.
-int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine) {
+int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine, const double2 **x1_out) {
   cudaStream_t st = h->stream;
   const double om = h->omega;
   const int L = h->n_levels;
   if (L < 2) return TOPO_OK;
   const int *done = &h->sc->done;
+  // smoothing sweeps on the coarse levels (the fine level always does nu_pre/nu_post = what topo_set_gmg set)
+  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
+  auto nu_pre_of = [&](int l) { return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_pre; };
+  auto nu_post_of = [&](int l) { return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_post; };
   // first level handled by the tail kernel
   int tail = L - 1;
   while (tail > 1 && h->levels[tail - 1].nn <= h->tail_max_nodes) --tail;
+  // sweeps per tail level: the deep, tiny levels are where the coarse solve loses accuracy on high-contrast
+  // designs and where a sweep costs next to nothing
+  auto tail_nu = [&](int l) -> int {
+    const int nn_l = h->levels[l].nn;
+    if (nn_l > TAIL_SMALL) return h->nu_tail_big;
+    return h->nu_tail_small;
+  };
   auto result_of = [&](int l) -> const double2 * {
     if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
-    return (h->nu_post & 1) ? h->levels[l].x2 : h->levels[l].x;
+    if (l >= tail) {                                 // tail levels: parity of the pointer swaps (see k_tail)
+      const int nu = tail_nu(l);
+      const int swaps = (nu > 1 ? nu - 1 : 0) + nu;
+      return (swaps & 1) ? h->levels[l].x2 : h->levels[l].x;
+    }
+    return (nu_post_of(l) & 1) ? h->levels[l].x2 : h->levels[l].x;
   };
 
   if (tail > 1) {
@@ -404,7 +446,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine)
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(F);
     KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
-    for (int s = 1; s < h->nu_pre; ++s) {
+    for (int s = 1; s < nu_pre_of(l); ++s) {
       KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
       KL(h, "k_lvl_resid", k_lvl_resid<<<blocks_for(F.nn), 128, 0, st>>>(V, done));
@@ -430,8 +472,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine)
     ta.coarse_inv = h->coarse_inv;
     ta.coarse_n = h->coarse_n;
     ta.omega = om;
-    ta.nu_pre = h->nu_pre;
-    ta.nu_post = h->nu_post;
+    for (int l = tail; l < L; ++l) ta.nu[l - tail] = tail_nu(l);
     ta.done = done;
     ta.dbg = h->tail_dbg;
     // one cluster; 16 CTAs needs the non-portable size, fall back to 8 (portable) or 1
@@ -476,13 +517,15 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine)
     } else {
       KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
     }
-    for (int s = 1; s < h->nu_post; ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
+    for (int s = 1; s < nu_post_of(l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }
       KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(W, om, done));
     }
   }
-  {
+  if (x1_out != nullptr) {
+    *x1_out = result_of(1);          // the caller's smoothing kernel prolongates on the fly
+  } else {
     GmgLevel &C = h->levels[1];
     KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), xhat_fine, h->fixed, h->nx, h->ny,
                                                                                        C.nx, done));

@@ -12,6 +12,7 @@
 // Dot products are warp-shuffle + block + ordered grid reductions (deterministic).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "topo_internal.cuh"
 
@@ -23,7 +24,7 @@ int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap,
                             double omega, int init);
 int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 *r, const double2 *xc, int cnx,
                              double2 *z, double omega, int init);
-int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine);
+int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine, const double2 **x1_out);
 
 namespace {
 
@@ -229,13 +230,15 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
       CUDA_TRY(cudaGetLastError());
     }
   } else {
+    const bool fuse_prolong = getenv("TOPO_FUSE_PROLONG") != nullptr;
     // one PCG iteration reading the buffers of parity `par` and writing those of parity par^1
     auto iteration = [&](int par) -> int {
       TOPO_TRY(topo_fine_pcg_matvec(h, h->z, pb[par], pb[par ^ 1], h->Ap));
       TOPO_TRY(topo_fine_update_resid0(h, pb[par ^ 1], h->Ap, ub[par], rb[par], ub[par ^ 1], rb[par ^ 1], xhat, res,
                                        h->omega, 0));
-      TOPO_TRY(topo_gmg_coarse(h, res, xhat));
-      TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[par ^ 1], nullptr, 0, h->z, h->omega, 0));
+      const double2 *x1 = nullptr;
+      TOPO_TRY(topo_gmg_coarse(h, res, xhat, fuse_prolong ? &x1 : nullptr));
+      TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[par ^ 1], x1, h->lvl_nx[1], h->z, h->omega, 0));
       return TOPO_OK;
     };
     CUDA_TRY(cudaMemsetAsync(pb[1], 0, vbytes, st));
@@ -244,8 +247,11 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
     KL(h, "k_set_bb", k_set_bb<<<1, 1, 0, st>>>(h->sc, h->red_out));
     // z0 = V(r0): the update kernel with alpha = 0 copies u, r into the parity-1 buffers
     TOPO_TRY(topo_fine_update_resid0(h, pb[1], h->Ap, ub[0], rb[0], ub[1], rb[1], xhat, res, h->omega, 1));
-    TOPO_TRY(topo_gmg_coarse(h, res, xhat));
-    TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[1], nullptr, 0, h->z, h->omega, 1));
+    {
+      const double2 *x1 = nullptr;
+      TOPO_TRY(topo_gmg_coarse(h, res, xhat, fuse_prolong ? &x1 : nullptr));
+      TOPO_TRY(topo_fine_prolong_smooth(h, xhat, rb[1], x1, h->lvl_nx[1], h->z, h->omega, 1));
+    }
 
     // Two iterations (parity 1 then 0) form a closed cycle of buffer roles: capture them once in a CUDA
     // graph (per handle) and replay it; converged iterations turn into no-op kernels.

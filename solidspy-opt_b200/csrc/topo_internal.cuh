@@ -121,6 +121,8 @@ struct topo_handle {
   int coarse_n;            // its dimension (2*nn of last level)
   double omega;
   int nu_pre, nu_post;
+  int nu_coarse;           // > 0: sweeps on levels >= 1 (overrides nu_pre/nu_post there)
+  int nu_tail_big, nu_tail_small;   // sweeps on tail levels with > / <= 1024 nodes
   unsigned long long *tail_dbg;   // device buffer for k_tail stage stamps (nullptr = off)
   int tail_max_nodes;
   bool use_graph, pcg_graph_valid;
