@@ -229,7 +229,7 @@ __global__ void k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny
     sm[t * W + N + t] = 1.0;
   }
   __syncthreads();
-  __shared__ double colk[64];
+  __shared__ double colk[96];
   for (int k = 0; k < N; ++k) {
     const double piv = sm[k * W + k];
     __syncthreads();
@@ -256,7 +256,10 @@ int topo_gmg_plan(topo_handle *h) {
   h->lvl_nx[0] = h->nx;
   h->lvl_ny[0] = h->ny;
   int nx = h->nx, ny = h->ny;
-  while (std::max(nx, ny) > 2 && h->n_levels < TOPO_MAX_LEVELS) {
+  // coarsen (ceil halving) until a level has at most COARSEST_MAX_NODES nodes: that level is solved exactly with
+  // a dense inverse (<= 96 DOFs), which is both cheaper and more accurate than smoothing three more tiny levels
+  const int coarsest_max_nodes = getenv("TOPO_COARSEST_NODES") ? atoi(getenv("TOPO_COARSEST_NODES")) : 48;
+  while ((nx + 1) * (ny + 1) > coarsest_max_nodes && std::max(nx, ny) > 1 && h->n_levels < TOPO_MAX_LEVELS) {
     nx = (nx + 1) / 2;
     ny = (ny + 1) / 2;
     h->lvl_nx[h->n_levels] = nx;
@@ -385,11 +388,16 @@ int topo_gmg_setup(topo_handle *h) {
   {
     GmgLevel &L = h->levels[h->n_levels - 1];
     const int N = h->coarse_n;
-    if (N > 48) {
+    if (N > 96) {
       topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
       return TOPO_EINVAL;
     }
-    KL(h, "k_coarse_invert", k_coarse_invert<<<1, 256, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv));
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 96 * 192)));
+      attr_done = true;
+    }
+    KL(h, "k_coarse_invert", k_coarse_invert<<<1, 512, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv));
   }
   CUDA_TRY(cudaGetLastError());
   h->gmg_valid = true;

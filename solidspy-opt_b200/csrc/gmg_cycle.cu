@@ -350,16 +350,19 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
   // computed identically); the small levels are finished by CTA 0, which publishes cur[lsmall] via the rule below
   if (rank == 0) {
     for (l = lsmall; l + 1 < a.n; ++l) tail_down(a, l, cur, t, T, bsync);
-    {  // coarsest: dense inverse
+    {  // coarsest: dense inverse, one warp per row (lanes stride the columns, shuffle reduction)
       const LevelView &C = a.lv[a.n - 1];
       const double *bb = reinterpret_cast<const double *>(C.b);
       const double *dd = reinterpret_cast<const double *>(C.dinv);
       double *xx = reinterpret_cast<double *>(C.x);
       const int N = a.coarse_n;
-      for (int i = t; i < N; i += T) {
+      const int lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+      for (int i = warp; i < N; i += nwarp) {
         double sacc = 0.0;
-        for (int j = 0; j < N; ++j) sacc = fma(a.coarse_inv[i * N + j], bb[j], sacc);
-        xx[i] = dd[i] != 0.0 ? sacc : 0.0;
+        for (int j = lane; j < N; j += 32) sacc = fma(a.coarse_inv[i * N + j], bb[j], sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+        if (lane == 0) xx[i] = dd[i] != 0.0 ? sacc : 0.0;
       }
       cur[a.n - 1] = C.x;
     }
