@@ -454,7 +454,8 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   a.ticket = h->ticket;
   a.sc = h->sc;
   // node columns per lane: 2 on wide meshes (overhead instructions amortised over two nodes), 1 otherwise
-  const int nc = h->fine_nc;
+  // (measured: the fused kinds lose more from the lower occupancy of 64-column strips than they gain)
+  const int nc = (KIND == FK_APPLY) ? h->fine_nc : 1;
   // chunk rows so that one wave of CTAs covers the mesh (~4 resident CTAs per SM)
   const int bx = div_up(h->nx + 1, 128 * nc);
   const int chunks = std::max(1, (148 * (nc == 1 ? 4 : 3)) / bx);

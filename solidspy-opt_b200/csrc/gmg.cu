@@ -230,16 +230,16 @@ __global__ void k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny
   }
   __syncthreads();
   __shared__ double colk[96];
+  // Gauss-Jordan: thread j owns column j of the augmented matrix (no div/mod, conflict-free shared accesses)
   for (int k = 0; k < N; ++k) {
-    const double piv = sm[k * W + k];
-    __syncthreads();
-    for (int j = threadIdx.x; j < W; j += blockDim.x) sm[k * W + j] /= piv;
-    // column k is read by every thread of a row while being zeroed: snapshot it first
+    const double pinv = 1.0 / sm[k * W + k];
     for (int i = threadIdx.x; i < N; i += blockDim.x) colk[i] = sm[i * W + k];
     __syncthreads();
-    for (int t = threadIdx.x; t < N * W; t += blockDim.x) {
-      const int i = t / W, j = t % W;
-      if (i != k) sm[i * W + j] = fma(-colk[i], sm[k * W + j], sm[i * W + j]);
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const double pk = sm[k * W + j] * pinv;
+      for (int i = 0; i < N; ++i)
+        if (i != k) sm[i * W + j] = fma(-colk[i], pk, sm[i * W + j]);
+      sm[k * W + j] = pk;
     }
     __syncthreads();
   }
