@@ -183,6 +183,62 @@ int topo_vec_mul_dev(topo_t *h, long long n_nodes, const double *a_dev, const do
 /* out_dev[0] = sum over node rows [row_lo, row_hi) of a.b  (ownership-restricted dot; deterministic) */
 int topo_vec_dot_dev(topo_t *h, const double *a_dev, const double *b_dev, int row_lo, int row_hi, double *out_dev);
 
+/* ---- row-slab SIMP iteration over several GPUs (BASELINE configs[4]) ------------------------
+ * The whole design iteration -- multigrid-preconditioned CG, sensitivity, filter, OC -- on a mesh split into
+ * `world` equal slabs of element rows, one handle (one GPU, one process) per slab.  The library never
+ * communicates: every call below runs one SEGMENT of the algorithm on the slab and names, in its comment, what
+ * the host must move before the next segment.  Three kinds of movement, all on device memory, all on the
+ * handle's stream (solidspy_opt/distributed.py does them with NCCL through torch.distributed):
+ *   exchange   send my first interface row / block to rank-1 and my last one to rank+1, receive theirs into the
+ *              handle's receive buffers (topo_dist_xchg_ptrs), then topo_dist_xchg_finish;
+ *   gather     all-gather of an equally sized block per rank (topo_dist_gather_ptrs);
+ *   all-reduce in place on a few device doubles (topo_dist_scalar_ptr).
+ * Vectors are stored ACCUMULATED (interface rows hold the full value on both neighbours); the fused kernels
+ * produce DISTRIBUTED results on interface rows (partial sums), which the exchange completes.  The multigrid
+ * levels 1..K-1 live on the slab; levels >= K are small, are assembled from the gathered level-K Galerkin cell
+ * matrices and run redundantly on every rank inside the tail kernel.  Mathematically the preconditioner is the
+ * single-GPU one, so iteration counts agree with topo_solve on the whole mesh.
+ * No counterpart in the reference (single process; scipy spsolve at optimize.py:437). */
+enum { TOPO_X_AP = 0, TOPO_X_R0 = 1, TOPO_X_Z = 2, TOPO_X_LEVEL_B = 3, TOPO_X_LEVEL_X2 = 4, TOPO_X_DIAG = 5, TOPO_X_FILTER = 6 };
+enum { TOPO_G_CELLS = 0, TOPO_G_BK = 1 };
+enum { TOPO_S_PAP = 0, TOPO_S_RR_RZ = 1, TOPO_S_BB = 2, TOPO_S_RED = 3 };
+/* Turns an ordinary handle (nx x ny_local, BC flags / loads / rho of ITS slab) into slab `rank` of `world`.
+ * K_request <= 0: K = first level of the global hierarchy with <= 10 000 nodes.  ny_local must be a multiple
+ * of 2^K. */
+int topo_dist_init(topo_t *h, int rank, int world, int K_request);
+int topo_dist_info(topo_t *h, int *rank, int *world, int *K, int *n_levels);
+/* device pointers of an exchange: send_lo -> rank-1 (lands in its recv_hi), send_hi -> rank+1 (its recv_lo) */
+int topo_dist_xchg_ptrs(topo_t *h, int what, int level, void **send_lo, void **send_hi, void **recv_lo,
+                        void **recv_hi, long long *n_doubles);
+int topo_dist_xchg_finish(topo_t *h, int what, int level);
+int topo_dist_gather_ptrs(topo_t *h, int what, void **send, void **recv, long long *n_doubles_per_rank);
+int topo_dist_scalar_ptr(topo_t *h, int what, void **ptr, int *n);
+/* first n doubles of the TOPO_S_RED block -> host (synchronises the stream) */
+int topo_dist_read_scalars(topo_t *h, double *out, int n);
+/* multigrid set-up after topo_simp_scale.  phase 0: slab-local Galerkin products (then: exchange TOPO_X_DIAG,
+ * gather TOPO_G_CELLS); phase 1: global levels. */
+int topo_dist_setup(topo_t *h, int phase);
+/* r0 = f - K u (then: exchange TOPO_X_R0, all-reduce TOPO_S_BB) */
+int topo_dist_solve_begin(topo_t *h, double rtol, int maxit, int warm);
+/* one PCG iteration = matvec, update, V-cycle (down 1..K-1, tail, up K-1..1), smooth, finish; `par` alternates
+ * 1, 0, 1, ... (buffer parity, as in topo_solve); the first pass is update/V-cycle/smooth/finish with init = 1. */
+int topo_dist_pcg_matvec(topo_t *h, int par);              /* then: exchange TOPO_X_AP, all-reduce TOPO_S_PAP */
+int topo_dist_pcg_update(topo_t *h, int par, int init);    /* then: K > 1 ? exchange TOPO_X_LEVEL_B level 1 : gather TOPO_G_BK */
+int topo_dist_vcycle_down(topo_t *h, int level);           /* then: level+1 < K ? exchange TOPO_X_LEVEL_B level+1 : gather TOPO_G_BK */
+int topo_dist_vcycle_tail(topo_t *h);
+int topo_dist_vcycle_up(topo_t *h, int level);             /* then: exchange TOPO_X_LEVEL_X2 level */
+int topo_dist_pcg_smooth(topo_t *h, int par, int init);    /* then: exchange TOPO_X_Z, all-reduce TOPO_S_RR_RZ */
+int topo_dist_pcg_finish(topo_t *h, int init);
+int topo_dist_solve_poll(topo_t *h, int *done, int *iters, double *relres);
+int topo_dist_solve_end(topo_t *h, int iters);
+/* TOPO_S_RED[1] = this slab's share of f.u (TOPO_S_RED[0] = objective share from topo_simp_sensitivity(.., NULL)) */
+int topo_dist_compliance_partial(topo_t *h);
+/* rho*dc of the slab's outer element rows -> send buffers (then: exchange TOPO_X_FILTER, topo_filter_sensitivity) */
+int topo_dist_filter_pack(topo_t *h, double rmin, double dy);
+/* OC bisection pieces (op table in csrc/simp.cu); between them the host all-reduces TOPO_S_RED */
+int topo_dist_oc(topo_t *h, int op, double move, double value, long long ne_global);
+int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* CUDA-event time (ms) of the most recent call of each stage on this handle. */
 typedef struct {

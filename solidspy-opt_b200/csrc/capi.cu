@@ -214,6 +214,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   return TOPO_OK;
 }
 
+void topo_dist_free(topo_handle *h);
+
 extern "C" int topo_destroy(topo_t *h) {
   if (!h) return TOPO_OK;
   cudaSetDevice(h->device);
@@ -239,12 +241,8 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaFree(h->d_load_node);
   cudaFree(h->d_load_fx);
   cudaFree(h->d_load_fy);
-  for (size_t l = 1; l < h->levels.size(); ++l) {
-    GmgLevel &L = h->levels[l];
-    cudaFree(L.cell);
-  }
-  cudaFree(h->lvl1_slab);
-  cudaFree(h->coarse_slab);
+  topo_gmg_free(h);
+  topo_dist_free(h);
   if (h->pcg_graph_exec) cudaGraphExecDestroy(h->pcg_graph_exec);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);

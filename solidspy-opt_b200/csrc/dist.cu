@@ -1,0 +1,439 @@
+// Row-slab decomposition of the SIMP design iteration over several GPUs (no counterpart in the
+// reference, which is single-process).  One handle = one slab of element rows on one GPU.  This file holds the
+// C-ABI entry points the host loop drives: the PCG iteration and the V-cycle cut into SEGMENTS at the points where
+// interface node rows must be completed by the neighbours (halo sum), where level-K data is gathered, and where
+// scalars are all-reduced.  The library never communicates itself: it exposes device pointers of what has to be
+// moved (topo_dist_xchg_ptrs / topo_dist_gather_ptrs / topo_dist_scalar_ptr) and finishes an exchange with a small
+// row kernel (topo_dist_xchg_finish); the host moves the bytes with NCCL (solidspy_opt/distributed.py).
+//
+// Vector forms (see DistState): u, p, x, z, r are ACCUMULATED; K_loc p, restricted residuals and local smoothing
+// results are DISTRIBUTED/partial on interface rows.
+//   Ap  = K_loc p                      -> halo sum          (p.Ap needs no weights: sum over ranks of p.Ap_loc)
+//   res = W r - K_loc x^               distributed, restricted as is (restriction is linear, no exchange)
+//   b_l = R res                        -> halo sum, then x = w D^-1 b needs the accumulated b
+//   x2  = x + w D^-1 (W b - A_loc x)   partial on interface rows: x2 <- x2 + x2_neighbour - x
+//   z   likewise; r.z partial = r.(z - (1-W) x~)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "topo_internal.cuh"
+
+int topo_fine_pcg_matvec(topo_handle *h, const double2 *z, const double2 *p_in, double2 *p_out, double2 *Ap);
+int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap, const double2 *u_in,
+                            const double2 *r_in, double2 *u_out, double2 *r_out, double2 *xhat, double2 *res,
+                            double omega, int init);
+int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 *r, const double2 *xc, int cnx,
+                             double2 *z, double omega, int init);
+int topo_mask_vector(topo_handle *h, double2 *v);
+int topo_dist_restrict_fine(topo_handle *h, const double2 *res_fine);
+int topo_dist_level_down(topo_handle *h, int l);
+int topo_dist_tail(topo_handle *h);
+int topo_dist_level_up(topo_handle *h, int l);
+int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine);
+int topo_dist_setup_local(topo_handle *h);
+int topo_dist_setup_global(topo_handle *h);
+
+namespace {
+
+inline int nblk(int64_t n, int t = 256) { return (int)std::min<int64_t>((n + t - 1) / t, 148 * 8); }
+
+// dst += src
+__global__ void k_row_add(double2 *__restrict__ dst, const double2 *__restrict__ src, int n, const int *done) {
+  if (done && *done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 a = dst[i];
+  const double2 b = src[i];
+  a.x += b.x; a.y += b.y;
+  dst[i] = a;
+}
+// dst = dst + src - base   (completes a locally smoothed interface row: see the file header)
+__global__ void k_row_add_sub(double2 *__restrict__ dst, const double2 *__restrict__ src, const double2 *__restrict__ base,
+                              int n, const int *done) {
+  if (done && *done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 a = dst[i];
+  const double2 b = src[i], c = base[i];
+  a.x = (a.x + b.x) - c.x; a.y = (a.y + b.y) - c.y;
+  dst[i] = a;
+}
+
+// sum_n W(row) a.b  (accumulated x accumulated)
+__global__ void k_dot_weighted(const double2 *__restrict__ a, const double2 *__restrict__ b, int npr, int ny, double wf,
+                               double wl, double *partials, unsigned int *ticket, double *out) {
+  const int64_t nn = (int64_t)npr * (ny + 1);
+  double v[1] = {0.0};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(n / npr);
+    const double w = r == 0 ? wf : (r == ny ? wl : 1.0);
+    const double2 x = a[n], y = b[n];
+    v[0] = fma(w * x.x, y.x, fma(w * x.y, y.y, v[0]));
+  }
+  grid_reduce<1>(v, partials, ticket, out);
+}
+
+__global__ void k_zero2d(double2 *p, int64_t nn) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x)
+    p[n] = make_double2(0.0, 0.0);
+}
+
+// scalar bookkeeping after the all-reduce of (rr, rz) in sc->aux[1..2] (what the last block of the fused kernels
+// does on a single GPU)
+__global__ void k_dist_pcg_finish(SolverScalars *sc, int init) {
+  if (!init && sc->done) return;
+  const double rr = sc->aux[1], rz = sc->aux[2];
+  sc->rr = rr;
+  if (!init) sc->iters += 1;
+  sc->rz[1] = init ? 0.0 : rz / sc->rz[0];
+  sc->rz[0] = rz;
+  if (rr <= sc->tol2 * sc->bb || !(rr == rr)) sc->done = 1;
+  else if (sc->iters >= sc->maxit) sc->done = 2;
+}
+__global__ void k_dist_set_bb(SolverScalars *sc) { sc->bb = sc->aux[3]; }
+
+int check(topo_handle *h) {
+  if (!h) return TOPO_EINVAL;
+  if (!h->dist.on) {
+    topo_set_error("handle is not in row-slab mode (call topo_dist_init first)");
+    return TOPO_ESTATE;
+  }
+  return TOPO_OK;
+}
+
+void free_dist(DistState &D) {
+  cudaFree(D.recv_lo); cudaFree(D.recv_hi);
+  cudaFree(D.diag_send_lo); cudaFree(D.diag_send_hi); cudaFree(D.diag_recv_lo); cudaFree(D.diag_recv_hi);
+  cudaFree(D.cellK_send); cudaFree(D.cellK_recv);
+  cudaFree(D.bK_send); cudaFree(D.bK_recv);
+  cudaFree(D.filt_send_lo); cudaFree(D.filt_send_hi); cudaFree(D.filt_recv_lo); cudaFree(D.filt_recv_hi);
+  D = DistState{};
+}
+
+}  // namespace
+
+void topo_dist_free(topo_handle *h) { free_dist(h->dist); }
+
+extern "C" int topo_dist_init(topo_t *h, int rank, int world, int K_request) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const int ny_global = h->ny * world;
+  // K: the first level of the GLOBAL hierarchy small enough for the tail kernel (or the coarsest one)
+  const int coarsest_max_nodes = getenv("TOPO_COARSEST_NODES") ? atoi(getenv("TOPO_COARSEST_NODES")) : 48;
+  int K = 0;
+  {
+    int nx = h->nx, ny = ny_global, l = 0;
+    while ((nx + 1) * (int64_t)(ny + 1) > coarsest_max_nodes && std::max(nx, ny) > 1) {
+      nx = (nx + 1) / 2; ny = (ny + 1) / 2; ++l;
+      if (K == 0 && (int64_t)(nx + 1) * (ny + 1) <= h->tail_max_nodes) K = l;
+    }
+    if (K == 0) K = l;
+    if (K_request > 0) K = std::min(K_request, std::max(l, 1));
+  }
+  if (K < 1) {
+    topo_set_error("topo_dist_init: the mesh is too small for a multigrid hierarchy");
+    return TOPO_EINVAL;
+  }
+  if (h->ny % (1 << K) != 0) {
+    topo_set_error("topo_dist_init: slab height %d must be a multiple of 2^K = %d (K = first global level)", h->ny, 1 << K);
+    return TOPO_EINVAL;
+  }
+  if (h->nu_pre != 1 || h->nu_post != 1 || h->nu_coarse > 0) {
+    topo_set_error("topo_dist_init: row-slab mode supports one smoothing sweep on the slab-local levels");
+    return TOPO_EINVAL;
+  }
+  topo_gmg_free(h);
+  free_dist(h->dist);
+  DistState &D = h->dist;
+  D.on = true;
+  D.rank = rank; D.world = world; D.K = K;
+  D.has_lo = rank > 0; D.has_hi = rank < world - 1;
+  D.ny_global = ny_global;
+  D.w_first = D.has_lo ? 0.5 : 1.0;
+  D.w_last = D.has_hi ? 0.5 : 1.0;
+  TOPO_TRY(topo_gmg_plan(h));
+  const size_t row = sizeof(double2) * (size_t)(h->nx + 1);
+  CUDA_TRY(cudaMalloc(&D.recv_lo, row));
+  CUDA_TRY(cudaMalloc(&D.recv_hi, row));
+  D.diag_count = 0;
+  for (int l = 0; l < K; ++l) D.diag_count += h->lvl_nx[l] + 1;
+  const size_t dbytes = sizeof(double2) * (size_t)D.diag_count;
+  CUDA_TRY(cudaMalloc(&D.diag_send_lo, dbytes)); CUDA_TRY(cudaMalloc(&D.diag_send_hi, dbytes));
+  CUDA_TRY(cudaMalloc(&D.diag_recv_lo, dbytes)); CUDA_TRY(cudaMalloc(&D.diag_recv_hi, dbytes));
+  CUDA_TRY(cudaMemset(D.diag_recv_lo, 0, dbytes)); CUDA_TRY(cudaMemset(D.diag_recv_hi, 0, dbytes));
+  const int nxK = h->lvl_nx[K], rowsK = h->ny >> K;
+  D.ncellK_loc = (long long)nxK * rowsK;
+  CUDA_TRY(cudaMalloc(&D.cellK_send, sizeof(double) * 64 * (size_t)D.ncellK_loc));
+  CUDA_TRY(cudaMalloc(&D.cellK_recv, sizeof(double) * 64 * (size_t)D.ncellK_loc * world));
+  D.bK_count = (long long)(nxK + 1) * (rowsK + 1);
+  CUDA_TRY(cudaMalloc(&D.bK_send, sizeof(double2) * (size_t)D.bK_count));
+  CUDA_TRY(cudaMalloc(&D.bK_recv, sizeof(double2) * (size_t)D.bK_count * world));
+  const size_t fbytes = sizeof(double) * 8 * (size_t)h->nx;      // FH_MAX = 8 element rows
+  CUDA_TRY(cudaMalloc(&D.filt_send_lo, fbytes)); CUDA_TRY(cudaMalloc(&D.filt_send_hi, fbytes));
+  CUDA_TRY(cudaMalloc(&D.filt_recv_lo, fbytes)); CUDA_TRY(cudaMalloc(&D.filt_recv_hi, fbytes));
+  D.filt_hy = 0;
+  h->diag_valid = h->gmg_valid = false;
+  h->pcg_graph_valid = false;
+  return TOPO_OK;
+}
+
+extern "C" int topo_dist_info(topo_t *h, int *rank, int *world, int *K, int *n_levels) {
+  TOPO_TRY(check(h));
+  if (rank) *rank = h->dist.rank;
+  if (world) *world = h->dist.world;
+  if (K) *K = h->dist.K;
+  if (n_levels) *n_levels = h->n_levels;
+  return TOPO_OK;
+}
+
+// What an exchange moves: send_lo goes to rank-1 (and arrives in ITS recv_hi), send_hi goes to rank+1 (arrives in
+// its recv_lo); n_doubles per direction.
+extern "C" int topo_dist_xchg_ptrs(topo_t *h, int what, int level, void **send_lo, void **send_hi, void **recv_lo,
+                                   void **recv_hi, long long *n_doubles) {
+  TOPO_TRY(check(h));
+  if (!send_lo || !send_hi || !recv_lo || !recv_hi || !n_doubles) return TOPO_EINVAL;
+  DistState &D = h->dist;
+  double2 *v = nullptr;
+  int npr = h->nx + 1, ny = h->ny;
+  *recv_lo = D.recv_lo; *recv_hi = D.recv_hi;
+  switch (what) {
+    case TOPO_X_AP: v = h->Ap; break;
+    case TOPO_X_R0: v = h->r; break;
+    case TOPO_X_Z: v = h->z; break;
+    case TOPO_X_LEVEL_B:
+    case TOPO_X_LEVEL_X2:
+      if (level < 1 || level >= D.K) { topo_set_error("exchange: level %d is not a slab-local coarse level", level); return TOPO_EINVAL; }
+      v = (what == TOPO_X_LEVEL_B) ? h->levels[level].b : h->levels[level].x2;
+      npr = h->levels[level].nx + 1; ny = h->levels[level].ny;
+      break;
+    case TOPO_X_DIAG:
+      *send_lo = D.diag_send_lo; *send_hi = D.diag_send_hi; *recv_lo = D.diag_recv_lo; *recv_hi = D.diag_recv_hi;
+      *n_doubles = 2 * D.diag_count;
+      return TOPO_OK;
+    case TOPO_X_FILTER:
+      *send_lo = D.filt_send_lo; *send_hi = D.filt_send_hi; *recv_lo = D.filt_recv_lo; *recv_hi = D.filt_recv_hi;
+      *n_doubles = (long long)D.filt_hy * h->nx;
+      return TOPO_OK;
+    default:
+      topo_set_error("exchange: unknown kind %d", what);
+      return TOPO_EINVAL;
+  }
+  *send_lo = v;
+  *send_hi = v + (size_t)ny * npr;
+  *n_doubles = 2LL * npr;
+  return TOPO_OK;
+}
+
+// completes the interface rows after the host moved the neighbours' rows into recv_lo / recv_hi
+extern "C" int topo_dist_xchg_finish(topo_t *h, int what, int level) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  cudaStream_t st = h->stream;
+  const int *done = &h->sc->done;
+  double2 *v = nullptr;
+  const double2 *base = nullptr;
+  int npr = h->nx + 1, ny = h->ny;
+  switch (what) {
+    case TOPO_X_AP: v = h->Ap; break;
+    case TOPO_X_R0: v = h->r; done = nullptr; break;
+    case TOPO_X_Z: v = h->z; base = h->tmp2; break;                 // x~ (x^ after the prolongation) lives in tmp2
+    case TOPO_X_LEVEL_B:
+    case TOPO_X_LEVEL_X2:
+      if (level < 1 || level >= D.K) return TOPO_EINVAL;
+      v = (what == TOPO_X_LEVEL_B) ? h->levels[level].b : h->levels[level].x2;
+      if (what == TOPO_X_LEVEL_X2) base = h->levels[level].x;
+      npr = h->levels[level].nx + 1; ny = h->levels[level].ny;
+      break;
+    case TOPO_X_DIAG:
+    case TOPO_X_FILTER:
+      return TOPO_OK;                                                // consumed by topo_dist_setup_global / topo_dist_filter
+    default:
+      return TOPO_EINVAL;
+  }
+  const size_t last = (size_t)ny * npr;
+  const int nb = (npr + 127) / 128;
+  if (base == nullptr) {
+    if (D.has_lo) KL(h, "k_row_add", k_row_add<<<nb, 128, 0, st>>>(v, D.recv_lo, npr, done));
+    if (D.has_hi) KL(h, "k_row_add", k_row_add<<<nb, 128, 0, st>>>(v + last, D.recv_hi, npr, done));
+  } else {
+    if (D.has_lo) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v, D.recv_lo, base, npr, done));
+    if (D.has_hi) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v + last, D.recv_hi, base + last, npr, done));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_dist_gather_ptrs(topo_t *h, int what, void **send, void **recv, long long *n_doubles_per_rank) {
+  TOPO_TRY(check(h));
+  if (!send || !recv || !n_doubles_per_rank) return TOPO_EINVAL;
+  DistState &D = h->dist;
+  if (what == TOPO_G_CELLS) {
+    *send = D.cellK_send; *recv = D.cellK_recv; *n_doubles_per_rank = 64 * D.ncellK_loc;
+  } else if (what == TOPO_G_BK) {
+    *send = D.bK_send; *recv = D.bK_recv; *n_doubles_per_rank = 2 * D.bK_count;
+  } else {
+    return TOPO_EINVAL;
+  }
+  return TOPO_OK;
+}
+
+// device scalars the host all-reduces in place
+extern "C" int topo_dist_scalar_ptr(topo_t *h, int what, void **ptr, int *n) {
+  TOPO_TRY(check(h));
+  if (!ptr || !n) return TOPO_EINVAL;
+  switch (what) {
+    case TOPO_S_PAP: *ptr = &h->sc->aux[0]; *n = 1; break;
+    case TOPO_S_RR_RZ: *ptr = &h->sc->aux[1]; *n = 2; break;
+    case TOPO_S_BB: *ptr = &h->sc->aux[3]; *n = 1; break;
+    case TOPO_S_RED: *ptr = h->red_out; *n = 16; break;
+    default: return TOPO_EINVAL;
+  }
+  return TOPO_OK;
+}
+
+extern "C" int topo_dist_read_scalars(topo_t *h, double *out, int n) {
+  TOPO_TRY(check(h));
+  if (!out || n < 1 || n > 16) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(out, h->red_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return TOPO_OK;
+}
+
+// ---- multigrid set-up ---------------------------------------------------------------------------------------
+extern "C" int topo_dist_setup(topo_t *h, int phase) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  return phase == 0 ? topo_dist_setup_local(h) : topo_dist_setup_global(h);
+}
+
+// ---- PCG in segments ----------------------------------------------------------------------------------------
+// buffer roles as in topo_solve (pcg.cu): parity `par` reads u/r/p of parity par and writes parity par^1
+#define DIST_BUFS                                                                                 \
+  double2 *ub[2] = {h->u, h->u2}, *rb[2] = {h->r, h->r2}, *pb[2] = {h->p, h->p2};                \
+  double2 *xhat = h->tmp2, *res = h->tmp;                                                        \
+  (void)ub; (void)rb; (void)pb; (void)xhat; (void)res
+
+// r0 = W f - K_loc u (distributed; host: exchange TOPO_X_R0), ||f||^2 partial (host: all-reduce TOPO_S_BB)
+extern "C" int topo_dist_solve_begin(topo_t *h, double rtol, int maxit, int warm) {
+  TOPO_TRY(check(h));
+  if (!h->loads_set || !h->cons_set) {
+    topo_set_error("topo_dist_solve_begin: set BC flags and loads first");
+    return TOPO_ESTATE;
+  }
+  if (!h->gmg_valid) {
+    topo_set_error("topo_dist_solve_begin: multigrid set-up missing (topo_dist_setup phases 0 and 1)");
+    return TOPO_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  DIST_BUFS;
+  cudaStream_t st = h->stream;
+  const int64_t nn = h->nn;
+  const size_t vbytes = sizeof(double2) * (size_t)nn;
+  if (!warm) KL(h, "k_zero2", k_zero2d<<<nblk(nn), 256, 0, st>>>(h->u, nn));
+  else TOPO_TRY(topo_mask_vector(h, h->u));
+  SolverScalars init = {};
+  init.tol2 = rtol * rtol;
+  init.maxit = maxit;
+  *h->sc_host = init;
+  CUDA_TRY(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(init), cudaMemcpyHostToDevice, st));
+  TOPO_TRY(topo_fine_residual(h, ub[0], h->f, rb[0]));
+  CUDA_TRY(cudaMemsetAsync(pb[1], 0, vbytes, st));
+  CUDA_TRY(cudaMemsetAsync(h->Ap, 0, vbytes, st));
+  KL(h, "k_dot_weighted", k_dot_weighted<<<nblk(nn), 256, 0, st>>>(h->f, h->f, h->nx + 1, h->ny, h->dist.w_first, h->dist.w_last,
+                                                                  h->partials, h->ticket, &h->sc->aux[3]));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// p' = z + beta p ; Ap = K_loc p' ; p'.Ap partial      (host: exchange TOPO_X_AP, all-reduce TOPO_S_PAP)
+extern "C" int topo_dist_pcg_matvec(topo_t *h, int par) {
+  TOPO_TRY(check(h));
+  DIST_BUFS;
+  return topo_fine_pcg_matvec(h, h->z, pb[par & 1], pb[(par & 1) ^ 1], h->Ap);
+}
+
+// u' = u + alpha p ; r' = r - alpha Ap ; rr partial ; x^ = w D^-1 r' ; res = W r' - K_loc x^ ; restrict res
+// (host: K > 1: exchange TOPO_X_LEVEL_B level 1 ; K == 1: gather TOPO_G_BK).  init: the alpha = 0 pass that
+// starts the solve (after TOPO_X_R0 / TOPO_S_BB).
+extern "C" int topo_dist_pcg_update(topo_t *h, int par, int init) {
+  TOPO_TRY(check(h));
+  DIST_BUFS;
+  par &= 1;
+  if (init) {
+    par = 0;
+    KL(h, "k_dist_set_bb", k_dist_set_bb<<<1, 1, 0, h->stream>>>(h->sc));
+  }
+  TOPO_TRY(topo_fine_update_resid0(h, pb[par ^ 1], h->Ap, ub[par], rb[par], ub[par ^ 1], rb[par ^ 1], xhat, res, h->omega, init));
+  return topo_dist_restrict_fine(h, res);
+}
+
+// level l (1 <= l < K) with b_l accumulated: pre-smoothing, residual, restriction
+// (host: l+1 < K: exchange TOPO_X_LEVEL_B level l+1 ; else gather TOPO_G_BK)
+extern "C" int topo_dist_vcycle_down(topo_t *h, int level) {
+  TOPO_TRY(check(h));
+  return topo_dist_level_down(h, level);
+}
+
+// global levels >= K from the gathered right-hand side (every rank, redundantly)
+extern "C" int topo_dist_vcycle_tail(topo_t *h) {
+  TOPO_TRY(check(h));
+  return topo_dist_tail(h);
+}
+
+// level l (K > l >= 1): coarse correction + post-smoothing (host: exchange TOPO_X_LEVEL_X2 level l)
+extern "C" int topo_dist_vcycle_up(topo_t *h, int level) {
+  TOPO_TRY(check(h));
+  return topo_dist_level_up(h, level);
+}
+
+// x~ = x^ + P x_1 ; z = x~ + w D^-1 (W r - K_loc x~) ; r.z partial  (host: exchange TOPO_X_Z, all-reduce TOPO_S_RR_RZ)
+extern "C" int topo_dist_pcg_smooth(topo_t *h, int par, int init) {
+  TOPO_TRY(check(h));
+  DIST_BUFS;
+  par = init ? 0 : (par & 1);
+  TOPO_TRY(topo_dist_prolong_fine(h, xhat));
+  return topo_fine_prolong_smooth(h, xhat, rb[par ^ 1], nullptr, h->lvl_nx[1], h->z, h->omega, init);
+}
+
+// beta, ||r||^2, iteration count, convergence flag from the all-reduced scalars
+extern "C" int topo_dist_pcg_finish(topo_t *h, int init) {
+  TOPO_TRY(check(h));
+  KL(h, "k_dist_pcg_finish", k_dist_pcg_finish<<<1, 1, 0, h->stream>>>(h->sc, init));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_dist_solve_poll(topo_t *h, int *done, int *iters, double *relres) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  SolverScalars *hs = h->sc_host;
+  CUDA_TRY(cudaMemcpyAsync(hs, h->sc, sizeof(SolverScalars), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (done) *done = hs->done;
+  if (iters) *iters = hs->iters;
+  if (relres) *relres = (hs->bb > 0.0) ? std::sqrt(hs->rr / hs->bb) : (hs->rr == 0.0 ? 0.0 : INFINITY);
+  return TOPO_OK;
+}
+
+// the solution of an odd number of updates lives in u2: bring it home
+extern "C" int topo_dist_solve_end(topo_t *h, int iters) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (((iters + 1) & 1) == 1)
+    CUDA_TRY(cudaMemcpyAsync(h->u, h->u2, sizeof(double2) * (size_t)h->nn, cudaMemcpyDeviceToDevice, h->stream));
+  return TOPO_OK;
+}
+
+// compliance pieces: red_out[1] = sum W f.u (partial)  -- red_out[0] is written by topo_dist_sensitivity
+extern "C" int topo_dist_compliance_partial(topo_t *h) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  KL(h, "k_dot_weighted", k_dot_weighted<<<nblk(h->nn), 256, 0, h->stream>>>(h->f, h->u, h->nx + 1, h->ny, h->dist.w_first,
+                                                                            h->dist.w_last, h->partials, h->ticket, h->red_out + 1));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}

@@ -85,6 +85,11 @@ struct FineArgs {
   int want_dot;              // FK_APPLY: reduce u.y into dot_out
   int check_done;            // early exit when sc->done
   int init;                  // FK_UPDATE_RESID0 / FK_PROLONG_SMOOTH: first pass (alpha = 0, beta = 0)
+  // row-slab mode (DistState): weights of node rows 0 and ny that turn an accumulated vector into a distributed
+  // one; dist != 0: dot products are left as per-rank partial sums in sc->aux[0..2] (pAp, rr, rz) for the host's
+  // all-reduce, the scalar bookkeeping happens afterwards (k_dist_pcg_finish)
+  double w_first, w_last;
+  int dist;
 };
 
 // Rows 0 and 1 of the element matrix (the row block of local node 0).  For a rectangular element of an
@@ -182,7 +187,8 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
   const int hoff = hcol_ok ? hc : 0, ehoff = ehalo_ok ? c0 - 1 : 0;
 
   double alpha = 0.0, beta = 0.0;
-  if (KIND == FK_UPDATE_RESID0 && !a.init) alpha = a.sc->rz[0] / a.sc->pAp;
+  if (KIND == FK_UPDATE_RESID0 && !a.init) alpha = a.sc->rz[0] / (a.dist ? a.sc->aux[0] : a.sc->pAp);
+  auto wrow = [&](int row) -> double { return row == 0 ? a.w_first : (row == a.ny ? a.w_last : 1.0); };
   if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) beta = a.sc->rz[1];     // rz[1] holds beta (pcg.cu)
   const double omega = a.omega;
   double dots[1] = {0.0};
@@ -247,7 +253,8 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
           a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
           a.out[1][n] = rn;
           a.out[2][n] = xh;
-          dots[0] = fma(rn.x, rn.x, fma(rn.y, rn.y, dots[0]));
+          const double wr = wrow(row);
+          dots[0] = fma(wr * rn.x, rn.x, fma(wr * rn.y, rn.y, dots[0]));
         }
         return xh;
       } else {  // FK_PROLONG_SMOOTH
@@ -333,6 +340,7 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
 #pragma unroll
         for (int j = 0; j < NC; ++j) fx[j] = fb[off + NC * lane + j];
       }
+      const double wr = (KIND == FK_RESID || KIND == FK_UPDATE_RESID0 || KIND == FK_PROLONG_SMOOTH) ? wrow(r) : 1.0;
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         double yx, yy, tx, ty;
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
             if (a.want_dot) dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
           } else if (KIND == FK_RESID) {
             const double2 b = rw[SW];
-            a.out[0][n] = make_double2((fx[j] & 1u) ? 0.0 : b.x - yx, (fx[j] & 2u) ? 0.0 : b.y - yy);
+            a.out[0][n] = make_double2((fx[j] & 1u) ? 0.0 : fma(wr, b.x, -yx), (fx[j] & 2u) ? 0.0 : fma(wr, b.y, -yy));
           } else if (KIND == FK_SMOOTH) {
             const double2 b = rw[SW], d = rw[2 * SW];
             a.out[0][n] = make_double2(fma(omega * d.x, b.x - yx, v.x), fma(omega * d.y, b.y - yy, v.y));
@@ -372,17 +380,20 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
           } else if (KIND == FK_UPDATE_RESID0) {
             const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
             const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
-            a.out[3][n] = make_double2(d.x != 0.0 ? rnx - yx : 0.0, d.y != 0.0 ? rny - yy : 0.0);
+            a.out[3][n] = make_double2(d.x != 0.0 ? fma(wr, rnx, -yx) : 0.0, d.y != 0.0 ? fma(wr, rny, -yy) : 0.0);
           } else {  // FK_PROLONG_SMOOTH
             const double2 rr = rw[SW], d = rw[2 * SW];
-            const double zx = fma(omega * d.x, rr.x - yx, v.x), zy = fma(omega * d.y, rr.y - yy, v.y);
+            const double zx = fma(omega * d.x, fma(wr, rr.x, -yx), v.x), zy = fma(omega * d.y, fma(wr, rr.y, -yy), v.y);
             a.out[0][n] = make_double2(zx, zy);
-            dots[0] = fma(rr.x, zx, fma(rr.y, zy, dots[0]));
+            // interface rows: z is completed by z_lo + z_hi - x~, so each side contributes r.(z - (1-w) x~)
+            const double wc = 1.0 - wr;
+            dots[0] = fma(rr.x, zx - wc * v.x, fma(rr.y, zy - wc * v.y, dots[0]));
           }
         }
       }
       n_out += npr;
     };
+    (void)wrow;
     // S rows per trip; window roles cycle through the 4 row images (4 divides S)
     for (int r = r0; r < r1; r += S) {
       step(IC<0>(), r, W0, W1, W2);
@@ -404,9 +415,9 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
   if (KIND == FK_APPLY) {
     if (a.want_dot) grid_reduce<1>(dots, a.partials, a.ticket, a.dot_out);
   } else if (KIND == FK_PCG_MATVEC || KIND == FK_PCG_MATVEC_J) {
-    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) a.sc->pAp = dots[0];
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0 && !a.dist) a.sc->pAp = dots[0];
   } else if (KIND == FK_UPDATE_RESID0) {
-    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) {
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux + (a.dist ? 1 : 0)) && t == 0 && !a.dist) {
       SolverScalars *sc = a.sc;
       sc->rr = dots[0];
       if (!a.init) sc->iters += 1;
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
       else if (sc->iters >= sc->maxit) sc->done = 2;
     }
   } else if (KIND == FK_PROLONG_SMOOTH) {
-    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux) && t == 0) {
+    if (grid_reduce<1>(dots, a.partials, a.ticket, a.sc->aux + (a.dist ? 2 : 0)) && t == 0 && !a.dist) {
       SolverScalars *sc = a.sc;
       sc->rz[1] = a.init ? 0.0 : dots[0] / sc->rz[0];      // beta for the next direction update
       sc->rz[0] = dots[0];
@@ -453,6 +464,9 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   a.partials = h->partials;
   a.ticket = h->ticket;
   a.sc = h->sc;
+  a.w_first = h->dist.on ? h->dist.w_first : 1.0;
+  a.w_last = h->dist.on ? h->dist.w_last : 1.0;
+  a.dist = h->dist.on ? 1 : 0;
   // node columns per lane: 2 on wide meshes (overhead instructions amortised over two nodes), 1 otherwise
   // (measured: the fused kinds lose more from the lower occupancy of 64-column strips than they gain)
   const int nc = (KIND == FK_APPLY) ? h->fine_nc : 1;

@@ -257,11 +257,18 @@ int topo_gmg_plan(topo_handle *h) {
   h->lvl_ny[0] = h->ny;
   int nx = h->nx, ny = h->ny;
   // coarsen (ceil halving) until a level has at most COARSEST_MAX_NODES nodes: that level is solved exactly with
-  // a dense inverse (<= 96 DOFs), which is both cheaper and more accurate than smoothing three more tiny levels
+  // a dense inverse (<= 96 DOFs), which is both cheaper and more accurate than smoothing three more tiny levels.
+  // Row-slab mode: levels < K halve the slab (its height is a multiple of 2^K), level K and deeper have the
+  // dimensions of the GLOBAL hierarchy (they are replicated on every rank).
   const int coarsest_max_nodes = getenv("TOPO_COARSEST_NODES") ? atoi(getenv("TOPO_COARSEST_NODES")) : 48;
-  while ((nx + 1) * (ny + 1) > coarsest_max_nodes && std::max(nx, ny) > 1 && h->n_levels < TOPO_MAX_LEVELS) {
+  const bool slab = h->dist.on;
+  while (h->n_levels < TOPO_MAX_LEVELS) {
+    const int l = h->n_levels;
+    if (!(slab && l <= h->dist.K) && !((nx + 1) * (ny + 1) > coarsest_max_nodes && std::max(nx, ny) > 1)) break;
     nx = (nx + 1) / 2;
-    ny = (ny + 1) / 2;
+    if (slab && l < h->dist.K) ny = ny / 2;
+    else if (slab && l == h->dist.K) ny = h->dist.ny_global >> h->dist.K;
+    else ny = (ny + 1) / 2;
     h->lvl_nx[h->n_levels] = nx;
     h->lvl_ny[h->n_levels] = ny;
     h->n_levels++;
@@ -368,8 +375,29 @@ static int upload_gtable(topo_handle *h) {
   return TOPO_OK;
 }
 
+static int invert_coarsest(topo_handle *h) {
+  GmgLevel &L = h->levels[h->n_levels - 1];
+  const int N = h->coarse_n;
+  if (N > 96) {
+    topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
+    return TOPO_EINVAL;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 96 * 192)));
+    attr_done = true;
+  }
+  KL(h, "k_coarse_invert", k_coarse_invert<<<1, 512, sizeof(double) * N * 2 * N, h->stream>>>(L.st, L.nx, L.ny, h->coarse_inv));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
 int topo_gmg_setup(topo_handle *h) {
   if (h->n_levels < 2) return TOPO_OK;
+  if (h->dist.on) {
+    topo_set_error("row-slab handle: use topo_dist_setup_local / topo_dist_setup_global");
+    return TOPO_ESTATE;
+  }
   cudaStream_t st = h->stream;
   TOPO_TRY(upload_gtable(h));
   {
@@ -385,23 +413,121 @@ int topo_gmg_setup(topo_handle *h) {
     GmgLevel &L = h->levels[l];
     KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
   }
-  {
-    GmgLevel &L = h->levels[h->n_levels - 1];
-    const int N = h->coarse_n;
-    if (N > 96) {
-      topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
-      return TOPO_EINVAL;
-    }
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 96 * 192)));
-      attr_done = true;
-    }
-    KL(h, "k_coarse_invert", k_coarse_invert<<<1, 512, sizeof(double) * N * 2 * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv));
-  }
-  CUDA_TRY(cudaGetLastError());
+  TOPO_TRY(invert_coarsest(h));
   h->gmg_valid = true;
   return TOPO_OK;
+}
+
+// ---- row-slab mode ------------------------------------------------------------------------------------------
+namespace {
+// raw diagonal (1/dinv, 0 where dinv == 0) of node rows 0 and ny of one level -> packed send buffers
+__global__ void k_dist_diag_pack(const double2 *__restrict__ dinv, int npr, int ny, double2 *__restrict__ lo,
+                                 double2 *__restrict__ hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npr) return;
+  const double2 a = dinv[i], b = dinv[(size_t)ny * npr + i];
+  lo[i] = make_double2(a.x != 0.0 ? 1.0 / a.x : 0.0, a.y != 0.0 ? 1.0 / a.y : 0.0);
+  hi[i] = make_double2(b.x != 0.0 ? 1.0 / b.x : 0.0, b.y != 0.0 ? 1.0 / b.y : 0.0);
+}
+// dinv = 1 / (own diagonal + the neighbour's) on one interface row
+__global__ void k_dist_diag_unpack(double2 *__restrict__ dinv_row, const double2 *__restrict__ mine,
+                                   const double2 *__restrict__ theirs, int npr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npr) return;
+  const double dx = mine[i].x + theirs[i].x, dy = mine[i].y + theirs[i].y;
+  dinv_row[i] = make_double2(mine[i].x > 0.0 && dx > 0.0 ? 1.0 / dx : 0.0, mine[i].y > 0.0 && dy > 0.0 ? 1.0 / dy : 0.0);
+}
+// gathered level-K cells [world][64][ncl] -> global SoA planes [64][world*ncl]
+__global__ void k_dist_cells_reorder(const double *__restrict__ recv, double *__restrict__ cell, int64_t ncl, int world) {
+  const int64_t tot = 64 * ncl * world;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t % ncl, q = t / ncl;
+    const int plane = (int)(q % 64), g = (int)(q / 64);
+    cell[(int64_t)plane * (ncl * world) + (int64_t)g * ncl + c] = recv[t];
+  }
+}
+}  // namespace
+
+// local part of the set-up: fine diagonal, Galerkin cells of the slab down to level K (the level-K cells go to the
+// gather send buffer), node stencils of the local levels, interface diagonals packed for the exchange
+int topo_dist_setup_local(topo_handle *h) {
+  DistState &D = h->dist;
+  if (!D.on) return TOPO_ESTATE;
+  cudaStream_t st = h->stream;
+  TOPO_TRY(topo_build_diag(h));
+  TOPO_TRY(upload_gtable(h));
+  const int K = D.K;
+  auto local_cells = [&](int l) -> double * { return l == K ? D.cellK_send : h->levels[l].cell; };
+  auto local_ny = [&](int l) { return h->ny >> l; };
+  {
+    const int nxc = h->lvl_nx[1], nyc = local_ny(1);
+    KL(h, "k_cells_level1", k_cells_level1<<<blocks_for((int64_t)nxc * nyc), 128, 0, st>>>(h->ke, h->scale, h->fixed, local_cells(1), h->nx, h->ny,
+                                                                                            nxc, nyc));
+  }
+  for (int l = 2; l <= K; ++l) {
+    const int nxf = h->lvl_nx[l - 1], nyf = local_ny(l - 1), nxc = h->lvl_nx[l], nyc = local_ny(l);
+    dim3 grid(blocks_for((int64_t)nxc * nyc), 4);
+    KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(local_cells(l - 1), local_cells(l), nxf, nyf, nxc, nyc));
+  }
+  for (int l = 1; l < K; ++l) {
+    GmgLevel &L = h->levels[l];
+    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+  }
+  long long off = 0;
+  for (int l = 0; l < K; ++l) {
+    const int npr = h->lvl_nx[l] + 1, ny = local_ny(l);
+    const double2 *dinv = (l == 0) ? h->dinv : h->levels[l].dinv;
+    KL(h, "k_dist_diag_pack", k_dist_diag_pack<<<blocks_for(npr), 128, 0, st>>>(dinv, npr, ny, D.diag_send_lo + off, D.diag_send_hi + off));
+    off += npr;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// after the host exchanged the interface diagonals and gathered the level-K cells
+int topo_dist_setup_global(topo_handle *h) {
+  DistState &D = h->dist;
+  if (!D.on) return TOPO_ESTATE;
+  cudaStream_t st = h->stream;
+  const int K = D.K;
+  long long off = 0;
+  for (int l = 0; l < K; ++l) {
+    const int npr = h->lvl_nx[l] + 1, ny = h->ny >> l;
+    double2 *dinv = (l == 0) ? h->dinv : h->levels[l].dinv;
+    if (D.has_lo)
+      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv, D.diag_send_lo + off, D.diag_recv_lo + off, npr));
+    if (D.has_hi)
+      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv + (size_t)ny * npr, D.diag_send_hi + off,
+                                                                                       D.diag_recv_hi + off, npr));
+    off += npr;
+  }
+  {
+    GmgLevel &G = h->levels[K];
+    KL(h, "k_dist_cells_reorder", k_dist_cells_reorder<<<std::min(blocks_for(64 * D.ncellK_loc * D.world, 256), 148 * 8), 256, 0, st>>>(
+           D.cellK_recv, G.cell, D.ncellK_loc, D.world));
+  }
+  for (int l = K + 1; l < h->n_levels; ++l) {
+    GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
+    dim3 grid(blocks_for(C.ncell), 4);
+    KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
+  }
+  for (int l = K; l < h->n_levels; ++l) {
+    GmgLevel &L = h->levels[l];
+    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+  }
+  TOPO_TRY(invert_coarsest(h));
+  h->gmg_valid = true;
+  return TOPO_OK;
+}
+
+void topo_gmg_free(topo_handle *h) {
+  for (size_t l = 1; l < h->levels.size(); ++l) cudaFree(h->levels[l].cell);
+  h->levels.clear();
+  cudaFree(h->lvl1_slab);
+  cudaFree(h->coarse_slab);
+  h->lvl1_slab = h->coarse_slab = nullptr;
+  h->n_levels = 1;
+  h->gmg_valid = false;
 }
 
 extern "C" int topo_gmg_info(topo_t *h, int *n_levels, int *nx_levels, int *ny_levels) {

@@ -112,7 +112,9 @@ struct LevelView {
   const double2 *dinv;
   double2 *x, *x2, *b, *r;
   int nx, ny;
+  double wf, wl;       // row-slab mode: weights of node rows 0 / ny that make a distributed copy of b (else 1)
 };
+__device__ __forceinline__ double row_weight(const LevelView &L, int r) { return r == 0 ? L.wf : (r == L.ny ? L.wl : 1.0); }
 
 // ---- per-node bodies shared by the multi-block kernels and the tail kernel -------------------------------
 // down: x = w dinv b ; r = b - A x   (x at neighbours recomputed from b, dinv)
@@ -130,7 +132,8 @@ __device__ __forceinline__ void node_down(const LevelView &L, int64_t n, double 
               ax, ay);
   const double2 bv = L.b[n], dv = L.dinv[n];
   L.x[n] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
-  L.r[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
+  const double wr = row_weight(L, r);
+  L.r[n] = make_double2(dv.x != 0.0 ? fma(wr, bv.x, -ax) : 0.0, dv.y != 0.0 ? fma(wr, bv.y, -ay) : 0.0);
 }
 
 // up: x~ = x + mask(P xc) ; x2 = x~ + w dinv (b - A x~)
@@ -159,7 +162,8 @@ __device__ __forceinline__ void node_smooth(const LevelView &L, int64_t n, doubl
   double ax, ay;
   stencil_row(L.st, nn, n, r, c, L.nx, L.ny, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
   const double2 bv = L.b[n], dv = L.dinv[n], xv = L.x[n];
-  L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
+  const double wr = row_weight(L, r);
+  L.x2[n] = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xv.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xv.y));
 }
 // residual of the current iterate (needed when nu_pre > 1): r = b - A x
 __device__ __forceinline__ void node_resid(const LevelView &L, int64_t n) {
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
   if (a.dbg && gt == 0) a.dbg[0] = 0;
   STAMP();
   double2 *cur[TAIL_MAX];                       // where each level's current iterate lives (x or x2)
-  {
+  if (a.r_parent != nullptr) {                  // row-slab mode: lv[0].b was assembled from the gathered slabs
     const LevelView &C = a.lv[0];
     const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
     for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny);
@@ -402,6 +406,116 @@ const char *lvl_name(const char *what, int l) {
 LevelView view_of(const GmgLevel &G) {
   LevelView v;
   v.st = G.st; v.dinv = G.dinv; v.x = G.x; v.x2 = G.x2; v.b = G.b; v.r = G.r; v.nx = G.nx; v.ny = G.ny;
+  v.wf = v.wl = 1.0;
+  return v;
+}
+
+// sweeps per tail level: the deep, tiny levels are where the coarse solve loses accuracy on high-contrast
+// designs and where a sweep costs next to nothing
+int tail_nu(const topo_handle *h, int l) {
+  return h->levels[l].nn > TAIL_SMALL ? h->nu_tail_big : h->nu_tail_small;
+}
+int nu_pre_of(const topo_handle *h, int l) {
+  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
+  return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_pre;
+}
+int nu_post_of(const topo_handle *h, int l) {
+  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
+  return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_post;
+}
+// first level handled by the tail kernel (row-slab mode: the first global level)
+int tail_start(const topo_handle *h) {
+  if (h->dist.on) return h->dist.K;
+  int tail = h->n_levels - 1;
+  while (tail > 1 && h->levels[tail - 1].nn <= h->tail_max_nodes) --tail;
+  return tail;
+}
+// where the final iterate of level l lives after the cycle
+const double2 *level_result(const topo_handle *h, int l, int tail) {
+  const int L = h->n_levels;
+  if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
+  if (l >= tail) {                                 // tail levels: parity of the pointer swaps (see k_tail)
+    const int nu = tail_nu(h, l);
+    const int swaps = (nu > 1 ? nu - 1 : 0) + nu;
+    return (swaps & 1) ? h->levels[l].x2 : h->levels[l].x;
+  }
+  return (nu_post_of(h, l) & 1) ? h->levels[l].x2 : h->levels[l].x;
+}
+
+// all levels >= tail in one cluster launch; r_parent == nullptr: levels[tail].b is already in place
+int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int pny) {
+  const int L = h->n_levels;
+  TailArgs ta = {};
+  ta.n = L - tail;
+  if (ta.n > TAIL_MAX) {
+    topo_set_error("multigrid tail has %d levels (max %d)", ta.n, TAIL_MAX);
+    return TOPO_EINVAL;
+  }
+  for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h->levels[l]);
+  ta.r_parent = r_parent; ta.pnx = pnx; ta.pny = pny;
+  ta.coarse_inv = h->coarse_inv;
+  ta.coarse_n = h->coarse_n;
+  ta.omega = h->omega;
+  for (int l = tail; l < L; ++l) ta.nu[l - tail] = tail_nu(h, l);
+  ta.done = &h->sc->done;
+  ta.dbg = h->tail_dbg;
+  // one cluster; 16 CTAs needs the non-portable size, fall back to 8 (portable) or 1
+  static int cluster_size = 0;
+  if (cluster_size == 0) {
+    cluster_size = 1;
+    if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      for (int cs : {16, 8, 4, 2}) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(cs); q.blockDim = dim3(1024);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        q.attrs = at; q.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_tail, &q) == cudaSuccess && ncl >= 1) { cluster_size = cs; break; }
+      }
+    }
+    cudaGetLastError();
+  }
+  const bool big_tail = h->levels[tail].nn > TAIL_SMALL;
+  const int cs = big_tail ? cluster_size : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
+  return TOPO_OK;
+}
+
+// ---- row-slab mode helpers ---------------------------------------------------------------------------------
+// global level-K right-hand side from the gathered per-rank pieces: rank g holds coarse rows
+// [g*rows, (g+1)*rows] (rows+1 node rows, the shared ones are partial sums)
+__global__ void k_dist_assemble_bK(const double2 *__restrict__ recv, double2 *__restrict__ b, int npr, int rows,
+                                   int world, const int *done) {
+  if (done && *done) return;
+  const int64_t nn = (int64_t)npr * ((int64_t)rows * world + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const int J = (int)(n / npr), I = (int)(n - (int64_t)J * npr);
+  const int g = J / rows, j = J - g * rows;
+  const int64_t per = (int64_t)(rows + 1) * npr;
+  double2 acc = make_double2(0.0, 0.0);
+  if (g < world) acc = recv[(int64_t)g * per + (int64_t)j * npr + I];
+  if (j == 0 && g > 0) {
+    const double2 t = recv[(int64_t)(g - 1) * per + (int64_t)rows * npr + I];
+    acc.x += t.x; acc.y += t.y;
+  }
+  b[n] = acc;
+}
+
+LevelView dist_view(const topo_handle *h, int l) {
+  LevelView v = view_of(h->levels[l]);
+  if (h->dist.on && l < h->dist.K) { v.wf = h->dist.w_first; v.wl = h->dist.w_last; }
   return v;
 }
 
@@ -416,30 +530,13 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   const double om = h->omega;
   const int L = h->n_levels;
   if (L < 2) return TOPO_OK;
+  if (h->dist.on) {
+    topo_set_error("row-slab handle: the V-cycle is driven segment by segment (topo_dist_*)");
+    return TOPO_ESTATE;
+  }
   const int *done = &h->sc->done;
-  // smoothing sweeps on the coarse levels (the fine level always does nu_pre/nu_post = what topo_set_gmg set)
-  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
-  auto nu_pre_of = [&](int l) { return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_pre; };
-  auto nu_post_of = [&](int l) { return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_post; };
-  // first level handled by the tail kernel
-  int tail = L - 1;
-  while (tail > 1 && h->levels[tail - 1].nn <= h->tail_max_nodes) --tail;
-  // sweeps per tail level: the deep, tiny levels are where the coarse solve loses accuracy on high-contrast
-  // designs and where a sweep costs next to nothing
-  auto tail_nu = [&](int l) -> int {
-    const int nn_l = h->levels[l].nn;
-    if (nn_l > TAIL_SMALL) return h->nu_tail_big;
-    return h->nu_tail_small;
-  };
-  auto result_of = [&](int l) -> const double2 * {
-    if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
-    if (l >= tail) {                                 // tail levels: parity of the pointer swaps (see k_tail)
-      const int nu = tail_nu(l);
-      const int swaps = (nu > 1 ? nu - 1 : 0) + nu;
-      return (swaps & 1) ? h->levels[l].x2 : h->levels[l].x;
-    }
-    return (nu_post_of(l) & 1) ? h->levels[l].x2 : h->levels[l].x;
-  };
+  const int tail = tail_start(h);
+  auto result_of = [&](int l) { return level_result(h, l, tail); };
 
   if (tail > 1) {
     GmgLevel &C = h->levels[1];
@@ -449,7 +546,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(F);
     KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
-    for (int s = 1; s < nu_pre_of(l); ++s) {
+    for (int s = 1; s < nu_pre_of(h, l); ++s) {
       KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
       KL(h, "k_lvl_resid", k_lvl_resid<<<blocks_for(F.nn), 128, 0, st>>>(V, done));
@@ -459,56 +556,8 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
       KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny, done));
     }
   }
-  {
-    TailArgs ta = {};
-    ta.n = L - tail;
-    if (ta.n > TAIL_MAX) {
-      topo_set_error("multigrid tail has %d levels (max %d)", ta.n, TAIL_MAX);
-      return TOPO_EINVAL;
-    }
-    for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h->levels[l]);
-    if (tail == 1) {
-      ta.r_parent = res_fine; ta.pnx = h->nx; ta.pny = h->ny;
-    } else {
-      ta.r_parent = h->levels[tail - 1].r; ta.pnx = h->levels[tail - 1].nx; ta.pny = h->levels[tail - 1].ny;
-    }
-    ta.coarse_inv = h->coarse_inv;
-    ta.coarse_n = h->coarse_n;
-    ta.omega = om;
-    for (int l = tail; l < L; ++l) ta.nu[l - tail] = tail_nu(l);
-    ta.done = done;
-    ta.dbg = h->tail_dbg;
-    // one cluster; 16 CTAs needs the non-portable size, fall back to 8 (portable) or 1
-    static int cluster_size = 0;
-    if (cluster_size == 0) {
-      cluster_size = 1;
-      if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-        for (int cs : {16, 8, 4, 2}) {
-          cudaLaunchConfig_t q = {};
-          q.gridDim = dim3(cs); q.blockDim = dim3(1024);
-          cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeClusterDimension;
-          at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-          q.attrs = at; q.numAttrs = 1;
-          int ncl = 0;
-          if (cudaOccupancyMaxActiveClusters(&ncl, k_tail, &q) == cudaSuccess && ncl >= 1) { cluster_size = cs; break; }
-        }
-      }
-      cudaGetLastError();
-    }
-    const bool big_tail = h->levels[tail].nn > TAIL_SMALL;
-    const int cs = big_tail ? cluster_size : 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs);
-    cfg.blockDim = dim3(1024);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
-  }
+  if (tail == 1) TOPO_TRY(launch_tail(h, tail, res_fine, h->nx, h->ny));
+  else TOPO_TRY(launch_tail(h, tail, h->levels[tail - 1].r, h->levels[tail - 1].nx, h->levels[tail - 1].ny));
   for (int l = tail - 1; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
     LevelView V = view_of(F);
@@ -520,7 +569,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     } else {
       KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
     }
-    for (int s = 1; s < nu_post_of(l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
+    for (int s = 1; s < nu_post_of(h, l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }
       KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(W, om, done));
@@ -533,6 +582,76 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), xhat_fine, h->fixed, h->nx, h->ny,
                                                                                        C.nx, done));
   }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// ---- row-slab mode: the V-cycle in segments; the host completes interface rows between them -----------------
+// (levels 1..K-1 are local to the slab, one sweep before/after; levels >= K are global and run in the tail kernel
+// on every rank redundantly)
+
+// b of the next level from a distributed residual: local level l+1 < K -> its b (distributed, the host halo-sums
+// it); l+1 == K -> the send buffer of the gather
+static int dist_restrict_from(topo_handle *h, int l, const double2 *r) {
+  const DistState &D = h->dist;
+  const int nxf = h->lvl_nx[l], nyf = (l == 0) ? h->ny : h->levels[l].ny;
+  const int *done = &h->sc->done;
+  if (l + 1 < D.K) {
+    GmgLevel &C = h->levels[l + 1];
+    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, h->stream>>>(r, C.b, nxf, nyf, C.nx, C.ny, done));
+  } else {
+    const int nxc = h->lvl_nx[D.K], nyc = nyf / 2;
+    KL(h, "k_restrict", k_restrict<<<blocks_for((int64_t)(nxc + 1) * (nyc + 1)), 128, 0, h->stream>>>(r, D.bK_send, nxf, nyf, nxc, nyc, done));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+int topo_dist_restrict_fine(topo_handle *h, const double2 *res_fine) { return dist_restrict_from(h, 0, res_fine); }
+
+// requires b_l accumulated: x = w D^-1 b ; r = W b - A_loc x (distributed) ; restrict
+int topo_dist_level_down(topo_handle *h, int l) {
+  if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
+  GmgLevel &F = h->levels[l];
+  KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, h->stream>>>(dist_view(h, l), h->omega, &h->sc->done));
+  return dist_restrict_from(h, l, F.r);
+}
+
+int topo_dist_tail(topo_handle *h) {
+  const DistState &D = h->dist;
+  if (!D.on) return TOPO_EINVAL;
+  GmgLevel &G = h->levels[D.K];
+  const int rows = (h->ny >> D.K);
+  KL(h, "k_dist_assemble_bK", k_dist_assemble_bK<<<blocks_for(G.nn), 128, 0, h->stream>>>(D.bK_recv, G.b, G.nx + 1, rows, D.world,
+                                                                                          &h->sc->done));
+  return launch_tail(h, D.K, nullptr, 0, 0);
+}
+
+// this slab's rows of the level-(l+1) result (global levels are indexed with the slab's row offset)
+static const double2 *dist_coarse_result(const topo_handle *h, int l_coarse) {
+  const DistState &D = h->dist;
+  const double2 *x = level_result(h, l_coarse, D.K);
+  if (l_coarse == D.K) x += (size_t)D.rank * (size_t)(h->ny >> D.K) * (size_t)(h->levels[D.K].nx + 1);
+  return x;
+}
+
+// x += P x_{l+1} ; x2 = x + w D^-1 (W b - A_loc x): complete on interior rows, partial on interface rows
+// (the host adds the neighbour's x2 row and subtracts x there: topo_dist_xchg_finish)
+int topo_dist_level_up(topo_handle *h, int l) {
+  if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
+  GmgLevel &F = h->levels[l];
+  const LevelView V = dist_view(h, l);
+  const int *done = &h->sc->done;
+  KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));
+  KL(h, lvl_name("up", l), k_lvl_smooth<<<blocks_for(F.nn), 128, 0, h->stream>>>(V, h->omega, done));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine) {
+  if (!h->dist.on) return TOPO_EINVAL;
+  KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, h->stream>>>(dist_coarse_result(h, 1), xhat_fine, h->fixed, h->nx,
+                                                                                           h->ny, h->lvl_nx[1], &h->sc->done));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }

@@ -181,6 +181,10 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
     topo_set_error("topo_solve: unknown preconditioner %d", precond);
     return TOPO_EINVAL;
   }
+  if (h->dist.on) {
+    topo_set_error("topo_solve: row-slab handle -- the solve is driven through topo_dist_*");
+    return TOPO_ESTATE;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   const int64_t nn = h->nn;
   const int nb = vec_blocks(nn);

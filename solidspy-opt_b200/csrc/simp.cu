@@ -66,9 +66,12 @@ struct FilterTaps {
 
 constexpr int FT = 32;                  // tile edge (elements)
 // out_i = sum_j w_ij rho_j dc_j / (sum_j w_ij * max(1e-3, rho_i)); taps in (dj, di) row-major order
+// Row-slab mode: ghost_lo / ghost_hi hold rho*dc of the hy element rows below / above the slab (nullptr at the
+// ends of the global mesh, where the stencil is truncated like the reference's).
 __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ FilterTaps taps, const double *__restrict__ rho,
                                                 const double *__restrict__ dc, double *__restrict__ out, int nx,
-                                                int ny) {
+                                                int ny, const double *__restrict__ ghost_lo,
+                                                const double *__restrict__ ghost_hi) {
   extern __shared__ double tile[];      // (FT+2hy) x (FT+2hx)
   const int hx = taps.hx, hy = taps.hy;
   const int tw = FT + 2 * hx, th = FT + 2 * hy;
@@ -77,9 +80,15 @@ __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ FilterTa
     const int ty = t / tw, tx = t - ty * tw;
     const int gx = x0 + tx - hx, gy = y0 + ty - hy;
     double q = 0.0;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) {
-      const size_t e = (size_t)gy * nx + gx;
-      q = rho[e] * dc[e];
+    if (gx >= 0 && gx < nx) {
+      if (gy >= 0 && gy < ny) {
+        const size_t e = (size_t)gy * nx + gx;
+        q = rho[e] * dc[e];
+      } else if (gy < 0 && ghost_lo != nullptr) {
+        q = ghost_lo[(size_t)(gy + hy) * nx + gx];          // rows -hy .. -1
+      } else if (gy >= ny && ghost_hi != nullptr) {
+        q = ghost_hi[(size_t)(gy - ny) * nx + gx];          // rows ny .. ny+hy-1
+      }
     }
     tile[t] = q;
   }
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ FilterTa
     if (gy >= ny) break;
     double num = 0.0, den = 0.0;
     for (int dj = -hy; dj <= hy; ++dj) {
-      const bool rowok = (gy + dj >= 0) && (gy + dj < ny);
+      const bool rowok = (gy + dj >= 0 || ghost_lo != nullptr) && (gy + dj < ny || ghost_hi != nullptr);
       const double *trow = tile + (ly + hy + dj) * tw + threadIdx.x + hx;
       for (int di = -hx; di <= hx; ++di) {
         const double w = taps.w[(dj + hy) * wrow + di + hx];
@@ -137,9 +146,21 @@ __global__ void __launch_bounds__(ET) k_oc_prep(const double *__restrict__ rho, 
 
 // EXACT bisection step with the reference's formula: gt = g + sum(rho_new(lmid) - rho);
 // gt > 0 ? l1 = lmid : l2 = lmid.  only_when_needed: run only if the fast pass asked for it.
+__device__ __forceinline__ void oc_decide_step(OcState *oc, double sum) {
+  const double lmid = 0.5 * (oc->l2 + oc->l1);
+  const double gt = oc->g + sum;
+  if (gt > 0.0) oc->l1 = lmid; else oc->l2 = lmid;
+  oc->gt = gt;
+  oc->lmid = lmid;
+  oc->steps += 1;
+  oc->need_exact = 0;
+  oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
+}
+// defer != 0 (row-slab mode): leave the per-rank sum in out[]; the decision is taken by k_oc_decide after the
+// host's all-reduce
 __global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, const double *__restrict__ dc,
                                                 int64_t ne, double move, int only_when_needed, double *partials,
-                                                unsigned int *ticket, double *out, OcState *oc) {
+                                                unsigned int *ticket, double *out, OcState *oc, int defer) {
   if (oc->done) return;
   if (only_when_needed && !oc->need_exact) return;
   const double lmid = 0.5 * (oc->l2 + oc->l1);
@@ -148,15 +169,7 @@ __global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, 
     const double rh = rho[e];
     v[0] += oc_candidate(rh, dc[e], lmid, move) - rh;
   }
-  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0) {
-    const double gt = oc->g + v[0];
-    if (gt > 0.0) oc->l1 = lmid; else oc->l2 = lmid;
-    oc->gt = gt;
-    oc->lmid = lmid;
-    oc->steps += 1;
-    oc->need_exact = 0;
-    oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
-  }
+  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc_decide_step(oc, v[0]);
 }
 
 // FAST pass: the 15 multipliers of the next 4 bisection levels (heap order, generated with exactly the
@@ -165,9 +178,38 @@ __global__ void __launch_bounds__(ET) k_oc_step(const double *__restrict__ rho, 
 // ulp (<= 1e-15 absolute), so a sum further than `margin` from zero has the reference's sign; a sum
 // inside the margin stops the walk and requests one exact step (k_oc_step) for that decision.
 constexpr int OC_LEVELS = 4, OC_CAND = (1 << OC_LEVELS) - 1;
+// walks the decision tree of one fast pass from the 15 candidate sums (+ the common part in v[OC_CAND])
+__device__ __forceinline__ void oc_decide_multi(OcState *oc, const double *v, double margin) {
+  double l1 = oc->l1, l2 = oc->l2;
+  int j = 0, steps = 0;
+  bool done = false, need = false;
+  double gt_last = oc->gt, lmid_last = oc->lmid;
+  for (int d = 0; d < OC_LEVELS; ++d) {
+    if (!((l2 - l1) / (l1 + l2) > 1e-3)) { done = true; break; }
+    double vj = 0.0;
+#pragma unroll
+    for (int q = 0; q < OC_CAND; ++q) vj = (q == j) ? v[q] : vj;
+    const double gt = oc->g + vj + v[OC_CAND];
+    const bool is_nan = !(gt == gt);
+    if (!is_nan && !(fabs(gt) > margin)) { need = true; break; }    // too close to call: the exact step decides
+    const double lmid = 0.5 * (l2 + l1);                            // == the candidate evaluated at heap node j
+    if (gt > 0.0) { l1 = lmid; j = 2 * j + 2; } else { l2 = lmid; j = 2 * j + 1; }   // NaN -> else, like the reference
+    gt_last = gt;
+    lmid_last = lmid;
+    ++steps;
+  }
+  if (!done && !need && !((l2 - l1) / (l1 + l2) > 1e-3)) done = true;
+  oc->l1 = l1;
+  oc->l2 = l2;
+  oc->gt = gt_last;
+  oc->lmid = lmid_last;
+  oc->steps += steps;
+  oc->need_exact = need ? 1 : 0;
+  oc->done = done ? 1 : 0;
+}
 __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho, const double *__restrict__ amp,
                                                  int64_t ne, double move, double margin, double *partials,
-                                                 unsigned int *ticket, double *out, OcState *oc) {
+                                                 unsigned int *ticket, double *out, OcState *oc, int defer) {
   if (oc->done || oc->need_exact) return;
   // candidate multipliers in heap order; each of the first 15 threads does ONE 1/sqrt and shares it
   __shared__ double s_tinv[OC_CAND];
@@ -212,40 +254,13 @@ __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho,
       for (int j = 0; j < OC_CAND; ++j) v[j] += fmax(cl, fmin(ch, am * tinv[j])) - rh;
     }
   }
-  if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0) {
-    double l1 = oc->l1, l2 = oc->l2;
-    int j = 0, steps = 0;
-    bool done = false, need = false;
-    double gt_last = oc->gt, lmid_last = oc->lmid;
-    for (int d = 0; d < OC_LEVELS; ++d) {
-      if (!((l2 - l1) / (l1 + l2) > 1e-3)) { done = true; break; }
-      double vj = 0.0;
-#pragma unroll
-      for (int q = 0; q < OC_CAND; ++q) vj = (q == j) ? v[q] : vj;
-      const double gt = oc->g + vj + v[OC_CAND];
-      const bool is_nan = !(gt == gt);
-      if (!is_nan && !(fabs(gt) > margin)) { need = true; break; }    // too close to call: the exact step decides
-      const double lmid = 0.5 * (l2 + l1);                            // == the candidate evaluated at heap node j
-      if (gt > 0.0) { l1 = lmid; j = 2 * j + 2; } else { l2 = lmid; j = 2 * j + 1; }   // NaN -> else, like the reference
-      gt_last = gt;
-      lmid_last = lmid;
-      ++steps;
-    }
-    if (!done && !need && !((l2 - l1) / (l1 + l2) > 1e-3)) done = true;
-    oc->l1 = l1;
-    oc->l2 = l2;
-    oc->gt = gt_last;
-    oc->lmid = lmid_last;
-    oc->steps += steps;
-    oc->need_exact = need ? 1 : 0;
-    oc->done = done ? 1 : 0;
-  }
+  if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc_decide_multi(oc, v, margin);
 }
 
 // exact gt at the last evaluated multiplier (what the reference returns as the new constraint value)
 __global__ void __launch_bounds__(ET) k_oc_final_gt(const double *__restrict__ rho, const double *__restrict__ dc,
                                                     int64_t ne, double move, double *partials, unsigned int *ticket,
-                                                    double *out, OcState *oc) {
+                                                    double *out, OcState *oc, int defer) {
   if (oc->steps == 0) return;
   const double lmid = oc->lmid;
   double v[1] = {0.0};
@@ -253,13 +268,14 @@ __global__ void __launch_bounds__(ET) k_oc_final_gt(const double *__restrict__ r
     const double rh = rho[e];
     v[0] += oc_candidate(rh, dc[e], lmid, move) - rh;
   }
-  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0) oc->gt = oc->g + v[0];
+  if (grid_reduce<1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc->gt = oc->g + v[0];
 }
 
 // rho_new at the LAST evaluated multiplier (what the reference returns) + change = max|rho_new - rho|
 __global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho, const double *__restrict__ dc,
                                                  double *__restrict__ rho_new, int64_t ne, double move,
-                                                 double *partials, unsigned int *ticket, double *out, OcState *oc) {
+                                                 double *partials, unsigned int *ticket, double *out, OcState *oc,
+                                                 int defer) {
   const double lmid = oc->lmid;
   const int steps = oc->steps;
   double v[1] = {0.0};
@@ -271,7 +287,24 @@ __global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho,
     const double d = fabs(rn - rh);
     v[0] = (d > v[0] || d != d) ? d : v[0];
   }
-  if (grid_reduce<1, true>(v, partials, ticket, out) && threadIdx.x == 0) oc->change = v[0];
+  if (grid_reduce<1, true>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc->change = v[0];
+}
+
+// row-slab mode: decisions from the all-reduced sums in red[]
+__global__ void k_oc_decide(OcState *oc, const double *red, double margin, int kind) {
+  if (kind == 0) {                     // fast pass (16 sums)
+    if (oc->done || oc->need_exact) return;
+    double v[OC_CAND + 1];
+    for (int j = 0; j <= OC_CAND; ++j) v[j] = red[j];
+    oc_decide_multi(oc, v, margin);
+  } else if (kind == 1) {              // exact step
+    if (oc->done || !oc->need_exact) return;
+    oc_decide_step(oc, red[0]);
+  } else if (kind == 2) {              // final gt
+    if (oc->steps > 0) oc->gt = oc->g + red[0];
+  } else {                             // change (max-reduced)
+    oc->change = red[0];
+  }
 }
 
 }  // namespace
@@ -316,14 +349,57 @@ extern "C" int topo_filter_sensitivity(topo_t *h, double rmin, double dx, double
       taps.w[(dj + taps.hy) * wrow + di + taps.hx] = rmin - std::sqrt((di * dx) * (di * dx) + (dj * dy) * (dj * dy));
   dim3 grid(div_up(h->nx, FT), div_up(h->ny, FT)), block(32, 8);
   const size_t smem = sizeof(double) * (FT + 2 * taps.hx) * (FT + 2 * taps.hy);
-  KL(h, "k_filter", k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny));
+  const double *glo = nullptr, *ghi = nullptr;
+  if (h->dist.on) {
+    if (taps.hy != h->dist.filt_hy) {
+      topo_set_error("row-slab filter: ghost rows were packed for hy=%d, the filter needs %d", h->dist.filt_hy, taps.hy);
+      return TOPO_ESTATE;
+    }
+    glo = h->dist.has_lo ? h->dist.filt_recv_lo : nullptr;
+    ghi = h->dist.has_hi ? h->dist.filt_recv_hi : nullptr;
+  }
+  KL(h, "k_filter", k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
   CUDA_TRY(cudaGetLastError());
   std::swap(h->dc, h->dc2);
   return TOPO_OK;
 }
 
+// row-slab mode: rho*dc of the first / last hy element rows -> send buffers (host: exchange TOPO_X_FILTER, then
+// topo_filter_sensitivity)
+namespace {
+__global__ void k_filter_pack(const double *__restrict__ rho, const double *__restrict__ dc, double *__restrict__ lo,
+                              double *__restrict__ hi, int nx, int ny, int hy) {
+  const int64_t n = (int64_t)hy * nx;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    lo[t] = rho[t] * dc[t];
+    const size_t e = (size_t)(ny - hy) * nx + t;
+    hi[t] = rho[e] * dc[e];
+  }
+}
+}  // namespace
+extern "C" int topo_dist_filter_pack(topo_t *h, double rmin, double dy) {
+  if (!h || !h->dist.on || !(rmin > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int hy = 0;
+  while (hy <= FH_MAX && rmin - (hy + 1) * dy > 0.0) hy++;
+  if (hy > FH_MAX || hy > h->ny) {
+    topo_set_error("row-slab filter: radius %.3g spans %d element rows (max %d, slab height %d)", rmin, hy, FH_MAX, h->ny);
+    return TOPO_EINVAL;
+  }
+  h->dist.filt_hy = hy;
+  if (hy > 0)
+    KL(h, "k_filter_pack", k_filter_pack<<<el_blocks((int64_t)hy * h->nx), ET, 0, h->stream>>>(h->rho, h->dc, h->dist.filt_send_lo,
+                                                                                             h->dist.filt_send_hi, h->nx, h->ny, hy));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
 extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change, int *nsteps) {
   if (!h || !g) return TOPO_EINVAL;
+  if (h->dist.on) {
+    topo_set_error("row-slab handle: the OC bisection is driven through topo_dist_oc");
+    return TOPO_ESTATE;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const int nb = el_blocks(h->ne);
@@ -340,9 +416,9 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   while (rounds < hard_cap) {
     for (int i = 0; i < batch; ++i) {
       KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
-                                                        h->red_out, h->oc));
+                                                        h->red_out, h->oc, 0));
       KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket,
-                                                      h->red_out, h->oc));
+                                                      h->red_out, h->oc, 0));
     }
     rounds += batch;
     CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
@@ -350,9 +426,9 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
     if (hs->done) break;
   }
   KL(h, "k_oc_final_gt", k_oc_final_gt<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket,
-                                                          h->red_out, h->oc));
+                                                          h->red_out, h->oc, 0));
   KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket,
-                                                    h->red_out, h->oc));
+                                                    h->red_out, h->oc, 0));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(h->ev1, st));
@@ -362,5 +438,73 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   *g = hs->gt;
   if (change) *change = hs->change;
   if (nsteps) *nsteps = hs->steps;
+  return TOPO_OK;
+}
+
+// ---- row-slab mode: the OC bisection in pieces around the host's all-reduces --------------------------------------
+// The sums of every pass are left per rank in red_out (TOPO_S_RED); after the all-reduce the decision kernel
+// runs on every rank with identical inputs, so all ranks walk the same bisection.
+//   op 0  begin(g = value)                       -> nothing to reduce
+//   op 1  fast pass                               -> all-reduce SUM 16, then op 2
+//   op 2  decide fast pass
+//   op 3  exact step (only if requested)          -> all-reduce SUM 1, then op 4
+//   op 4  decide exact step
+//   op 5  final gt                                -> all-reduce SUM 1, then op 6
+//   op 6  decide final gt
+//   op 7  apply (rho_new, change partial)         -> all-reduce MAX 1, then op 8
+//   op 8  set change, swap rho <-> rho_new
+// ne_global sizes the rounding margin of the fast pass like the single-GPU path.
+extern "C" int topo_dist_oc(topo_t *h, int op, double move, double value, long long ne_global) {
+  if (!h || !h->dist.on) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int nb = el_blocks(h->ne);
+  double *amp = h->sens;
+  const double margin = 64.0 * 2.220446049250313e-16 * (double)ne_global + 1e-12;
+  switch (op) {
+    case 0:
+      KL(h, "k_oc_init", k_oc_init<<<1, 1, 0, st>>>(h->oc, value));
+      KL(h, "k_oc_prep", k_oc_prep<<<nb, ET, 0, st>>>(h->rho, h->dc, amp, h->ne));
+      break;
+    case 1:
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+                                                                        h->red_out, h->oc, 1));
+      break;
+    case 2: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 0)); break;
+    case 3:
+      KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket, h->red_out, h->oc, 1));
+      break;
+    case 4: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 1)); break;
+    case 5:
+      CUDA_TRY(cudaMemsetAsync(h->red_out, 0, sizeof(double), st));      // zero steps: the kernel returns early
+      KL(h, "k_oc_final_gt", k_oc_final_gt<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc, 1));
+      break;
+    case 6: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 2)); break;
+    case 7:
+      KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out,
+                                                        h->oc, 1));
+      break;
+    case 8:
+      KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 3));
+      std::swap(h->rho, h->rho_new);
+      break;
+    default:
+      return TOPO_EINVAL;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change) {
+  if (!h || !h->dist.on) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  OcState *hs = h->oc_host;
+  CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (done) *done = hs->done;
+  if (need_exact) *need_exact = hs->need_exact;
+  if (steps) *steps = hs->steps;
+  if (gt) *gt = hs->gt;
+  if (change) *change = hs->change;
   return TOPO_OK;
 }

@@ -76,6 +76,28 @@ struct GmgLevel {
   uint8_t *fixed;
 };
 
+// Row-slab decomposition: this handle is slab `rank` of `world` equal slabs of a mesh with ny_global
+// element rows.  Vectors are stored in ACCUMULATED form (interface node rows hold the full value on both
+// neighbours); a local operator application yields a DISTRIBUTED result (partial sums on interface rows) that
+// the host completes with a halo sum.  Where a kernel needs a distributed copy of an accumulated vector it
+// scales the interface rows by w_first / w_last (1/2 each side = a partition of unity).
+struct DistState {
+  bool on;
+  int rank, world, K;                  // K = first level that is global (replicated on every rank)
+  bool has_lo, has_hi;
+  int ny_global;
+  double w_first, w_last;
+  double2 *recv_lo, *recv_hi;          // one node row of the fine grid each (largest exchange)
+  double2 *diag_send_lo, *diag_send_hi, *diag_recv_lo, *diag_recv_hi;   // interface diagonals of levels 0..K-1
+  long long diag_count;                // double2 per side
+  double *cellK_send, *cellK_recv;     // level-K cell matrices: [64][ncellK_loc] -> [world][64][ncellK_loc]
+  long long ncellK_loc;
+  double2 *bK_send, *bK_recv;          // level-K right-hand side: (rowsK_loc+1) x nprK per rank
+  long long bK_count;                  // double2 per rank
+  double *filt_send_lo, *filt_send_hi, *filt_recv_lo, *filt_recv_hi;    // rho*dc of hy element rows
+  int filt_hy;
+};
+
 struct topo_handle {
   int device;
   int nx, ny;
@@ -142,6 +164,7 @@ struct topo_handle {
   topo_timing timing;
   int matvec_rows_per_chunk;
   int fine_nc;                    // node columns per lane of the stage-1 kernel (1 or 2)
+  DistState dist;
 };
 
 // Kernel launch wrapper: counts the launch and, in profile mode, brackets it with CUDA events on the
@@ -175,6 +198,7 @@ int topo_build_diag(topo_handle *h);
 int topo_gmg_plan(topo_handle *h);
 int topo_gmg_setup(topo_handle *h);
 int topo_apply_loads(topo_handle *h);
+void topo_gmg_free(topo_handle *h);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------

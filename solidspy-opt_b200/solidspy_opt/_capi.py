@@ -28,7 +28,18 @@ SYMBOLS = [
     "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
     "topo_profile_matvec", "topo_profile_read", "topo_profile_report", "topo_set_stream", "topo_matvec_dev",
     "topo_diag_dev", "topo_vec_axpby_dev", "topo_vec_mul_dev", "topo_vec_dot_dev",
+    "topo_dist_init", "topo_dist_info", "topo_dist_xchg_ptrs", "topo_dist_xchg_finish", "topo_dist_gather_ptrs",
+    "topo_dist_scalar_ptr", "topo_dist_read_scalars", "topo_dist_setup", "topo_dist_solve_begin",
+    "topo_dist_pcg_matvec", "topo_dist_pcg_update", "topo_dist_vcycle_down", "topo_dist_vcycle_tail",
+    "topo_dist_vcycle_up", "topo_dist_pcg_smooth", "topo_dist_pcg_finish", "topo_dist_solve_poll",
+    "topo_dist_solve_end", "topo_dist_compliance_partial", "topo_dist_filter_pack", "topo_dist_oc",
+    "topo_dist_oc_state",
 ]
+
+# row-slab mode: exchange kinds, gather kinds, scalar blocks (include/topo_b200.h)
+X_AP, X_R0, X_Z, X_LEVEL_B, X_LEVEL_X2, X_DIAG, X_FILTER = range(7)
+G_CELLS, G_BK = range(2)
+S_PAP, S_RR_RZ, S_BB, S_RED = range(4)
 
 
 class TopoError(RuntimeError):
@@ -115,6 +126,29 @@ def load_library():
         "topo_vec_axpby_dev": [vp, C.c_longlong, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p],
         "topo_vec_mul_dev": [vp, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
         "topo_vec_dot_dev": [vp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+        "topo_dist_init": [vp, C.c_int, C.c_int, C.c_int],
+        "topo_dist_info": [vp, ip, ip, ip, ip],
+        "topo_dist_xchg_ptrs": [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                C.POINTER(C.c_longlong)],
+        "topo_dist_xchg_finish": [vp, C.c_int, C.c_int],
+        "topo_dist_gather_ptrs": [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_longlong)],
+        "topo_dist_scalar_ptr": [vp, C.c_int, C.POINTER(vp), ip],
+        "topo_dist_read_scalars": [vp, dp, C.c_int],
+        "topo_dist_setup": [vp, C.c_int],
+        "topo_dist_solve_begin": [vp, C.c_double, C.c_int, C.c_int],
+        "topo_dist_pcg_matvec": [vp, C.c_int],
+        "topo_dist_pcg_update": [vp, C.c_int, C.c_int],
+        "topo_dist_vcycle_down": [vp, C.c_int],
+        "topo_dist_vcycle_tail": [vp],
+        "topo_dist_vcycle_up": [vp, C.c_int],
+        "topo_dist_pcg_smooth": [vp, C.c_int, C.c_int],
+        "topo_dist_pcg_finish": [vp, C.c_int],
+        "topo_dist_solve_poll": [vp, ip, ip, dp],
+        "topo_dist_solve_end": [vp, C.c_int],
+        "topo_dist_compliance_partial": [vp],
+        "topo_dist_filter_pack": [vp, C.c_double, C.c_double],
+        "topo_dist_oc": [vp, C.c_int, C.c_double, C.c_double, C.c_longlong],
+        "topo_dist_oc_state": [vp, ip, ip, ip, dp, dp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -246,6 +280,10 @@ class Topo:
     def simp_scale(self, penal, emin, emax):
         _check(self.lib.topo_simp_scale(self.h, penal, emin, emax))
 
+    def simp_sensitivity_partial(self, penal, emin, emax):
+        """Sensitivity kernel only; the objective stays on the device (TOPO_S_RED[0])."""
+        _check(self.lib.topo_simp_sensitivity(self.h, penal, emin, emax, None))
+
     def simp_sensitivity(self, penal, emin, emax):
         obj = C.c_double(0)
         _check(self.lib.topo_simp_sensitivity(self.h, penal, emin, emax, C.byref(obj)))
@@ -324,6 +362,53 @@ class Topo:
 
     def set_gmg(self, omega=0.7, nu_pre=1, nu_post=1):
         _check(self.lib.topo_set_gmg(self.h, omega, nu_pre, nu_post))
+
+    # ---- row-slab mode (include/topo_b200.h, "row-slab SIMP iteration") ----
+    def dist_init(self, rank, world, K=0):
+        _check(self.lib.topo_dist_init(self.h, int(rank), int(world), int(K)))
+        r, w, k, n = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(self.lib.topo_dist_info(self.h, C.byref(r), C.byref(w), C.byref(k), C.byref(n)))
+        return k.value, n.value
+
+    def dist_xchg_ptrs(self, what, level=0):
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_longlong(0)
+        _check(self.lib.topo_dist_xchg_ptrs(self.h, what, level, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
+        return a.value, b.value, c.value, d.value, n.value
+
+    def dist_xchg_finish(self, what, level=0):
+        _check(self.lib.topo_dist_xchg_finish(self.h, what, level))
+
+    def dist_gather_ptrs(self, what):
+        a, b = C.c_void_p(), C.c_void_p()
+        n = C.c_longlong(0)
+        _check(self.lib.topo_dist_gather_ptrs(self.h, what, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def dist_scalar_ptr(self, what):
+        a, n = C.c_void_p(), C.c_int(0)
+        _check(self.lib.topo_dist_scalar_ptr(self.h, what, C.byref(a), C.byref(n)))
+        return a.value, n.value
+
+    def dist_read_scalars(self, n):
+        out = np.zeros(n)
+        _check(self.lib.topo_dist_read_scalars(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return out
+
+    def dist_call(self, name, *args):
+        """Thin passthrough for the segment calls (topo_dist_<name>)."""
+        _check(getattr(self.lib, "topo_dist_" + name)(self.h, *args))
+
+    def dist_solve_poll(self):
+        d, it, rel = C.c_int(0), C.c_int(0), C.c_double(0)
+        _check(self.lib.topo_dist_solve_poll(self.h, C.byref(d), C.byref(it), C.byref(rel)))
+        return d.value, it.value, rel.value
+
+    def dist_oc_state(self):
+        d, ne, st = C.c_int(0), C.c_int(0), C.c_int(0)
+        gt, ch = C.c_double(0), C.c_double(0)
+        _check(self.lib.topo_dist_oc_state(self.h, C.byref(d), C.byref(ne), C.byref(st), C.byref(gt), C.byref(ch)))
+        return d.value, ne.value, st.value, gt.value, ch.value
 
     def timer_start(self):
         _check(self.lib.topo_timer_start(self.h))

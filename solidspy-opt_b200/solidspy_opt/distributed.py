@@ -168,3 +168,306 @@ class SlabSolver:
             rz = rz_new
             it += 1
         return u, it, (rr/bb)**0.5 if bb > 0 else 0.0
+
+
+# ======================================================================================================================
+# The whole SIMP design iteration on row slabs (multigrid-preconditioned CG, sensitivity, filter, OC)
+# ======================================================================================================================
+class _DevMem:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class SlabSimp:
+    """SIMP on an ``nx x ny`` mesh split into ``world`` equal slabs of element rows.
+
+    Two deployments of the SAME host loop:
+
+    * ``dist`` = ``torch.distributed`` (NCCL): this process owns ONE slab on its GPU, ``world`` = number of processes;
+      interface rows travel with grouped send/recv, level-K blocks with all-gather, scalars with all-reduce, all on
+      ``self.stream`` -- and one pair of PCG iterations (kernels + collectives) is captured in a CUDA graph.
+    * ``dist`` = None: this process owns ALL ``world`` slabs on one GPU and moves the rows with device copies --
+      the single-GPU test double of the multi-GPU path (same kernels, same segments, same arithmetic).
+
+    The library (``libtopo_b200``) runs the segments; this class only moves bytes between them
+    (``include/topo_b200.h``, section "row-slab SIMP iteration").  There is no CPU fallback.
+    """
+
+    def __init__(self, nx, ny, ke, cons, loads, volfrac=0.5, penal=3.0, emin=1e-9, emax=1.0, rmin=None, dx=1.0, dy=1.0,
+                 move=0.2, rtol=1e-9, maxit=2000, world=None, dist=None, device=0, K=0, use_graph=True):
+        import torch
+        from solidspy_opt import _capi
+        self.torch, self._capi, self.dist = torch, _capi, dist
+        if dist is not None:
+            self.world, self.rank0, local = dist.get_world_size(), dist.get_rank(), 1
+        else:
+            self.world, self.rank0, local = int(world), 0, int(world)
+        if ny % self.world:
+            raise ValueError("ny = %d is not a multiple of the number of slabs %d" % (ny, self.world))
+        self.nx, self.ny, self.nyl = int(nx), int(ny), ny//self.world
+        self.ne_global = self.nx*self.ny
+        self.penal, self.emin, self.emax, self.move = float(penal), float(emin), float(emax), float(move)
+        self.rmin = float(rmin) if rmin is not None else None
+        self.dx, self.dy, self.rtol, self.maxit, self.volfrac = float(dx), float(dy), float(rtol), int(maxit), float(volfrac)
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.use_graph = bool(use_graph) and dist is not None
+        self._graph = None
+        self.graph_error = None
+        npr = self.nx + 1
+        cons = np.asarray(cons).reshape(self.ny + 1, npr, 2)
+        loads = np.asarray(loads, dtype=np.float64).reshape(-1, 3)
+        self.slabs, self.ranks = [], []
+        with torch.cuda.stream(self.stream):
+            for i in range(local):
+                g = self.rank0 + i
+                r0 = g*self.nyl
+                t = _capi.Topo(self.nx, self.nyl, ke, device=device)
+                t.set_stream(self.stream.cuda_stream)
+                t.set_cons(cons[r0:r0 + self.nyl + 1].reshape(-1, 2))
+                node = loads[:, 0].astype(np.int64)
+                row = node//npr
+                sel = (row >= r0) & (row <= r0 + self.nyl)            # interface loads exist on both slabs (accumulated f)
+                ll = loads[sel].copy()
+                ll[:, 0] = node[sel] - r0*npr
+                t.set_loads(ll.reshape(-1, 3))
+                self.K, self.n_levels = t.dist_init(g, self.world, K)
+                t.fill(_capi.F_RHO, self.volfrac)
+                self.slabs.append(t)
+                self.ranks.append(g)
+        self._views = {}
+        self.halo_bytes = 0
+        self.collectives = 0
+
+    # ---- device views ------------------------------------------------------------------------------------------------
+    def _view(self, ptr, n):
+        return self.torch.as_tensor(_DevMem(ptr, n), device=self.device)
+
+    def _xchg_views(self, i, what, level):
+        key = ("x", i, what, level)
+        v = self._views.get(key)
+        if v is None or what == self._capi.X_FILTER:
+            a, b, c, d, n = self.slabs[i].dist_xchg_ptrs(what, level)
+            v = tuple(self._view(p, max(n, 1))[:n] for p in (a, b, c, d))
+            self._views[key] = v
+        return v
+
+    def _gather_views(self, i, what):
+        key = ("g", i, what)
+        v = self._views.get(key)
+        if v is None:
+            a, b, n = self.slabs[i].dist_gather_ptrs(what)
+            v = (self._view(a, n), self._view(b, n*self.world))
+            self._views[key] = v
+        return v
+
+    def _scalar_view(self, i, what):
+        key = ("s", i, what)
+        v = self._views.get(key)
+        if v is None:
+            p, n = self.slabs[i].dist_scalar_ptr(what)
+            v = self._view(p, n)
+            self._views[key] = v
+        return v
+
+    # ---- movement ----------------------------------------------------------------------------------------------------
+    def exchange(self, what, level=0):
+        """Interface rows / blocks to both neighbours, then the library's finishing kernel."""
+        vs = [self._xchg_views(i, what, level) for i in range(len(self.slabs))]
+        if vs[0][0].numel() > 0:
+            for i in range(len(self.slabs) - 1):                       # neighbours inside this process
+                vs[i + 1][2].copy_(vs[i][1])                           # my last row -> upper neighbour's recv_lo
+                vs[i][3].copy_(vs[i + 1][0])                           # its first row -> my recv_hi
+            if self.dist is not None and self.world > 1:
+                dist, ops = self.dist, []
+                lo_rank, hi_rank = self.ranks[0] - 1, self.ranks[-1] + 1
+                if lo_rank >= 0:
+                    ops += [dist.P2POp(dist.isend, vs[0][0], lo_rank), dist.P2POp(dist.irecv, vs[0][2], lo_rank)]
+                if hi_rank < self.world:
+                    ops += [dist.P2POp(dist.isend, vs[-1][1], hi_rank), dist.P2POp(dist.irecv, vs[-1][3], hi_rank)]
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            self.halo_bytes += 8*vs[0][0].numel()*2
+            self.collectives += 1
+        for t in self.slabs:
+            t.dist_xchg_finish(what, level)
+
+    def gather(self, what):
+        vs = [self._gather_views(i, what) for i in range(len(self.slabs))]
+        if self.dist is not None:
+            self.dist.all_gather_into_tensor(vs[0][1], vs[0][0])
+        else:
+            n = vs[0][0].numel()
+            for send_i, (send, _) in enumerate(vs):
+                for _, recv in vs:
+                    recv[send_i*n:(send_i + 1)*n].copy_(send)
+        self.collectives += 1
+
+    def allreduce(self, what, n, op="sum"):
+        vs = [self._scalar_view(i, what)[:n] for i in range(len(self.slabs))]
+        if self.dist is not None:
+            self.dist.all_reduce(vs[0], op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
+        elif len(vs) > 1:
+            st = self.torch.stack(vs)
+            tot = st.sum(0) if op == "sum" else st.max(0).values
+            for v in vs:
+                v.copy_(tot)
+        self.collectives += 1
+
+    def _all(self, name, *args):
+        for t in self.slabs:
+            t.dist_call(name, *args)
+
+    # ---- stage 2: multigrid-preconditioned CG ----------------------------------------------------------------------------
+    def setup(self):
+        c = self._capi
+        self._all("setup", 0)
+        self.exchange(c.X_DIAG)
+        self.gather(c.G_CELLS)
+        self._all("setup", 1)
+
+    def _cycle(self, par, init):
+        """update + V-cycle + smoothing: everything of an iteration after the K p product."""
+        c, K = self._capi, self.K
+        self._all("pcg_update", par, init)
+        for l in range(1, K):
+            self.exchange(c.X_LEVEL_B, l)
+            self._all("vcycle_down", l)
+        self.gather(c.G_BK)
+        self._all("vcycle_tail")
+        for l in range(K - 1, 0, -1):
+            self._all("vcycle_up", l)
+            self.exchange(c.X_LEVEL_X2, l)
+        self._all("pcg_smooth", par, init)
+        self.exchange(c.X_Z)
+        self.allreduce(c.S_RR_RZ, 2)
+        self._all("pcg_finish", init)
+
+    def _iteration(self, par):
+        c = self._capi
+        self._all("pcg_matvec", par)
+        self.exchange(c.X_AP)
+        self.allreduce(c.S_PAP, 1)
+        self._cycle(par, 0)
+
+    def _pair(self):
+        if not self.use_graph:
+            self._iteration(1)
+            self._iteration(0)
+            return
+        torch = self.torch
+        if self._graph is None:
+            try:
+                g = torch.cuda.CUDAGraph()
+                self.stream.synchronize()
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="relaxed"):
+                    self._iteration(1)
+                    self._iteration(0)
+                self._graph = g
+            except Exception as exc:                                   # keep running eagerly, but say so
+                self.graph_error = repr(exc)
+                self.use_graph = False
+                self.stream.synchronize()
+                self._iteration(1)
+                self._iteration(0)
+                return
+        self._graph.replay()
+
+    def solve(self, warm=True):
+        c = self._capi
+        self._all("solve_begin", self.rtol, self.maxit, 1 if warm else 0)
+        self.exchange(c.X_R0)
+        self.allreduce(c.S_BB, 1)
+        self._cycle(0, 1)
+        launched = 0
+        while True:
+            done, iters, relres = self.slabs[0].dist_solve_poll()
+            if done or launched >= self.maxit:
+                break
+            for _ in range(2):
+                self._pair()
+            launched += 4
+        self._all("solve_end", iters)
+        if done != 1:
+            raise self._capi.TopoError(self._capi.ENOCONV, "row-slab PCG did not converge: %d iterations, relative "
+                                                           "residual %.3e" % (iters, relres))
+        return iters, relres
+
+    # ---- stage 4: OC bisection ---------------------------------------------------------------------------------------------
+    def oc_update(self, g):
+        c, ne, mv = self._capi, self.ne_global, self.move
+        self._all("oc", 0, mv, float(g), ne)
+        rounds = 0
+        while rounds < 700:
+            for _ in range(8):
+                self._all("oc", 1, mv, 0.0, ne)
+                self.allreduce(c.S_RED, 16)
+                self._all("oc", 2, mv, 0.0, ne)
+            rounds += 8
+            done, need, _, _, _ = self.slabs[0].dist_oc_state()
+            if need:                                                   # a sum inside the rounding margin: exact step
+                self._all("oc", 3, mv, 0.0, ne)
+                self.allreduce(c.S_RED, 1)
+                self._all("oc", 4, mv, 0.0, ne)
+                continue
+            if done:
+                break
+        self._all("oc", 5, mv, 0.0, ne)
+        self.allreduce(c.S_RED, 1)
+        self._all("oc", 6, mv, 0.0, ne)
+        self._all("oc", 7, mv, 0.0, ne)
+        self.allreduce(c.S_RED, 1, op="max")
+        self._all("oc", 8, mv, 0.0, ne)
+        _, _, steps, gt, change = self.slabs[0].dist_oc_state()
+        return gt, change, steps
+
+    # ---- one design iteration (reference optimize.py:428-456) ------------------------------------------------------------------
+    def step(self, g, warm=True):
+        """Returns (g_new, dict(compliance, objective, change, cg_iters, relres, oc_steps))."""
+        c, torch = self._capi, self.torch
+        with torch.cuda.stream(self.stream):
+            for t in self.slabs:
+                t.simp_scale(self.penal, self.emin, self.emax)
+            self.setup()
+            iters, relres = self.solve(warm)
+            for t in self.slabs:
+                t.simp_sensitivity_partial(self.penal, self.emin, self.emax)
+                t.dist_call("compliance_partial")
+            self.allreduce(c.S_RED, 2)
+            obj, comp = self.slabs[0].dist_read_scalars(2)
+            if self.rmin is not None:
+                for t in self.slabs:
+                    t.dist_call("filter_pack", self.rmin, self.dy)
+                self.exchange(c.X_FILTER)
+                for t in self.slabs:
+                    t.filter_sensitivity(self.rmin, self.dx, self.dy)
+            g, change, steps = self.oc_update(g)
+        return g, {"compliance": float(comp), "objective": float(obj), "change": change, "cg_iters": iters,
+                   "relres": relres, "oc_steps": steps}
+
+    # ---- state transfer ----------------------------------------------------------------------------------------------------
+    def set_rho(self, rho_global):
+        rho = np.asarray(rho_global, dtype=np.float64).reshape(self.ny, self.nx)
+        for t, g in zip(self.slabs, self.ranks):
+            t.set(self._capi.F_RHO, rho[g*self.nyl:(g + 1)*self.nyl].reshape(-1))
+
+    def local_rho(self):
+        return np.concatenate([t.get(self._capi.F_RHO).reshape(self.nyl, self.nx) for t in self.slabs])
+
+    def local_u(self):
+        """Displacements of this process' slabs, node rows stacked without the duplicated interface rows."""
+        out = []
+        for i, t in enumerate(self.slabs):
+            u = t.get(self._capi.F_U).reshape(self.nyl + 1, self.nx + 1, 2)
+            out.append(u if i == len(self.slabs) - 1 else u[:-1])
+        return np.concatenate(out)
+
+    def close(self):
+        self._graph = None
+        self._views = {}
+        for t in self.slabs:
+            t.close()
+        self.slabs = []

@@ -83,18 +83,56 @@ def _simp_loop(topo, nx, ny, dx, dy, r_min, niter, penal, precond, rtol, maxit, 
     return topo.get(_capi.F_RHO)
 
 
+def _simp_slab_loop(nx, ny, kloc, cons, loads, dx, dy, r_min, niter, penal, rtol, maxit, history, verbose, slabs,
+                    dist, device):
+    """Body of reference optimize.py:419-456 on a mesh split into row slabs (one GPU per slab with ``dist`` =
+    torch.distributed, or ``slabs`` slabs on one GPU).  Returns this process' part of rho (all of it when
+    ``dist`` is None)."""
+    from .distributed import SlabSimp
+    sim = SlabSimp(nx, ny, kloc, cons, loads, volfrac=0.5, penal=penal, emin=1e-9, emax=1.0, rmin=r_min, dx=dx, dy=dy,
+                   move=0.2, rtol=rtol, maxit=maxit, world=slabs, dist=dist, device=device)
+    try:
+        change, g = 10.0, 0.0
+        for _ in range(niter):
+            if change < 0.01:
+                if verbose:
+                    print('Convergence reached')
+                break
+            g, res = sim.step(g)
+            change = res["change"]
+            if history is not None:
+                for k in ("compliance", "objective", "change", "cg_iters", "relres", "oc_steps"):
+                    history.setdefault(k, []).append(res[k])
+                history.setdefault("g", []).append(g)
+                if history.get("keep_rho", False):
+                    history.setdefault("rho", []).append(sim.local_rho().reshape(-1))
+        return sim.local_rho().reshape(-1)
+    finally:
+        sim.close()
+
+
 def SIMP(length, height, nx, ny, dirs, positions, niter, penal, plot=False, *, n=1, r_min=None, r_factor=4,
-         precond="gmg", rtol=DEFAULT_RTOL_SIMP, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+         precond="gmg", rtol=DEFAULT_RTOL_SIMP, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True,
+         slabs=None, dist=None):
     """SIMP compliance minimisation of a rectangular beam (reference optimize.py:360-465).
 
     Returns ``rho`` (nx*ny,) float64.  Keyword-only extras: ``n`` support selector of ``beam``
     (reference hard-codes 1, :394), ``r_min``/``r_factor`` filter radius (reference: 4 element
     widths, :404), solver controls, ``history`` dict to collect per-iteration scalars.
+    ``dist`` = an initialised ``torch.distributed`` (NCCL, one process per GPU): the mesh is split into row slabs,
+    one per rank, and the return value is this rank's rows of rho; ``slabs`` = N runs the same slab algorithm with
+    N slabs on one GPU.
     """
     nodes, mats, els, loads, _ = beam(L=length, H=height, nx=nx, ny=ny, dirs=dirs, positions=positions, n=n)
     if r_min is None:
         r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*r_factor             # :404
     kloc = kloc_simp(mats[0, 0], mats[0, 1])                                        # :406-416
+    if slabs is not None or dist is not None:
+        rho = _simp_slab_loop(nx, ny, kloc, nodes[:, 3:5], loads, length/nx, height/ny, r_min, niter, penal, rtol, maxit,
+                              history, verbose, slabs, dist, device)
+        if plot and dist is None:
+            _plot_density(rho, nx, ny)
+        return rho
     with _capi.Topo(nx, ny, kloc, device=device) as topo:
         topo.set_cons(nodes[:, 3:5])
         topo.set_loads(loads)

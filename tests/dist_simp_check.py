@@ -1,0 +1,108 @@
+"""Multi-GPU check of the row-slab SIMP iteration (run under torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tests/dist_simp_check.py
+Every rank owns one slab (SlabSimp over NCCL); rank 0 also runs the whole mesh on a single-GPU handle and the
+per-iteration compliance / density / iteration counts are compared.  With DIST_BIG=NXxNY a large mesh is timed as
+well (graph-captured PCG, then eager).  Prints one JSON line on rank 0; exit code 0 = all checks passed."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "solidspy-opt_b200"))
+from solidspy_opt import _capi                                   # noqa: E402
+from solidspy_opt.Utils.beams import beam                         # noqa: E402
+from solidspy_opt.distributed import SlabSimp                     # noqa: E402
+from solidspy_opt.optimize import kloc_simp                       # noqa: E402
+
+
+def model(nx, ny):
+    nodes, mats, els, loads, _ = beam(L=float(nx), H=float(ny), nx=nx, ny=ny, dirs=np.array([[0, -1]]),
+                                      positions=np.array([[ny//2 + 1, 1]]), n=1)
+    return nodes[:, 3:5].astype(np.int8), loads, kloc_simp(mats[0, 0], mats[0, 1])
+
+
+def gather_rho(sim, world):
+    mine = torch.as_tensor(sim.local_rho()).cuda()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return torch.cat(parts).cpu().numpy().reshape(-1)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = {"world": world, "ok": True}
+    # ---- correctness against the single-GPU path -----------------------------------------------------------------
+    nx, ny = 384, 64*world
+    cons, loads, ke = model(nx, ny)
+    steps = 4
+    for use_graph in (True, False):
+        sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph)
+        g, hist = 0.0, []
+        for _ in range(steps):
+            g, res = sim.step(g)
+            hist.append((res["compliance"], res["cg_iters"], res["oc_steps"], g))
+        rho = gather_rho(sim, world)
+        key = "graph" if use_graph else "eager"
+        out[key + "_used"] = bool(sim.use_graph)
+        out[key + "_error"] = sim.graph_error
+        out["K"] = sim.K
+        sim.close()
+        if rank == 0:
+            with _capi.Topo(nx, ny, ke, device=local) as full:
+                full.set_cons(cons)
+                full.set_loads(loads)
+                full.fill(_capi.F_RHO, 0.5)
+                params = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=2.5, dx=1.0, dy=1.0, move=0.2, rtol=1e-10,
+                                          precond=_capi.PRECOND_GMG, maxit=2000, warm=1)
+                g1, worst_c, its = 0.0, 0.0, []
+                for k in range(steps):
+                    g1, r = full.simp_step(params, g1)
+                    worst_c = max(worst_c, abs(hist[k][0] - r.compliance)/abs(r.compliance))
+                    its.append((r.cg_iters, hist[k][1]))
+                    if hist[k][2] != r.oc_steps:
+                        out["ok"] = False
+                drho = float(np.abs(rho - full.get(_capi.F_RHO)).max())
+            out[key] = {"compliance_rel": worst_c, "drho_max": drho, "cg_iters_single_vs_slabs": its}
+            if worst_c > 1e-8 or drho > 1e-7:
+                out["ok"] = False
+    # ---- timing on a large mesh ------------------------------------------------------------------------------------
+    big = os.environ.get("DIST_BIG", "")
+    if big:
+        nx, ny = (int(v) for v in big.lower().split("x"))
+        cons, loads, ke = model(nx, ny)
+        for use_graph in (True, False):
+            sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph)
+            g = 0.0
+            for _ in range(3):
+                g, res = sim.step(g)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n, its = 5, []
+            for _ in range(n):
+                g, res = sim.step(g)
+                its.append(res["cg_iters"])
+            torch.cuda.synchronize()
+            dist.barrier()
+            dt = (time.perf_counter() - t0)/n
+            key = "big_graph" if use_graph else "big_eager"
+            out[key] = {"mesh": "%dx%d" % (nx, ny), "ms_per_step": dt*1e3, "it_per_s": 1.0/dt, "cg_iters": its,
+                        "graph_used": bool(sim.use_graph), "graph_error": sim.graph_error, "K": sim.K}
+            sim.close()
+    if rank == 0:
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if out["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -421,6 +421,20 @@ def test_slab_matvec_and_pcg_on_two_gpus(capi):
     assert json.loads(line)["ok"]
 
 
+def test_slab_simp_on_two_gpus(capi):
+    """The full row-slab design iteration over NCCL against the single-GPU path (needs >= 2 GPUs on the box)."""
+    import subprocess, sys, os, json
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(root, "tests", "dist_simp_check.py")],
+                       capture_output=True, text=True, env=dict(os.environ, DIST_BIG=""), timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]
+
+
 def test_handle_lifecycle_and_errors(capi):
     """Repeated create/destroy does not leak device memory; bad arguments return error codes, not crashes."""
     import ctypes as C
@@ -456,3 +470,96 @@ def test_handle_lifecycle_and_errors(capi):
         t.set_loads(np.array([[65*8 + 64, 0.0, -1.0]]))
         it, rel, code = t.solve(capi.PRECOND_JACOBI, 1e-12, 5, warm=False, raise_on_noconv=False)
         assert code == capi.ENOCONV and it == 5 and rel > 1e-12
+
+
+# ---- row-slab decomposition: several slabs on ONE GPU exercise every kernel / segment of the multi-GPU path ----
+def _slab_case(nx, ny, world, K, rho=None, seed=3):
+    """(SlabSimp, single-GPU Topo) on the same cantilever with the same (random) density."""
+    from solidspy_opt import _capi
+    from solidspy_opt.Utils.beams import beam
+    from solidspy_opt.distributed import SlabSimp
+    from solidspy_opt.optimize import kloc_simp
+    nodes, mats, els, loads, _ = beam(L=float(nx), H=float(ny), nx=nx, ny=ny, dirs=np.array([[0, -1]]),
+                                      positions=np.array([[ny//2 + 1, 1]]), n=1)     # mid-height of the free end
+    ke = kloc_simp(mats[0, 0], mats[0, 1])
+    if rho is None:
+        rho = np.random.default_rng(seed).uniform(0.05, 1.0, nx*ny)
+    sim = SlabSimp(nx, ny, ke, nodes[:, 3:5], loads, rmin=2.5, world=world, K=K, rtol=1e-10)
+    sim.set_rho(rho)
+    topo = _capi.Topo(nx, ny, ke)
+    topo.set_cons(nodes[:, 3:5])
+    topo.set_loads(loads)
+    topo.set(_capi.F_RHO, rho)
+    return sim, topo
+
+
+@pytest.mark.parametrize("nx,ny,world,tail_max", [(128, 64, 2, 10000), (96, 64, 4, 500), (256, 128, 4, 600),
+                                                  (130, 96, 3, 10000), (512, 256, 8, 300)])
+def test_slab_solve_equals_single_gpu(capi, monkeypatch, nx, ny, world, tail_max):
+    """Same preconditioner, same Krylov iteration: the slab solve reproduces topo_solve on the whole mesh.
+    ``tail_max`` (nodes of the first tail level) moves the first global level K: 1, 2, 3, 1, 4."""
+    import torch
+    from solidspy_opt import _capi
+    monkeypatch.setenv("TOPO_TAIL_MAX", str(tail_max))
+    sim, topo = _slab_case(nx, ny, world, 0)
+    try:
+        topo.simp_scale(3.0, 1e-9, 1.0)
+        it1, rel1, _ = topo.solve(_capi.PRECOND_GMG, 1e-10, 2000, warm=False)
+        u1 = topo.get(_capi.F_U).reshape(ny + 1, nx + 1, 2)
+        with torch.cuda.stream(sim.stream):
+            for t in sim.slabs:
+                t.simp_scale(3.0, 1e-9, 1.0)
+            sim.setup()
+            it2, rel2 = sim.solve(warm=False)
+        u2 = sim.local_u()
+        assert rel2 <= 1e-10
+        assert abs(it1 - it2) <= 1, (it1, it2)
+        assert np.abs(u1 - u2).max() <= 1e-7*np.abs(u1).max()
+        # interface rows are bit-identical on both neighbours (accumulated form)
+        for a, b in zip(sim.slabs[:-1], sim.slabs[1:]):
+            ua = a.get(_capi.F_U).reshape(sim.nyl + 1, nx + 1, 2)[-1]
+            ub = b.get(_capi.F_U).reshape(sim.nyl + 1, nx + 1, 2)[0]
+            assert np.array_equal(ua, ub)
+    finally:
+        sim.close()
+        topo.close()
+
+
+@pytest.mark.parametrize("world,K", [(2, 0), (4, 2)])
+def test_slab_design_iterations_equal_single_gpu(capi, world, K):
+    """Five full design iterations (solve, sensitivity, filter with ghost rows, OC with all-reduced sums)."""
+    from solidspy_opt import _capi
+    nx, ny = 96, 64
+    sim, topo = _slab_case(nx, ny, world, K, rho=np.full(nx*ny, 0.5))
+    try:
+        params = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=2.5, dx=1.0, dy=1.0, move=0.2, rtol=1e-10,
+                                  precond=_capi.PRECOND_GMG, maxit=2000, warm=1)
+        g1 = g2 = 0.0
+        for k in range(5):
+            g1, res = topo.simp_step(params, g1)
+            g2, r2 = sim.step(g2)
+            assert r2["compliance"] == pytest.approx(res.compliance, rel=1e-8)
+            assert r2["objective"] == pytest.approx(res.objective, rel=1e-8)
+            assert r2["oc_steps"] == res.oc_steps
+            assert g2 == pytest.approx(g1, abs=1e-6)
+            assert np.abs(sim.local_rho().reshape(-1) - topo.get(_capi.F_RHO)).max() <= 1e-8, "iteration %d" % k
+    finally:
+        sim.close()
+        topo.close()
+
+
+@pytest.mark.parametrize("case,slabs", [("c1", 2), ("c2", 2)])
+def test_slab_simp_trajectory_matches_reference(capi, case, slabs):
+    """The reference goldens through the slab path (what runs one slab per GPU under torch.distributed)."""
+    from solidspy_opt.optimize import SIMP
+    g = golden("simp_" + case)
+    hist = {"keep_rho": True}
+    rho = SIMP(float(g["length"]), float(g["height"]), int(g["nx"]), int(g["ny"]), g["dirs"], g["positions"],
+               int(g["niter"]), int(g["penal"]), history=hist, verbose=False, slabs=slabs)
+    n = len(g["compliance"])
+    assert len(hist["compliance"]) == n
+    assert np.allclose(hist["compliance"], g["compliance"], rtol=1e-6, atol=0)
+    for k in range(n):
+        assert np.abs(hist["rho"][k] - g["rho"][k]).max() <= 1e-6, "iteration %d" % k
+    assert np.abs(rho - g["rho_final"]).max() <= 1e-6
+    assert np.allclose(hist["g"], g["g"], rtol=0, atol=1e-5)
