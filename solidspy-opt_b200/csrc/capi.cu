@@ -136,6 +136,29 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->nn = (int64_t)(nx + 1) * (ny + 1);
   h->ne = (int64_t)nx * ny;
   std::memcpy(h->ke.k, ke, sizeof(double) * 64);
+  {
+    // ke = sum_k l_k l_k^T by diagonally pivoted outer-product Cholesky (ke is PSD of rank 5: three rigid-body
+    // modes).  The sensitivity kernel evaluates u^T ke u as sum_k (l_k . u)^2: never negative, and the rigid
+    // part of u cancels inside each 8-term dot product instead of between 64 large terms.
+    double A[64];
+    std::memcpy(A, ke, sizeof(A));
+    std::memset(h->ke_factor.k, 0, sizeof(h->ke_factor.k));
+    double dmax = 0.0;
+    for (int i = 0; i < 8; ++i) dmax = fmax(dmax, A[i * 8 + i]);
+    bool used[8] = {false, false, false, false, false, false, false, false};
+    for (int k = 0; k < 8; ++k) {
+      int p = -1;
+      for (int i = 0; i < 8; ++i)
+        if (!used[i] && (p < 0 || A[i * 8 + i] > A[p * 8 + p])) p = i;
+      if (p < 0 || !(A[p * 8 + p] > 1e-10 * dmax)) break;
+      used[p] = true;
+      const double inv = 1.0 / std::sqrt(A[p * 8 + p]);
+      double *l = h->ke_factor.k + 8 * k;
+      for (int i = 0; i < 8; ++i) l[i] = A[i * 8 + p] * inv;
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) A[i * 8 + j] -= l[i] * l[j];
+    }
+  }
   h->omega = 0.7;
   h->nu_pre = 1;
   h->nu_post = 1;

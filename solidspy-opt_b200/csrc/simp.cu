@@ -29,8 +29,13 @@ __global__ void k_simp_scale(const double *__restrict__ rho, double *__restrict_
     scale[e] = emin + pow(rho[e], penal) * (emax - emin);
 }
 
-// s_e = u_e^T ke u_e ; dc_e = (-penal rho^(penal-1) (emax-emin)) s_e ; objective += scale_e s_e
-__global__ void __launch_bounds__(ET) k_simp_sens(const __grid_constant__ KeParam ke, const double2 *__restrict__ u,
+// s_e = u_e^T ke u_e ; dc_e = (-penal rho^(penal-1) (emax-emin)) s_e ; objective += scale_e s_e   (optimize.py:443-444)
+// Evaluated as sum_k (l_k . d)^2 with ke = sum_k l_k l_k^T and d = u_e minus the displacement of local node 0
+// (ke annihilates translations): the reference's u^T ke u loses all digits where u_e is almost a rigid motion
+// (free end of a long cantilever: |u|^2 |ke| eps exceeds the true energy on fine meshes) and then turns
+// NEGATIVE at random, which np.sqrt(-dc/lmid) converts into NaN densities (solver.py:441).  Same value to
+// rounding where the reference is accurate; non-negative everywhere.
+__global__ void __launch_bounds__(ET) k_simp_sens(const __grid_constant__ KeParam lf, const double2 *__restrict__ u,
                                                   const double *__restrict__ rho, const double *__restrict__ scale,
                                                   double *__restrict__ dc, int nx, int ny, double penal, double emin,
                                                   double emax, double *partials, unsigned int *ticket, double *out) {
@@ -41,14 +46,14 @@ __global__ void __launch_bounds__(ET) k_simp_sens(const __grid_constant__ KePara
     const int r = (int)(e / nx), c = (int)(e - (int64_t)r * nx);
     const double2 *p = u + (size_t)r * npr + c;
     const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + npr + 1), q3 = __ldg(p + npr);
-    const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+    const double d[6] = {q1.x - q0.x, q1.y - q0.y, q2.x - q0.x, q2.y - q0.y, q3.x - q0.x, q3.y - q0.y};
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {      // (u^T ke)[j] * u[j], summed over j (same contraction order as :443)
+    for (int k = 0; k < 8; ++k) {
       double t = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t = fma(w[i], ke.k[i * 8 + j], t);
-      s = fma(t, w[j], s);
+      for (int i = 0; i < 6; ++i) t = fma(lf.k[8 * k + 2 + i], d[i], t);
+      s = fma(t, t, s);
     }
     const double rh = rho[e];
     dc[e] = (-penal * powp(rh, penal - 1.0) * (emax - emin)) * s;
@@ -322,7 +327,7 @@ extern "C" int topo_simp_scale(topo_t *h, double penal, double emin, double emax
 extern "C" int topo_simp_sensitivity(topo_t *h, double penal, double emin, double emax, double *objective) {
   if (!h) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
-  KL(h, "k_simp_sens", k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
+  KL(h, "k_simp_sens", k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke_factor, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
                                                       emax, h->partials, h->ticket, h->red_out));
   CUDA_TRY(cudaGetLastError());
   if (objective) {

@@ -103,6 +103,7 @@ struct topo_handle {
   int nx, ny;
   int64_t nn, ne;
   KeParam ke;
+  KeParam ke_factor;    // rows l_k of a pivoted Cholesky factor: ke = sum_k l_k l_k^T (zero rows beyond the rank)
   cudaStream_t stream;
   bool owns_stream;
 

@@ -391,6 +391,8 @@ class SlabSimp:
                 self._pair()
             launched += 4
         self._all("solve_end", iters)
+        if relres != relres:
+            raise self._capi.TopoError(self._capi.ENOCONV, "row-slab PCG produced NaN (singular system?)")
         if done != 1:
             raise self._capi.TopoError(self._capi.ENOCONV, "row-slab PCG did not converge: %d iterations, relative "
                                                            "residual %.3e" % (iters, relres))

@@ -15,15 +15,17 @@ import torch.distributed as dist
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, os.path.join(ROOT, "solidspy-opt_b200"))
 from solidspy_opt import _capi                                   # noqa: E402
-from solidspy_opt.Utils.beams import beam                         # noqa: E402
 from solidspy_opt.distributed import SlabSimp                     # noqa: E402
 from solidspy_opt.optimize import kloc_simp                       # noqa: E402
 
 
 def model(nx, ny):
-    nodes, mats, els, loads, _ = beam(L=float(nx), H=float(ny), nx=nx, ny=ny, dirs=np.array([[0, -1]]),
-                                      positions=np.array([[ny//2 + 1, 1]]), n=1)
-    return nodes[:, 3:5].astype(np.int8), loads, kloc_simp(mats[0, 0], mats[0, 1])
+    """Cantilever of beam(n=1) without building the element table: column 0 clamped, unit load at mid-height of the
+    free end."""
+    cons = np.zeros((ny + 1, nx + 1, 2), dtype=np.int8)
+    cons[:, 0, :] = -1
+    loads = np.array([[(nx + 1)*(ny//2) + nx, 0.0, -1.0]])
+    return cons.reshape(-1, 2), loads, kloc_simp(206.8e9, 0.28)
 
 
 def gather_rho(sim, world):
