@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-9)
     ap.add_argument("--precond", default="gmg", choices=["gmg", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab-simp", action="store_true", help="skip the 8192x4096 row-slab design-iteration measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -254,6 +255,67 @@ def main():
                 "halo_bytes_per_rank_per_matvec": S.halo_bytes_per_exchange, "scaling": "strong",
                 "note": "row slabs, one interface node row exchanged each way per product (NCCL P2P), host-driven"}
 
+    def slab_simp(n_warm=3, n_timed=5):
+        """The WHOLE design iteration on the 8192x4096 mesh (BASELINE configs[4]) split into row slabs, one per rank:
+        multigrid-PCG, sensitivity, filter and OC with NCCL halo sums / gathers / all-reduces between the library's
+        segments (solidspy_opt.distributed.SlabSimp).  Strong scaling: rank 0 also times the same steps on ONE GPU
+        with the ordinary single-handle path.  Device time (CUDA events), max over ranks."""
+        from solidspy_opt.distributed import SlabSimp
+        bx, by = 8192, 4096
+        ke = kloc_simp(206.8e9, 0.28)
+        cons_b = np.zeros((by + 1, bx + 1, 2), dtype=np.int8)
+        cons_b[:, 0, :] = -1
+        loads_b = np.array([[(bx + 1)*(by//4) - 1, 0.0, -1.0]])
+        out = {"mesh": [bx, by], "n_gpus": world, "scaling": "strong", "steps": n_timed, "warmup": n_warm}
+        single_ms = None
+        if rank == 0:
+            with _capi.Topo(bx, by, ke, device=local_rank) as big:
+                big.set_cons(cons_b.reshape(-1, 2))
+                big.set_loads(loads_b)
+                big.fill(_capi.F_RHO, 0.5)
+                pb = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=4.0, dx=1.0, dy=1.0, move=0.2, rtol=args.rtol,
+                                      precond=_capi.PRECOND_GMG, maxit=100000, warm=1)
+                g, its1 = 0.0, []
+                for i in range(n_warm + n_timed):
+                    if i == n_warm:
+                        big.timer_start()
+                    g, r = big.simp_step(pb, g)
+                    if i >= n_warm:
+                        its1.append(r.cg_iters)
+                single_ms = big.timer_stop()/n_timed
+                out["single_gpu"] = {"ms_per_step": single_ms, "it_per_s": 1e3/single_ms, "cg_iters": its1,
+                                     "compliance_last": r.compliance}
+        if world > 1:
+            sim = SlabSimp(bx, by, ke, cons_b, loads_b, rmin=4.0, dist=dist, device=local_rank, rtol=args.rtol,
+                           maxit=100000, use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0")
+            g, its, stage = 0.0, [], {}
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(n_warm + n_timed):
+                if i == n_warm:
+                    barrier()
+                    c0 = sim.collectives
+                    with torch.cuda.stream(sim.stream):
+                        ev0.record()
+                g, r = sim.step(g)
+                if i >= n_warm:
+                    its.append(r["cg_iters"])
+                    for k, v in r["stage_ms"].items():
+                        stage[k] = stage.get(k, 0.0) + v/n_timed
+            with torch.cuda.stream(sim.stream):
+                ev1.record()
+            barrier()
+            ms = allmax(ev0.elapsed_time(ev1)/n_timed)
+            out.update(ms_per_step=ms, it_per_s=1e3/ms, cg_iters=its, stage_ms=stage, first_global_level=sim.K,
+                       cuda_graph=bool(sim.use_graph), graph_error=sim.graph_error, compliance_last=r["compliance"],
+                       host_collective_calls_per_step=(sim.collectives - c0)/n_timed,
+                       note="one slab of %d element rows per GPU; accumulated vectors, halo sums of interface node rows, "
+                            "level-%d operator gathered and solved redundantly; NCCL via torch.distributed, one pair "
+                            "of PCG iterations (kernels + collectives) per CUDA graph" % (by//world, sim.K))
+            if single_ms is not None:
+                out["speedup_vs_single_gpu"] = single_ms/ms
+            sim.close()
+        return out
+
     def allmax(x):
         if world == 1:
             return x
@@ -263,6 +325,7 @@ def main():
 
     ms_dev_max, ms_e2e_max = allmax(ms_dev), allmax(ms_e2e)
     slab = slab_matvec()
+    slab_full = slab_simp() if not args.no_slab_simp else None
     if rank == 0:
         peak, peak_src = measured_peak()
         # ALGORITHMIC bytes per launch of each variant of the stage-1 kernel (fp64):
@@ -294,6 +357,7 @@ def main():
                     "d2h_bytes_per_step": 8*ne, "ms_per_step": ms_e2e_max/args.steps},
             "gpu_launches": int(launches),
             "slab_matvec": slab,
+            "slab_simp": slab_full,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"] if dom else None,
                          "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",

@@ -237,7 +237,7 @@ int topo_dist_compliance_partial(topo_t *h);
 int topo_dist_filter_pack(topo_t *h, double rmin, double dy);
 /* OC bisection pieces (op table in csrc/simp.cu); between them the host all-reduces TOPO_S_RED */
 int topo_dist_oc(topo_t *h, int op, double move, double value, long long ne_global);
-int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change);
+int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change, double *lmid);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* CUDA-event time (ms) of the most recent call of each stage on this handle. */

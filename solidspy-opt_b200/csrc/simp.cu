@@ -139,7 +139,33 @@ __global__ void k_oc_init(OcState *oc, double g) {
   oc->steps = 0;
   oc->change = 0.0;
   oc->need_exact = 0;
+  oc->ka = -1.0;
+  oc->kb = 1e300;
   oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
+}
+
+// Bisection steps whose outcome is already known from the measured bracket (ka, kb): the reference's loop
+// (solver.py:441-447) is replayed with its own arithmetic, only the evaluation of gt is skipped.
+__device__ __forceinline__ void oc_fastforward(OcState *oc) {
+  if (oc->done || oc->need_exact) return;
+  double l1 = oc->l1, l2 = oc->l2, lmid_last = oc->lmid;
+  const double ka = oc->ka, kb = oc->kb;
+  int steps = 0;
+  bool done = false;
+  for (int it = 0; it < 4096; ++it) {
+    if (!((l2 - l1) / (l1 + l2) > 1e-3)) { done = true; break; }
+    const double lmid = 0.5 * (l2 + l1);
+    if (lmid >= kb) l2 = lmid;            // gt(lmid) <= gt(kb) < 0
+    else if (lmid <= ka) l1 = lmid;       // gt(lmid) >= gt(ka) > 0
+    else break;
+    lmid_last = lmid;
+    ++steps;
+  }
+  oc->l1 = l1;
+  oc->l2 = l2;
+  oc->lmid = lmid_last;
+  oc->steps += steps;
+  oc->done = done ? 1 : 0;
 }
 
 // A_e = rho sqrt(-dc): rho*sqrt(-dc/lmid) == A_e / sqrt(lmid) up to a few ulp
@@ -160,6 +186,7 @@ __device__ __forceinline__ void oc_decide_step(OcState *oc, double sum) {
   oc->steps += 1;
   oc->need_exact = 0;
   oc->done = ((oc->l2 - oc->l1) / (oc->l1 + oc->l2) > 1e-3) ? 0 : 1;
+  oc_fastforward(oc);
 }
 // defer != 0 (row-slab mode): leave the per-rank sum in out[]; the decision is taken by k_oc_decide after the
 // host's all-reduce
@@ -211,14 +238,31 @@ __device__ __forceinline__ void oc_decide_multi(OcState *oc, const double *v, do
   oc->steps += steps;
   oc->need_exact = need ? 1 : 0;
   oc->done = done ? 1 : 0;
+  oc_fastforward(oc);
+}
+// probe pass: sums at the 15 multipliers base*2^(j-7) only tighten the bracket (no bisection step is taken)
+__device__ __forceinline__ void oc_decide_probe(OcState *oc, const double *v, double margin, double base) {
+  double ka = oc->ka, kb = oc->kb;
+  for (int j = 0; j < OC_CAND; ++j) {
+    const double lam = ldexp(base, j - 7);
+    const double gt = oc->g + v[j] + v[OC_CAND];
+    if (gt > margin) ka = fmax(ka, lam);
+    else if (gt < -margin) kb = fmin(kb, lam);
+  }
+  oc->ka = ka;
+  oc->kb = kb;
+  oc_fastforward(oc);
 }
 __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho, const double *__restrict__ amp,
                                                  int64_t ne, double move, double margin, double *partials,
-                                                 unsigned int *ticket, double *out, OcState *oc, int defer) {
+                                                 unsigned int *ticket, double *out, OcState *oc, int defer,
+                                                 double probe_base) {
   if (oc->done || oc->need_exact) return;
   // candidate multipliers in heap order; each of the first 15 threads does ONE 1/sqrt and shares it
   __shared__ double s_tinv[OC_CAND];
-  if (threadIdx.x < OC_CAND) {
+  if (probe_base > 0.0) {
+    if (threadIdx.x < OC_CAND) s_tinv[threadIdx.x] = 1.0 / sqrt(ldexp(probe_base, (int)threadIdx.x - 7));
+  } else if (threadIdx.x < OC_CAND) {
     double lo[OC_CAND], hi[OC_CAND], lmj = 0.0;
     lo[0] = oc->l1;
     hi[0] = oc->l2;
@@ -259,7 +303,10 @@ __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho,
       for (int j = 0; j < OC_CAND; ++j) v[j] += fmax(cl, fmin(ch, am * tinv[j])) - rh;
     }
   }
-  if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc_decide_multi(oc, v, margin);
+  if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) {
+    if (probe_base > 0.0) oc_decide_probe(oc, v, margin, probe_base);
+    else oc_decide_multi(oc, v, margin);
+  }
 }
 
 // exact gt at the last evaluated multiplier (what the reference returns as the new constraint value)
@@ -296,12 +343,13 @@ __global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho,
 }
 
 // row-slab mode: decisions from the all-reduced sums in red[]
-__global__ void k_oc_decide(OcState *oc, const double *red, double margin, int kind) {
-  if (kind == 0) {                     // fast pass (16 sums)
+__global__ void k_oc_decide(OcState *oc, const double *red, double margin, int kind, double probe_base) {
+  if (kind == 0 || kind == 4) {        // fast pass / probe pass (16 sums)
     if (oc->done || oc->need_exact) return;
     double v[OC_CAND + 1];
     for (int j = 0; j <= OC_CAND; ++j) v[j] = red[j];
-    oc_decide_multi(oc, v, margin);
+    if (kind == 4) oc_decide_probe(oc, v, margin, probe_base);
+    else oc_decide_multi(oc, v, margin);
   } else if (kind == 1) {              // exact step
     if (oc->done || !oc->need_exact) return;
     oc_decide_step(oc, red[0]);
@@ -417,11 +465,18 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   OcState *hs = h->oc_host;
   hs->done = 0;
   int rounds = 0;
-  const int batch = 12, hard_cap = 700;    // the bracket [0,1e9] underflows after ~1100 halvings = 275 rounds
+  const int hard_cap = 700;                // the bracket [0,1e9] underflows after ~1100 halvings = 275 rounds
+  // with a multiplier from the previous design iteration the probe pass brackets the root within a factor 2 and
+  // ~3 fast passes finish the bisection (instead of ~23): poll after 4 rounds, else after 12
+  const bool probe = h->oc_lam_prev > 0.0 && !getenv("TOPO_OC_NO_PROBE");
+  if (probe)
+    KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+                                                                      h->red_out, h->oc, 0, h->oc_lam_prev));
   while (rounds < hard_cap) {
+    const int batch = probe ? 4 : 12;
     for (int i = 0; i < batch; ++i) {
       KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
-                                                        h->red_out, h->oc, 0));
+                                                        h->red_out, h->oc, 0, 0.0));
       KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket,
                                                       h->red_out, h->oc, 0));
     }
@@ -440,6 +495,7 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaEventElapsedTime(&h->timing.oc_ms, h->ev0, h->ev1));
   std::swap(h->rho, h->rho_new);          // rho_new now holds the previous design
+  h->oc_lam_prev = (hs->steps > 0 && hs->lmid > 0.0 && hs->lmid < 1e300) ? hs->lmid : 0.0;
   *g = hs->gt;
   if (change) *change = hs->change;
   if (nsteps) *nsteps = hs->steps;
@@ -458,6 +514,8 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
 //   op 6  decide final gt
 //   op 7  apply (rho_new, change partial)         -> all-reduce MAX 1, then op 8
 //   op 8  set change, swap rho <-> rho_new
+//   op 9  probe pass around value = the previous multiplier -> all-reduce SUM 16, then op 10
+//   op 10 tighten the bracket from the probe sums (value as in op 9)
 // ne_global sizes the rounding margin of the fast pass like the single-GPU path.
 extern "C" int topo_dist_oc(topo_t *h, int op, double move, double value, long long ne_global) {
   if (!h || !h->dist.on) return TOPO_EINVAL;
@@ -473,24 +531,29 @@ extern "C" int topo_dist_oc(topo_t *h, int op, double move, double value, long l
       break;
     case 1:
       KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
-                                                                        h->red_out, h->oc, 1));
+                                                                        h->red_out, h->oc, 1, 0.0));
       break;
-    case 2: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 0)); break;
+    case 2: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 0, 0.0)); break;
+    case 9:                                   // probe pass around `value` (the previous multiplier) -> all-reduce 16, op 10
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, 148 * 2), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+                                                                        h->red_out, h->oc, 1, value));
+      break;
+    case 10: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 4, value)); break;
     case 3:
       KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket, h->red_out, h->oc, 1));
       break;
-    case 4: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 1)); break;
+    case 4: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 1, 0.0)); break;
     case 5:
       CUDA_TRY(cudaMemsetAsync(h->red_out, 0, sizeof(double), st));      // zero steps: the kernel returns early
       KL(h, "k_oc_final_gt", k_oc_final_gt<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket, h->red_out, h->oc, 1));
       break;
-    case 6: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 2)); break;
+    case 6: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 2, 0.0)); break;
     case 7:
       KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket, h->red_out,
                                                         h->oc, 1));
       break;
     case 8:
-      KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 3));
+      KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 3, 0.0));
       std::swap(h->rho, h->rho_new);
       break;
     default:
@@ -500,7 +563,8 @@ extern "C" int topo_dist_oc(topo_t *h, int op, double move, double value, long l
   return TOPO_OK;
 }
 
-extern "C" int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change) {
+extern "C" int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change,
+                                  double *lmid) {
   if (!h || !h->dist.on) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
   OcState *hs = h->oc_host;
@@ -511,5 +575,6 @@ extern "C" int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *st
   if (steps) *steps = hs->steps;
   if (gt) *gt = hs->gt;
   if (change) *change = hs->change;
+  if (lmid) *lmid = hs->lmid;
   return TOPO_OK;
 }

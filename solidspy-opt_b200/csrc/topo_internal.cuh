@@ -57,6 +57,9 @@ struct OcState {
   int steps, done;
   int need_exact;   // the next bisection decision must come from the exact (reference-formula) pass
   int pad;
+  // gt(lambda) is non-increasing in lambda: gt(ka) > margin and gt(kb) < -margin were MEASURED (probe pass around
+  // the previous design iteration's multiplier), so every bisection midpoint <= ka or >= kb has a known decision
+  double ka, kb;
 };
 
 // Coarse-level stencil coefficients are stored in fp32: they only shape the PRECONDITIONER (the outer PCG
@@ -129,6 +132,7 @@ struct topo_handle {
   SolverScalars *sc_host;  // pinned
   OcState *oc;             // device
   OcState *oc_host;        // pinned
+  double oc_lam_prev;      // last multiplier of the previous OC update (0: none) -- centre of the probe pass
   double *kmax;            // device scalar: max diagonal of K over free DOFs
   unsigned long long *sel; // radix-select scratch
 

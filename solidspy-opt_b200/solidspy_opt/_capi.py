@@ -148,7 +148,7 @@ def load_library():
         "topo_dist_compliance_partial": [vp],
         "topo_dist_filter_pack": [vp, C.c_double, C.c_double],
         "topo_dist_oc": [vp, C.c_int, C.c_double, C.c_double, C.c_longlong],
-        "topo_dist_oc_state": [vp, ip, ip, ip, dp, dp],
+        "topo_dist_oc_state": [vp, ip, ip, ip, dp, dp, dp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -406,9 +406,10 @@ class Topo:
 
     def dist_oc_state(self):
         d, ne, st = C.c_int(0), C.c_int(0), C.c_int(0)
-        gt, ch = C.c_double(0), C.c_double(0)
-        _check(self.lib.topo_dist_oc_state(self.h, C.byref(d), C.byref(ne), C.byref(st), C.byref(gt), C.byref(ch)))
-        return d.value, ne.value, st.value, gt.value, ch.value
+        gt, ch, lm = C.c_double(0), C.c_double(0), C.c_double(0)
+        _check(self.lib.topo_dist_oc_state(self.h, C.byref(d), C.byref(ne), C.byref(st), C.byref(gt), C.byref(ch),
+                                           C.byref(lm)))
+        return d.value, ne.value, st.value, gt.value, ch.value, lm.value
 
     def timer_start(self):
         _check(self.lib.topo_timer_start(self.h))

@@ -239,6 +239,7 @@ class SlabSimp:
                 self.slabs.append(t)
                 self.ranks.append(g)
         self._views = {}
+        self._lam_prev = 0.0
         self.halo_bytes = 0
         self.collectives = 0
 
@@ -402,14 +403,19 @@ class SlabSimp:
     def oc_update(self, g):
         c, ne, mv = self._capi, self.ne_global, self.move
         self._all("oc", 0, mv, float(g), ne)
-        rounds = 0
+        probe = self._lam_prev > 0.0
+        if probe:                                                      # bracket the root around the previous multiplier
+            self._all("oc", 9, mv, self._lam_prev, ne)
+            self.allreduce(c.S_RED, 16)
+            self._all("oc", 10, mv, self._lam_prev, ne)
+        rounds, batch = 0, (4 if probe else 8)
         while rounds < 700:
-            for _ in range(8):
+            for _ in range(batch):
                 self._all("oc", 1, mv, 0.0, ne)
                 self.allreduce(c.S_RED, 16)
                 self._all("oc", 2, mv, 0.0, ne)
-            rounds += 8
-            done, need, _, _, _ = self.slabs[0].dist_oc_state()
+            rounds += batch
+            done, need = self.slabs[0].dist_oc_state()[:2]
             if need:                                                   # a sum inside the rounding margin: exact step
                 self._all("oc", 3, mv, 0.0, ne)
                 self.allreduce(c.S_RED, 1)
@@ -423,32 +429,43 @@ class SlabSimp:
         self._all("oc", 7, mv, 0.0, ne)
         self.allreduce(c.S_RED, 1, op="max")
         self._all("oc", 8, mv, 0.0, ne)
-        _, _, steps, gt, change = self.slabs[0].dist_oc_state()
+        _, _, steps, gt, change, lmid = self.slabs[0].dist_oc_state()
+        self._lam_prev = lmid if (steps > 0 and 0.0 < lmid < 1e300) else 0.0
         return gt, change, steps
 
     # ---- one design iteration (reference optimize.py:428-456) ------------------------------------------------------------------
     def step(self, g, warm=True):
-        """Returns (g_new, dict(compliance, objective, change, cg_iters, relres, oc_steps))."""
+        """Returns (g_new, dict(compliance, objective, change, cg_iters, relres, oc_steps, stage_ms))."""
         c, torch = self._capi, self.torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         with torch.cuda.stream(self.stream):
+            ev[0].record()
             for t in self.slabs:
                 t.simp_scale(self.penal, self.emin, self.emax)
             self.setup()
+            ev[1].record()
             iters, relres = self.solve(warm)
+            ev[2].record()
             for t in self.slabs:
                 t.simp_sensitivity_partial(self.penal, self.emin, self.emax)
                 t.dist_call("compliance_partial")
             self.allreduce(c.S_RED, 2)
             obj, comp = self.slabs[0].dist_read_scalars(2)
+            ev[3].record()
             if self.rmin is not None:
                 for t in self.slabs:
                     t.dist_call("filter_pack", self.rmin, self.dy)
                 self.exchange(c.X_FILTER)
                 for t in self.slabs:
                     t.filter_sensitivity(self.rmin, self.dx, self.dy)
+            ev[4].record()
             g, change, steps = self.oc_update(g)
+            ev[5].record()
+            ev[5].synchronize()
+        names = ("setup", "solve", "sens", "filter", "oc")
+        stage_ms = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
         return g, {"compliance": float(comp), "objective": float(obj), "change": change, "cg_iters": iters,
-                   "relres": relres, "oc_steps": steps}
+                   "relres": relres, "oc_steps": steps, "stage_ms": stage_ms}
 
     # ---- state transfer ----------------------------------------------------------------------------------------------------
     def set_rho(self, rho_global):
