@@ -287,7 +287,8 @@ def main():
                                      "compliance_last": r.compliance}
         if world > 1:
             sim = SlabSimp(bx, by, ke, cons_b, loads_b, rmin=4.0, dist=dist, device=local_rank, rtol=args.rtol,
-                           maxit=100000, use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0")
+                           maxit=100000, use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0",
+                   transport=os.environ.get("TOPO_DIST_TRANSPORT", "p2p"))
             g, its, stage = 0.0, [], {}
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for i in range(n_warm + n_timed):
@@ -307,6 +308,8 @@ def main():
             ms = allmax(ev0.elapsed_time(ev1)/n_timed)
             out.update(ms_per_step=ms, it_per_s=1e3/ms, cg_iters=its, stage_ms=stage, first_global_level=sim.K,
                        cuda_graph=bool(sim.use_graph), graph_error=sim.graph_error, compliance_last=r["compliance"],
+                       transport="peer memory (CUDA IPC over NVLink) for the PCG loop, NCCL for set-up" if sim.p2p else "NCCL",
+                       p2p_error=sim.p2p_error,
                        host_collective_calls_per_step=(sim.collectives - c0)/n_timed,
                        note="one slab of %d element rows per GPU; accumulated vectors, halo sums of interface node rows, "
                             "level-%d operator gathered and solved redundantly; NCCL via torch.distributed, one pair "

@@ -225,7 +225,7 @@ int topo_dist_solve_begin(topo_t *h, double rtol, int maxit, int warm);
 int topo_dist_pcg_matvec(topo_t *h, int par);              /* then: exchange TOPO_X_AP, all-reduce TOPO_S_PAP */
 int topo_dist_pcg_update(topo_t *h, int par, int init);    /* then: K > 1 ? exchange TOPO_X_LEVEL_B level 1 : gather TOPO_G_BK */
 int topo_dist_vcycle_down(topo_t *h, int level);           /* then: level+1 < K ? exchange TOPO_X_LEVEL_B level+1 : gather TOPO_G_BK */
-int topo_dist_vcycle_tail(topo_t *h);
+int topo_dist_vcycle_tail(topo_t *h, int p2p);             /* p2p != 0: pieces arrived through topo_dist_p2p_gather */
 int topo_dist_vcycle_up(topo_t *h, int level);             /* then: exchange TOPO_X_LEVEL_X2 level */
 int topo_dist_pcg_smooth(topo_t *h, int par, int init);    /* then: exchange TOPO_X_Z, all-reduce TOPO_S_RR_RZ */
 int topo_dist_pcg_finish(topo_t *h, int init);
@@ -238,6 +238,17 @@ int topo_dist_filter_pack(topo_t *h, double rmin, double dy);
 /* OC bisection pieces (op table in csrc/simp.cu); between them the host all-reduces TOPO_S_RED */
 int topo_dist_oc(topo_t *h, int op, double move, double value, long long ne_global);
 int topo_dist_oc_state(topo_t *h, int *done, int *need_exact, int *steps, double *gt, double *change, double *lmid);
+/* Peer-memory transport (NVLink / NVSwitch) for the movements of the PCG loop: every slab owns a region its peers
+ * map (CUDA IPC between processes) and write into, payload first, then a sequence number (st.release.sys); the
+ * consumer kernel spins on its own memory (ld.acquire.sys, bounded).  Replaces the NCCL launch of a node-row
+ * exchange / level-K gather / scalar all-reduce by two small kernels: phase 0 pushes and never waits, phase 1
+ * waits for the peers' data and completes the operation.  Every rank must issue the same sequence of calls. */
+int topo_dist_p2p_export(topo_t *h, void *ipc_handle_64, void **local_ptr);
+int topo_dist_p2p_attach(topo_t *h, const void *ipc_handles /* world x 64 bytes */, void *const *local_ptrs /* or NULL */);
+int topo_dist_p2p_xchg(topo_t *h, int phase, int what, int level);
+int topo_dist_p2p_gather(topo_t *h, int phase);              /* TOPO_G_BK; then topo_dist_vcycle_tail(h, 1) */
+int topo_dist_p2p_allreduce(topo_t *h, int phase, int what, int n, int is_max);
+int topo_dist_p2p_error(topo_t *h, int *error);              /* 1: a wait gave up (peer missing) */
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* CUDA-event time (ms) of the most recent call of each stage on this handle. */

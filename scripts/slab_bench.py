@@ -60,7 +60,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9,
-                   use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0")
+                   use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0",
+                   transport=os.environ.get("TOPO_DIST_TRANSPORT", "p2p"))
     g, its, stage = 0.0, [], {}
     for k in range(warm + steps):
         if k == warm:
@@ -77,7 +78,8 @@ def main():
     dist.barrier()
     dt = (time.perf_counter() - t0)/steps
     out.update(ms_per_step=dt*1e3, it_per_s=1.0/dt, cg_iters=its, stage_ms=stage, K=sim.K, graph=bool(sim.use_graph),
-               graph_error=sim.graph_error, path="row slabs over NCCL", host_collective_calls_per_step=(sim.collectives - c0)/steps)
+               graph_error=sim.graph_error, p2p=bool(sim.p2p), p2p_error=sim.p2p_error,
+               path="row slabs, %s transport" % ("peer-memory" if sim.p2p else "NCCL"), host_collective_calls_per_step=(sim.collectives - c0)/steps)
     if rank == 0:
         print(json.dumps(out))
     sim.close()

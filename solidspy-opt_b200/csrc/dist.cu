@@ -28,7 +28,7 @@ int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 
 int topo_mask_vector(topo_handle *h, double2 *v);
 int topo_dist_restrict_fine(topo_handle *h, const double2 *res_fine);
 int topo_dist_level_down(topo_handle *h, int l);
-int topo_dist_tail(topo_handle *h);
+int topo_dist_tail(topo_handle *h, int p2p);
 int topo_dist_level_up(topo_handle *h, int l);
 int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine);
 int topo_dist_setup_local(topo_handle *h);
@@ -108,6 +108,11 @@ void free_dist(DistState &D) {
   cudaFree(D.cellK_send); cudaFree(D.cellK_recv);
   cudaFree(D.bK_send); cudaFree(D.bK_recv);
   cudaFree(D.filt_send_lo); cudaFree(D.filt_send_hi); cudaFree(D.filt_recv_lo); cudaFree(D.filt_recv_hi);
+  for (int r = 0; r < TOPO_P2P_MAXW; ++r)
+    if (D.p2p_opened[r]) cudaIpcCloseMemHandle(D.p2p_peer[r]);
+  cudaFree(D.p2p_region);
+  cudaFree(D.p2p_cnt);
+  cudaGetLastError();
   D = DistState{};
 }
 
@@ -174,6 +179,22 @@ extern "C" int topo_dist_init(topo_t *h, int rank, int world, int K_request) {
   CUDA_TRY(cudaMalloc(&D.filt_send_lo, fbytes)); CUDA_TRY(cudaMalloc(&D.filt_send_hi, fbytes));
   CUDA_TRY(cudaMalloc(&D.filt_recv_lo, fbytes)); CUDA_TRY(cudaMalloc(&D.filt_recv_hi, fbytes));
   D.filt_hy = 0;
+  {
+    // peer-memory region (mapped by the peers through topo_dist_p2p_attach) + local counters
+    const size_t rowb = (sizeof(double2) * (size_t)(h->nx + 1) + 255) & ~(size_t)255;
+    const size_t gb = (sizeof(double2) * (size_t)D.bK_count * world + 255) & ~(size_t)255;
+    D.p2p_row_stride = rowb;
+    D.p2p_gather_stride = gb;
+    D.p2p_off_lo = (sizeof(P2PHeader) + 4095) & ~(size_t)4095;
+    D.p2p_off_hi = D.p2p_off_lo + 2 * rowb;
+    D.p2p_off_gather = D.p2p_off_hi + 2 * rowb;
+    D.p2p_bytes = D.p2p_off_gather + 2 * gb;
+    CUDA_TRY(cudaMalloc(&D.p2p_region, D.p2p_bytes));
+    CUDA_TRY(cudaMemset(D.p2p_region, 0, D.p2p_bytes));
+    CUDA_TRY(cudaMalloc(&D.p2p_cnt, sizeof(P2PCounters)));
+    CUDA_TRY(cudaMemset(D.p2p_cnt, 0, sizeof(P2PCounters)));
+    D.p2p_on = false;
+  }
   h->diag_valid = h->gmg_valid = false;
   h->pcg_graph_valid = false;
   return TOPO_OK;
@@ -379,9 +400,10 @@ extern "C" int topo_dist_vcycle_down(topo_t *h, int level) {
 }
 
 // global levels >= K from the gathered right-hand side (every rank, redundantly)
-extern "C" int topo_dist_vcycle_tail(topo_t *h) {
+extern "C" int topo_dist_vcycle_tail(topo_t *h, int p2p) {
   TOPO_TRY(check(h));
-  return topo_dist_tail(h);
+  if (p2p && !h->dist.p2p_on) return TOPO_ESTATE;
+  return topo_dist_tail(h, p2p);
 }
 
 // level l (K > l >= 1): coarse correction + post-smoothing (host: exchange TOPO_X_LEVEL_X2 level l)
@@ -435,5 +457,295 @@ extern "C" int topo_dist_compliance_partial(topo_t *h) {
   KL(h, "k_dot_weighted", k_dot_weighted<<<nblk(h->nn), 256, 0, h->stream>>>(h->f, h->u, h->nx + 1, h->ny, h->dist.w_first,
                                                                             h->dist.w_last, h->partials, h->ticket, h->red_out + 1));
   CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// =====================================================================================================================
+// Peer-memory transport (NVLink / NVSwitch): the same exchanges, gathers and all-reduces without NCCL launches
+// =====================================================================================================================
+namespace {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded spin (~ seconds): a missing peer must not hang the GPU
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long seq, unsigned int *error) {
+  if (*reinterpret_cast<volatile unsigned int *>(error)) return false;   // a previous wait already gave up
+  for (long long it = 0; it < (1ll << 24); ++it) {
+    if (ld_acquire_sys(flag) >= seq) return true;
+    __nanosleep(64);
+  }
+  *error = 1u;
+  return false;
+}
+
+__device__ __forceinline__ P2PHeader *hdr(char *region) { return reinterpret_cast<P2PHeader *>(region); }
+
+// my first node row -> lower neighbour's recv_hi, my last node row -> upper neighbour's recv_lo, then the flags
+__global__ void __launch_bounds__(1024) k_p2p_push_rows(const double2 *__restrict__ row_lo, const double2 *__restrict__ row_hi,
+                                                        int n, char *peer_lo, char *peer_hi, size_t off_lo, size_t off_hi,
+                                                        size_t stride, P2PCounters *c) {
+  const unsigned long long seq = c->halo_push + 1;
+  const size_t buf = (size_t)(seq & 1ull) * stride;
+  if (peer_lo != nullptr) {
+    double2 *dst = reinterpret_cast<double2 *>(peer_lo + off_hi + buf);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = row_lo[i];
+  }
+  if (peer_hi != nullptr) {
+    double2 *dst = reinterpret_cast<double2 *>(peer_hi + off_lo + buf);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = row_hi[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (peer_lo != nullptr) st_release_sys(&hdr(peer_lo)->flag_from_hi, seq);
+    if (peer_hi != nullptr) st_release_sys(&hdr(peer_hi)->flag_from_lo, seq);
+    c->halo_push = seq;
+  }
+}
+
+// block 0: first row, block 1: last row.  dst += recv  or  dst = dst + recv - base
+__global__ void __launch_bounds__(1024) k_p2p_finish_rows(double2 *__restrict__ v_lo, double2 *__restrict__ v_hi,
+                                                          const double2 *__restrict__ base_lo, const double2 *__restrict__ base_hi,
+                                                          int n, char *region, int has_lo, int has_hi, size_t off_lo, size_t off_hi,
+                                                          size_t stride, P2PCounters *c) {
+  const unsigned long long seq = c->halo_wait + 1;
+  const size_t buf = (size_t)(seq & 1ull) * stride;
+  const bool lo = blockIdx.x == 0;
+  if (lo ? has_lo : has_hi) {
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = wait_flag(lo ? &hdr(region)->flag_from_lo : &hdr(region)->flag_from_hi, seq, &c->error);
+    __syncthreads();
+    if (ok) {
+      const double2 *src = reinterpret_cast<const double2 *>(region + (lo ? off_lo : off_hi) + buf);
+      double2 *dst = lo ? v_lo : v_hi;
+      const double2 *base = lo ? base_lo : base_hi;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double2 a = dst[i];
+        const double2 b = src[i];
+        if (base != nullptr) {
+          const double2 q = base[i];
+          a.x = (a.x + b.x) - q.x; a.y = (a.y + b.y) - q.y;
+        } else {
+          a.x += b.x; a.y += b.y;
+        }
+        dst[i] = a;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&c->ticket[0], 1u) == gridDim.x - 1) {
+      c->ticket[0] = 0u;
+      c->halo_wait = seq;
+    }
+  }
+}
+
+// block r: my level-K piece -> rank r's gather buffer, slot [my rank], then the flag
+struct PeerTable {
+  char *p[TOPO_P2P_MAXW];
+};
+__global__ void __launch_bounds__(1024) k_p2p_gather_push(const double2 *__restrict__ src, long long n, PeerTable peers, int my_rank,
+                                                          size_t off_gather, size_t stride, P2PCounters *c) {
+  const unsigned long long seq = c->gather_push + 1;
+  char *peer = peers.p[blockIdx.x];
+  double2 *dst = reinterpret_cast<double2 *>(peer + off_gather + (size_t)(seq & 1ull) * stride) + (size_t)my_rank * n;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(&hdr(peer)->flag_gather[my_rank], seq);
+    __threadfence();
+    if (atomicAdd(&c->ticket[1], 1u) == gridDim.x - 1) {
+      c->ticket[1] = 0u;
+      c->gather_push = seq;
+    }
+  }
+}
+// thread r waits for rank r's piece
+__global__ void k_p2p_gather_wait(char *region, int world, P2PCounters *c) {
+  const unsigned long long seq = c->gather_wait + 1;
+  if ((int)threadIdx.x < world) wait_flag(&hdr(region)->flag_gather[threadIdx.x], seq, &c->error);
+  __syncthreads();
+  if (threadIdx.x == 0) c->gather_wait = seq;
+}
+
+// thread r: my n partial sums -> rank r's slot [parity][my rank], then the flag
+__global__ void k_p2p_scalar_push(const double *__restrict__ vals, int n, PeerTable peers, int my_rank, int world, P2PCounters *c) {
+  const unsigned long long seq = c->scal_push + 1;
+  if ((int)threadIdx.x < world) {
+    P2PHeader *H = hdr(peers.p[threadIdx.x]);
+    double *dst = H->scalar_slot[seq & 1ull][my_rank];
+    for (int j = 0; j < n; ++j) dst[j] = vals[j];
+    __threadfence_system();
+    st_release_sys(&H->flag_scalar[my_rank], seq);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) c->scal_push = seq;
+}
+// waits for every rank's partial sums, folds them in rank order (identical on all ranks), writes them back
+__global__ void k_p2p_scalar_reduce(double *__restrict__ vals, int n, char *region, int world, int is_max, P2PCounters *c) {
+  const unsigned long long seq = c->scal_wait + 1;
+  if ((int)threadIdx.x < world) wait_flag(&hdr(region)->flag_scalar[threadIdx.x], seq, &c->error);
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    const P2PHeader *H = hdr(region);
+    double acc = H->scalar_slot[seq & 1ull][0][threadIdx.x];
+    for (int r = 1; r < world; ++r) {
+      const double t = H->scalar_slot[seq & 1ull][r][threadIdx.x];
+      acc = is_max ? ((t > acc || t != t) ? t : acc) : acc + t;
+    }
+    vals[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) c->scal_wait = seq;
+}
+
+int p2p_check(topo_handle *h) {
+  TOPO_TRY(check(h));
+  if (!h->dist.p2p_on) {
+    topo_set_error("peer-memory transport not attached (topo_dist_p2p_attach)");
+    return TOPO_ESTATE;
+  }
+  return TOPO_OK;
+}
+
+PeerTable peer_table(const DistState &D) {
+  PeerTable t;
+  for (int r = 0; r < TOPO_P2P_MAXW; ++r) t.p[r] = D.p2p_peer[r];
+  return t;
+}
+
+}  // namespace
+
+// 64-byte CUDA IPC handle of this slab's region (for peers in other processes) and its address (for peers in this one)
+extern "C" int topo_dist_p2p_export(topo_t *h, void *ipc_handle_64, void **local_ptr) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (ipc_handle_64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(cudaIpcGetMemHandle(&mh, h->dist.p2p_region));
+    std::memcpy(ipc_handle_64, &mh, 64);
+  }
+  if (local_ptr) *local_ptr = h->dist.p2p_region;
+  return TOPO_OK;
+}
+
+// regions of ALL ranks: local_ptrs[r] != NULL -> a handle of this process (used as is), else ipc_handles + 64*r is
+// opened (peer access over NVLink).  Entry [own rank] is ignored.
+extern "C" int topo_dist_p2p_attach(topo_t *h, const void *ipc_handles, void *const *local_ptrs) {
+  TOPO_TRY(check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  if (D.world > TOPO_P2P_MAXW) {
+    topo_set_error("peer-memory transport supports at most %d slabs", TOPO_P2P_MAXW);
+    return TOPO_EINVAL;
+  }
+  for (int r = 0; r < D.world; ++r) {
+    if (r == D.rank) { D.p2p_peer[r] = D.p2p_region; continue; }
+    if (local_ptrs && local_ptrs[r]) { D.p2p_peer[r] = static_cast<char *>(local_ptrs[r]); continue; }
+    if (!ipc_handles) return TOPO_EINVAL;
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, static_cast<const char *>(ipc_handles) + 64 * (size_t)r, 64);
+    void *p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    D.p2p_peer[r] = static_cast<char *>(p);
+    D.p2p_opened[r] = true;
+  }
+  D.p2p_on = true;
+  return TOPO_OK;
+}
+
+// exchange through peer memory.  phase 0: push my interface rows (never waits); phase 1: wait for the neighbours'
+// rows and complete mine.  Row kinds only (TOPO_X_AP, _R0, _Z, _LEVEL_B, _LEVEL_X2).
+extern "C" int topo_dist_p2p_xchg(topo_t *h, int phase, int what, int level) {
+  TOPO_TRY(p2p_check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  double2 *v = nullptr;
+  const double2 *base = nullptr;
+  int npr = h->nx + 1, ny = h->ny;
+  switch (what) {
+    case TOPO_X_AP: v = h->Ap; break;
+    case TOPO_X_R0: v = h->r; break;
+    case TOPO_X_Z: v = h->z; base = h->tmp2; break;
+    case TOPO_X_LEVEL_B:
+    case TOPO_X_LEVEL_X2:
+      if (level < 1 || level >= D.K) return TOPO_EINVAL;
+      v = (what == TOPO_X_LEVEL_B) ? h->levels[level].b : h->levels[level].x2;
+      if (what == TOPO_X_LEVEL_X2) base = h->levels[level].x;
+      npr = h->levels[level].nx + 1; ny = h->levels[level].ny;
+      break;
+    default:
+      topo_set_error("peer-memory exchange: kind %d is not a node-row exchange", what);
+      return TOPO_EINVAL;
+  }
+  const size_t last = (size_t)ny * npr;
+  char *peer_lo = D.has_lo ? D.p2p_peer[D.rank - 1] : nullptr;
+  char *peer_hi = D.has_hi ? D.p2p_peer[D.rank + 1] : nullptr;
+  if (phase == 0) {
+    KL(h, "k_p2p_push_rows", k_p2p_push_rows<<<1, 1024, 0, h->stream>>>(v, v + last, npr, peer_lo, peer_hi, D.p2p_off_lo, D.p2p_off_hi,
+                                                                        D.p2p_row_stride, D.p2p_cnt));
+  } else {
+    KL(h, "k_p2p_finish_rows", k_p2p_finish_rows<<<2, 1024, 0, h->stream>>>(v, v + last, base, base ? base + last : nullptr, npr,
+                                                                            D.p2p_region, D.has_lo ? 1 : 0, D.has_hi ? 1 : 0,
+                                                                            D.p2p_off_lo, D.p2p_off_hi, D.p2p_row_stride, D.p2p_cnt));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// level-K right-hand-side pieces to every rank (phase 0) / wait for all pieces (phase 1; then topo_dist_vcycle_tail(h, 1))
+extern "C" int topo_dist_p2p_gather(topo_t *h, int phase) {
+  TOPO_TRY(p2p_check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  if (phase == 0) {
+    KL(h, "k_p2p_gather_push", k_p2p_gather_push<<<D.world, 1024, 0, h->stream>>>(D.bK_send, D.bK_count, peer_table(D), D.rank,
+                                                                                D.p2p_off_gather, D.p2p_gather_stride, D.p2p_cnt));
+  } else {
+    KL(h, "k_p2p_gather_wait", k_p2p_gather_wait<<<1, 32, 0, h->stream>>>(D.p2p_region, D.world, D.p2p_cnt));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// all-reduce of the first n doubles of a scalar block (TOPO_S_*), sum or max, folded in rank order on every rank
+extern "C" int topo_dist_p2p_allreduce(topo_t *h, int phase, int what, int n, int is_max) {
+  TOPO_TRY(p2p_check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  void *ptr = nullptr;
+  int nmax = 0;
+  TOPO_TRY(topo_dist_scalar_ptr(h, what, &ptr, &nmax));
+  if (n < 1 || n > nmax || n > 16) return TOPO_EINVAL;
+  if (phase == 0) {
+    KL(h, "k_p2p_scalar_push", k_p2p_scalar_push<<<1, 32, 0, h->stream>>>(static_cast<const double *>(ptr), n, peer_table(D), D.rank, D.world,
+                                                                        D.p2p_cnt));
+  } else {
+    KL(h, "k_p2p_scalar_reduce", k_p2p_scalar_reduce<<<1, 32, 0, h->stream>>>(static_cast<double *>(ptr), n, D.p2p_region, D.world, is_max,
+                                                                            D.p2p_cnt));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// 1 if a peer wait timed out since the handle was created
+extern "C" int topo_dist_p2p_error(topo_t *h, int *error) {
+  TOPO_TRY(check(h));
+  if (!error) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  P2PCounters c;
+  CUDA_TRY(cudaMemcpyAsync(&c, h->dist.p2p_cnt, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *error = (int)c.error;
   return TOPO_OK;
 }

@@ -495,9 +495,12 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
 // ---- row-slab mode helpers ---------------------------------------------------------------------------------
 // global level-K right-hand side from the gathered per-rank pieces: rank g holds coarse rows
 // [g*rows, (g+1)*rows] (rows+1 node rows, the shared ones are partial sums)
-__global__ void k_dist_assemble_bK(const double2 *__restrict__ recv, double2 *__restrict__ b, int npr, int rows,
+// (peer-memory transport: the pieces sit in one of two buffers, selected by the parity of the gather sequence number)
+__global__ void k_dist_assemble_bK(const double2 *__restrict__ recv0, const double2 *__restrict__ recv1,
+                                   const unsigned long long *seq, double2 *__restrict__ b, int npr, int rows,
                                    int world, const int *done) {
   if (done && *done) return;
+  const double2 *__restrict__ recv = (seq != nullptr && (*seq & 1ull)) ? recv1 : recv0;
   const int64_t nn = (int64_t)npr * ((int64_t)rows * world + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nn) return;
@@ -617,13 +620,20 @@ int topo_dist_level_down(topo_handle *h, int l) {
   return dist_restrict_from(h, l, F.r);
 }
 
-int topo_dist_tail(topo_handle *h) {
+int topo_dist_tail(topo_handle *h, int p2p) {
   const DistState &D = h->dist;
   if (!D.on) return TOPO_EINVAL;
   GmgLevel &G = h->levels[D.K];
   const int rows = (h->ny >> D.K);
-  KL(h, "k_dist_assemble_bK", k_dist_assemble_bK<<<blocks_for(G.nn), 128, 0, h->stream>>>(D.bK_recv, G.b, G.nx + 1, rows, D.world,
-                                                                                          &h->sc->done));
+  if (p2p) {
+    const double2 *r0 = reinterpret_cast<const double2 *>(D.p2p_region + D.p2p_off_gather);
+    const double2 *r1 = reinterpret_cast<const double2 *>(D.p2p_region + D.p2p_off_gather + D.p2p_gather_stride);
+    KL(h, "k_dist_assemble_bK", k_dist_assemble_bK<<<blocks_for(G.nn), 128, 0, h->stream>>>(r0, r1, &D.p2p_cnt->gather_wait, G.b, G.nx + 1,
+                                                                                            rows, D.world, &h->sc->done));
+  } else {
+    KL(h, "k_dist_assemble_bK", k_dist_assemble_bK<<<blocks_for(G.nn), 128, 0, h->stream>>>(D.bK_recv, nullptr, nullptr, G.b, G.nx + 1, rows,
+                                                                                            D.world, &h->sc->done));
+  }
   return launch_tail(h, D.K, nullptr, 0, 0);
 }
 

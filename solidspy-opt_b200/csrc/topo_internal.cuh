@@ -84,6 +84,26 @@ struct GmgLevel {
 // neighbours); a local operator application yields a DISTRIBUTED result (partial sums on interface rows) that
 // the host completes with a halo sum.  Where a kernel needs a distributed copy of an accumulated vector it
 // scales the interface rows by w_first / w_last (1/2 each side = a partition of unity).
+// Peer-memory transport of the row-slab mode (NVLink/NVSwitch): every rank owns one cudaMalloc'd REGION that its
+// peers map (CUDA IPC across processes, plain pointers inside one process) and WRITE into -- interface rows,
+// level-K right-hand-side pieces, scalar partial sums -- followed by a monotonically increasing sequence number
+// (st.release.sys).  The consumer kernel spins on its own memory (ld.acquire.sys) until the number arrives.
+// Payload buffers are double-buffered by the parity of the sequence number: a rank can be at most one exchange
+// ahead of its neighbour.  Counters live in local, unshared memory.
+#define TOPO_P2P_MAXW 16
+struct P2PHeader {                       // start of the region; written by peers
+  unsigned long long flag_from_lo, flag_from_hi;           // halo rows: sequence number of the neighbour's last push
+  unsigned long long flag_gather[TOPO_P2P_MAXW];           // by rank
+  unsigned long long flag_scalar[TOPO_P2P_MAXW];
+  double scalar_slot[2][TOPO_P2P_MAXW][16];
+};
+struct P2PCounters {                     // local
+  unsigned long long halo_push, halo_wait, gather_push, gather_wait, scal_push, scal_wait;
+  unsigned int ticket[4];
+  unsigned int error;                    // a wait gave up (peer never wrote): results are invalid
+  unsigned int pad;
+};
+
 struct DistState {
   bool on;
   int rank, world, K;                  // K = first level that is global (replicated on every rank)
@@ -99,6 +119,13 @@ struct DistState {
   long long bK_count;                  // double2 per rank
   double *filt_send_lo, *filt_send_hi, *filt_recv_lo, *filt_recv_hi;    // rho*dc of hy element rows
   int filt_hy;
+  // peer-memory transport
+  bool p2p_on;
+  char *p2p_region;                    // P2PHeader | recv_lo[2][npr] | recv_hi[2][npr] | gather_recv[2][world][bK_count]
+  size_t p2p_bytes, p2p_off_lo, p2p_off_hi, p2p_off_gather, p2p_row_stride, p2p_gather_stride;
+  char *p2p_peer[TOPO_P2P_MAXW];       // mapped regions by rank (own region at [rank])
+  bool p2p_opened[TOPO_P2P_MAXW];      // mapped through cudaIpcOpenMemHandle (must be closed)
+  P2PCounters *p2p_cnt;
 };
 
 struct topo_handle {

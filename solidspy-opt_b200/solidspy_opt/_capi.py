@@ -33,7 +33,8 @@ SYMBOLS = [
     "topo_dist_pcg_matvec", "topo_dist_pcg_update", "topo_dist_vcycle_down", "topo_dist_vcycle_tail",
     "topo_dist_vcycle_up", "topo_dist_pcg_smooth", "topo_dist_pcg_finish", "topo_dist_solve_poll",
     "topo_dist_solve_end", "topo_dist_compliance_partial", "topo_dist_filter_pack", "topo_dist_oc",
-    "topo_dist_oc_state",
+    "topo_dist_oc_state", "topo_dist_p2p_export", "topo_dist_p2p_attach", "topo_dist_p2p_xchg", "topo_dist_p2p_gather",
+    "topo_dist_p2p_allreduce", "topo_dist_p2p_error",
 ]
 
 # row-slab mode: exchange kinds, gather kinds, scalar blocks (include/topo_b200.h)
@@ -139,7 +140,13 @@ def load_library():
         "topo_dist_pcg_matvec": [vp, C.c_int],
         "topo_dist_pcg_update": [vp, C.c_int, C.c_int],
         "topo_dist_vcycle_down": [vp, C.c_int],
-        "topo_dist_vcycle_tail": [vp],
+        "topo_dist_vcycle_tail": [vp, C.c_int],
+        "topo_dist_p2p_export": [vp, C.c_void_p, C.POINTER(vp)],
+        "topo_dist_p2p_attach": [vp, C.c_void_p, C.POINTER(vp)],
+        "topo_dist_p2p_xchg": [vp, C.c_int, C.c_int, C.c_int],
+        "topo_dist_p2p_gather": [vp, C.c_int],
+        "topo_dist_p2p_allreduce": [vp, C.c_int, C.c_int, C.c_int, C.c_int],
+        "topo_dist_p2p_error": [vp, ip],
         "topo_dist_vcycle_up": [vp, C.c_int],
         "topo_dist_pcg_smooth": [vp, C.c_int, C.c_int],
         "topo_dist_pcg_finish": [vp, C.c_int],
@@ -398,6 +405,25 @@ class Topo:
     def dist_call(self, name, *args):
         """Thin passthrough for the segment calls (topo_dist_<name>)."""
         _check(getattr(self.lib, "topo_dist_" + name)(self.h, *args))
+
+    def dist_p2p_export(self):
+        """(64-byte CUDA IPC handle, device address) of this slab's peer-memory region."""
+        buf = (C.c_ubyte*64)()
+        ptr = C.c_void_p()
+        _check(self.lib.topo_dist_p2p_export(self.h, buf, C.byref(ptr)))
+        return bytes(buf), ptr.value
+
+    def dist_p2p_attach(self, ipc_handles, local_ptrs):
+        """ipc_handles: list of 64-byte handles by rank (or None); local_ptrs: list of addresses by rank (0 = use IPC)."""
+        world = len(local_ptrs)
+        blob = b"".join(hh if hh is not None else bytes(64) for hh in (ipc_handles or [None]*world))
+        arr = (C.c_void_p*world)(*[C.c_void_p(p or None) for p in local_ptrs])
+        _check(self.lib.topo_dist_p2p_attach(self.h, blob, arr))
+
+    def dist_p2p_error(self):
+        e = C.c_int(0)
+        _check(self.lib.topo_dist_p2p_error(self.h, C.byref(e)))
+        return e.value
 
     def dist_solve_poll(self):
         d, it, rel = C.c_int(0), C.c_int(0), C.c_double(0)

@@ -197,7 +197,8 @@ class SlabSimp:
     """
 
     def __init__(self, nx, ny, ke, cons, loads, volfrac=0.5, penal=3.0, emin=1e-9, emax=1.0, rmin=None, dx=1.0, dy=1.0,
-                 move=0.2, rtol=1e-9, maxit=2000, world=None, dist=None, device=0, K=0, use_graph=True):
+                 move=0.2, rtol=1e-9, maxit=2000, world=None, dist=None, device=0, K=0, use_graph=True,
+                 transport="p2p"):
         import torch
         from solidspy_opt import _capi
         self.torch, self._capi, self.dist = torch, _capi, dist
@@ -239,9 +240,37 @@ class SlabSimp:
                 self.slabs.append(t)
                 self.ranks.append(g)
         self._views = {}
+        self.p2p, self.p2p_error = False, None
+        if transport == "p2p":
+            self._attach_p2p()
         self._lam_prev = 0.0
         self.halo_bytes = 0
         self.collectives = 0
+
+    # ---- peer-memory transport -----------------------------------------------------------------------------------------
+    def _attach_p2p(self):
+        """Map the peers' regions (CUDA IPC between processes).  All ranks agree on success, else everyone stays on
+        NCCL for the PCG-loop movements too."""
+        ok = 1
+        try:
+            if self.dist is None:
+                ptrs = [t.dist_p2p_export()[1] for t in self.slabs]
+                for t in self.slabs:
+                    t.dist_p2p_attach(None, ptrs)
+            else:
+                handle, _ = self.slabs[0].dist_p2p_export()
+                handles = [None]*self.world
+                self.dist.all_gather_object(handles, handle)
+                self.slabs[0].dist_p2p_attach(handles, [0]*self.world)
+        except Exception as exc:                                           # e.g. IPC not permitted in this container
+            ok, self.p2p_error = 0, repr(exc)
+        if self.dist is not None:
+            flag = self.torch.tensor([ok], dtype=self.torch.int32, device=self.device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        self.p2p = bool(ok)
+
+    _ROW_KINDS = (0, 1, 2, 3, 4)          # X_AP, X_R0, X_Z, X_LEVEL_B, X_LEVEL_X2
 
     # ---- device views ------------------------------------------------------------------------------------------------
     def _view(self, ptr, n):
@@ -277,6 +306,13 @@ class SlabSimp:
     # ---- movement ----------------------------------------------------------------------------------------------------
     def exchange(self, what, level=0):
         """Interface rows / blocks to both neighbours, then the library's finishing kernel."""
+        if self.p2p and what in self._ROW_KINDS:
+            for t in self.slabs:                                           # every push before any wait
+                t.dist_call("p2p_xchg", 0, what, level)
+            for t in self.slabs:
+                t.dist_call("p2p_xchg", 1, what, level)
+            self.collectives += 1
+            return
         vs = [self._xchg_views(i, what, level) for i in range(len(self.slabs))]
         if vs[0][0].numel() > 0:
             for i in range(len(self.slabs) - 1):                       # neighbours inside this process
@@ -297,6 +333,11 @@ class SlabSimp:
             t.dist_xchg_finish(what, level)
 
     def gather(self, what):
+        if self.p2p and what == self._capi.G_BK:
+            self._all("p2p_gather", 0)
+            self._all("p2p_gather", 1)
+            self.collectives += 1
+            return
         vs = [self._gather_views(i, what) for i in range(len(self.slabs))]
         if self.dist is not None:
             self.dist.all_gather_into_tensor(vs[0][1], vs[0][0])
@@ -308,6 +349,11 @@ class SlabSimp:
         self.collectives += 1
 
     def allreduce(self, what, n, op="sum"):
+        if self.p2p:
+            self._all("p2p_allreduce", 0, what, n, 1 if op == "max" else 0)
+            self._all("p2p_allreduce", 1, what, n, 1 if op == "max" else 0)
+            self.collectives += 1
+            return
         vs = [self._scalar_view(i, what)[:n] for i in range(len(self.slabs))]
         if self.dist is not None:
             self.dist.all_reduce(vs[0], op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
@@ -338,7 +384,7 @@ class SlabSimp:
             self.exchange(c.X_LEVEL_B, l)
             self._all("vcycle_down", l)
         self.gather(c.G_BK)
-        self._all("vcycle_tail")
+        self._all("vcycle_tail", 1 if self.p2p else 0)
         for l in range(K - 1, 0, -1):
             self._all("vcycle_up", l)
             self.exchange(c.X_LEVEL_X2, l)
@@ -392,6 +438,8 @@ class SlabSimp:
                 self._pair()
             launched += 4
         self._all("solve_end", iters)
+        if self.p2p and any(t.dist_p2p_error() for t in self.slabs):
+            raise self._capi.TopoError(self._capi.ECUDA, "peer-memory transport: a wait for a neighbour's data timed out")
         if relres != relres:
             raise self._capi.TopoError(self._capi.ENOCONV, "row-slab PCG produced NaN (singular system?)")
         if done != 1:

@@ -45,16 +45,17 @@ def main():
     nx, ny = 384, 64*world
     cons, loads, ke = model(nx, ny)
     steps = 4
-    for use_graph in (True, False):
-        sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph)
+    for transport, use_graph in (("p2p", True), ("nccl", True), ("nccl", False)):
+        sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph,
+                       transport=transport)
         g, hist = 0.0, []
         for _ in range(steps):
             g, res = sim.step(g)
             hist.append((res["compliance"], res["cg_iters"], res["oc_steps"], g))
         rho = gather_rho(sim, world)
-        key = "graph" if use_graph else "eager"
-        out[key + "_used"] = bool(sim.use_graph)
-        out[key + "_error"] = sim.graph_error
+        key = transport + ("_graph" if use_graph else "_eager")
+        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p)}
+        out[key + "_error"] = [sim.graph_error, sim.p2p_error]
         out["K"] = sim.K
         sim.close()
         if rank == 0:
@@ -80,8 +81,9 @@ def main():
     if big:
         nx, ny = (int(v) for v in big.lower().split("x"))
         cons, loads, ke = model(nx, ny)
-        for use_graph in (True, False):
-            sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph)
+        for transport, use_graph in (("p2p", True), ("nccl", True)):
+            sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph,
+                           transport=transport)
             g = 0.0
             for _ in range(3):
                 g, res = sim.step(g)
@@ -95,9 +97,10 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             dt = (time.perf_counter() - t0)/n
-            key = "big_graph" if use_graph else "big_eager"
+            key = "big_" + transport
             out[key] = {"mesh": "%dx%d" % (nx, ny), "ms_per_step": dt*1e3, "it_per_s": 1.0/dt, "cg_iters": its,
-                        "graph_used": bool(sim.use_graph), "graph_error": sim.graph_error, "K": sim.K}
+                        "graph_used": bool(sim.use_graph), "graph_error": sim.graph_error, "p2p": bool(sim.p2p),
+                        "p2p_error": sim.p2p_error, "K": sim.K}
             sim.close()
     if rank == 0:
         print(json.dumps(out))

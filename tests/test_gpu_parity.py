@@ -473,7 +473,7 @@ def test_handle_lifecycle_and_errors(capi):
 
 
 # ---- row-slab decomposition: several slabs on ONE GPU exercise every kernel / segment of the multi-GPU path ----
-def _slab_case(nx, ny, world, K, rho=None, seed=3):
+def _slab_case(nx, ny, world, K, rho=None, seed=3, transport="p2p"):
     """(SlabSimp, single-GPU Topo) on the same cantilever with the same (random) density."""
     from solidspy_opt import _capi
     from solidspy_opt.Utils.beams import beam
@@ -484,7 +484,8 @@ def _slab_case(nx, ny, world, K, rho=None, seed=3):
     ke = kloc_simp(mats[0, 0], mats[0, 1])
     if rho is None:
         rho = np.random.default_rng(seed).uniform(0.05, 1.0, nx*ny)
-    sim = SlabSimp(nx, ny, ke, nodes[:, 3:5], loads, rmin=2.5, world=world, K=K, rtol=1e-10)
+    sim = SlabSimp(nx, ny, ke, nodes[:, 3:5], loads, rmin=2.5, world=world, K=K, rtol=1e-10, transport=transport)
+    assert sim.p2p == (transport == "p2p"), sim.p2p_error
     sim.set_rho(rho)
     topo = _capi.Topo(nx, ny, ke)
     topo.set_cons(nodes[:, 3:5])
@@ -495,13 +496,16 @@ def _slab_case(nx, ny, world, K, rho=None, seed=3):
 
 @pytest.mark.parametrize("nx,ny,world,tail_max", [(128, 64, 2, 10000), (96, 64, 4, 500), (256, 128, 4, 600),
                                                   (130, 96, 3, 10000), (512, 256, 8, 300)])
-def test_slab_solve_equals_single_gpu(capi, monkeypatch, nx, ny, world, tail_max):
+@pytest.mark.parametrize("transport", ["p2p", "copies"])
+def test_slab_solve_equals_single_gpu(capi, monkeypatch, nx, ny, world, tail_max, transport):
     """Same preconditioner, same Krylov iteration: the slab solve reproduces topo_solve on the whole mesh.
-    ``tail_max`` (nodes of the first tail level) moves the first global level K: 1, 2, 3, 1, 4."""
+    ``tail_max`` (nodes of the first tail level) moves the first global level K: 1, 2, 3, 1, 5.  ``transport``: rows,
+    level-K pieces and scalars through the peer-memory kernels, or moved by the host between segments (the NCCL
+    path of a multi-process run; device copies here)."""
     import torch
     from solidspy_opt import _capi
     monkeypatch.setenv("TOPO_TAIL_MAX", str(tail_max))
-    sim, topo = _slab_case(nx, ny, world, 0)
+    sim, topo = _slab_case(nx, ny, world, 0, transport=transport)
     try:
         topo.simp_scale(3.0, 1e-9, 1.0)
         it1, rel1, _ = topo.solve(_capi.PRECOND_GMG, 1e-10, 2000, warm=False)
@@ -525,12 +529,12 @@ def test_slab_solve_equals_single_gpu(capi, monkeypatch, nx, ny, world, tail_max
         topo.close()
 
 
-@pytest.mark.parametrize("world,K", [(2, 0), (4, 2)])
-def test_slab_design_iterations_equal_single_gpu(capi, world, K):
+@pytest.mark.parametrize("world,K,transport", [(2, 0, "p2p"), (4, 2, "p2p"), (4, 2, "copies")])
+def test_slab_design_iterations_equal_single_gpu(capi, world, K, transport):
     """Five full design iterations (solve, sensitivity, filter with ghost rows, OC with all-reduced sums)."""
     from solidspy_opt import _capi
     nx, ny = 96, 64
-    sim, topo = _slab_case(nx, ny, world, K, rho=np.full(nx*ny, 0.5))
+    sim, topo = _slab_case(nx, ny, world, K, rho=np.full(nx*ny, 0.5), transport=transport)
     try:
         params = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=2.5, dx=1.0, dy=1.0, move=0.2, rtol=1e-10,
                                   precond=_capi.PRECOND_GMG, maxit=2000, warm=1)
