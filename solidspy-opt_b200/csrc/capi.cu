@@ -173,6 +173,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->pcg_graph_launches = 0;
   h->n_loads = 0;
   h->oc_lam_prev = 0.0;
+  h->last_pcg_iters = 0;
   h->loads_set = h->cons_set = h->diag_valid = h->gmg_valid = false;
   h->d_load_node = nullptr;
   h->d_load_fx = h->d_load_fy = nullptr;

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restr
 // cluster barrier (barrier.cluster, release/acquire: global writes of one CTA are visible to the others
 // after it) between stages; the smallest levels are finished by CTA 0 alone with __syncthreads.
 constexpr int TAIL_MAX = 16;
-constexpr int TAIL_SMALL = 1024;
+constexpr int TAIL_THREADS = 768;     // 80 registers per thread: the small-level path keeps a node's operator in registers
+constexpr int TAIL_SMALL = TAIL_THREADS;
 struct TailArgs {
   LevelView lv[TAIL_MAX];
   int n;                       // number of levels in the tail (the last one is the coarsest)
@@ -329,7 +330,105 @@ __device__ __forceinline__ void tail_up(const TailArgs &a, int l, double2 **cur,
   cur[l] = L.x;
 }
 
-__global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs a) {
+// ---- small levels (<= TAIL_THREADS nodes): one thread per node, operator in registers -------------------------------------
+// A sweep of the generic path costs ~400 instructions per node (index arithmetic, bounds, 9 stencil + 9 vector
+// loads, conversions) and the 18 warps of a 561-node level are ISSUE bound on one SM: ~1 us per stage.  Here a
+// thread keeps its node's 9 stencil blocks (fp32, as stored), D^-1 and b in registers for all sweeps of a
+// phase; the iterate travels between threads as an fp32 copy in shared memory, so a sweep is 9 LDS.64 + 36 FFMA
+// + the fp64 update + one barrier.  The products A x are therefore formed in fp32 (operands rounded like the
+// stencils already are); iterate, right-hand side and residual stay fp64.  Result of a level: always in L.x.
+struct SmallNode {
+  float4 st[9];
+  double2 dinv, b, x;
+  int n, npr, valid;          // valid = last node index (clamp for neighbours outside the level)
+};
+__device__ __forceinline__ void small_load(const LevelView &L, int t, SmallNode &N) {
+  const int npr = L.nx + 1, nn = npr * (L.ny + 1);
+  N.n = t; N.npr = npr; N.valid = nn - 1;
+  if (t >= nn) return;
+  const int r = t / npr, c = t - r * npr;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int rr = r + k / 3 - 1, cc = c + k % 3 - 1;
+    const bool ok = rr >= 0 && rr <= L.ny && cc >= 0 && cc <= L.nx;
+    N.st[k] = ok ? __ldg(reinterpret_cast<const float4 *>(L.st) + (size_t)k * nn + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  N.dinv = L.dinv[t];
+  N.b = L.b[t];
+}
+// (A x)(node) from the fp32 copy of the iterate
+__device__ __forceinline__ void small_apply(const SmallNode &N, const float2 *__restrict__ xs, float &ax, float &ay) {
+  ax = 0.f; ay = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int m = min(max(N.n + (k / 3 - 1) * N.npr + (k % 3 - 1), 0), N.valid);   // missing neighbours: zero coefficient
+    const float2 xv = xs[m];
+    ax = fmaf(N.st[k].x, xv.x, ax); ax = fmaf(N.st[k].y, xv.y, ax);
+    ay = fmaf(N.st[k].z, xv.x, ay); ay = fmaf(N.st[k].w, xv.y, ay);
+  }
+}
+__device__ __forceinline__ void small_sweeps(SmallNode &N, bool active, float2 (*xs)[TAIL_THREADS], int &cur, int nsweeps, double omega) {
+  for (int s = 0; s < nsweeps; ++s) {
+    if (active) {
+      float ax, ay;
+      small_apply(N, xs[cur], ax, ay);
+      N.x.x = fma(omega * N.dinv.x, N.b.x - (double)ax, N.x.x);
+      N.x.y = fma(omega * N.dinv.y, N.b.y - (double)ay, N.x.y);
+      xs[cur ^ 1][N.n] = make_float2((float)N.x.x, (float)N.x.y);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+// pre-smoothing from a zero guess (nu sweeps), residual, restriction into the next level's b
+__device__ __noinline__ void small_down(const TailArgs &a, int l, float2 (*xs)[TAIL_THREADS], int t, int T) {
+  const LevelView &L = a.lv[l];
+  const int nn = (L.nx + 1) * (L.ny + 1);
+  const bool active = t < nn;
+  SmallNode N;
+  small_load(L, t, N);
+  int cur = 0;
+  if (active) {
+    N.x = make_double2(a.omega * N.dinv.x * N.b.x, a.omega * N.dinv.y * N.b.y);
+    xs[0][t] = make_float2((float)N.x.x, (float)N.x.y);
+  }
+  __syncthreads();
+  small_sweeps(N, active, xs, cur, a.nu[l] - 1, a.omega);
+  if (active) {
+    float ax, ay;
+    small_apply(N, xs[cur], ax, ay);
+    L.x[t] = N.x;
+    L.r[t] = make_double2(N.dinv.x != 0.0 ? N.b.x - (double)ax : 0.0, N.dinv.y != 0.0 ? N.b.y - (double)ay : 0.0);
+  }
+  __syncthreads();
+  const LevelView &C = a.lv[l + 1];
+  const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
+  for (int n = t; n < nnc; n += T) C.b[n] = restrict_node(L.r, n % nprc, n / nprc, L.nx, L.ny);
+  __syncthreads();
+}
+// coarse correction + nu post-smoothing sweeps
+__device__ __noinline__ void small_up(const TailArgs &a, int l, float2 (*xs)[TAIL_THREADS], int t) {
+  const LevelView &L = a.lv[l];
+  const LevelView &C = a.lv[l + 1];
+  const int npr = L.nx + 1, nn = npr * (L.ny + 1);
+  const bool active = t < nn;
+  SmallNode N;
+  small_load(L, t, N);
+  int cur = 0;
+  if (active) {
+    const double2 p = prolong_node(C.x, t % npr, t / npr, L.nx, L.ny, C.nx + 1);   // small levels leave their result in x
+    N.x = L.x[t];
+    if (N.dinv.x != 0.0) N.x.x += p.x;
+    if (N.dinv.y != 0.0) N.x.y += p.y;
+    xs[0][t] = make_float2((float)N.x.x, (float)N.x.y);
+  }
+  __syncthreads();
+  small_sweeps(N, active, xs, cur, a.nu[l], a.omega);
+  if (active) L.x[t] = N.x;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ TailArgs a) {
   if (a.done && *a.done) return;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
@@ -353,7 +452,8 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
   // every rank must know where the iterates of the big levels ended (same arithmetic on all ranks: cur[] is
   // computed identically); the small levels are finished by CTA 0, which publishes cur[lsmall] via the rule below
   if (rank == 0) {
-    for (l = lsmall; l + 1 < a.n; ++l) tail_down(a, l, cur, t, T, bsync);
+    __shared__ float2 xs[2][TAIL_THREADS];
+    for (l = lsmall; l + 1 < a.n; ++l) small_down(a, l, xs, t, T);
     {  // coarsest: dense inverse, one warp per row (lanes stride the columns, shuffle reduction)
       const LevelView &C = a.lv[a.n - 1];
       const double *bb = reinterpret_cast<const double *>(C.b);
@@ -372,19 +472,10 @@ __global__ void __launch_bounds__(1024) k_tail(const __grid_constant__ TailArgs 
     }
     __syncthreads();
     STAMP();
-    for (l = a.n - 2; l >= lsmall; --l) tail_up(a, l, cur, t, T, bsync);
+    for (l = a.n - 2; l >= lsmall; --l) small_up(a, l, xs, t);
   }
-  // the final iterate of a level lives in x for an even number of pointer swaps, in x2 otherwise; that parity
-  // depends only on nu[l], so the other ranks can compute it without communication
-  if (lsmall < a.n) {
-    const LevelView &C = a.lv[lsmall];
-    if (lsmall == a.n - 1) cur[lsmall] = C.x;
-    else {
-      const int nu = a.nu[lsmall];
-      const int swaps = (nu > 1 ? nu - 1 : 0) + nu;           // pre-smoothing swaps + post-smoothing swaps
-      cur[lsmall] = (swaps & 1) ? C.x2 : C.x;
-    }
-  }
+  // small levels (and the coarsest) leave their result in x
+  if (lsmall < a.n) cur[lsmall] = a.lv[lsmall].x;
   csync();
   STAMP();
   for (l = lsmall - 1; l >= 0; --l) tail_up(a, l, cur, gt, GT, csync);
@@ -435,6 +526,7 @@ const double2 *level_result(const topo_handle *h, int l, int tail) {
   const int L = h->n_levels;
   if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
   if (l >= tail) {                                 // tail levels: parity of the pointer swaps (see k_tail)
+    if (h->levels[l].nn <= TAIL_SMALL) return h->levels[l].x;      // small levels keep their iterate in x
     const int nu = tail_nu(h, l);
     const int swaps = (nu > 1 ? nu - 1 : 0) + nu;
     return (swaps & 1) ? h->levels[l].x2 : h->levels[l].x;
@@ -466,7 +558,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
     if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       for (int cs : {16, 8, 4, 2}) {
         cudaLaunchConfig_t q = {};
-        q.gridDim = dim3(cs); q.blockDim = dim3(1024);
+        q.gridDim = dim3(cs); q.blockDim = dim3(TAIL_THREADS);
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -481,7 +573,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   const int cs = big_tail ? cluster_size : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs);
-  cfg.blockDim = dim3(1024);
+  cfg.blockDim = dim3(TAIL_THREADS);
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -181,6 +181,7 @@ struct topo_handle {
   int tail_max_nodes;
   bool use_graph, pcg_graph_valid;
   cudaGraphExec_t pcg_graph_exec;
+  int last_pcg_iters;          // iterations of the previous multigrid-PCG solve (sizes the first batch of the next)
   int pcg_graph_launches;      // levels with at most this many nodes run inside the single-CTA tail kernel
 
   void *slab_nodal, *slab_elem;   // allocation bases (field pointers get swapped)

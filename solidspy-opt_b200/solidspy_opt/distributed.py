@@ -244,6 +244,7 @@ class SlabSimp:
         if transport == "p2p":
             self._attach_p2p()
         self._lam_prev = 0.0
+        self._last_iters = 0
         self.halo_bytes = 0
         self.collectives = 0
 
@@ -434,9 +435,16 @@ class SlabSimp:
             done, iters, relres = self.slabs[0].dist_solve_poll()
             if done or launched >= self.maxit:
                 break
-            for _ in range(2):
+            # consecutive design iterations need almost the same number of PCG iterations: enqueue the expected
+            # count (minus one) before the first poll, then poll after every pair
+            if self._last_iters > 4:
+                pairs = (self._last_iters - 1)//2 if launched == 0 else 1
+            else:
+                pairs = 2
+            for _ in range(max(1, pairs)):
                 self._pair()
-            launched += 4
+            launched += 2*max(1, pairs)
+        self._last_iters = iters
         self._all("solve_end", iters)
         if self.p2p and any(t.dist_p2p_error() for t in self.slabs):
             raise self._capi.TopoError(self._capi.ECUDA, "peer-memory transport: a wait for a neighbour's data timed out")
