@@ -76,6 +76,24 @@ def main():
             out[key] = {"compliance_rel": worst_c, "drho_max": drho, "cg_iters_single_vs_slabs": its}
             if worst_c > 1e-8 or drho > 1e-7:
                 out["ok"] = False
+    # ---- the reference's own trajectory (golden fixture of config 1, 60x60) through SIMP(dist=...) ------------------------
+    gpath = os.path.join(ROOT, "tests", "golden", "simp_c1.npz")
+    if world == 2 and os.path.exists(gpath):
+        from solidspy_opt.optimize import SIMP
+        gld = np.load(gpath, allow_pickle=True)
+        hist = {}
+        rho_mine = SIMP(float(gld["length"]), float(gld["height"]), int(gld["nx"]), int(gld["ny"]), gld["dirs"], gld["positions"],
+                        int(gld["niter"]), int(gld["penal"]), history=hist, verbose=False, dist=dist, device=local)
+        mine = torch.as_tensor(rho_mine).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        rho_all = torch.cat(parts).cpu().numpy()
+        n = len(gld["compliance"])
+        c_err = float(np.max(np.abs(np.array(hist["compliance"][:n]) - gld["compliance"])/np.abs(gld["compliance"])))
+        r_err = float(np.abs(rho_all - gld["rho_final"]).max())
+        out["golden_c1"] = {"iterations": len(hist["compliance"]), "expected": n, "compliance_rel": c_err, "rho_final_abs": r_err}
+        if len(hist["compliance"]) != n or c_err > 1e-6 or r_err > 1e-6:
+            out["ok"] = False
     # ---- timing on a large mesh ------------------------------------------------------------------------------------
     big = os.environ.get("DIST_BIG", "")
     if big:
