@@ -237,21 +237,8 @@ __global__ void k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny
     __syncthreads();
     for (int j = threadIdx.x; j < W; j += blockDim.x) {
       const double pk = sm[k * W + j] * pinv;
-      // 8 rows per trip, all loads before the stores (shared-memory stores would otherwise serialise the next loads)
-      for (int i0 = 0; i0 < N; i0 += 8) {
-        double a[8], c[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = min(i0 + q, N - 1);
-          a[q] = sm[i * W + j];
-          c[q] = colk[i];
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = i0 + q;
-          if (i < N && i != k) sm[i * W + j] = fma(-c[q], pk, a[q]);
-        }
-      }
+      for (int i = 0; i < N; ++i)
+        if (i != k) sm[i * W + j] = fma(-colk[i], pk, sm[i * W + j]);
       sm[k * W + j] = pk;
     }
     __syncthreads();
