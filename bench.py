@@ -364,7 +364,14 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"] if dom else None,
                          "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"] if dom else None, "traffic": None, "peak_source": peak_src,
+                         "frac": dom["frac"] if dom else None,
+                         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+                         # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_k_fine_update_resid0.txt);
+                         # only meaningful for the mesh and kernel it was captured on
+                         "traffic": (208947712 + 103414016) if (dom and dom["kernel"] == "k_fine<update_resid0>"
+                                                                and (nx, ny) == (2048, 1024)) else None,
+                         "traffic_source": "profiles/r1_ncu_k_fine_update_resid0.txt",
+                         "peak_source": peak_src,
                          "avg_launch_us": dom["avg_launch_us"] if dom else None,
                          "launches_timed": dom["launches"] if dom else 0,
                          "algorithmic_bytes_per_launch": dom["algorithmic_bytes"] if dom else None,
