@@ -335,7 +335,9 @@ def main():
         # nodal vectors are 16 B/node, element scales 8 B/element, BC flags 1 B/node
         alg = {"k_fine<apply>": 32*nn + 8*ne, "k_fine<resid>": 48*nn + 8*ne + nn,
                "k_fine<pcg_matvec>": 64*nn + 8*ne + nn, "k_fine<pcg_matvec_jacobi>": 80*nn + 8*ne + nn,
-               "k_fine<update_resid0>": 144*nn + 8*ne, "k_fine<smooth_dot>": 64*nn + 8*ne,
+               # x^, res and the D^-1 copy of the fused passes are float2 (8 B/node): update reads p, Ap, u, r (64) +
+               # D^-1 (8) and writes u, r (32) + x^, res (16); smooth_dot reads x^ (8), r (16), D^-1 (8), writes z (16)
+               "k_fine<update_resid0>": 120*nn + 8*ne, "k_fine<smooth_dot>": 48*nn + 8*ne,
                "k_fine<smooth>": 64*nn + 8*ne}
         fine = [(nm, n, ms) for nm, n, ms in report if nm in alg]
         kernels = [{"kernel": nm, "launches": n, "avg_launch_us": ms*1e3/n, "algorithmic_bytes": alg[nm],
@@ -368,7 +370,7 @@ def main():
                          # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
                          # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_k_fine_update_resid0.txt);
                          # only meaningful for the mesh and kernel it was captured on
-                         "traffic": (208947712 + 103414016) if (dom and dom["kernel"] == "k_fine<update_resid0>"
+                         "traffic": (189564160 + 73890560) if (dom and dom["kernel"] == "k_fine<update_resid0>"
                                                                 and (nx, ny) == (2048, 1024)) else None,
                          "traffic_source": "profiles/r1_ncu_k_fine_update_resid0.txt",
                          "peak_source": peak_src,

@@ -204,6 +204,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   double **evs[nev] = {&h->rho, &h->rho_new, &h->dc, &h->dc2, &h->scale, &h->sens, &h->sens_prev};
   for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * (size_t)h->ne;
   CUDA_TRY(cudaMalloc(&h->nodal, sizeof(double) * (size_t)h->nn));
+  CUDA_TRY(cudaMalloc(&h->dinv_f, sizeof(float2) * (size_t)h->nn));
   CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn + 64));          // + slack: the stage-1 kernel reads aligned words
   CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn + 64, h->stream));
   CUDA_TRY(cudaMalloc(&h->keep, (size_t)h->ne));
@@ -252,6 +253,7 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaEventDestroy(h->ev_t1);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   cudaFree(h->nodal);
+  cudaFree(h->dinv_f);
   cudaFree(h->fixed);
   cudaFree(h->keep);
   cudaFree(h->partials);

@@ -49,13 +49,21 @@ __global__ void k_row_add(double2 *__restrict__ dst, const double2 *__restrict__
   dst[i] = a;
 }
 // dst = dst + src - base   (completes a locally smoothed interface row: see the file header)
+// (base_f32: the base row is a float2 array -- the fine-grid x~)
 __global__ void k_row_add_sub(double2 *__restrict__ dst, const double2 *__restrict__ src, const double2 *__restrict__ base,
-                              int n, const int *done) {
+                              int base_f32, int n, const int *done) {
   if (done && *done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 a = dst[i];
-  const double2 b = src[i], c = base[i];
+  const double2 b = src[i];
+  double2 c;
+  if (base_f32) {
+    const float2 f = reinterpret_cast<const float2 *>(base)[i];
+    c = make_double2((double)f.x, (double)f.y);
+  } else {
+    c = base[i];
+  }
   a.x = (a.x + b.x) - c.x; a.y = (a.y + b.y) - c.y;
   dst[i] = a;
 }
@@ -280,8 +288,10 @@ extern "C" int topo_dist_xchg_finish(topo_t *h, int what, int level) {
     if (D.has_lo) KL(h, "k_row_add", k_row_add<<<nb, 128, 0, st>>>(v, D.recv_lo, npr, done));
     if (D.has_hi) KL(h, "k_row_add", k_row_add<<<nb, 128, 0, st>>>(v + last, D.recv_hi, npr, done));
   } else {
-    if (D.has_lo) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v, D.recv_lo, base, npr, done));
-    if (D.has_hi) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v + last, D.recv_hi, base + last, npr, done));
+    const int f32 = (what == TOPO_X_Z) ? 1 : 0;                     // x~ is a float2 array: its last row starts at float2 index `last`
+    const double2 *base_hi = f32 ? reinterpret_cast<const double2 *>(reinterpret_cast<const float2 *>(base) + last) : base + last;
+    if (D.has_lo) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v, D.recv_lo, base, f32, npr, done));
+    if (D.has_hi) KL(h, "k_row_add_sub", k_row_add_sub<<<nb, 128, 0, st>>>(v + last, D.recv_hi, base_hi, f32, npr, done));
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(1024) k_p2p_push_rows(const double2 *__restric
 // block 0: first row, block 1: last row.  dst += recv  or  dst = dst + recv - base
 __global__ void __launch_bounds__(1024) k_p2p_finish_rows(double2 *__restrict__ v_lo, double2 *__restrict__ v_hi,
                                                           const double2 *__restrict__ base_lo, const double2 *__restrict__ base_hi,
-                                                          int n, char *region, int has_lo, int has_hi, size_t off_lo, size_t off_hi,
+                                                          int base_f32, int n, char *region, int has_lo, int has_hi, size_t off_lo, size_t off_hi,
                                                           size_t stride, P2PCounters *c) {
   const unsigned long long seq = c->halo_wait + 1;
   const size_t buf = (size_t)(seq & 1ull) * stride;
@@ -529,7 +539,13 @@ __global__ void __launch_bounds__(1024) k_p2p_finish_rows(double2 *__restrict__ 
         double2 a = dst[i];
         const double2 b = src[i];
         if (base != nullptr) {
-          const double2 q = base[i];
+          double2 q;
+          if (base_f32) {
+            const float2 f = reinterpret_cast<const float2 *>(base)[i];
+            q = make_double2((double)f.x, (double)f.y);
+          } else {
+            q = base[i];
+          }
           a.x = (a.x + b.x) - q.x; a.y = (a.y + b.y) - q.y;
         } else {
           a.x += b.x; a.y += b.y;
@@ -695,7 +711,10 @@ extern "C" int topo_dist_p2p_xchg(topo_t *h, int phase, int what, int level) {
     KL(h, "k_p2p_push_rows", k_p2p_push_rows<<<1, 1024, 0, h->stream>>>(v, v + last, npr, peer_lo, peer_hi, D.p2p_off_lo, D.p2p_off_hi,
                                                                         D.p2p_row_stride, D.p2p_cnt));
   } else {
-    KL(h, "k_p2p_finish_rows", k_p2p_finish_rows<<<2, 1024, 0, h->stream>>>(v, v + last, base, base ? base + last : nullptr, npr,
+    const int f32 = (what == TOPO_X_Z) ? 1 : 0;
+    const double2 *base_hi = !base ? nullptr
+                             : (f32 ? reinterpret_cast<const double2 *>(reinterpret_cast<const float2 *>(base) + last) : base + last);
+    KL(h, "k_p2p_finish_rows", k_p2p_finish_rows<<<2, 1024, 0, h->stream>>>(v, v + last, base, base_hi, f32, npr,
                                                                             D.p2p_region, D.has_lo ? 1 : 0, D.has_hi ? 1 : 0,
                                                                             D.p2p_off_lo, D.p2p_off_hi, D.p2p_row_stride, D.p2p_cnt));
   }

@@ -60,14 +60,28 @@ enum {
 
 // ring depth per kind (S slots, S-2 rows in flight per warp); the row loop is unrolled by S and the
 // register window cycles through 4 row images, so slots and window roles are compile-time
+// F32MASK: bit k set = raw input k is a float2 array in global memory (the vectors that exist only inside the
+// preconditioner -- x^, res, and the fp32 copy of D^-1 -- are stored in fp32: they carry 18 % of the fine-grid
+// traffic of a PCG iteration and the multigrid correction is accurate to a few per cent anyway).  Such an input
+// still owns a double2 slot per node in the ring; only its low 8 bytes are copied and read.
 template <int K> struct FK;
-template <> struct FK<FK_APPLY> { static constexpr int NIN = 1, S = 8; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_RESID> { static constexpr int NIN = 2, S = 8; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_SMOOTH> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = false; };
-template <> struct FK<FK_PCG_MATVEC> { static constexpr int NIN = 2, S = 8; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_PCG_MATVEC_J> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_UPDATE_RESID0> { static constexpr int NIN = 5, S = 4; static constexpr bool DERIVE = true; };
-template <> struct FK<FK_PROLONG_SMOOTH> { static constexpr int NIN = 3, S = 4; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_APPLY> { static constexpr int NIN = 1, S = 8, F32MASK = 0; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_RESID> { static constexpr int NIN = 2, S = 8, F32MASK = 0; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_SMOOTH> { static constexpr int NIN = 3, S = 4, F32MASK = 0; static constexpr bool DERIVE = false; };
+template <> struct FK<FK_PCG_MATVEC> { static constexpr int NIN = 2, S = 8, F32MASK = 0; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PCG_MATVEC_J> { static constexpr int NIN = 3, S = 4, F32MASK = 0; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_UPDATE_RESID0> { static constexpr int NIN = 5, S = 4, F32MASK = 1 << 4; static constexpr bool DERIVE = true; };
+template <> struct FK<FK_PROLONG_SMOOTH> { static constexpr int NIN = 3, S = 4, F32MASK = (1 << 0) | (1 << 2); static constexpr bool DERIVE = true; };
+
+// value of raw input k at a ring position (fp32 inputs sit in the low half of their slot)
+template <int KIND, int K>
+__device__ __forceinline__ double2 raw_in(const double2 *rw, int SW) {
+  if ((FK<KIND>::F32MASK >> K) & 1) {
+    const float2 f = *reinterpret_cast<const float2 *>(rw + K * SW);
+    return make_double2((double)f.x, (double)f.y);
+  }
+  return rw[K * SW];
+}
 
 struct FineArgs {
   const double2 *in[5];
@@ -204,13 +218,23 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
 #pragma unroll
       for (int k = 0; k < NIN; ++k) {
         double2 *dst = raw + (SL * NIN + k) * SW;
-        const double2 *src = a.in[k] + rowoff;
+        if ((FK<KIND>::F32MASK >> k) & 1) {
+          const float2 *src = reinterpret_cast<const float2 *>(a.in[k]) + rowoff;
 #pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          const bool ok = cl + j < npr;
-          cp_async16(dst + sl + j, src + (ok ? cl + j : 0), row_ok && ok);
+          for (int j = 0; j < NC; ++j) {
+            const bool ok = cl + j < npr;
+            cp_async8(dst + sl + j, src + (ok ? cl + j : 0), row_ok && ok);
+          }
+          if (has_halo) cp_async8(dst + hs, src + hoff, row_ok && hcol_ok);
+        } else {
+          const double2 *src = a.in[k] + rowoff;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            const bool ok = cl + j < npr;
+            cp_async16(dst + sl + j, src + (ok ? cl + j : 0), row_ok && ok);
+          }
+          if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
         }
-        if (has_halo) cp_async16(dst + hs, src + hoff, row_ok && hcol_ok);
       }
       const bool erow_ok = q >= 1 && q <= a.ny;
       const double *esrc = a.scale + (size_t)(erow_ok ? q - 1 : 0) * a.nx;
@@ -246,19 +270,19 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
         if (store) a.out[0][n] = v;
         return v;
       } else if (KIND == FK_UPDATE_RESID0) {
-        const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = rw[4 * SW];
+        const double2 p = rw[0], ap = rw[SW], u = rw[2 * SW], r = rw[3 * SW], d = raw_in<KIND, 4>(rw, SW);
         const double2 rn = make_double2(d.x != 0.0 ? fma(-alpha, ap.x, r.x) : 0.0, d.y != 0.0 ? fma(-alpha, ap.y, r.y) : 0.0);
         const double2 xh = make_double2(omega * d.x * rn.x, omega * d.y * rn.y);
         if (store) {
           a.out[0][n] = make_double2(fma(alpha, p.x, u.x), fma(alpha, p.y, u.y));
           a.out[1][n] = rn;
-          a.out[2][n] = xh;
+          reinterpret_cast<float2 *>(a.out[2])[n] = make_float2((float)xh.x, (float)xh.y);
           const double wr = wrow(row);
           dots[0] = fma(wr * rn.x, rn.x, fma(wr * rn.y, rn.y, dots[0]));
         }
         return xh;
       } else {  // FK_PROLONG_SMOOTH
-        const double2 xh = rw[0], d = rw[2 * SW];
+        const double2 xh = raw_in<KIND, 0>(rw, SW), d = raw_in<KIND, 2>(rw, SW);
         double px = 0.0, py = 0.0;
         if (in_dom && a.coarse != nullptr) {
           int I0, I1, J0, J1;
@@ -378,11 +402,12 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
             a.out[1][n] = make_double2(yx, yy);
             dots[0] = fma(v.x, yx, fma(v.y, yy, dots[0]));
           } else if (KIND == FK_UPDATE_RESID0) {
-            const double2 ap = rw[SW], rr = rw[3 * SW], d = rw[4 * SW];
+            const double2 ap = rw[SW], rr = rw[3 * SW], d = raw_in<KIND, 4>(rw, SW);
             const double rnx = fma(-alpha, ap.x, rr.x), rny = fma(-alpha, ap.y, rr.y);
-            a.out[3][n] = make_double2(d.x != 0.0 ? fma(wr, rnx, -yx) : 0.0, d.y != 0.0 ? fma(wr, rny, -yy) : 0.0);
+            reinterpret_cast<float2 *>(a.out[3])[n] =
+                make_float2(d.x != 0.0 ? (float)fma(wr, rnx, -yx) : 0.f, d.y != 0.0 ? (float)fma(wr, rny, -yy) : 0.f);
           } else {  // FK_PROLONG_SMOOTH
-            const double2 rr = rw[SW], d = rw[2 * SW];
+            const double2 rr = rw[SW], d = raw_in<KIND, 2>(rw, SW);
             const double zx = fma(omega * d.x, fma(wr, rr.x, -yx), v.x), zy = fma(omega * d.y, fma(wr, rr.y, -yy), v.y);
             a.out[0][n] = make_double2(zx, zy);
             // interface rows: z is completed by z_lo + z_hi - x~, so each side contributes r.(z - (1-w) x~)
@@ -482,8 +507,9 @@ int launch_fine(topo_handle *h, FineArgs &a) {
 // max diagonal over free DOFs (= K.max() of the reference's equilibrium guard, optimize.py:455: the
 // largest entry of an SPD matrix sits on its diagonal).
 __global__ void k_build_diag(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
-                             const uint8_t *__restrict__ fixed, double2 *__restrict__ dinv, int nx, int ny,
-                             double *partials, unsigned int *ticket, double *kmax_out) {
+                             const uint8_t *__restrict__ fixed, double2 *__restrict__ dinv,
+                             float2 *__restrict__ dinv_f, int nx, int ny, double *partials, unsigned int *ticket,
+                             double *kmax_out) {
   const int64_t nn = (int64_t)(nx + 1) * (ny + 1);
   double mx = 0.0;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
@@ -505,6 +531,7 @@ __global__ void k_build_diag(const __grid_constant__ KeParam ke, const double *_
       iy = dy > 0.0 ? 1.0 / dy : 0.0;
     }
     dinv[n] = make_double2(ix, iy);
+    dinv_f[n] = make_float2((float)ix, (float)iy);
   }
   double v[1] = {mx};
   grid_reduce<1, true>(v, partials, ticket, kmax_out);
@@ -571,7 +598,7 @@ int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap,
   a.in[1] = Ap;
   a.in[2] = u_in;
   a.in[3] = r_in;
-  a.in[4] = h->dinv;
+  a.in[4] = reinterpret_cast<const double2 *>(h->dinv_f);     // fp32 copy (FK<FK_UPDATE_RESID0>::F32MASK)
   a.out[0] = u_out;
   a.out[1] = r_out;
   a.out[2] = xhat;
@@ -586,9 +613,9 @@ int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap,
 int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 *r, const double2 *xc, int cnx,
                              double2 *z, double omega, int init) {
   FineArgs a = {};
-  a.in[0] = xhat;
+  a.in[0] = xhat;                                             // float2 array
   a.in[1] = r;
-  a.in[2] = h->dinv;
+  a.in[2] = reinterpret_cast<const double2 *>(h->dinv_f);     // fp32 copy
   a.out[0] = z;
   a.coarse = xc;
   a.cnx = cnx;
@@ -600,7 +627,7 @@ int topo_fine_prolong_smooth(topo_handle *h, const double2 *xhat, const double2 
 
 int topo_build_diag(topo_handle *h) {
   const int blocks = (int)std::min<int64_t>(div_up(h->nn, 256), 1184);
-  KL(h, "k_build_diag", k_build_diag<<<blocks, 256, 0, h->stream>>>(h->ke, h->scale, h->fixed, h->dinv, h->nx, h->ny,
+  KL(h, "k_build_diag", k_build_diag<<<blocks, 256, 0, h->stream>>>(h->ke, h->scale, h->fixed, h->dinv, h->dinv_f, h->nx, h->ny,
                                                                       h->partials, h->ticket, h->kmax));
   CUDA_TRY(cudaGetLastError());
   h->diag_valid = true;

@@ -452,12 +452,14 @@ __global__ void k_dist_diag_pack(const double2 *__restrict__ dinv, int npr, int 
   hi[i] = make_double2(b.x != 0.0 ? 1.0 / b.x : 0.0, b.y != 0.0 ? 1.0 / b.y : 0.0);
 }
 // dinv = 1 / (own diagonal + the neighbour's) on one interface row
-__global__ void k_dist_diag_unpack(double2 *__restrict__ dinv_row, const double2 *__restrict__ mine,
-                                   const double2 *__restrict__ theirs, int npr) {
+__global__ void k_dist_diag_unpack(double2 *__restrict__ dinv_row, float2 *__restrict__ dinv_f_row,
+                                   const double2 *__restrict__ mine, const double2 *__restrict__ theirs, int npr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npr) return;
   const double dx = mine[i].x + theirs[i].x, dy = mine[i].y + theirs[i].y;
-  dinv_row[i] = make_double2(mine[i].x > 0.0 && dx > 0.0 ? 1.0 / dx : 0.0, mine[i].y > 0.0 && dy > 0.0 ? 1.0 / dy : 0.0);
+  const double2 v = make_double2(mine[i].x > 0.0 && dx > 0.0 ? 1.0 / dx : 0.0, mine[i].y > 0.0 && dy > 0.0 ? 1.0 / dy : 0.0);
+  dinv_row[i] = v;
+  if (dinv_f_row != nullptr) dinv_f_row[i] = make_float2((float)v.x, (float)v.y);     // fine grid: fp32 copy
 }
 // gathered level-K cells [world][64][ncl] -> global SoA planes [64][world*ncl]
 __global__ void k_dist_cells_reorder(const double *__restrict__ recv, double *__restrict__ cell, int64_t ncl, int world) {
@@ -516,11 +518,14 @@ int topo_dist_setup_global(topo_handle *h) {
   for (int l = 0; l < K; ++l) {
     const int npr = h->lvl_nx[l] + 1, ny = h->ny >> l;
     double2 *dinv = (l == 0) ? h->dinv : h->levels[l].dinv;
+    float2 *dinv_f = (l == 0) ? h->dinv_f : nullptr;
+    const size_t last = (size_t)ny * npr;
     if (D.has_lo)
-      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv, D.diag_send_lo + off, D.diag_recv_lo + off, npr));
+      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv, dinv_f, D.diag_send_lo + off, D.diag_recv_lo + off,
+                                                                                       npr));
     if (D.has_hi)
-      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv + (size_t)ny * npr, D.diag_send_hi + off,
-                                                                                       D.diag_recv_hi + off, npr));
+      KL(h, "k_dist_diag_unpack", k_dist_diag_unpack<<<blocks_for(npr), 128, 0, st>>>(dinv + last, dinv_f ? dinv_f + last : nullptr,
+                                                                                       D.diag_send_hi + off, D.diag_recv_hi + off, npr));
     off += npr;
   }
   {

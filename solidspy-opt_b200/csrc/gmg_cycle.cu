@@ -36,7 +36,8 @@ __device__ __forceinline__ void prolong_taps(int i, int nf, int &I0, int &I1, do
   else { I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w0 = 0.5; w1 = 0.5; }
 }
 
-__device__ __forceinline__ double2 restrict_node(const double2 *__restrict__ rf, int I, int J, int nxf, int nyf) {
+template <class V2>
+__device__ __forceinline__ double2 restrict_node(const V2 *__restrict__ rf, int I, int J, int nxf, int nyf) {
   const int nprf = nxf + 1;
   int X, Y;
   double wxl, wxr, wyl, wyr;
@@ -51,9 +52,9 @@ __device__ __forceinline__ double2 restrict_node(const double2 *__restrict__ rf,
     for (int di = -1; di <= 1; ++di) {
       const double w = wy[dj + 1] * wx[di + 1];
       if (w == 0.0) continue;
-      const double2 v = rf[(size_t)(Y + dj) * nprf + (X + di)];
-      sx = fma(w, v.x, sx);
-      sy = fma(w, v.y, sy);
+      const V2 v = rf[(size_t)(Y + dj) * nprf + (X + di)];
+      sx = fma(w, (double)v.x, sx);
+      sy = fma(w, (double)v.y, sy);
     }
   }
   return make_double2(sx, sy);
@@ -224,7 +225,8 @@ __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int 
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_resid(L, n);
 }
-__global__ void __launch_bounds__(128) k_restrict(const double2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
+template <class V2>
+__global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
                                                   int nyf, int nxc, int nyc, const int *done) {
   if (done && *done) return;
   const int nprc = nxc + 1;
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(128) k_restrict(const double2 *__restrict__ rf
   bc[n] = restrict_node(rf, I, J, nxf, nyf);
 }
 // fine grid: x^ += mask(P x1)   (constrained DOFs stay zero)
-__global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, double2 *__restrict__ xf,
+// (the fine-grid x^ is a float2 array: see FK<>::F32MASK in fine.cu)
+__global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, float2 *__restrict__ xf,
                                                           const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
                                                           const int *done) {
   if (done && *done) return;
@@ -246,9 +249,9 @@ __global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restr
   const int j = (int)(n / nprf), i = (int)(n - (int64_t)j * nprf);
   const double2 p = prolong_node(xc, i, j, nxf, nyf, nxc + 1);
   const unsigned m = fixed[n];
-  double2 acc = xf[n];
-  if (!(m & 1u)) acc.x += p.x;
-  if (!(m & 2u)) acc.y += p.y;
+  float2 acc = xf[n];
+  if (!(m & 1u)) acc.x = (float)((double)acc.x + p.x);
+  if (!(m & 2u)) acc.y = (float)((double)acc.y + p.y);
   xf[n] = acc;
 }
 
@@ -262,7 +265,8 @@ constexpr int TAIL_SMALL = TAIL_THREADS;
 struct TailArgs {
   LevelView lv[TAIL_MAX];
   int n;                       // number of levels in the tail (the last one is the coarsest)
-  const double2 *r_parent;     // residual of the level above the tail
+  const double2 *r_parent;     // residual of the level above the tail (a float2 array when that level is the fine grid)
+  int parent_f32;
   int pnx, pny;                // its size
   const double *coarse_inv;
   int coarse_n;
@@ -442,7 +446,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ T
   if (a.r_parent != nullptr) {                  // row-slab mode: lv[0].b was assembled from the gathered slabs
     const LevelView &C = a.lv[0];
     const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
-    for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny);
+    if (a.parent_f32) {
+      const float2 *rp = reinterpret_cast<const float2 *>(a.r_parent);
+      for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(rp, n % nprc, n / nprc, a.pnx, a.pny);
+    } else {
+      for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny);
+    }
   }
   csync();
   STAMP();
@@ -535,7 +544,7 @@ const double2 *level_result(const topo_handle *h, int l, int tail) {
 }
 
 // all levels >= tail in one cluster launch; r_parent == nullptr: levels[tail].b is already in place
-int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int pny) {
+int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int pny, int parent_f32 = 0) {
   const int L = h->n_levels;
   TailArgs ta = {};
   ta.n = L - tail;
@@ -544,7 +553,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
     return TOPO_EINVAL;
   }
   for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h->levels[l]);
-  ta.r_parent = r_parent; ta.pnx = pnx; ta.pny = pny;
+  ta.r_parent = r_parent; ta.pnx = pnx; ta.pny = pny; ta.parent_f32 = parent_f32;
   ta.coarse_inv = h->coarse_inv;
   ta.coarse_n = h->coarse_n;
   ta.omega = h->omega;
@@ -635,7 +644,8 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
 
   if (tail > 1) {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(res_fine, C.b, h->nx, h->ny, C.nx, C.ny, done));
+    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx,
+                                                                     C.ny, done));
   }
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
@@ -651,7 +661,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
       KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny, done));
     }
   }
-  if (tail == 1) TOPO_TRY(launch_tail(h, tail, res_fine, h->nx, h->ny));
+  if (tail == 1) TOPO_TRY(launch_tail(h, tail, res_fine, h->nx, h->ny, 1));
   else TOPO_TRY(launch_tail(h, tail, h->levels[tail - 1].r, h->levels[tail - 1].nx, h->levels[tail - 1].ny));
   for (int l = tail - 1; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
@@ -674,7 +684,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     *x1_out = result_of(1);          // the caller's smoothing kernel prolongates on the fly
   } else {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), xhat_fine, h->fixed, h->nx, h->ny,
+    KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx, h->ny,
                                                                                        C.nx, done));
   }
   CUDA_TRY(cudaGetLastError());
@@ -691,13 +701,13 @@ static int dist_restrict_from(topo_handle *h, int l, const double2 *r) {
   const DistState &D = h->dist;
   const int nxf = h->lvl_nx[l], nyf = (l == 0) ? h->ny : h->levels[l].ny;
   const int *done = &h->sc->done;
-  if (l + 1 < D.K) {
-    GmgLevel &C = h->levels[l + 1];
-    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, h->stream>>>(r, C.b, nxf, nyf, C.nx, C.ny, done));
-  } else {
-    const int nxc = h->lvl_nx[D.K], nyc = nyf / 2;
-    KL(h, "k_restrict", k_restrict<<<blocks_for((int64_t)(nxc + 1) * (nyc + 1)), 128, 0, h->stream>>>(r, D.bK_send, nxf, nyf, nxc, nyc, done));
-  }
+  // the fine-grid residual (l == 0) is a float2 array, level residuals are double2
+  const float2 *rf32 = reinterpret_cast<const float2 *>(r);
+  double2 *dst = (l + 1 < D.K) ? h->levels[l + 1].b : D.bK_send;
+  const int nxc = h->lvl_nx[l + 1], nyc = nyf / 2;
+  const int nb = blocks_for((int64_t)(nxc + 1) * (nyc + 1));
+  if (l == 0) KL(h, "k_restrict", k_restrict<<<nb, 128, 0, h->stream>>>(rf32, dst, nxf, nyf, nxc, nyc, done));
+  else KL(h, "k_restrict", k_restrict<<<nb, 128, 0, h->stream>>>(r, dst, nxf, nyf, nxc, nyc, done));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -752,7 +762,7 @@ int topo_dist_level_up(topo_handle *h, int l) {
 
 int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine) {
   if (!h->dist.on) return TOPO_EINVAL;
-  KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, h->stream>>>(dist_coarse_result(h, 1), xhat_fine, h->fixed, h->nx,
+  KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, h->stream>>>(dist_coarse_result(h, 1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx,
                                                                                            h->ny, h->lvl_nx[1], &h->sc->done));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;

@@ -139,6 +139,7 @@ struct topo_handle {
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
+  float2 *dinv_f;      // fp32 copy of dinv for the fused multigrid-PCG passes (tmp = res and tmp2 = x^ hold float2 there)
   double *rho, *rho_new, *dc, *dc2, *scale, *sens, *sens_prev, *nodal;
   uint8_t *fixed, *keep;
   int8_t *cons_host_shadow;
