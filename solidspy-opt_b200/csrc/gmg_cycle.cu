@@ -1,13 +1,16 @@
-// Coarse part of the multigrid V-cycle (levels >= 1): node-stencil kernels, transfers, and the
-// single-CTA "tail" kernel that runs all small levels in one launch.  Set-up (Galerkin products) is in
-// gmg.cu.  No counterpart in the reference (it calls SuperLU, optimize.py:437).
+// Coarse part of the multigrid V-cycle (levels >= 1): node-stencil kernels, transfers, and the "tail" kernel that
+// runs all small levels in one thread-block-cluster launch.  Set-up (Galerkin products) is in gmg.cu.  No counterpart
+// in the reference (it calls SuperLU, optimize.py:437).
 //
 // Per level with a zero initial guess and one damped-Jacobi sweep before / after the coarse correction:
 //   down:  x = w D^-1 b ; r = b - A x          (one kernel: x of the 9 neighbours is recomputed on the fly)
 //          b_coarse = P^T r                     (restrict)
 //   up:    x~ = x + P x_coarse ; x' = x~ + w D^-1 (b - A x~)   (one kernel, x~ of the neighbours on the fly)
-// Levels with few nodes are latency/launch bound, so every level from `tail_level` on is handled by ONE
-// CTA of 1024 threads that walks down and up with __syncthreads between stages.
+// Levels with few nodes are latency/launch bound, so every level from the first with <= tail_max_nodes nodes on is
+// handled by ONE launch of a 16-CTA cluster (640..768 threads per CTA): levels with more than TAIL_SMALL nodes are
+// worked on by the whole cluster with barrier.cluster between stages, the smaller ones by CTA 0 alone with the
+// node operators in registers, the coarsest by a dense inverse.  The row-slab drivers (topo_dist_*) at the end of
+// the file run the same kernels level by level around the host's exchanges.
 #include <algorithm>
 
 #include <cooperative_groups.h>
