@@ -262,7 +262,7 @@ int topo_timer_start(topo_t *h);
 int topo_timer_stop(topo_t *h, float *ms);
 /* Per-launch CUDA-event timing of the stage-1 kernel (all variants of the fine-grid K application)
  * while enabled; read returns the number of launches recorded and their summed duration. */
-int topo_profile_matvec(topo_t *h, int enable);
+int topo_profile_matvec(topo_t *h, int enable);   /* switching off discards the recorded data: read the report first */
 int topo_profile_read(topo_t *h, int *launches, float *total_ms);
 /* While profiling is enabled EVERY kernel launch of the handle is bracketed by events; the report is a
  * text table "kernel count total_ms" (one line per kernel, sorted by time) written into buf. */
