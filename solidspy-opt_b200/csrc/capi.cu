@@ -164,7 +164,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->nu_post = 1;
   h->nu_coarse = getenv("TOPO_NU_COARSE") ? atoi(getenv("TOPO_NU_COARSE")) : 0;
   h->nu_tail_big = getenv("TOPO_NU_TAIL_BIG") ? atoi(getenv("TOPO_NU_TAIL_BIG")) : 2;
-  h->nu_tail_small = getenv("TOPO_NU_TAIL_SMALL") ? atoi(getenv("TOPO_NU_TAIL_SMALL")) : 8;
+  h->nu_tail_small = getenv("TOPO_NU_TAIL_SMALL") ? atoi(getenv("TOPO_NU_TAIL_SMALL")) : 12;
   h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
   h->tail_dbg = nullptr;
   h->use_graph = getenv("TOPO_NO_GRAPH") ? false : true;

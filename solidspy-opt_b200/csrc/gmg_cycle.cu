@@ -669,7 +669,8 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   for (int l = tail - 1; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
     LevelView V = view_of(F);
-    if (F.nn > 200000) {
+    static const int unfused_min = getenv("TOPO_UNFUSED_MIN") ? atoi(getenv("TOPO_UNFUSED_MIN")) : 200000;
+    if (F.nn > unfused_min) {
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel
       KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, done));
