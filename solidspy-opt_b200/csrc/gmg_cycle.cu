@@ -289,8 +289,22 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // nu pre-smoothing sweeps from a zero guess, then the residual, then its restriction.  Sweep 1 is pointwise
 // (x = w D^-1 b); for nu == 1 it is fused with the residual (node_down).  Sweeps ping-pong x <-> x2 through local
 // pointer swaps; the iterate ends in x for odd nu and in x2 for even nu -- recorded in cur[l].
+// does tail level l start its pre-smoothing from x0 = w D^-1 b stored by the stage that produced b?  (cluster
+// levels with more than one sweep: the pointwise first sweep rides in the producer's stage instead of costing a
+// cluster barrier of its own)
+__device__ __forceinline__ bool tail_wants_x0(const TailArgs &a, int l) {
+  return l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL && a.nu[l] > 1;
+}
+__device__ __forceinline__ void tail_store_b(const TailArgs &a, int l, int n, double2 bv, bool x0) {
+  const LevelView &C = a.lv[l];
+  C.b[n] = bv;
+  if (x0) {
+    const double2 dv = C.dinv[n];
+    C.x[n] = make_double2(a.omega * dv.x * bv.x, a.omega * dv.y * bv.y);
+  }
+}
 template <class Sync>
-__device__ __forceinline__ void tail_down(const TailArgs &a, int l, double2 **cur, int gt, int GT, Sync sync) {
+__device__ __forceinline__ void tail_down(const TailArgs &a, int l, double2 **cur, int gt, int GT, Sync sync, bool x0_ready) {
   LevelView L = a.lv[l];
   const int nn = (L.nx + 1) * (L.ny + 1);
   const int nu = a.nu[l];
@@ -299,8 +313,10 @@ __device__ __forceinline__ void tail_down(const TailArgs &a, int l, double2 **cu
     sync();
     STAMP();
   } else {
-    for (int n = gt; n < nn; n += GT) node_smooth0(L, n, a.omega);
-    sync();
+    if (!x0_ready) {
+      for (int n = gt; n < nn; n += GT) node_smooth0(L, n, a.omega);
+      sync();
+    }
     for (int s = 1; s < nu; ++s) {
       for (int n = gt; n < nn; n += GT) node_smooth(L, n, a.omega);      // L.x -> L.x2
       sync();
@@ -313,7 +329,8 @@ __device__ __forceinline__ void tail_down(const TailArgs &a, int l, double2 **cu
   cur[l] = L.x;
   const LevelView &C = a.lv[l + 1];
   const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
-  for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(L.r, n % nprc, n / nprc, L.nx, L.ny);
+  const bool x0 = tail_wants_x0(a, l + 1);
+  for (int n = gt; n < nnc; n += GT) tail_store_b(a, l + 1, n, restrict_node(L.r, n % nprc, n / nprc, L.nx, L.ny), x0);
   sync();
   STAMP();
 }
@@ -449,17 +466,20 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ T
   if (a.r_parent != nullptr) {                  // row-slab mode: lv[0].b was assembled from the gathered slabs
     const LevelView &C = a.lv[0];
     const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
+    const bool x0 = tail_wants_x0(a, 0);
     if (a.parent_f32) {
       const float2 *rp = reinterpret_cast<const float2 *>(a.r_parent);
-      for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(rp, n % nprc, n / nprc, a.pnx, a.pny);
+      for (int n = gt; n < nnc; n += GT) tail_store_b(a, 0, n, restrict_node(rp, n % nprc, n / nprc, a.pnx, a.pny), x0);
     } else {
-      for (int n = gt; n < nnc; n += GT) C.b[n] = restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny);
+      for (int n = gt; n < nnc; n += GT) tail_store_b(a, 0, n, restrict_node(a.r_parent, n % nprc, n / nprc, a.pnx, a.pny), x0);
     }
   }
   csync();
   STAMP();
   int l = 0;
-  for (; l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL; ++l) tail_down(a, l, cur, gt, GT, csync);
+  // (row-slab mode: the first level's b was assembled by another kernel, so its x0 is not there yet)
+  for (; l + 1 < a.n && (a.lv[l].nx + 1) * (a.lv[l].ny + 1) > TAIL_SMALL; ++l)
+    tail_down(a, l, cur, gt, GT, csync, (l > 0 || a.r_parent != nullptr) && tail_wants_x0(a, l));
   const int lsmall = l;
   // every rank must know where the iterates of the big levels ended (same arithmetic on all ranks: cur[] is
   // computed identically); the small levels are finished by CTA 0, which publishes cur[lsmall] via the rule below
