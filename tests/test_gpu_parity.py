@@ -567,3 +567,35 @@ def test_slab_simp_trajectory_matches_reference(capi, case, slabs):
         assert np.abs(hist["rho"][k] - g["rho"][k]).max() <= 1e-6, "iteration %d" % k
     assert np.abs(rho - g["rho_final"]).max() <= 1e-6
     assert np.allclose(hist["g"], g["g"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("nx,ny,world,kind", [(480, 160, 5, "mbb"), (120, 64, 4, "right_partial"), (96, 64, 2, "scattered")])
+def test_slab_design_iterations_other_supports(capi, nx, ny, world, kind):
+    """Row slabs with constraints that are NOT the same on every slab (MBB rollers + one support in slab 0 -- the
+    BASELINE config-2 mesh -- beam_2-style partial clamping, scattered pinned DOFs) and a load on an interface row."""
+    from solidspy_opt import _capi
+    from solidspy_opt.distributed import SlabSimp
+    from solidspy_opt.optimize import kloc_simp
+    cons = _cons(nx, ny, kind, np.random.default_rng(5))
+    nyl = ny//world
+    loads = np.array([[(nx + 1)*nyl + nx//2, 0.0, -1.0], [(nx + 1)*ny + 3*nx//4, 0.5, -0.25]])   # first one on an interface row
+    ke = kloc_simp(206.8e9, 0.28)
+    sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, world=world, rtol=1e-10)
+    topo = _capi.Topo(nx, ny, ke)
+    try:
+        topo.set_cons(cons)
+        topo.set_loads(loads)
+        topo.fill(_capi.F_RHO, 0.5)
+        params = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=2.5, dx=1.0, dy=1.0, move=0.2, rtol=1e-10,
+                                  precond=_capi.PRECOND_GMG, maxit=5000, warm=1)
+        g1 = g2 = 0.0
+        for k in range(4):
+            g1, res = topo.simp_step(params, g1)
+            g2, r2 = sim.step(g2)
+            assert abs(r2["cg_iters"] - res.cg_iters) <= 1, (k, r2["cg_iters"], res.cg_iters)
+            assert r2["compliance"] == pytest.approx(res.compliance, rel=1e-8)
+            assert r2["oc_steps"] == res.oc_steps
+            assert np.abs(sim.local_rho().reshape(-1) - topo.get(_capi.F_RHO)).max() <= 1e-7, "iteration %d" % k
+    finally:
+        sim.close()
+        topo.close()
