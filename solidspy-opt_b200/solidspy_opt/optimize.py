@@ -13,6 +13,8 @@ filter, OC / rank-select removal).  Keyword-only extras (``precond``, ``rtol``, 
 ``history`` ...) default to the reference's behaviour; ``*_from_model`` variants take the
 ``{"nodes","cons","elements","mats","loads"}`` dict of the SolidsPy README (reference README.rst:134-141).
 """
+import time
+
 import numpy as np
 
 from solidspy_opt import _capi
@@ -232,6 +234,8 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
         C_h = np.zeros(niter)
         error = 1000
         for i in range(niter):
+            if history is not None:
+                history.setdefault("wall_time", []).append(time.perf_counter())    # start of every design iteration
             if verbose:
                 print("Number of elements: {}".format(nels))                       # :279
             n_kept = int(np.count_nonzero(mask))
@@ -252,7 +256,7 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
             n_new, n_prot = topo.beso_apply(alpha_del, protect)                    # :328-331
             mask = topo.get(_capi.F_KEEP).astype(bool)
             C_h[i] = C
-            if history is not None:
+            if history is not None and not history.get("timing_only", False):
                 history.setdefault("kept_ids", []).append(np.flatnonzero(mask))
                 history.setdefault("alpha", []).append(alpha_del)
                 history.setdefault("C", []).append(C)
