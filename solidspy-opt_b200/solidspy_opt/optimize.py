@@ -156,7 +156,7 @@ def _model_grid(data):
 
 
 def SIMP_from_model(data, niter, penal, *, r_min=None, r_factor=4, precond="gmg", rtol=DEFAULT_RTOL_SIMP,
-                    maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, rho0=None):
+                    maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, rho0=None, slabs=None, dist=None):
     """SIMP on a model given as the SolidsPy dict ``{"nodes","cons","elements","mats","loads"}``
     (reference README.rst:134-141), restricted to structured quad4 grids with square elements.
     ``mats[0] = (E, nu)``; ``loads`` rows ``[node, fx, fy]``; ``cons`` (N_n, 2) with -1 = constrained."""
@@ -167,6 +167,11 @@ def SIMP_from_model(data, niter, penal, *, r_min=None, r_factor=4, precond="gmg"
     if r_min is None:
         r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*r_factor
     kloc = kloc_simp(mats[0, 0], mats[0, 1])
+    if slabs is not None or dist is not None:                 # row slabs (see SIMP): this process' rows of rho
+        if rho0 is not None:
+            raise ValueError("rho0 is not supported on row slabs")
+        return _simp_slab_loop(nx, ny, kloc, np.asarray(data["cons"]), np.asarray(data["loads"], dtype=float), dx, dy,
+                               r_min, niter, penal, rtol, maxit, history, verbose, slabs, dist, device)
     with _capi.Topo(nx, ny, kloc, device=device) as topo:
         topo.set_cons(np.asarray(data["cons"]))
         topo.set_loads(np.asarray(data["loads"], dtype=float))
