@@ -159,7 +159,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
         for (int j = 0; j < 8; ++j) A[i * 8 + j] -= l[i] * l[j];
     }
   }
-  h->omega = 0.7;
+  h->omega = getenv("TOPO_OMEGA") ? atof(getenv("TOPO_OMEGA")) : 0.7;
   h->nu_pre = 1;
   h->nu_post = 1;
   h->nu_coarse = getenv("TOPO_NU_COARSE") ? atoi(getenv("TOPO_NU_COARSE")) : 0;

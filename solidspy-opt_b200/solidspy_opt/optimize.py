@@ -209,8 +209,23 @@ def _model_arrays(data):
     return nx*dx, ny*dy, nx, ny, (nodes, mats, els, loads, BC)
 
 
+GMG_ATTEMPT_CAP = 400      # PCG iterations granted to the multigrid preconditioner before the Jacobi restart (ESO/BESO)
+
+
 def _solve(topo, precond, rtol, maxit, stats):
-    it, rel, code = topo.solve(_PRECOND[precond], rtol, maxit, warm=True, raise_on_noconv=False)
+    """K u = f on the current element set (replaces spsolve, optimize.py:61,84,161,181,260,298).  ESO designs are
+    hard 0/1: once thin or corner-connected members appear, the coarse multigrid levels glue parts the fine mesh
+    separates and multigrid-PCG can stall (measured: 96x40 ESO_stress, fifth solve: 1e-5 after 3000 iterations where
+    Jacobi-PCG needs 913).  So the multigrid attempt is capped and a stalled solve restarts, on the GPU, with the
+    Jacobi preconditioner, which converges on any SPD system."""
+    p = _PRECOND[precond]
+    gmg = p == _capi.PRECOND_GMG
+    it, rel, code = topo.solve(p, rtol, min(maxit, GMG_ATTEMPT_CAP) if gmg else maxit, warm=True, raise_on_noconv=False)
+    if gmg and code == _capi.ENOCONV:
+        it2, rel, code = topo.solve(_capi.PRECOND_JACOBI, rtol, maxit, warm=bool(rel < 1.0), raise_on_noconv=False)
+        it += it2
+        if stats is not None:
+            stats["jacobi_restarts"] = stats.get("jacobi_restarts", 0) + 1
     if stats is not None:
         stats.setdefault("cg_iters", []).append(it)
         stats.setdefault("relres", []).append(rel)

@@ -623,3 +623,23 @@ def test_beso_removal_sets_match_oracle_midsize(capi, nx, ny, niter):
         assert np.array_equal(a, b), "removal %d: %d vs %d kept, %d differ" % (k, a.size, b.size, np.setxor1d(a, b).size)
     assert np.array_equal(ELS, ELS_ref)
     assert np.array_equal(nodes, nodes_ref)
+
+
+@pytest.mark.parametrize("kind,nx,ny,niter", [("eso_stiff", 96, 40, 30), ("eso_stress", 96, 40, 12), ("eso_stress", 150, 50, 12)])
+def test_eso_removal_sets_match_oracle_midsize(capi, kind, nx, ny, niter):
+    """ESO beyond the reference fixtures, against the CPU restatement (direct solver); load off the mirror axis."""
+    import solidspy_opt.optimize as opt
+    fn, fn_ref = (opt.ESO_stiff, t1.eso_stiff) if kind == "eso_stiff" else (opt.ESO_stress, t1.eso_stress)
+    dirs, pos = np.array([[0, -1]]), np.array([[ny//4 + 1, 1]])
+    hist, ref = {}, {}
+    ELS, nodes = fn(nx, ny, nx, ny, dirs, pos, niter, 0.005, 0.05, 0.5, history=hist, verbose=False)
+    with np.errstate(all="ignore"):
+        ELS_ref, nodes_ref = fn_ref(nx, ny, nx, ny, dirs, pos, niter, 0.005, 0.05, 0.5, history=ref)
+    C = np.array(ref["C"])
+    n_ok = len(ref["els_ids"]) if np.all(np.isfinite(C)) else int(np.argmax(~np.isfinite(C))) - 1
+    assert n_ok >= 2 and len(hist["els_ids"]) >= n_ok
+    for k, (a, b) in enumerate(zip(hist["els_ids"][:n_ok], ref["els_ids"][:n_ok])):
+        assert np.array_equal(a, b), "removal %d: %d vs %d present, %d differ" % (k, a.size, b.size, np.setxor1d(a, b).size)
+    if n_ok == len(ref["els_ids"]):
+        assert np.array_equal(ELS, ELS_ref)
+        assert np.array_equal(nodes, nodes_ref)
