@@ -411,7 +411,17 @@ extern "C" int topo_simp_step(topo_t *h, const topo_simp_params *p, double *g_in
   CUDA_TRY(cudaEventRecord(h->evs[0], st));
   TOPO_TRY(topo_simp_scale(h, p->penal, p->emin, p->emax));
   CUDA_TRY(cudaEventRecord(h->evs[1], st));
-  int s = topo_solve(h, p->precond, p->rtol, p->maxit, p->warm, &res->cg_iters, &res->relres);
+  // the multigrid attempt is capped; a stalled solve restarts from its last iterate with the Jacobi preconditioner
+  // (converges on any SPD system) -- a safety net: SIMP designs keep Emin > 0 and have not needed it in any run
+  const int gmg_cap = 4000;
+  const bool gmg = p->precond == TOPO_PRECOND_GMG;
+  int s = topo_solve(h, p->precond, p->rtol, gmg ? std::min(p->maxit, gmg_cap) : p->maxit, p->warm, &res->cg_iters, &res->relres);
+  if (gmg && s == TOPO_ENOCONV && p->maxit > gmg_cap) {
+    int it2 = 0;
+    const int warm2 = (res->relres == res->relres && res->relres < 1.0) ? 1 : 0;
+    s = topo_solve(h, TOPO_PRECOND_JACOBI, p->rtol, p->maxit, warm2, &it2, &res->relres);
+    res->cg_iters += it2;
+  }
   res->status = s;
   if (s != TOPO_OK && s != TOPO_ENOCONV) return s;
   CUDA_TRY(cudaEventRecord(h->evs[2], st));
