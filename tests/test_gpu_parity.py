@@ -643,3 +643,48 @@ def test_eso_removal_sets_match_oracle_midsize(capi, kind, nx, ny, niter):
     if n_ok == len(ref["els_ids"]):
         assert np.array_equal(ELS, ELS_ref)
         assert np.array_equal(nodes, nodes_ref)
+
+
+@pytest.mark.parametrize("nx,ny,L,H,penal,r_factor,n,pos", [
+    (48, 24, 48.0, 24.0, 2, 4, 1, [[7, 1]]),            # penal = 2 (numpy's ** 2 fast path, optimize.py:444)
+    (40, 30, 40.0, 30.0, 4, 3, 1, [[20, 1], [5, 1]]),   # penal = 4, two loads, r = 3 elements
+    (36, 18, 72.0, 36.0, 3, 2, 1, [[10, 3]]),           # 2 x 2 elements, load off the edge column
+    (45, 15, 45.0, 15.0, 3, 5, 2, [[8, 1]]),            # beam_2 supports, r = 5 elements
+    (33, 21, 33.0, 21.0, 1, 4, 1, [[11, 1]]),           # penal = 1 (no penalisation)
+])
+def test_simp_parameter_sweep_matches_oracle(capi, nx, ny, L, H, penal, r_factor, n, pos):
+    """SIMP outside the fixtures' parameters: penalisation exponents, filter radii, element sizes, support kinds,
+    several loads -- 8 design iterations each against the CPU restatement (direct solver)."""
+    from solidspy_opt.optimize import SIMP
+    pos = np.array(pos)
+    dirs = np.tile([0, -1], (pos.shape[0], 1))
+    hist, ref = {"keep_rho": True}, {}
+    rho = SIMP(L, H, nx, ny, dirs, pos, 8, penal, n=n, r_factor=r_factor, history=hist, verbose=False)
+    rho_ref = t1.simp(L, H, nx, ny, dirs, pos, 8, penal, n=n, r_factor=float(r_factor), history=ref)
+    assert len(hist["compliance"]) == len(ref["compliance"])
+    assert np.allclose(hist["compliance"], ref["compliance"], rtol=1e-6)
+    for k in range(len(ref["compliance"])):
+        assert np.abs(hist["rho"][k] - ref["rho"][k]).max() <= 1e-6, k
+    assert np.abs(rho - rho_ref).max() <= 1e-6
+    # ... and on two row slabs where the mesh allows it (slab height even)
+    if ny % 4 == 0:
+        hist2 = {}
+        rho2 = SIMP(L, H, nx, ny, dirs, pos, 8, penal, n=n, r_factor=r_factor, history=hist2, verbose=False, slabs=2)
+        assert np.allclose(hist2["compliance"], ref["compliance"], rtol=1e-6)
+        assert np.abs(rho2 - rho_ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("nx,ny,ER,volfrac,pos", [(40, 24, 0.02, 0.6, [[7, 1]]), (50, 20, 0.08, 0.4, [[6, 1], [15, 1]]),
+                                                  (64, 32, 0.05, 0.5, [[9, 2]])])
+def test_beso_parameter_sweep_matches_oracle(capi, nx, ny, ER, volfrac, pos):
+    """BESO with other evolution ratios / volume targets / loads: bit-identical kept sets against the CPU restatement."""
+    from solidspy_opt.optimize import BESO
+    pos = np.array(pos)
+    dirs = np.tile([0, -1], (pos.shape[0], 1))
+    hist, ref = {}, {}
+    ELS, nodes = BESO(nx, ny, nx, ny, dirs, pos, 12, 1e-3, ER, volfrac, history=hist, verbose=False)
+    ELS_ref, nodes_ref = t1.beso(nx, ny, nx, ny, dirs, pos, 12, 1e-3, ER, volfrac, history=ref)
+    assert len(hist["kept_ids"]) == len(ref["kept_ids"])
+    for k, (a, b) in enumerate(zip(hist["kept_ids"], ref["kept_ids"])):
+        assert np.array_equal(a, b), "removal %d: %d differ" % (k, np.setxor1d(a, b).size)
+    assert np.array_equal(ELS, ELS_ref) and np.array_equal(nodes, nodes_ref)
