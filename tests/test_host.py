@@ -130,3 +130,31 @@ def test_create_rejects_non_rectangular_element_matrix(lib_built):
     with pytest.raises(_capi.TopoError) as ei:
         _capi.Topo(4, 4, ke)
     assert ei.value.code in (_capi.EINVAL, _capi.ENODEV)
+
+
+def test_slab_path_has_no_cpu_fallback_and_validates_its_arguments(lib_built):
+    """The row-slab entry point (multi-GPU algorithm) fails loudly without a device and rejects meshes it cannot split."""
+    from solidspy_opt.distributed import SlabSimp
+    from solidspy_opt.optimize import SIMP
+    ke = t1.kloc_closed_form(1.0, 0.3)
+    cons = np.zeros((5*8, 2), dtype=np.int8)
+    with pytest.raises(ValueError):                                       # 7 element rows cannot form 2 equal slabs
+        SlabSimp(4, 7, ke, cons, np.zeros((0, 3)), world=2)
+    try:
+        _capi.device_count()
+    except _capi.TopoError:
+        with pytest.raises(Exception):
+            SIMP(8, 8, 8, 8, np.array([[0, -1]]), np.array([[1, 1]]), 2, 3, verbose=False, slabs=2)
+
+
+def test_header_documents_what_every_slab_segment_hands_to_the_host():
+    """Each segment call of the row-slab API names the movement the host has to perform next (exchange kind /
+    gather / all-reduce) -- the contract a binding in another host language relies on."""
+    header = open(os.path.join(ROOT, "include", "topo_b200.h")).read()
+    for fn, needs in [("topo_dist_pcg_matvec", "TOPO_X_AP"), ("topo_dist_pcg_update", "TOPO_X_LEVEL_B"),
+                      ("topo_dist_vcycle_down", "TOPO_G_BK"), ("topo_dist_vcycle_up", "TOPO_X_LEVEL_X2"),
+                      ("topo_dist_pcg_smooth", "TOPO_S_RR_RZ"), ("topo_dist_solve_begin", "TOPO_S_BB"),
+                      ("topo_dist_filter_pack", "TOPO_X_FILTER")]:
+        line = [l for l in header.splitlines() if fn + "(" in l]
+        i = header.index(fn + "(")
+        assert needs in header[max(0, i - 400):i + 400], (fn, needs)
