@@ -210,7 +210,7 @@ constexpr int CI_MAXN = 96, CI_RG = 8, CI_ROWS = CI_MAXN / CI_RG;
 __global__ void __launch_bounds__(CI_MAXN * CI_RG) k_coarse_invert(const stencil_t *__restrict__ st, int nx, int ny,
                                                                   double *__restrict__ inv) {
   extern __shared__ double A[];                 // N x N
-  __shared__ double colk[CI_MAXN], rowk[CI_MAXN];
+  __shared__ double colk[CI_MAXN], rowk[CI_MAXN], diag0[CI_MAXN];
   const int npr = nx + 1, nn = npr * (ny + 1), N = 2 * nn;
   const int tid = threadIdx.x, nthr = blockDim.x;
   for (int t = tid; t < N * N; t += nthr) A[t] = 0.0;
@@ -231,12 +231,19 @@ __global__ void __launch_bounds__(CI_MAXN * CI_RG) k_coarse_invert(const stencil
     }
   }
   __syncthreads();
-  for (int t = tid; t < N; t += nthr)
+  for (int t = tid; t < N; t += nthr) {
     if (!(A[t * N + t] > 0.0)) A[t * N + t] = 1.0;
+    diag0[t] = A[t * N + t];
+  }
   __syncthreads();
   const int j = tid % CI_MAXN, g = tid / CI_MAXN;
   for (int k = 0; k < N; ++k) {
-    const double pinv = 1.0 / A[k * N + k];
+    // Perforated designs (ESO: elements removed, orphaned nodes pinned) can leave the coarsest operator singular
+    // -- floating islands, hinges -- without any zero diagonal.  A direction whose pivot has dropped below the
+    // accuracy of the fp32 stencil the matrix was read from is removed from the inverse (row and column zeroed)
+    // instead of being amplified by 1/pivot; a consistent right-hand side has no component along it.
+    const double piv = A[k * N + k];
+    const double pinv = (piv > 1e-6 * diag0[k]) ? 1.0 / piv : 0.0;
     if (tid < N) {
       colk[tid] = A[tid * N + k];
       rowk[tid] = (tid == k) ? pinv : A[k * N + tid] * pinv;

@@ -209,7 +209,7 @@ def _model_arrays(data):
     return nx*dx, ny*dy, nx, ny, (nodes, mats, els, loads, BC)
 
 
-GMG_ATTEMPT_CAP = 400      # PCG iterations granted to the multigrid preconditioner before the Jacobi restart (ESO/BESO)
+GMG_ATTEMPT_CAP = int(__import__("os").environ.get("TOPO_GMG_ATTEMPT_CAP", "400"))      # PCG iterations granted to the multigrid preconditioner before the Jacobi restart (ESO/BESO)
 
 
 def _solve(topo, precond, rtol, maxit, stats):
