@@ -15,7 +15,6 @@ int topo_mask_vector(topo_handle *h, double2 *v);
 
 namespace {
 
-#define LAUNCHED(h) ((h)->timing.kernel_launches++)
 constexpr int ET = 256;
 inline int el_blocks(int64_t n) { return (int)std::min<int64_t>(div_up(n, ET), 148 * 8); }
 

@@ -18,7 +18,6 @@
 
 namespace {
 
-#define LAUNCHED(h) ((h)->timing.kernel_launches++)
 
 // ---- child geometry ---------------------------------------------------------------------------
 // 1-D child type t: 0 = first child of a 2-cell parent, 1 = second child, 2 = only child (parent == child)

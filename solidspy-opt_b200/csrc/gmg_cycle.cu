@@ -21,7 +21,6 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-#define LAUNCHED(h) ((h)->timing.kernel_launches++)
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
 
 // ---- transfers: 1-D rules --------------------------------------------------------------------------------------

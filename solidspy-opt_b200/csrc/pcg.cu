@@ -144,7 +144,6 @@ __global__ void k_set_bb(SolverScalars *sc, const double *bb) {
 
 }  // namespace
 
-#define LAUNCHED(h) ((h)->timing.kernel_launches++)
 
 int topo_apply_loads(topo_handle *h) {
   const int64_t nn = h->nn;

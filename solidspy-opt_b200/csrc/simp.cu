@@ -8,7 +8,6 @@
 
 namespace {
 
-#define LAUNCHED(h) ((h)->timing.kernel_launches++)
 constexpr int ET = 256;
 inline int el_blocks(int64_t n) { return (int)std::min<int64_t>(div_up(n, ET), 148 * 8); }
 
