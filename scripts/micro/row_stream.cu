@@ -1,0 +1,220 @@
+// Microbenchmark behind the plan for the stage-1 kernels: how fast can a marching kernel with the
+// decomposition of k_fine (a warp owns 64 node columns + 2 halo columns, 4 independent warps per CTA, chunks of rows,
+// warp-private shared-memory ring) STREAM a row-major array of double2 from HBM, when the ring is fed
+//   (A) by per-lane cp.async (LDGSTS, what fine.cu does today), or
+//   (B) by TMA 2-D tile loads (cp.async.bulk.tensor, one request per ROWS x 66 columns box, completion on an mbarrier)?
+// Both variants read every node once (+ halo columns) and write 16 B per node, like the plain product without its
+// arithmetic.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o row_stream row_stream.cu
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e__)); exit(1); } } while (0)
+
+constexpr int WC = 64, SW = WC + 2;           // own / staged node columns per warp
+constexpr int BOX_ROWS = 4;                    // rows per TMA request
+constexpr int SLOTS = 4;                       // ring slots per warp (each BOX_ROWS rows) -> 16 rows resident
+constexpr int S_LDG = 8;                       // ring slots of the cp.async variant (one row each)
+
+// ---------------------------------------------------------------------------------------------------------------
+// (A) per-lane cp.async
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, unsigned sz) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(128, 4) k_ldgsts(const double2 *__restrict__ u, double2 *__restrict__ y, int nx, int ny,
+                                                   int rows_per_chunk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw) + warp * S_LDG * SW;
+  const int npr = nx + 1;
+  const int c0 = (blockIdx.x * 4 + warp) * WC;
+  if (c0 >= npr) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, ny + 1);
+  auto issue = [&](int q) {
+    double2 *dst = ring + (q % S_LDG) * SW;
+    const bool row_ok = q >= 0 && q <= ny;
+    const double2 *src = u + (size_t)(row_ok ? q : 0) * npr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * lane + j;
+      cp_async16(dst + 1 + 2 * lane + j, src + (c < npr ? c : 0), (row_ok && c < npr) ? 16u : 0u);
+    }
+    if (lane < 2) {
+      const int c = lane == 0 ? c0 - 1 : c0 + WC;
+      const bool ok = c >= 0 && c < npr;
+      cp_async16(dst + (lane == 0 ? 0 : SW - 1), src + (ok ? c : 0), (row_ok && ok) ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  for (int k = 0; k < S_LDG - 1; ++k) issue(r0 + k);
+  for (int r = r0; r < r1; ++r) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S_LDG - 2) : "memory");
+    __syncwarp();
+    const double2 *row = ring + (r % S_LDG) * SW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * lane + j;
+      const double2 a = row[2 * lane + j], b = row[1 + 2 * lane + j], d = row[2 + 2 * lane + j];
+      if (c < npr) y[(size_t)r * npr + c] = make_double2(a.x + b.x + d.x, a.y + b.y + d.y);
+    }
+    __syncwarp();
+    issue(r + S_LDG - 1);
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (B) TMA 2-D tiles
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (long long it = 0; !done && it < (1ll << 26); ++it) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(tm), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+constexpr int BOX_BYTES = BOX_ROWS * SW * 16;                       // 4224
+constexpr int SLOT_STRIDE = (BOX_BYTES + 127) / 128 * 128;          // 128-byte aligned slots
+__global__ void __launch_bounds__(128, 4) k_tma(const __grid_constant__ CUtensorMap tm, double2 *__restrict__ y, int nx, int ny,
+                                                int rows_per_chunk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[4][SLOTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *ring = smem_raw + (size_t)warp * SLOTS * SLOT_STRIDE;
+  const int npr = nx + 1;
+  const int c0 = (blockIdx.x * 4 + warp) * WC;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, ny + 1);
+  if (lane == 0)
+    for (int s = 0; s < SLOTS; ++s) mbar_init(&bars[warp][s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncwarp();
+  if (c0 >= npr) return;
+  const int nbox = (r1 - r0 + BOX_ROWS - 1) / BOX_ROWS;
+  auto issue = [&](int b) {                                         // lane 0 only
+    if (b >= nbox) return;
+    const int s = b % SLOTS;
+    mbar_expect_tx(&bars[warp][s], BOX_BYTES);
+    tma_load_2d(ring + (size_t)s * SLOT_STRIDE, &tm, 2 * (c0 - 1), r0 + b * BOX_ROWS, &bars[warp][s]);   // OOB -> zero fill
+  };
+  if (lane == 0)
+    for (int b = 0; b < SLOTS - 1; ++b) issue(b);
+  for (int b = 0; b < nbox; ++b) {
+    const int s = b % SLOTS;
+    mbar_wait(&bars[warp][s], (unsigned)((b / SLOTS) & 1));
+    const double2 *box = reinterpret_cast<const double2 *>(ring + (size_t)s * SLOT_STRIDE);
+#pragma unroll
+    for (int rr = 0; rr < BOX_ROWS; ++rr) {
+      const int r = r0 + b * BOX_ROWS + rr;
+      if (r < r1) {
+        const double2 *row = box + rr * SW;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = c0 + 2 * lane + j;
+          const double2 a = row[2 * lane + j], m = row[1 + 2 * lane + j], d = row[2 + 2 * lane + j];
+          if (c < npr) y[(size_t)r * npr + c] = make_double2(a.x + m.x + d.x, a.y + m.y + d.y);
+        }
+      }
+    }
+    __syncwarp();                                                   // every lane is done with the slot that box b+SLOTS-1 reuses
+    if (lane == 0) issue(b + SLOTS - 1);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main(int argc, char **argv) {
+  const int nx = argc > 1 ? atoi(argv[1]) : 8192, ny = argc > 2 ? atoi(argv[2]) : 4096;
+  const int npr = nx + 1;
+  const size_t nn = (size_t)npr * (ny + 1);
+  double2 *u, *y;
+  CK(cudaMalloc(&u, nn * sizeof(double2)));
+  CK(cudaMalloc(&y, nn * sizeof(double2)));
+  CK(cudaMemset(u, 0, nn * sizeof(double2)));
+  {  // u = 1 everywhere: y must be 3 in the interior columns, 2 on the first/last column
+    double2 *h = (double2 *)malloc(nn * sizeof(double2));
+    for (size_t i = 0; i < nn; ++i) h[i] = make_double2(1.0, 2.0);
+    CK(cudaMemcpy(u, h, nn * sizeof(double2), cudaMemcpyHostToDevice));
+    free(h);
+  }
+  const int bx = (npr + 4 * WC - 1) / (4 * WC);
+  const int chunks = (148 * 4) / bx > 0 ? (148 * 4) / bx : 1;
+  int rows = (ny + 1 + chunks - 1) / chunks;
+  rows = (rows + BOX_ROWS - 1) / BOX_ROWS * BOX_ROWS;
+  dim3 grid(bx, (ny + 1 + rows - 1) / rows);
+  printf("mesh %dx%d: %.1f MB read + %.1f MB written per launch, grid %dx%d, %d rows per chunk\n", nx, ny, nn * 16e-6, nn * 16e-6,
+         grid.x, grid.y, rows);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  auto check = [&](const char *name) {
+    double2 *h = (double2 *)malloc(nn * sizeof(double2));
+    CK(cudaMemcpy(h, y, nn * sizeof(double2), cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (int r = 0; r <= ny; ++r)
+      for (int c = 0; c < npr; ++c) {
+        const double want = (c == 0 || c == nx) ? 2.0 : 3.0;
+        if (h[(size_t)r * npr + c].x != want || h[(size_t)r * npr + c].y != 2 * want) ++bad;
+      }
+    printf("  %s: %zu wrong values\n", name, bad);
+    free(h);
+  };
+  {
+    const size_t smem = 4 * S_LDG * SW * sizeof(double2);
+    CK(cudaFuncSetAttribute(k_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaMemset(y, 0, nn * sizeof(double2)));
+    for (int i = 0; i < 3; ++i) k_ldgsts<<<grid, 128, smem>>>(u, y, nx, ny, rows);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) k_ldgsts<<<grid, 128, smem>>>(u, y, nx, ny, rows);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("(A) per-lane cp.async : %.1f us  %.0f GB/s\n", ms / 20 * 1e3, nn * 32.0 / (ms / 20) / 1e6);
+    check("cp.async");
+  }
+  {
+    EncodeFn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
+    if (!encode) { printf("cuTensorMapEncodeTiled not available\n"); return 1; }
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)2 * npr, (cuuint64_t)(ny + 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)npr * 16};
+    const cuuint32_t box[2] = {2 * SW, BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, u, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return 1; }
+    const size_t smem = 4 * (size_t)SLOTS * SLOT_STRIDE;
+    CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaMemset(y, 0, nn * sizeof(double2)));
+    for (int i = 0; i < 3; ++i) k_tma<<<grid, 128, smem>>>(tm, y, nx, ny, rows);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) k_tma<<<grid, 128, smem>>>(tm, y, nx, ny, rows);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("(B) TMA 2-D tiles     : %.1f us  %.0f GB/s\n", ms / 20 * 1e3, nn * 32.0 / (ms / 20) / 1e6);
+    check("TMA");
+  }
+  return 0;
+}
