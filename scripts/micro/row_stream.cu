@@ -68,6 +68,87 @@ __global__ void __launch_bounds__(128, 4) k_ldgsts(const double2 *__restrict__ u
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// (C) per-lane cp.async + the 72 DFMA of the plain product per node (uniform element scale, no BC flags): every step
+//     re-reads the three node rows it needs from the ring (no register row images carried across steps)
+// ---------------------------------------------------------------------------------------------------------------
+struct KeRow { double r0[8], r1[8]; };
+template <bool FLIP>
+__device__ __forceinline__ void row_terms(const KeRow &k, const double2 &q0, const double2 &q1, const double2 &q2,
+                                          const double2 &q3, double &tx, double &ty) {
+  if (!FLIP) {
+    tx = k.r0[0] * q0.x;            ty = k.r1[0] * q0.x;
+    tx = fma(k.r0[1], q0.y, tx);    ty = fma(k.r1[1], q0.y, ty);
+    tx = fma(k.r0[2], q1.x, tx);    ty = fma(k.r1[2], q1.x, ty);
+    tx = fma(k.r0[3], q1.y, tx);    ty = fma(k.r1[3], q1.y, ty);
+    tx = fma(k.r0[4], q2.x, tx);    ty = fma(k.r1[4], q2.x, ty);
+    tx = fma(k.r0[5], q2.y, tx);    ty = fma(k.r1[5], q2.y, ty);
+    tx = fma(k.r0[6], q3.x, tx);    ty = fma(k.r1[6], q3.x, ty);
+    tx = fma(k.r0[7], q3.y, tx);    ty = fma(k.r1[7], q3.y, ty);
+  } else {
+    tx = k.r0[0] * q0.x;            ty = k.r1[1] * q0.y;
+    tx = fma(-k.r0[1], q0.y, tx);   ty = fma(-k.r1[0], q0.x, ty);
+    tx = fma(k.r0[2], q1.x, tx);    ty = fma(-k.r1[2], q1.x, ty);
+    tx = fma(-k.r0[3], q1.y, tx);   ty = fma(k.r1[3], q1.y, ty);
+    tx = fma(k.r0[4], q2.x, tx);    ty = fma(-k.r1[4], q2.x, ty);
+    tx = fma(-k.r0[5], q2.y, tx);   ty = fma(k.r1[5], q2.y, ty);
+    tx = fma(k.r0[6], q3.x, tx);    ty = fma(-k.r1[6], q3.x, ty);
+    tx = fma(-k.r0[7], q3.y, tx);   ty = fma(k.r1[7], q3.y, ty);
+  }
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ldgsts_math(const __grid_constant__ KeRow kparam, const double2 *__restrict__ u,
+                                                            double2 *__restrict__ y, int nx, int ny, int rows_per_chunk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const KeRow ke = kparam;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw) + warp * S_LDG * SW;
+  const int npr = nx + 1;
+  const int c0 = (blockIdx.x * 4 + warp) * WC;
+  if (c0 >= npr) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, ny + 1);
+  auto issue = [&](int q) {
+    double2 *dst = ring + ((q + S_LDG) % S_LDG) * SW;
+    const bool row_ok = q >= 0 && q <= ny;
+    const double2 *src = u + (size_t)(row_ok ? q : 0) * npr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * lane + j;
+      cp_async16(dst + 1 + 2 * lane + j, src + (c < npr ? c : 0), (row_ok && c < npr) ? 16u : 0u);
+    }
+    if (lane < 2) {
+      const int c = lane == 0 ? c0 - 1 : c0 + WC;
+      const bool ok = c >= 0 && c < npr;
+      cp_async16(dst + (lane == 0 ? 0 : SW - 1), src + (ok ? c : 0), (row_ok && ok) ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  for (int k = 0; k < S_LDG - 1; ++k) issue(r0 - 1 + k);            // rows r0-1 .. r0+S-3
+  for (int r = r0; r < r1; ++r) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S_LDG - 4) : "memory");   // rows up to r+1 have landed
+    __syncwarp();
+    const double2 *pm = ring + ((r - 1 + S_LDG) % S_LDG) * SW + 2 * lane;
+    const double2 *pc = ring + ((r + S_LDG) % S_LDG) * SW + 2 * lane;
+    const double2 *pp = ring + ((r + 1 + S_LDG) % S_LDG) * SW + 2 * lane;
+    double2 um[4], uc[4], up[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { um[i] = pm[i]; uc[i] = pc[i]; up[i] = pp[i]; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double yx, yy, tx, ty;
+      row_terms<false>(ke, uc[j + 1], uc[j + 2], up[j + 2], up[j + 1], tx, ty); yx = tx; yy = ty;
+      row_terms<true>(ke, uc[j + 1], uc[j], up[j], up[j + 1], tx, ty); yx += tx; yy += ty;
+      row_terms<false>(ke, uc[j + 1], uc[j], um[j], um[j + 1], tx, ty); yx += tx; yy += ty;
+      row_terms<true>(ke, uc[j + 1], uc[j + 2], um[j + 2], um[j + 1], tx, ty); yx += tx; yy += ty;
+      const int c = c0 + 2 * lane + j;
+      if (c < npr) y[(size_t)r * npr + c] = make_double2(yx, yy);
+    }
+    __syncwarp();
+    issue(r + S_LDG - 2);
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // (B) TMA 2-D tiles
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -189,6 +270,27 @@ int main(int argc, char **argv) {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("(A) per-lane cp.async : %.1f us  %.0f GB/s\n", ms / 20 * 1e3, nn * 32.0 / (ms / 20) / 1e6);
     check("cp.async");
+  }
+  {
+    KeRow kr;
+    for (int i = 0; i < 8; ++i) { kr.r0[i] = 0.1 * (i + 1); kr.r1[i] = 0.05 * (8 - i); }
+    const size_t smem = 4 * S_LDG * SW * sizeof(double2);
+    auto run = [&](auto kern, const char *name) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int i = 0; i < 3; ++i) kern<<<grid, 128, smem>>>(kr, u, y, nx, ny, rows);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < 20; ++i) kern<<<grid, 128, smem>>>(kr, u, y, nx, ny, rows);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+      printf("(C) cp.async + 72 DFMA/node, rows re-read from the ring, %s: %.1f us  %.0f GB/s  (%d registers)\n", name, ms / 20 * 1e3,
+             nn * 32.0 / (ms / 20) / 1e6, fa.numRegs);
+    };
+    run(k_ldgsts_math<4>, "4 CTAs/SM");
+    run(k_ldgsts_math<5>, "5 CTAs/SM");
+    run(k_ldgsts_math<6>, "6 CTAs/SM");
   }
   {
     EncodeFn encode = nullptr;
