@@ -148,6 +148,83 @@ __global__ void __launch_bounds__(128, MINB) k_ldgsts_math(const __grid_constant
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// (D) = (C) + per-element scale streamed through a second ring with 8-byte cp.async
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ldgsts_math_scale(const __grid_constant__ KeRow kparam, const double2 *__restrict__ u,
+                                                            double2 *__restrict__ y, int nx, int ny, int rows_per_chunk,
+                                                            const double *__restrict__ scale) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const KeRow ke = kparam;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw) + warp * S_LDG * SW;
+  double *ering = reinterpret_cast<double *>(reinterpret_cast<double2 *>(smem_raw) + 4 * S_LDG * SW) + warp * S_LDG * SW;
+  const int npr = nx + 1;
+  const int c0 = (blockIdx.x * 4 + warp) * WC;
+  if (c0 >= npr) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, ny + 1);
+  auto issue = [&](int q) {
+    double2 *dst = ring + ((q + S_LDG) % S_LDG) * SW;
+    const bool row_ok = q >= 0 && q <= ny;
+    const double2 *src = u + (size_t)(row_ok ? q : 0) * npr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * lane + j;
+      cp_async16(dst + 1 + 2 * lane + j, src + (c < npr ? c : 0), (row_ok && c < npr) ? 16u : 0u);
+    }
+    if (lane < 2) {
+      const int c = lane == 0 ? c0 - 1 : c0 + WC;
+      const bool ok = c >= 0 && c < npr;
+      cp_async16(dst + (lane == 0 ? 0 : SW - 1), src + (ok ? c : 0), (row_ok && ok) ? 16u : 0u);
+    }
+    {  // scales of element row q-1 (columns c0-1 .. c0+63), 8-byte copies
+      const bool erow_ok = q >= 1 && q <= ny;
+      const double *esrc = scale + (size_t)(erow_ok ? q - 1 : 0) * nx;
+      double *edst = ering + ((q + S_LDG) % S_LDG) * SW;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = c0 + 2 * lane + j;
+        const unsigned s8 = (unsigned)__cvta_generic_to_shared(edst + 1 + 2 * lane + j);
+        const unsigned sz = (erow_ok && c < nx) ? 8u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s8), "l"(esrc + (c < nx ? c : 0)), "r"(sz) : "memory");
+      }
+      if (lane == 0) {
+        const unsigned s8 = (unsigned)__cvta_generic_to_shared(edst);
+        const unsigned sz = (erow_ok && c0 > 0) ? 8u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s8), "l"(esrc + (c0 > 0 ? c0 - 1 : 0)), "r"(sz) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  for (int k = 0; k < S_LDG - 1; ++k) issue(r0 - 1 + k);            // rows r0-1 .. r0+S-3
+  for (int r = r0; r < r1; ++r) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S_LDG - 4) : "memory");   // rows up to r+1 have landed
+    __syncwarp();
+    const double2 *pm = ring + ((r - 1 + S_LDG) % S_LDG) * SW + 2 * lane;
+    const double2 *pc = ring + ((r + S_LDG) % S_LDG) * SW + 2 * lane;
+    const double2 *pp = ring + ((r + 1 + S_LDG) % S_LDG) * SW + 2 * lane;
+    double2 um[4], uc[4], up[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { um[i] = pm[i]; uc[i] = pc[i]; up[i] = pp[i]; }
+    const double *ec = ering + ((r + S_LDG) % S_LDG) * SW + 2 * lane, *ep = ering + ((r + 1 + S_LDG) % S_LDG) * SW + 2 * lane;
+    double eb[3], ea[3];                     // element rows r-1 (below) and r (above), columns c-1 .. c+1
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { eb[i] = ec[i]; ea[i] = ep[i]; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double yx, yy, tx, ty;
+      row_terms<false>(ke, uc[j + 1], uc[j + 2], up[j + 2], up[j + 1], tx, ty); yx = ea[j + 1] * tx; yy = ea[j + 1] * ty;
+      row_terms<true>(ke, uc[j + 1], uc[j], up[j], up[j + 1], tx, ty); yx = fma(ea[j], tx, yx); yy = fma(ea[j], ty, yy);
+      row_terms<false>(ke, uc[j + 1], uc[j], um[j], um[j + 1], tx, ty); yx = fma(eb[j], tx, yx); yy = fma(eb[j], ty, yy);
+      row_terms<true>(ke, uc[j + 1], uc[j + 2], um[j + 2], um[j + 1], tx, ty); yx = fma(eb[j + 1], tx, yx); yy = fma(eb[j + 1], ty, yy);
+      const int c = c0 + 2 * lane + j;
+      if (c < npr) y[(size_t)r * npr + c] = make_double2(yx, yy);
+    }
+    __syncwarp();
+    issue(r + S_LDG - 2);
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // (B) TMA 2-D tiles
 // ---------------------------------------------------------------------------------------------------------------
@@ -232,7 +309,9 @@ int main(int argc, char **argv) {
   CK(cudaMemset(u, 0, nn * sizeof(double2)));
   {  // u = 1 everywhere: y must be 3 in the interior columns, 2 on the first/last column
     double2 *h = (double2 *)malloc(nn * sizeof(double2));
-    for (size_t i = 0; i < nn; ++i) h[i] = make_double2(1.0, 2.0);
+    const bool rnd = argc > 3 && atoi(argv[3]) != 0;      // random data: same timing expected (checks are skipped)
+    for (size_t i = 0; i < nn; ++i)
+      h[i] = rnd ? make_double2((double)rand() / RAND_MAX - 0.5, (double)rand() / RAND_MAX - 0.5) : make_double2(1.0, 2.0);
     CK(cudaMemcpy(u, h, nn * sizeof(double2), cudaMemcpyHostToDevice));
     free(h);
   }
@@ -289,6 +368,30 @@ int main(int argc, char **argv) {
              nn * 32.0 / (ms / 20) / 1e6, fa.numRegs);
     };
     run(k_ldgsts_math<4>, "4 CTAs/SM");
+    {
+      double *scale;
+      CK(cudaMalloc(&scale, (size_t)nx * ny * sizeof(double)));
+      {
+        double *hs = (double *)malloc((size_t)nx * ny * sizeof(double));
+        for (size_t i = 0; i < (size_t)nx * ny; ++i) hs[i] = 1e-9 + (double)rand() / RAND_MAX;
+        CK(cudaMemcpy(scale, hs, (size_t)nx * ny * sizeof(double), cudaMemcpyHostToDevice));
+        free(hs);
+      }
+      const size_t smem2 = smem + 4 * S_LDG * SW * sizeof(double);
+      auto kern = k_ldgsts_math_scale<4>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      for (int i = 0; i < 3; ++i) kern<<<grid, 128, smem2>>>(kr, u, y, nx, ny, rows, scale);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < 20; ++i) kern<<<grid, 128, smem2>>>(kr, u, y, nx, ny, rows, scale);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+      printf("(D) (C) + element scales through an 8-byte cp.async ring: %.1f us  %.0f GB/s algorithmic incl. scales  (%d registers)\n",
+             ms / 20 * 1e3, (nn * 32.0 + (double)nx * ny * 8.0) / (ms / 20) / 1e6, fa.numRegs);
+      CK(cudaFree(scale));
+    }
     run(k_ldgsts_math<5>, "5 CTAs/SM");
     run(k_ldgsts_math<6>, "6 CTAs/SM");
   }
