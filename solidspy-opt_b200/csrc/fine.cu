@@ -104,6 +104,7 @@ struct FineArgs {
   // all-reduce, the scalar bookkeeping happens afterwards (k_dist_pcg_finish)
   double w_first, w_last;
   int dist;
+  int pdl_early;              // programmatic dependent launch: release the dependents at kernel entry
 };
 
 // Rows 0 and 1 of the element matrix (the row block of local node 0).  For a rectangular element of an
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
   // in the ring as aligned 4-byte words (a direct byte load prefetched one row ahead was the dominant stall)
   constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID);
   constexpr int FWORDS = (WC + 3 + 3) / 4;               // aligned words covering the warp's WC flag bytes
+  pdl_enter(a.pdl_early != 0);
   if (a.check_done && a.sc->done) return;
   const KeRow ke = kparam;                                // 16 constants -> (uniform) registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -460,22 +462,28 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
 
 template <int KIND, int NC>
 int launch_fine_nc(topo_handle *h, FineArgs &a) {
-  dim3 grid(div_up(h->nx + 1, 4 * Geo<NC>::WC), div_up(h->ny + 1, a.rows_per_chunk));
+  static int resident = 0;                                 // CTAs of this variant that fit one SM
+  const size_t smem = 4 * (size_t)warp_smem_bytes<KIND, NC>();
+  if (resident == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fine<KIND, NC>, BW, smem));
+    resident = std::max(1, occ);
+  }
+  // chunk rows so that one wave of CTAs covers the mesh
+  const int bx = div_up(h->nx + 1, 4 * Geo<NC>::WC);
+  const int chunks = std::max(1, (148 * resident) / bx);
+  a.rows_per_chunk = std::max(8, div_up(h->ny + 1, chunks));
+  dim3 grid(bx, div_up(h->ny + 1, a.rows_per_chunk));
   if ((int64_t)grid.x * grid.y > TOPO_MAX_PARTIAL_BLOCKS) {
     topo_set_error("fine-grid launch too large for the reduction buffer");
     return TOPO_EINVAL;
-  }
-  static bool attr_set = false;
-  const size_t smem = 4 * (size_t)warp_smem_bytes<KIND, NC>();
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   KeRow kr;
   for (int j = 0; j < 8; ++j) { kr.r0[j] = h->ke.k[j]; kr.r1[j] = h->ke.k[8 + j]; }
   static const char *const names[7] = {"k_fine<apply>", "k_fine<resid>", "k_fine<pcg_matvec>", "k_fine<pcg_matvec_jacobi>",
                                        "k_fine<update_resid0>", "k_fine<smooth_dot>", "k_fine<smooth>"};
-  KL(h, names[KIND], k_fine<KIND, NC><<<grid, BW, smem, h->stream>>>(kr, a));
+  KL(h, names[KIND], CUDA_TRY(topo_launch(h, k_fine<KIND, NC>, grid, dim3(BW), smem, kr, a)));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -492,13 +500,12 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   a.w_first = h->dist.on ? h->dist.w_first : 1.0;
   a.w_last = h->dist.on ? h->dist.w_last : 1.0;
   a.dist = h->dist.on ? 1 : 0;
-  // node columns per lane: 2 on wide meshes (overhead instructions amortised over two nodes), 1 otherwise
-  // (measured: the fused kinds lose more from the lower occupancy of 64-column strips than they gain)
-  const int nc = (KIND == FK_APPLY) ? h->fine_nc : 1;
-  // chunk rows so that one wave of CTAs covers the mesh (~4 resident CTAs per SM)
-  const int bx = div_up(h->nx + 1, 128 * nc);
-  const int chunks = std::max(1, (148 * (nc == 1 ? 4 : 3)) / bx);
-  a.rows_per_chunk = std::max(8, div_up(h->ny + 1, chunks));
+  a.pdl_early = (h->pdl & 2) ? 1 : 0;
+  // node columns per lane: 2 for the plain product on wide meshes (overhead instructions amortised over two
+  // nodes), 1 for the fused kinds (measured: they lose more from the lower occupancy of 64-column strips than
+  // they gain); TOPO_FINE_NC_MASK (bit KIND set = two columns for that kind) is the experiment knob
+  static const int nc_mask = getenv("TOPO_FINE_NC_MASK") ? atoi(getenv("TOPO_FINE_NC_MASK")) : 0;
+  const int nc = (KIND == FK_APPLY) ? h->fine_nc : (((nc_mask >> KIND) & 1) && h->nx + 1 >= 1024 ? 2 : 1);
   if (nc == 2) return launch_fine_nc<KIND, 2>(h, a);
   return launch_fine_nc<KIND, 1>(h, a);
 }

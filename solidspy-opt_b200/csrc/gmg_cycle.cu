@@ -21,6 +21,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+__constant__ int c_pdl_early;   // programmatic dependent launch: the level kernels release their dependents at entry
+
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
 
 // ---- transfers: 1-D rules --------------------------------------------------------------------------------------
@@ -197,6 +199,7 @@ __device__ __forceinline__ void node_prolong_add(const LevelView &L, const doubl
 
 // ---- multi-block kernels (large coarse levels) ------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omega, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,24 +207,28 @@ __global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omeg
 }
 __global__ void __launch_bounds__(128) k_lvl_up(const LevelView L, const double2 *__restrict__ xc, int cnx,
                                                 double omega, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_up(L, xc, cnx, n, omega);
 }
 __global__ void __launch_bounds__(128) k_lvl_prolong(const LevelView L, const double2 *__restrict__ xc, int cnx, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_prolong_add(L, xc, cnx, n);
 }
 __global__ void __launch_bounds__(128) k_lvl_smooth(const LevelView L, double omega, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_smooth(L, n, omega);
 }
 __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,6 +237,7 @@ __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int 
 template <class V2>
 __global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
                                                   int nyf, int nxc, int nyc, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int nprc = nxc + 1;
   const int64_t nnc = (int64_t)nprc * (nyc + 1);
@@ -243,6 +251,7 @@ __global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, dou
 __global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, float2 *__restrict__ xf,
                                                           const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
                                                           const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int nprf = nxf + 1;
   const int64_t nnf = (int64_t)nprf * (nyf + 1);
@@ -452,6 +461,7 @@ __device__ __noinline__ void small_up(const TailArgs &a, int l, float2 (*xs)[TAI
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ TailArgs a) {
+  pdl_enter(c_pdl_early != 0);
   if (a.done && *a.done) return;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
@@ -606,11 +616,16 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   cfg.gridDim = dim3(cs);
   cfg.blockDim = dim3(TAIL_THREADS);
   cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if ((h->pdl & 1) && !h->dist.on) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
   return TOPO_OK;
 }
@@ -622,6 +637,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
 __global__ void k_dist_assemble_bK(const double2 *__restrict__ recv0, const double2 *__restrict__ recv1,
                                    const unsigned long long *seq, double2 *__restrict__ b, int npr, int rows,
                                    int world, const int *done) {
+  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const double2 *__restrict__ recv = (seq != nullptr && (*seq & 1ull)) ? recv1 : recv0;
   const int64_t nn = (int64_t)npr * ((int64_t)rows * world + 1);
@@ -663,24 +679,32 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   const int *done = &h->sc->done;
   const int tail = tail_start(h);
   auto result_of = [&](int l) { return level_result(h, l, tail); };
+  static int pdl_early_set = -1;
+  if (pdl_early_set != ((h->pdl & 4) ? 1 : 0)) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {      // (the first V-cycle of a solve is never captured)
+      pdl_early_set = (h->pdl & 4) ? 1 : 0;
+      CUDA_TRY(cudaMemcpyToSymbol(c_pdl_early, &pdl_early_set, sizeof(int)));
+    }
+  }
 
   if (tail > 1) {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx,
-                                                                     C.ny, done));
+    KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict<float2>, dim3(blocks_for(C.nn)), dim3(128), 0, reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx, C.ny, done)));
   }
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(F);
-    KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+    KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, k_lvl_down, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
     for (int s = 1; s < nu_pre_of(h, l); ++s) {
-      KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
-      KL(h, "k_lvl_resid", k_lvl_resid<<<blocks_for(F.nn), 128, 0, st>>>(V, done));
+      KL(h, "k_lvl_resid", CUDA_TRY(topo_launch(h, k_lvl_resid, dim3(blocks_for(F.nn)), dim3(128), 0, V, done)));
     }
     if (l + 1 < tail) {
       GmgLevel &C = h->levels[l + 1];
-      KL(h, "k_restrict", k_restrict<<<blocks_for(C.nn), 128, 0, st>>>(F.r, C.b, F.nx, F.ny, C.nx, C.ny, done));
+      KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict<double2>, dim3(blocks_for(C.nn)), dim3(128), 0, F.r, C.b, F.nx, F.ny, C.nx, C.ny, done)));
     }
   }
   if (tail == 1) TOPO_TRY(launch_tail(h, tail, res_fine, h->nx, h->ny, 1));
@@ -692,23 +716,22 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     if (F.nn > unfused_min) {
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel
-      KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, done));
-      KL(h, lvl_name("up", l), k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(V, om, done));
+      KL(h, "k_lvl_prolong", CUDA_TRY(topo_launch(h, k_lvl_prolong, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
     } else {
-      KL(h, lvl_name("up", l), k_lvl_up<<<blocks_for(F.nn), 128, 0, st>>>(V, result_of(l + 1), C.nx, om, done));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, k_lvl_up, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, om, done)));
     }
     for (int s = 1; s < nu_post_of(h, l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }
-      KL(h, "k_lvl_smooth", k_lvl_smooth<<<blocks_for(F.nn), 128, 0, st>>>(W, om, done));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, W, om, done)));
     }
   }
   if (x1_out != nullptr) {
     *x1_out = result_of(1);          // the caller's smoothing kernel prolongates on the fly
   } else {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, st>>>(result_of(1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx, h->ny,
-                                                                                       C.nx, done));
+    KL(h, "k_prolong_add_fine", CUDA_TRY(topo_launch(h, k_prolong_add_fine, dim3(blocks_for(h->nn)), dim3(128), 0, result_of(1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx, h->ny, C.nx, done)));
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;

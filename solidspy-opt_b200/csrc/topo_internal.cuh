@@ -181,6 +181,7 @@ struct topo_handle {
   unsigned long long *tail_dbg;   // device buffer for k_tail stage stamps (nullptr = off)
   int tail_max_nodes;
   bool use_graph, pcg_graph_valid;
+  int pdl;                     // programmatic dependent launch for the kernels of the single-GPU PCG loop (TOPO_PDL)
   cudaGraphExec_t pcg_graph_exec;
   int last_pcg_iters;          // iterations of the previous multigrid-PCG solve (sizes the first batch of the next)
   int pcg_graph_launches;      // levels with at most this many nodes run inside the single-CTA tail kernel
@@ -235,6 +236,37 @@ int topo_apply_loads(topo_handle *h);
 void topo_gmg_free(topo_handle *h);
 
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A PCG iteration is ~16 short kernels in one stream; with the launch attribute
+// below the CTAs of kernel N+1 become resident while the last CTAs of kernel N drain (launch latency and the
+// prologue up to the first global access overlap the predecessor's tail).  Contract: EVERY kernel launched through
+// topo_launch calls pdl_enter() before its first global-memory access (including the early-exit test of the
+// convergence flag): it allows its own dependents to be scheduled and then waits until all prerequisite grids
+// have completed and flushed, so the data dependences are exactly those of plain stream order (transitively:
+// a grid cannot complete before its own wait has returned).  Without the attribute both instructions are no-ops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter(bool early_trigger) {
+  if (early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KA, class... A>
+static inline cudaError_t topo_launch(topo_handle *h, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem,
+                                      A &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  if ((h->pdl & 1) && !h->dist.on) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // Deterministic two-stage grid reduction.  Every block reduces its values in a fixed order and stores
 // one partial per slot; the block that draws the last ticket folds the partials in index order, so
