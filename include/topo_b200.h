@@ -163,6 +163,14 @@ int topo_beso_save_history(topo_t *h);
  * divided by max (strain_nodes contract; strain_els solver.py:281-316; optimize.py:86-92).
  * E, nu: material; dx, dy: element size. */
 int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double dx, double dy);
+/* Nodal strains and stresses of the current displacements: corner-point values of the adjacent elements averaged per
+ * node -- the (E_nodes, S_nodes) pair of pos.strain_nodes that the reference computes after every solve and hands to
+ * its field plots (optimize.py:63,86,102-103,163,183,201-202,262,300,347-348).  present_only != 0: only elements
+ * still present contribute (ESO, whose `els` shrinks); 0: all elements (BESO keeps the full `els`).  Nodes without a
+ * contributing element hold NaN (0/0), as in the reference.  Outputs: 3*N_n doubles each, component-major
+ * (exx | eyy | gxy planes, sxx | syy | txy planes). */
+int topo_strain_nodes(topo_t *h, double E, double nu, double dx, double dy, int present_only,
+                      double *strain_host, double *stress_host);
 
 /* ---- multi-GPU building blocks (row slabs) --------------------------------------------
  * One process per GPU owns a slab of element rows as an ordinary handle (nx x ny_local); interface node

@@ -249,21 +249,25 @@ struct StressTab {
 };
 
 // nodal stresses: corner stresses of the present adjacent elements (ascending element id), / count
+// WITH_STRAIN: the nodal strains as well (planes 3..5 of sn) -- the E_nodes / S_nodes pair of strain_nodes that the
+// reference hands to its field plots (optimize.py:63,86,163,183,262,300); keep == nullptr: every element counts
+// (BESO never shortens `els`)
+template <bool WITH_STRAIN>
 __global__ void __launch_bounds__(ET) k_stress_nodes(const __grid_constant__ StressTab T,
                                                      const double2 *__restrict__ u, const uint8_t *__restrict__ keep,
-                                                     double *__restrict__ sn /* 3 planes x nn */, int nx, int ny) {
+                                                     double *__restrict__ sn /* 3 (6) planes x nn */, int nx, int ny) {
   const int npr = nx + 1;
   const int64_t nn = (int64_t)npr * (ny + 1);
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
     int cnt = 0;
     // ascending element id: SW (this node is local 2), SE (3), NW (1), NE (0)
     const int er[4] = {r - 1, r - 1, r, r}, ec[4] = {c - 1, c, c - 1, c}, la[4] = {2, 3, 1, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (er[q] < 0 || er[q] >= ny || ec[q] < 0 || ec[q] >= nx) continue;
-      if (!keep[(size_t)er[q] * nx + ec[q]]) continue;
+      if (keep != nullptr && !keep[(size_t)er[q] * nx + ec[q]]) continue;
       const double2 *p = u + (size_t)er[q] * npr + ec[q];
       const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + npr + 1), q3 = __ldg(p + npr);
       const double w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
@@ -278,11 +282,17 @@ __global__ void __launch_bounds__(ET) k_stress_nodes(const __grid_constant__ Str
       s0 = add(add(s0, mul(T.f1, eps[0])), mul(T.f2, eps[1]));
       s1 = add(add(s1, mul(T.f2, eps[0])), mul(T.f1, eps[1]));
       s2 = add(s2, mul(T.shear, eps[2]));
+      if (WITH_STRAIN) { e0 = add(e0, eps[0]); e1 = add(e1, eps[1]); e2 = add(e2, eps[2]); }
       ++cnt;
     }
     sn[n] = s0 / cnt;
     sn[nn + n] = s1 / cnt;
     sn[2 * nn + n] = s2 / cnt;
+    if (WITH_STRAIN) {
+      sn[3 * nn + n] = e0 / cnt;
+      sn[4 * nn + n] = e1 / cnt;
+      sn[5 * nn + n] = e2 / cnt;
+    }
   }
 }
 
@@ -462,9 +472,7 @@ extern "C" int topo_beso_save_history(topo_t *h) {
   return TOPO_OK;
 }
 
-extern "C" int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double dx, double dy) {
-  if (!h || !(dx > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
-  CUDA_TRY(cudaSetDevice(h->device));
+static StressTab make_stress_tab(double E, double nu, double dx, double dy) {
   StressTab T;
   const double ri[4] = {-1.0, 1.0, 1.0, -1.0}, si[4] = {-1.0, -1.0, 1.0, 1.0};
   for (int k = 0; k < 4; ++k) {
@@ -482,12 +490,35 @@ extern "C" int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double 
   T.shear = E / (2 * (1 + nu));
   T.f1 = E / (1 - nu * nu);
   T.f2 = nu * E / (1 - nu * nu);
+  return T;
+}
+
+extern "C" int topo_vonmises_sensitivity(topo_t *h, double E, double nu, double dx, double dy) {
+  if (!h || !(dx > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const StressTab T = make_stress_tab(E, nu, dx, dy);
   cudaStream_t st = h->stream;
-  double *sn = reinterpret_cast<double *>(h->tmp);       // 3*nn doubles fit in tmp (2*nn) + tmp2? no: use z,p
-  sn = reinterpret_cast<double *>(h->z);                 // z and p are contiguous scratch outside a solve
-  KL(h, "k_stress_nodes", k_stress_nodes<<<el_blocks(h->nn), ET, 0, st>>>(T, h->u, h->keep, sn, h->nx, h->ny));
+  double *sn = reinterpret_cast<double *>(h->z);         // z and p are contiguous scratch outside a solve
+  KL(h, "k_stress_nodes", k_stress_nodes<false><<<el_blocks(h->nn), ET, 0, st>>>(T, h->u, h->keep, sn, h->nx, h->ny));
   KL(h, "k_vonmises", k_vonmises<<<el_blocks(h->ne), ET, 0, st>>>(sn, h->keep, h->sens, h->nx, h->ny, h->partials, h->ticket, h->red_out));
   KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->red_out, h->ne));
   CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+extern "C" int topo_strain_nodes(topo_t *h, double E, double nu, double dx, double dy, int present_only,
+                                 double *strain_host, double *stress_host) {
+  if (!h || !strain_host || !stress_host || !(dx > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const StressTab T = make_stress_tab(E, nu, dx, dy);
+  cudaStream_t st = h->stream;
+  double *sn = reinterpret_cast<double *>(h->z);         // z, p and Ap are contiguous scratch outside a solve: 6 planes
+  KL(h, "k_stress_nodes", k_stress_nodes<true><<<el_blocks(h->nn), ET, 0, st>>>(T, h->u, present_only ? h->keep : nullptr, sn,
+                                                                                  h->nx, h->ny));
+  CUDA_TRY(cudaGetLastError());
+  const size_t plane3 = sizeof(double) * 3 * (size_t)h->nn;
+  CUDA_TRY(cudaMemcpyAsync(stress_host, sn, plane3, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(strain_host, sn + 3 * (size_t)h->nn, plane3, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return TOPO_OK;
 }

@@ -24,7 +24,7 @@ SYMBOLS = [
     "topo_matvec_device", "topo_solve", "topo_compliance", "topo_equilibrium_check", "topo_simp_scale",
     "topo_simp_sensitivity", "topo_filter_sensitivity", "topo_oc_update", "topo_simp_step",
     "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_rank_select",
-    "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity",
+    "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity", "topo_strain_nodes",
     "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
     "topo_profile_matvec", "topo_profile_read", "topo_profile_report", "topo_set_stream", "topo_matvec_dev",
     "topo_diag_dev", "topo_vec_axpby_dev", "topo_vec_mul_dev", "topo_vec_dot_dev",
@@ -113,6 +113,7 @@ def load_library():
         "topo_eso_apply": [vp, C.c_double, C.c_void_p, C.c_int, i64p],
         "topo_beso_save_history": [vp],
         "topo_vonmises_sensitivity": [vp, C.c_double, C.c_double, C.c_double, C.c_double],
+        "topo_strain_nodes": [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p],
         "topo_get_timing": [vp, C.POINTER(Timing)],
         "topo_gmg_info": [vp, ip, ip, ip],
         "topo_set_gmg": [vp, C.c_double, C.c_int, C.c_int],
@@ -354,6 +355,15 @@ class Topo:
 
     def vonmises_sensitivity(self, E, nu, dx, dy):
         _check(self.lib.topo_vonmises_sensitivity(self.h, E, nu, dx, dy))
+
+    def strain_nodes(self, E, nu, dx, dy, present_only=True):
+        """(E_nodes, S_nodes), each (N_n, 3): nodal strains / stresses of the current displacements (the
+        ``pos.strain_nodes`` pair of the reference, optimize.py:63,86,163,183,262,300)."""
+        eps = np.empty((3, self.nn))
+        sig = np.empty((3, self.nn))
+        _check(self.lib.topo_strain_nodes(self.h, E, nu, dx, dy, 1 if present_only else 0, eps.ctypes.data,
+                                          sig.ctypes.data))
+        return np.ascontiguousarray(eps.T), np.ascontiguousarray(sig.T)
 
     def timing(self):
         t = Timing()

@@ -238,11 +238,11 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
     """Bi-directional ESO (reference optimize.py:215-356), quirks included: the full
     mesh is solved every iteration and removal acts by pinning the DOFs of orphaned nodes.
     Returns ``(ELS, nodes)``."""
-    if plot:
-        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
     nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device, _model)
+    fields = _want_fields(plot, history)
     with topo:
         eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :255-261
+        _store_fields(fields, topo, mats, length/nx, height/ny, "I", present_only=False)   # :261-262
         r_min = np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])*1                    # :264
         w4, w2x, w2y, we = beso_weights(nodes, els, nx, ny, r_min)
         vol_el = volume(els[:1], length, height, nx, ny)[0]
@@ -264,6 +264,7 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
                 break
             ELS_mask = mask                                                        # :290
             eq_ok = _solve(topo, precond, rtol, maxit, history)                    # :293-299
+            _store_fields(fields, topo, mats, length/nx, height/ny, "", present_only=False)    # :299-300 (full `els`)
             C = 0.5*topo.compliance()                                              # :334 (same f, u)
             topo.energy_sensitivity()                                              # :304
             topo.beso_filter(w4, w2x, w2y, we, average_with_prev=(i > 0))          # :305-311
@@ -293,14 +294,46 @@ def BESO(length, height, nx, ny, dirs, positions, niter, t, ER, volfrac, plot=Fa
             topo.beso_save_history()                                               # :344
         nodes[:, 3:5] = topo.get_cons()
     ELS = None if ELS_mask is None else _els_rows(nx, np.flatnonzero(ELS_mask))
+    _finish_fields(fields, plot, history, els, ELS, nodes)                         # :346-354
     return ELS, nodes
 
 
+def _want_fields(plot, history):
+    """Dict that collects the plotted fields (reference: UCI, E_nodesI, S_nodesI, UC, E_nodes, S_nodes), or None.
+    Asked for by ``plot=True`` or ``history["keep_fields"]`` (the fields without matplotlib)."""
+    return {} if (plot or (history is not None and history.get("keep_fields", False))) else None
+
+
+def _store_fields(fields, topo, mats, dx, dy, suffix, present_only):
+    """Complete displacements and nodal strains / stresses of the solve just finished (pos.complete_disp +
+    pos.strain_nodes after every spsolve of the reference) -- computed only when somebody will look at them."""
+    if fields is None:
+        return
+    fields["UC" + suffix] = topo.get(_capi.F_U).reshape(-1, 2)
+    fields["E_nodes" + suffix], fields["S_nodes" + suffix] = topo.strain_nodes(mats[0, 0], mats[0, 1], dx, dy,
+                                                                               present_only=present_only)
+
+
+def _finish_fields(fields, plot, history, elsI, ELS, nodes):
+    if fields is None:
+        return
+    if history is not None:
+        history["fields"] = fields
+    if plot:
+        if ELS is None or "UC" not in fields:
+            # the reference would fail here with an undefined `UC` (its loop never solved); nothing to draw
+            raise RuntimeError("plot=True: the optimisation loop stopped before its first solve, no fields to plot")
+        from . import plots
+        plots.eso_plots(elsI, ELS, nodes, fields)
+
+
 def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit, device,
-         history, verbose, model=None):
+         history, verbose, model=None, plot=False):
     nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device, model)
+    fields = _want_fields(plot, history)
     with topo:
         eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :56-61 / :156-161
+        _store_fields(fields, topo, mats, length/nx, height/ny, "I", present_only=True)    # :62-63 / :162-163
         if kind == "stiff":
             niter, RR, ER = 200, 0.005, 0.05                                       # :165-167 overrides the caller
         vol_el = volume(els[:1], length, height, nx, ny)[0]
@@ -317,6 +350,7 @@ def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
                 break
             ELS_mask = mask                                                        # :76 / :192
             eq_ok = _solve(topo, precond, rtol, maxit, history)
+            _store_fields(fields, topo, mats, length/nx, height/ny, "", present_only=True)     # :85-86 / :182-183
             if kind == "stiff":
                 if verbose:
                     print("Number of elements: {}".format(n_present))              # :185
@@ -331,6 +365,7 @@ def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
             RR += ER                                                               # :99 / :198
         nodes[:, 3:5] = topo.get_cons()
     ELS = None if ELS_mask is None else _els_rows(nx, np.flatnonzero(ELS_mask))
+    _finish_fields(fields, plot, history, els, ELS, nodes)                         # :101-109 / :200-208
     return ELS, nodes
 
 
@@ -338,20 +373,16 @@ def ESO_stiff(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, p
               rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
     """Stiffness-based ESO (reference optimize.py:116-210).  As in the reference, ``niter``, ``RR`` and
     ``ER`` are overridden by 200, 0.005, 0.05 (:165-167).  Returns ``(ELS, nodes)``."""
-    if plot:
-        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
     return _eso("stiff", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
-                device, history, verbose)
+                device, history, verbose, plot=plot)
 
 
 def ESO_stress(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False, *, precond="gmg",
                rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
     """Stress-based ESO (reference optimize.py:16-111): von Mises of element-averaged nodal stresses.
     Returns ``(ELS, nodes)``."""
-    if plot:
-        raise NotImplementedError("field plots are outside the accelerated path (SURVEY.md 8f-3)")
     return _eso("stress", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
-                device, history, verbose)
+                device, history, verbose, plot=plot)
 
 
 def BESO_from_model(data, niter, t, ER, volfrac, **kw):

@@ -688,3 +688,64 @@ def test_beso_parameter_sweep_matches_oracle(capi, nx, ny, ER, volfrac, pos):
     for k, (a, b) in enumerate(zip(hist["kept_ids"], ref["kept_ids"])):
         assert np.array_equal(a, b), "removal %d: %d differ" % (k, np.setxor1d(a, b).size)
     assert np.array_equal(ELS, ELS_ref) and np.array_equal(nodes, nodes_ref)
+
+
+# ---- plot=True outputs: the fields the reference hands to its plots, and the plot calls themselves ----
+def _compat_pos():
+    import os
+    import sys
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "compat")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import solidspy.postprocesor as pos
+    return pos
+
+
+@pytest.mark.parametrize("kind", ["eso_stress", "eso_stiff", "beso"])
+def test_plot_fields_match_strain_nodes(capi, kind):
+    """UCI/E_nodesI/S_nodesI and UC/E_nodes/S_nodes (optimize.py:62-63,85-86,162-163,182-183,261-262,299-300) against
+    the oracle's strain_nodes fed with the same displacements: ESO averages over present elements (orphan nodes
+    NaN), BESO over the full mesh."""
+    import solidspy_opt.optimize as opt
+    pos = _compat_pos()
+    nx, ny = 30, 20
+    dirs, positions = np.array([[0, -1]]), np.array([[5, 1]])
+    hist = {"keep_fields": True}
+    if kind == "beso":
+        ELS, nodes = opt.BESO(30.0, 20.0, nx, ny, dirs, positions, 4, 0.001, 0.05, 0.5, history=hist, verbose=False)
+    else:
+        fn = opt.ESO_stress if kind == "eso_stress" else opt.ESO_stiff
+        ELS, nodes = fn(30.0, 20.0, nx, ny, dirs, positions, 4, 0.02, 0.03, 0.5, history=hist, verbose=False)
+    f = hist["fields"]
+    from solidspy_opt.Utils.beams import beam
+    els_full = beam(L=30.0, H=20.0, nx=nx, ny=ny, dirs=dirs, positions=positions, n=1)[2]
+    mats = np.array([[E0, NU]])
+    nodes0 = nodes.copy()
+    E_i, S_i = pos.strain_nodes(nodes0, els_full, mats, f["UCI"])
+    # 1e-12 of the field's magnitude (components that cancel to ~0 carry the rounding of the larger terms)
+    tol_e, tol_s = 1e-12*np.abs(E_i).max(), 1e-12*np.abs(S_i).max()
+    assert np.allclose(f["E_nodesI"], E_i, rtol=1e-12, atol=tol_e)
+    assert np.allclose(f["S_nodesI"], S_i, rtol=1e-12, atol=tol_s)
+    els_last = els_full if kind == "beso" else ELS
+    assert kind == "beso" or ELS.shape[0] < els_full.shape[0]          # something was removed
+    E_l, S_l = pos.strain_nodes(nodes0, els_last, mats, f["UC"])
+    assert np.array_equal(np.isnan(f["E_nodes"]), np.isnan(E_l))
+    assert np.allclose(f["E_nodes"], E_l, rtol=1e-12, atol=tol_e, equal_nan=True)
+    assert np.allclose(f["S_nodes"], S_l, rtol=1e-12, atol=tol_s, equal_nan=True)
+    clamped = nodes[:, 1] == nodes[:, 1].min()                           # the left edge (orphan nodes are pinned later)
+    assert f["UC"].shape == (nodes.shape[0], 2) and np.all(f["UC"][clamped] == 0.0)
+
+
+def test_plot_true_draws_the_reference_figures(capi, monkeypatch):
+    """plot=True (optimize.py:101-109): two fields_plot calls (8 contour figures each) + the design picture, on the
+    triangulations of the initial and of the final element set.  matplotlib is not installed: a recording stand-in."""
+    import solidspy_opt.optimize as opt
+    from test_host import fake_matplotlib
+    calls = fake_matplotlib(monkeypatch)
+    nx, ny = 24, 12
+    ELS, nodes = opt.ESO_stiff(24.0, 12.0, nx, ny, np.array([[0, -1]]), np.array([[3, 1]]), 3, 0.01, 0.02, 0.5,
+                               plot=True, verbose=False)
+    tris = [c for c in calls if c[0] == "Triangulation"]
+    cont = [c for c in calls if c[0] == "tricontourf"]
+    assert len(cont) == 17 and len(tris) == 2*3 + 1
+    assert tris[0][1] == 2*nx*ny and tris[-1][1] == 2*ELS.shape[0]

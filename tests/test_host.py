@@ -158,3 +158,66 @@ def test_header_documents_what_every_slab_segment_hands_to_the_host():
         line = [l for l in header.splitlines() if fn + "(" in l]
         i = header.index(fn + "(")
         assert needs in header[max(0, i - 400):i + 400], (fn, needs)
+
+
+# ---- plot plumbing: no matplotlib in this image, so a recording stand-in ------------------------------
+def fake_matplotlib(monkeypatch):
+    """Installs stand-ins for matplotlib / matplotlib.pyplot / matplotlib.tri that record the calls the plot
+    helpers make; returns the call list."""
+    import sys
+    import types
+    calls = []
+
+    class Triangulation:
+        def __init__(self, x, y, triangles):
+            self.x, self.y, self.triangles = np.asarray(x), np.asarray(y), np.asarray(triangles)
+            assert self.triangles.min() >= 0 and self.triangles.max() < self.x.size
+            calls.append(("Triangulation", self.triangles.shape[0]))
+
+        def set_mask(self, mask):
+            calls.append(("set_mask", int(np.count_nonzero(mask))))
+
+    def rec(name):
+        def f(*a, **k):
+            calls.append((name,) + tuple(type(x).__name__ for x in a))
+            return types.SimpleNamespace(show=lambda: None)
+        return f
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    for n in ("figure", "tricontourf", "colorbar", "title", "axis", "ion"):
+        setattr(plt, n, rec(n))
+    tri = types.ModuleType("matplotlib.tri")
+    tri.Triangulation = Triangulation
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot, mpl.tri = plt, tri
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    monkeypatch.setitem(sys.modules, "matplotlib.tri", tri)
+    return calls
+
+
+def test_mesh2tri_and_plot_calls(monkeypatch):
+    """Triangles of the quad4 mesh ((n0,n1,n2), (n2,n3,n0) per element) and the figure sequence of the reference's
+    plot branch (optimize.py:101-109): 2 x (2 displacement + 3 strain + 3 stress) contour figures + the design."""
+    from solidspy_opt import plots
+    from solidspy_opt.Utils.beams import beam
+    nodes, mats, els, loads, BC = beam(L=6.0, H=4.0, nx=6, ny=4, dirs=np.array([[0, -1]]),
+                                       positions=np.array([[1, 1]]), n=1)
+    x, y, tri = plots.mesh2tri(nodes, els)
+    assert tri.shape == (48, 3) and np.array_equal(tri[0], els[0, [3, 4, 5]]) and np.array_equal(tri[1], els[0, [5, 6, 3]])
+    # every triangle is counter-clockwise with half the element's area
+    area = 0.5*((x[tri[:, 1]] - x[tri[:, 0]])*(y[tri[:, 2]] - y[tri[:, 0]]) -
+                (x[tri[:, 2]] - x[tri[:, 0]])*(y[tri[:, 1]] - y[tri[:, 0]]))
+    assert np.allclose(area, 0.5)
+    calls = fake_matplotlib(monkeypatch)
+    nn = nodes.shape[0]
+    rng = np.random.default_rng(0)
+    fields = {k: rng.normal(size=(nn, 2 if k.startswith("UC") else 3))
+              for k in ("UCI", "E_nodesI", "S_nodesI", "UC", "E_nodes", "S_nodes")}
+    fields["E_nodes"][nn - 1] = np.nan                             # a node without a contributing element
+    ELS = els[1:]
+    plots.eso_plots(els, ELS, nodes, fields)
+    assert sum(c[0] == "tricontourf" for c in calls) == 17
+    assert [c[1] for c in calls if c[0] == "Triangulation"] == [48]*3 + [46]*4
+    masks = [c[1] for c in calls if c[0] == "set_mask"]
+    assert len(masks) == 16 and sum(m > 0 for m in masks) == 3      # the three strain figures of the final design
