@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
 
 template <int KIND, int NC>
 int launch_fine_nc(topo_handle *h, FineArgs &a) {
-  static int resident = 0;                                 // CTAs of this variant that fit one SM
+  static int resident_dev[TOPO_MAX_DEVICES] = {};          // CTAs of this variant that fit one SM (0: not set up yet)
+  int &resident = resident_dev[topo_dev_slot(h)];
   const size_t smem = 4 * (size_t)warp_smem_bytes<KIND, NC>();
   if (resident == 0) {
     CUDA_TRY(cudaFuncSetAttribute(k_fine<KIND, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -417,7 +417,8 @@ static int invert_coarsest(topo_handle *h) {
     topo_set_error("coarsest multigrid level too large for the dense inverse (N=%d)", N);
     return TOPO_EINVAL;
   }
-  static bool attr_done = false;
+  static bool attr_done_dev[TOPO_MAX_DEVICES] = {};
+  bool &attr_done = attr_done_dev[topo_dev_slot(h)];
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CI_MAXN * CI_MAXN)));
     attr_done = true;

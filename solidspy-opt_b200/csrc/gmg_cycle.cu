@@ -593,7 +593,8 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   ta.done = &h->sc->done;
   ta.dbg = h->tail_dbg;
   // one cluster; 16 CTAs needs the non-portable size, fall back to 8 (portable) or 1
-  static int cluster_size = 0;
+  static int cluster_size_dev[TOPO_MAX_DEVICES] = {};
+  int &cluster_size = cluster_size_dev[topo_dev_slot(h)];
   if (cluster_size == 0) {
     cluster_size = 1;
     if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
@@ -679,13 +680,16 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   const int *done = &h->sc->done;
   const int tail = tail_start(h);
   auto result_of = [&](int l) { return level_result(h, l, tail); };
-  static int pdl_early_set = -1;
+  static int pdl_early_dev[TOPO_MAX_DEVICES] = {};       // value + 1 of c_pdl_early on each device (0: never written)
+  int &pdl_early_slot = pdl_early_dev[topo_dev_slot(h)];
+  int pdl_early_set = pdl_early_slot - 1;
   if (pdl_early_set != ((h->pdl & 4) ? 1 : 0)) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     if (cap == cudaStreamCaptureStatusNone) {      // (the first V-cycle of a solve is never captured)
       pdl_early_set = (h->pdl & 4) ? 1 : 0;
       CUDA_TRY(cudaMemcpyToSymbol(c_pdl_early, &pdl_early_set, sizeof(int)));
+      pdl_early_slot = pdl_early_set + 1;
     }
   }
 

@@ -225,6 +225,10 @@ static inline void topo_prof_post(topo_handle *h) {
   } while (0)
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// Function attributes (dynamic shared memory, cluster size) and __constant__ symbols are per DEVICE: one-time set-up
+// flags in the launch helpers are indexed by the handle's device so that handles on several GPUs can share a process.
+constexpr int TOPO_MAX_DEVICES = 64;
+static inline int topo_dev_slot(const topo_handle *h) { return h->device & (TOPO_MAX_DEVICES - 1); }
 
 // ---- kernels / drivers implemented across translation units ----
 int topo_fine_matvec(topo_handle *h, const double2 *u, double2 *y);                  // y = A u
