@@ -226,13 +226,6 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   k_fill<<<nblk(h->ne), 256, 0, h->stream>>>(h->scale, h->ne, 1.0);
   CUDA_TRY(cudaGetLastError());
 
-  // matvec chunking: aim at ~4 resident blocks per SM in a single wave
-  {
-    const int bx = div_up(nx + 1, 128);
-    int chunks = std::max(1, (148 * 4) / bx);
-    int rows = std::max(8, div_up(ny + 1, chunks));
-    h->matvec_rows_per_chunk = rows;
-  }
   h->fine_nc = getenv("TOPO_FINE_NC") ? atoi(getenv("TOPO_FINE_NC")) : (nx + 1 >= 1024 ? 2 : 1);
   if (h->fine_nc != 2) h->fine_nc = 1;
   int s = topo_gmg_plan(h);

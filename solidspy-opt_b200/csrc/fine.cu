@@ -471,9 +471,10 @@ int launch_fine_nc(topo_handle *h, FineArgs &a) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fine<KIND, NC>, BW, smem));
     resident = std::max(1, occ);
   }
-  // chunk rows so that one wave of CTAs covers the mesh
+  // chunk rows so that one wave of CTAs covers the mesh (TOPO_FINE_WAVES: more, shorter chunks -- experiment knob)
+  static const double waves = getenv("TOPO_FINE_WAVES") ? atof(getenv("TOPO_FINE_WAVES")) : 1.0;
   const int bx = div_up(h->nx + 1, 4 * Geo<NC>::WC);
-  const int chunks = std::max(1, (148 * resident) / bx);
+  const int chunks = std::max(1, (int)(waves * 148 * resident) / bx);
   a.rows_per_chunk = std::max(8, div_up(h->ny + 1, chunks));
   dim3 grid(bx, div_up(h->ny + 1, a.rows_per_chunk));
   if ((int64_t)grid.x * grid.y > TOPO_MAX_PARTIAL_BLOCKS) {

@@ -197,7 +197,6 @@ struct topo_handle {
   std::vector<cudaEvent_t> prof_ev;   // pairs
   std::vector<const char *> prof_name;
   topo_timing timing;
-  int matvec_rows_per_chunk;
   int fine_nc;                    // node columns per lane of the stage-1 kernel (1 or 2)
   DistState dist;
 };
