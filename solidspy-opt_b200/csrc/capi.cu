@@ -168,8 +168,6 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
   h->tail_dbg = nullptr;
   h->use_graph = getenv("TOPO_NO_GRAPH") ? false : true;
-  // bit 0: launch attribute on; bit 1: fine-grid kernels let their dependents in at once; bit 2: so do the level kernels
-  h->pdl = getenv("TOPO_PDL") ? atoi(getenv("TOPO_PDL")) : 0;
   h->pcg_graph_valid = false;
   h->pcg_graph_exec = nullptr;
   h->pcg_graph_launches = 0;

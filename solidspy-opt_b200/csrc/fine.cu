@@ -104,7 +104,6 @@ struct FineArgs {
   // all-reduce, the scalar bookkeeping happens afterwards (k_dist_pcg_finish)
   double w_first, w_last;
   int dist;
-  int pdl_early;              // programmatic dependent launch: release the dependents at kernel entry
 };
 
 // Rows 0 and 1 of the element matrix (the row block of local node 0).  For a rectangular element of an
@@ -175,7 +174,6 @@ __global__ void __launch_bounds__(BW, NC == 1 ? 4 : 3) k_fine(const __grid_const
   // in the ring as aligned 4-byte words (a direct byte load prefetched one row ahead was the dominant stall)
   constexpr bool NEEDS_FIXED = (KIND == FK_APPLY || KIND == FK_RESID);
   constexpr int FWORDS = (WC + 3 + 3) / 4;               // aligned words covering the warp's WC flag bytes
-  pdl_enter(a.pdl_early != 0);
   if (a.check_done && a.sc->done) return;
   const KeRow ke = kparam;                                // 16 constants -> (uniform) registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -502,7 +500,6 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   a.w_first = h->dist.on ? h->dist.w_first : 1.0;
   a.w_last = h->dist.on ? h->dist.w_last : 1.0;
   a.dist = h->dist.on ? 1 : 0;
-  a.pdl_early = (h->pdl & 2) ? 1 : 0;
   // node columns per lane: 2 for the plain product on wide meshes (overhead instructions amortised over two
   // nodes), 1 for the fused kinds (measured: they lose more from the lower occupancy of 64-column strips than
   // they gain); TOPO_FINE_NC_MASK (bit KIND set = two columns for that kind) is the experiment knob

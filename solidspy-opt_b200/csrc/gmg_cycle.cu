@@ -21,8 +21,6 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-__constant__ int c_pdl_early;   // programmatic dependent launch: the level kernels release their dependents at entry
-
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
 
 // ---- transfers: 1-D rules --------------------------------------------------------------------------------------
@@ -102,9 +100,9 @@ __device__ __forceinline__ void rc_of(int64_t n, int npr, int &r, int &c) {
 // the block node m stores towards n.  Reading planes 4..8 only (self, E, NW, N, NE -- at n and at the four backward
 // neighbours, whose entries sit in cache lines the neighbouring threads fetch anyway) cuts the stencil stream of a
 // level from 144 to 80 B per node; the big levels are bound by exactly that stream.
-template <class Get>
+template <bool SYM, class Get>
 __device__ __forceinline__ void stencil_row(const stencil_t *__restrict__ st, int64_t nn, int64_t n, int r, int c, int nx,
-                                            int ny, bool sym, Get get, double &ax, double &ay) {
+                                            int ny, Get get, double &ax, double &ay) {
   ax = 0.0;
   ay = 0.0;
   const float4 *__restrict__ pl = reinterpret_cast<const float4 *>(st);
@@ -117,7 +115,7 @@ __device__ __forceinline__ void stencil_row(const stencil_t *__restrict__ st, in
       if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
       const int nb = 3 * (dr + 1) + (dc + 1);
       const double2 xv = get(rr, cc);
-      if (sym && nb < 4) {
+      if (SYM && nb < 4) {
         // A[n, m] = A[m, n]^T ; node m keeps A[m, n] in plane 8 - nb
         const float4 cf = pl[(size_t)(8 - nb) * nn + (n + (int64_t)dr * npr + dc)];
         ax = fma((double)cf.x, xv.x, ax);
@@ -148,13 +146,14 @@ __device__ __forceinline__ double row_weight(const LevelView &L, int r) { return
 
 // ---- per-node bodies shared by the multi-block kernels and the tail kernel -------------------------------
 // down: x = w dinv b ; r = b - A x   (x at neighbours recomputed from b, dinv)
+template <bool SYM = false>
 __device__ __forceinline__ void node_down(const LevelView &L, int64_t n, double omega) {
   const int npr = L.nx + 1;
   const int64_t nn = (int64_t)npr * (L.ny + 1);
   int r, c;
   rc_of(n, npr, r, c);
   double ax, ay;
-  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, L.sym != 0,
+  stencil_row<SYM>(L.st, nn, n, r, c, L.nx, L.ny,
               [&](int rr, int cc) {
                 const size_t m = (size_t)rr * npr + cc;
                 const double2 bv = L.b[m], dv = L.dinv[m];
@@ -168,6 +167,7 @@ __device__ __forceinline__ void node_down(const LevelView &L, int64_t n, double 
 }
 
 // up: x~ = x + mask(P xc) ; x2 = x~ + w dinv (b - A x~)
+template <bool SYM = false>
 __device__ __forceinline__ void node_up(const LevelView &L, const double2 *__restrict__ xc, int cnx, int64_t n,
                                         double omega) {
   const int npr = L.nx + 1, nprc = cnx + 1;
@@ -181,31 +181,33 @@ __device__ __forceinline__ void node_up(const LevelView &L, const double2 *__res
     return make_double2(dv.x != 0.0 ? xv.x + p.x : 0.0, dv.y != 0.0 ? xv.y + p.y : 0.0);
   };
   double ax, ay;
-  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, L.sym != 0, xt, ax, ay);
+  stencil_row<SYM>(L.st, nn, n, r, c, L.nx, L.ny, xt, ax, ay);
   const double2 bv = L.b[n], dv = L.dinv[n], xv = xt(r, c);
   L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xv.x), fma(omega * dv.y, bv.y - ay, xv.y));
 }
 
 // plain extra smoothing sweep: x2 = x + w dinv (b - A x)
+template <bool SYM = false>
 __device__ __forceinline__ void node_smooth(const LevelView &L, int64_t n, double omega) {
   const int npr = L.nx + 1;
   const int64_t nn = (int64_t)npr * (L.ny + 1);
   int r, c;
   rc_of(n, npr, r, c);
   double ax, ay;
-  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, L.sym != 0, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
+  stencil_row<SYM>(L.st, nn, n, r, c, L.nx, L.ny, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
   const double2 bv = L.b[n], dv = L.dinv[n], xv = L.x[n];
   const double wr = row_weight(L, r);
   L.x2[n] = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xv.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xv.y));
 }
 // residual of the current iterate (needed when nu_pre > 1): r = b - A x
+template <bool SYM = false>
 __device__ __forceinline__ void node_resid(const LevelView &L, int64_t n) {
   const int npr = L.nx + 1;
   const int64_t nn = (int64_t)npr * (L.ny + 1);
   int r, c;
   rc_of(n, npr, r, c);
   double ax, ay;
-  stencil_row(L.st, nn, n, r, c, L.nx, L.ny, L.sym != 0, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
+  stencil_row<SYM>(L.st, nn, n, r, c, L.nx, L.ny, [&](int rr, int cc) { return L.x[(size_t)rr * npr + cc]; }, ax, ay);
   const double2 bv = L.b[n], dv = L.dinv[n];
   L.r[n] = make_double2(dv.x != 0.0 ? bv.x - ax : 0.0, dv.y != 0.0 ? bv.y - ay : 0.0);
 }
@@ -228,46 +230,44 @@ __device__ __forceinline__ void node_prolong_add(const LevelView &L, const doubl
 }
 
 // ---- multi-block kernels (large coarse levels) ------------------------------------------------------------
+template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omega, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_down(L, n, omega);
+  if (n < nn) node_down<SYM>(L, n, omega);
 }
+template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_up(const LevelView L, const double2 *__restrict__ xc, int cnx,
                                                 double omega, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_up(L, xc, cnx, n, omega);
+  if (n < nn) node_up<SYM>(L, xc, cnx, n, omega);
 }
 __global__ void __launch_bounds__(128) k_lvl_prolong(const LevelView L, const double2 *__restrict__ xc, int cnx, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_prolong_add(L, xc, cnx, n);
 }
+template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_smooth(const LevelView L, double omega, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_smooth(L, n, omega);
+  if (n < nn) node_smooth<SYM>(L, n, omega);
 }
+template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_resid(L, n);
+  if (n < nn) node_resid<SYM>(L, n);
 }
 template <class V2>
 __global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
                                                   int nyf, int nxc, int nyc, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int nprc = nxc + 1;
   const int64_t nnc = (int64_t)nprc * (nyc + 1);
@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, dou
 __global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, float2 *__restrict__ xf,
                                                           const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
                                                           const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const int nprf = nxf + 1;
   const int64_t nnf = (int64_t)nprf * (nyf + 1);
@@ -493,7 +492,6 @@ __device__ __noinline__ void small_up(const TailArgs &a, int l, float2 (*xs)[TAI
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ TailArgs a) {
-  pdl_enter(c_pdl_early != 0);
   if (a.done && *a.done) return;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
@@ -653,16 +651,11 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   cfg.gridDim = dim3(cs);
   cfg.blockDim = dim3(TAIL_THREADS);
   cfg.stream = h->stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if ((h->pdl & 1) && !h->dist.on) {
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.numAttrs = 2;
-  }
   KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
   return TOPO_OK;
 }
@@ -674,7 +667,6 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
 __global__ void k_dist_assemble_bK(const double2 *__restrict__ recv0, const double2 *__restrict__ recv1,
                                    const unsigned long long *seq, double2 *__restrict__ b, int npr, int rows,
                                    int world, const int *done) {
-  pdl_enter(c_pdl_early != 0);
   if (done && *done) return;
   const double2 *__restrict__ recv = (seq != nullptr && (*seq & 1ull)) ? recv1 : recv0;
   const int64_t nn = (int64_t)npr * ((int64_t)rows * world + 1);
@@ -717,19 +709,6 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   const int *done = &h->sc->done;
   const int tail = tail_start(h);
   auto result_of = [&](int l) { return level_result(h, l, tail); };
-  static int pdl_early_dev[TOPO_MAX_DEVICES] = {};       // value + 1 of c_pdl_early on each device (0: never written)
-  int &pdl_early_slot = pdl_early_dev[topo_dev_slot(h)];
-  int pdl_early_set = pdl_early_slot - 1;
-  if (pdl_early_set != ((h->pdl & 4) ? 1 : 0)) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    if (cap == cudaStreamCaptureStatusNone) {      // (the first V-cycle of a solve is never captured)
-      pdl_early_set = (h->pdl & 4) ? 1 : 0;
-      CUDA_TRY(cudaMemcpyToSymbol(c_pdl_early, &pdl_early_set, sizeof(int)));
-      pdl_early_slot = pdl_early_set + 1;
-    }
-  }
-
   if (tail > 1) {
     GmgLevel &C = h->levels[1];
     KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict<float2>, dim3(blocks_for(C.nn)), dim3(128), 0, reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx, C.ny, done)));
@@ -737,11 +716,11 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(F);
-    KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, k_lvl_down, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+    KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down<true> : k_lvl_down<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
     for (int s = 1; s < nu_pre_of(h, l); ++s) {
-      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
-      KL(h, "k_lvl_resid", CUDA_TRY(topo_launch(h, k_lvl_resid, dim3(blocks_for(F.nn)), dim3(128), 0, V, done)));
+      KL(h, "k_lvl_resid", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_resid<true> : k_lvl_resid<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, done)));
     }
     if (l + 1 < tail) {
       GmgLevel &C = h->levels[l + 1];
@@ -758,14 +737,14 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel
       KL(h, "k_lvl_prolong", CUDA_TRY(topo_launch(h, k_lvl_prolong, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, done)));
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
     } else {
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, k_lvl_up, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, om, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up<true> : k_lvl_up<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, om, done)));
     }
     for (int s = 1; s < nu_post_of(h, l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }
-      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, k_lvl_smooth, dim3(blocks_for(F.nn)), dim3(128), 0, W, om, done)));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, W.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, W, om, done)));
     }
   }
   if (x1_out != nullptr) {
@@ -805,7 +784,9 @@ int topo_dist_restrict_fine(topo_handle *h, const double2 *res_fine) { return di
 int topo_dist_level_down(topo_handle *h, int l) {
   if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
   GmgLevel &F = h->levels[l];
-  KL(h, lvl_name("down", l), k_lvl_down<<<blocks_for(F.nn), 128, 0, h->stream>>>(dist_view(h, l), h->omega, &h->sc->done));
+  const LevelView V = dist_view(h, l);
+  KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down<true> : k_lvl_down<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V,
+                                                  h->omega, &h->sc->done)));
   return dist_restrict_from(h, l, F.r);
 }
 
@@ -842,7 +823,8 @@ int topo_dist_level_up(topo_handle *h, int l) {
   const LevelView V = dist_view(h, l);
   const int *done = &h->sc->done;
   KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));
-  KL(h, lvl_name("up", l), k_lvl_smooth<<<blocks_for(F.nn), 128, 0, h->stream>>>(V, h->omega, done));
+  KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V,
+                                                h->omega, done)));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }

@@ -181,7 +181,6 @@ struct topo_handle {
   unsigned long long *tail_dbg;   // device buffer for k_tail stage stamps (nullptr = off)
   int tail_max_nodes;
   bool use_graph, pcg_graph_valid;
-  int pdl;                     // programmatic dependent launch for the kernels of the single-GPU PCG loop (TOPO_PDL)
   cudaGraphExec_t pcg_graph_exec;
   int last_pcg_iters;          // iterations of the previous multigrid-PCG solve (sizes the first batch of the next)
   int pcg_graph_launches;      // levels with at most this many nodes run inside the single-CTA tail kernel
@@ -240,18 +239,12 @@ void topo_gmg_free(topo_handle *h);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
-// Programmatic dependent launch.  A PCG iteration is ~16 short kernels in one stream; with the launch attribute
-// below the CTAs of kernel N+1 become resident while the last CTAs of kernel N drain (launch latency and the
-// prologue up to the first global access overlap the predecessor's tail).  Contract: EVERY kernel launched through
-// topo_launch calls pdl_enter() before its first global-memory access (including the early-exit test of the
-// convergence flag): it allows its own dependents to be scheduled and then waits until all prerequisite grids
-// have completed and flushed, so the data dependences are exactly those of plain stream order (transitively:
-// a grid cannot complete before its own wait has returned).  Without the attribute both instructions are no-ops.
+// Kernel launch through cudaLaunchKernelEx (one place for launch attributes).  Programmatic dependent launch was
+// tried here for the ~16 short kernels of a PCG iteration (griddepcontrol.wait at every kernel entry, optional early
+// release of the dependents): inside the CUDA graph it made the design iteration slower in every combination
+// (8.9-10.0 ms against 8.8 ms on 2048x1024) and the entry instructions alone cost the level kernels time, so it was
+// removed again.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_enter(bool early_trigger) {
-  if (early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
 template <class... KA, class... A>
 static inline cudaError_t topo_launch(topo_handle *h, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem,
                                       A &&...args) {
@@ -260,13 +253,6 @@ static inline cudaError_t topo_launch(topo_handle *h, void (*kern)(KA...), dim3 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
-  cudaLaunchAttribute at[1];
-  if ((h->pdl & 1) && !h->dist.on) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-  }
   return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
 }
 
