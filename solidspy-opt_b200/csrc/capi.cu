@@ -180,6 +180,11 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   std::memset(&h->timing, 0, sizeof(h->timing));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->owns_stream = true;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming));
+  h->inv_pending = false;
+  h->inv_overlap = getenv("TOPO_NO_INV_OVERLAP") ? false : true;
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&h->evs[i]));
@@ -239,6 +244,7 @@ extern "C" int topo_destroy(topo_t *h) {
   if (!h) return TOPO_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->side);
   cudaFree(h->slab_nodal);
   cudaFree(h->slab_elem);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(h->evs[i]);
@@ -267,6 +273,9 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   if (h->owns_stream) cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->side);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_inv);
   cudaGetLastError();
   delete h;
   return TOPO_OK;

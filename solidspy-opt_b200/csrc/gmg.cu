@@ -423,8 +423,22 @@ static int invert_coarsest(topo_handle *h) {
     CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CI_MAXN * CI_MAXN)));
     attr_done = true;
   }
-  KL(h, "k_coarse_invert", k_coarse_invert<<<1, CI_MAXN * CI_RG, sizeof(double) * N * N, h->stream>>>(L.st, L.nx, L.ny, h->coarse_inv));
+  // Single-GPU path outside profile mode: the inversion runs on the side stream, forked here (the coarsest stencil
+  // is in place) and joined by the first tail launch of the solve (launch_tail) -- everything in between (the other
+  // levels' stencils, residual, first fine-grid pass, levels 1..3 going down) does not need the inverse.
+  const bool overlap = h->inv_overlap && !h->prof_on && !h->dist.on;
+  cudaStream_t st = h->stream;
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    st = h->side;
+  }
+  KL(h, "k_coarse_invert", k_coarse_invert<<<1, CI_MAXN * CI_RG, sizeof(double) * N * N, st>>>(L.st, L.nx, L.ny, h->coarse_inv));
   CUDA_TRY(cudaGetLastError());
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(h->ev_inv, h->side));
+    h->inv_pending = true;
+  }
   return TOPO_OK;
 }
 
@@ -445,11 +459,12 @@ int topo_gmg_setup(topo_handle *h) {
     dim3 grid(blocks_for(C.ncell), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
-  for (int l = 1; l < h->n_levels; ++l) {
+  // coarsest level first: its dense inverse (side stream) then overlaps the stencils of the other levels
+  for (int l = h->n_levels - 1; l >= 1; --l) {
     GmgLevel &L = h->levels[l];
     KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+    if (l == h->n_levels - 1) TOPO_TRY(invert_coarsest(h));
   }
-  TOPO_TRY(invert_coarsest(h));
   h->gmg_valid = true;
   return TOPO_OK;
 }

@@ -632,7 +632,9 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   if (cluster_size == 0) {
     cluster_size = 1;
     if (cudaFuncSetAttribute(k_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      static const int cs_max = getenv("TOPO_TAIL_CLUSTER") ? atoi(getenv("TOPO_TAIL_CLUSTER")) : 16;
       for (int cs : {16, 8, 4, 2}) {
+        if (cs > cs_max) continue;
         cudaLaunchConfig_t q = {};
         q.gridDim = dim3(cs); q.blockDim = dim3(TAIL_THREADS);
         cudaLaunchAttribute at[1];
@@ -644,6 +646,14 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
       }
     }
     cudaGetLastError();
+  }
+  if (h->inv_pending) {     // join the side stream that inverts the coarsest operator (first tail launch of a solve)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->stream, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_inv, 0));
+      h->inv_pending = false;
+    }
   }
   const bool big_tail = h->levels[tail].nn > TAIL_SMALL;
   const int cs = big_tail ? cluster_size : 1;

@@ -136,6 +136,11 @@ struct topo_handle {
   KeParam ke_factor;    // rows l_k of a pivoted Cholesky factor: ke = sum_k l_k l_k^T (zero rows beyond the rank)
   cudaStream_t stream;
   bool owns_stream;
+  // side stream for the dense coarsest-level inverse (one latency-bound CTA, ~165 us): it overlaps the rest of the
+  // multigrid set-up and the first fine-grid passes of the solve; the first tail launch waits for ev_inv
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_inv;
+  bool inv_pending, inv_overlap;
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
