@@ -317,6 +317,7 @@ struct TailArgs {
   const int *done;
   unsigned long long *dbg;     // optional: globaltimer stamps at stage boundaries (thread 0 of CTA 0)
   int ds_rows[TAIL_MAX];       // k_tail_ds: node rows per CTA on each cluster level
+  int ds_mode;                 // k_tail_ds: 1 = cluster barrier after every sweep, 2 = neighbour hand-over (st.async + mbarrier)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -505,8 +506,19 @@ __device__ __noinline__ void small_up(const TailArgs &a, int l, float2 (*xs)[TAI
 // Products A x are formed in fp32 as on the small levels (numpy prototype: identical PCG iteration counts).
 constexpr int DS_XS = 1536;        // floats2 per iterate buffer: (rows per CTA + 2 halo rows) * nodes per row
 constexpr int DS_MAXLV = 3;        // cluster levels the shared-memory plan has room for
-constexpr size_t DS_SMEM_BYTES = sizeof(float2) * 2 * DS_XS + sizeof(double2) * TAIL_THREADS * (1 + 2 * DS_MAXLV);
+constexpr size_t DS_SMEM_BYTES = sizeof(float2) * 2 * DS_XS + sizeof(double2) * TAIL_THREADS * (1 + 2 * DS_MAXLV) + 16;
+// TOPO_TAIL_DS=2 (NOT YET RUN ON A GPU: written after the round's GPU budget was spent): inside a smoothing phase the
+// cluster-wide barrier is replaced by a neighbour-to-neighbour hand-over.  Halo values go out with st.async, which
+// credits the receiving CTA's mbarrier (one per iterate buffer) with their bytes; a CTA arms that mbarrier with the
+// bytes its one or two neighbours will send, waits for it and does a __syncthreads.  Why this is enough: a block
+// reads only its neighbours' halo rows; a neighbour can start the next sweep (and overwrite the halo row of the
+// buffer I am reading) only after ALL boundary-row threads of mine have pushed, and each of them reads before it
+// pushes.  Phase boundaries (residual -> restriction, result -> prolongation) keep the cluster-wide barrier.
 struct DsSmem {
+  unsigned long long *bar;         // two mbarriers, one per iterate buffer (mode 2)
+  int mode;                        // 1: cluster.sync() after every sweep, 2: neighbour hand-over
+  unsigned uses[2];                // completed phases of each mbarrier (same sequence on every thread of the cluster)
+  unsigned expect;                 // bytes this CTA receives per sweep on the current level
   float2 *xs[2];                   // iterate copies incl. halo rows (local row 0 = row below the block)
   double2 *rs;                     // residual of the block's own nodes (read remotely by the restriction)
   double2 *xd[DS_MAXLV], *bd[DS_MAXLV];   // fp64 iterate and right-hand side of the own nodes, per cluster level
@@ -546,15 +558,61 @@ __device__ __forceinline__ void ds_load(const LevelView &L, int R, const DsNode 
   }
   N.dinv = L.dinv[d.g];
 }
-// own value into the local block and into the neighbours' halo rows
-__device__ __forceinline__ void ds_publish(cg::cluster_group &cl, float2 *buf, const DsNode &d, int rank, const double2 &x) {
+__device__ __forceinline__ unsigned ds_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned ds_mapa(unsigned local_addr, unsigned rank) {      // same offset in CTA `rank`
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void ds_mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = ds_smem_u32(bar);
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 24)) __trap();          // a protocol error must not hang the device
+  }
+}
+// own value into the local block and into the neighbours' halo rows of iterate buffer b
+__device__ __forceinline__ void ds_publish(cg::cluster_group &cl, const DsSmem &S, int b, const DsNode &d, int rank, const double2 &x) {
+  float2 *buf = S.xs[b];
+  if (S.mode == 2 && threadIdx.x == 0)        // arm this use of the buffer's mbarrier: my arrival + the neighbours' bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ds_smem_u32(S.bar + b)), "r"(S.expect) : "memory");
   if (!d.active) return;
   const float2 v = make_float2((float)x.x, (float)x.y);
   buf[d.loc] = v;
-  if (d.push_lo >= 0) cl.map_shared_rank(buf, rank - 1)[d.push_lo] = v;
-  if (d.push_hi >= 0) cl.map_shared_rank(buf, rank + 1)[d.push_hi] = v;
+  if (S.mode == 2) {
+    const unsigned long long bits = ((unsigned long long)__float_as_uint(v.y) << 32) | (unsigned long long)__float_as_uint(v.x);
+    if (d.push_lo >= 0)
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::
+                   "r"(ds_mapa(ds_smem_u32(buf + d.push_lo), rank - 1)), "l"(bits), "r"(ds_mapa(ds_smem_u32(S.bar + b), rank - 1)) : "memory");
+    if (d.push_hi >= 0)
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::
+                   "r"(ds_mapa(ds_smem_u32(buf + d.push_hi), rank + 1)), "l"(bits), "r"(ds_mapa(ds_smem_u32(S.bar + b), rank + 1)) : "memory");
+  } else {
+    if (d.push_lo >= 0) cl.map_shared_rank(buf, rank - 1)[d.push_lo] = v;
+    if (d.push_hi >= 0) cl.map_shared_rank(buf, rank + 1)[d.push_hi] = v;
+  }
 }
-__device__ __forceinline__ void ds_sweeps(cg::cluster_group &cl, const DsSmem &S, const DsNode &d, int rank, SmallNode &N,
+// iterate buffer b is complete (own values and both halo rows) and every thread of the CTA may read it
+__device__ __forceinline__ void ds_handover(cg::cluster_group &cl, DsSmem &S, int b) {
+  if (S.mode == 2) {
+    ds_mbar_wait(S.bar + b, S.uses[b] & 1u);
+    S.uses[b] += 1;
+    __syncthreads();
+  } else {
+    cl.sync();
+  }
+}
+// bytes a CTA receives per sweep on a level: one halo row from each neighbour that exists
+__device__ __forceinline__ unsigned ds_expect_bytes(const LevelView &L, int R, int rank) {
+  const int npr = L.nx + 1, nrows = L.ny + 1;
+  const int r0 = min(rank * R, nrows), r1 = min(r0 + R, nrows);
+  if (r1 <= r0) return 0u;
+  return 8u * (unsigned)npr * ((r0 > 0 ? 1u : 0u) + (r1 < nrows ? 1u : 0u));
+}
+__device__ __forceinline__ void ds_sweeps(cg::cluster_group &cl, DsSmem &S, const DsNode &d, int rank, SmallNode &N,
                                           int &cur, int nsweeps, double omega) {
   for (int s = 0; s < nsweeps; ++s) {
     if (d.active) {
@@ -563,8 +621,8 @@ __device__ __forceinline__ void ds_sweeps(cg::cluster_group &cl, const DsSmem &S
       N.x.x = fma(omega * N.dinv.x, N.b.x - (double)ax, N.x.x);
       N.x.y = fma(omega * N.dinv.y, N.b.y - (double)ay, N.x.y);
     }
-    ds_publish(cl, S.xs[cur ^ 1], d, rank, N.x);
-    cl.sync();
+    ds_publish(cl, S, cur ^ 1, d, rank, N.x);
+    ds_handover(cl, S, cur ^ 1);
     cur ^= 1;
   }
 }
@@ -622,18 +680,19 @@ __device__ __forceinline__ double2 ds_prolong(cg::cluster_group &cl, double2 *xc
 // pre-smoothing of cluster level l from a zero guess (nu sweeps), residual, restriction.  `b` = right-hand side of this
 // thread's node; returns the right-hand side of its node on level l+1 when that is a cluster level too, otherwise
 // (first small level) the restricted residual goes to global memory for CTA 0.
-__device__ __noinline__ double2 ds_down(const TailArgs &a, int l, bool next_is_cluster, const DsSmem &S, cg::cluster_group &cl,
+__device__ __noinline__ double2 ds_down(const TailArgs &a, int l, bool next_is_cluster, DsSmem &S, cg::cluster_group &cl,
                                         int rank, int t, int gt, int GT, double2 b) {
   const LevelView &L = a.lv[l];
   const int R = a.ds_rows[l];
   const DsNode d = ds_node(L, R, rank, t);
+  S.expect = ds_expect_bytes(L, R, rank);
   SmallNode N;
   ds_load(L, R, d, N);
   N.b = b;
   N.x = make_double2(a.omega * N.dinv.x * b.x, a.omega * N.dinv.y * b.y);
   int cur = 0;
-  ds_publish(cl, S.xs[0], d, rank, N.x);
-  cl.sync();
+  ds_publish(cl, S, 0, d, rank, N.x);
+  ds_handover(cl, S, 0);
   ds_sweeps(cl, S, d, rank, N, cur, a.nu[l] - 1, a.omega);
   if (d.active) {
     float ax, ay;
@@ -656,12 +715,13 @@ __device__ __noinline__ double2 ds_down(const TailArgs &a, int l, bool next_is_c
 }
 // coarse correction + nu post-smoothing sweeps of cluster level l; the result stays in xd[l] (and goes to global
 // memory for the first tail level, whose result the next kernel prolongates)
-__device__ __noinline__ void ds_up(const TailArgs &a, int l, bool next_is_cluster, const DsSmem &S, cg::cluster_group &cl,
+__device__ __noinline__ void ds_up(const TailArgs &a, int l, bool next_is_cluster, DsSmem &S, cg::cluster_group &cl,
                                    int rank, int t) {
   const LevelView &L = a.lv[l];
   const LevelView &C = a.lv[l + 1];
   const int R = a.ds_rows[l];
   const DsNode d = ds_node(L, R, rank, t);
+  S.expect = ds_expect_bytes(L, R, rank);
   SmallNode N;
   ds_load(L, R, d, N);
   N.b = make_double2(0.0, 0.0);
@@ -675,8 +735,8 @@ __device__ __noinline__ void ds_up(const TailArgs &a, int l, bool next_is_cluste
     if (N.dinv.y != 0.0) N.x.y += p.y;
   }
   int cur = 0;
-  ds_publish(cl, S.xs[0], d, rank, N.x);
-  cl.sync();
+  ds_publish(cl, S, 0, d, rank, N.x);
+  ds_handover(cl, S, 0);
   ds_sweeps(cl, S, d, rank, N, cur, a.nu[l], a.omega);
   if (d.active) {
     S.xd[l][d.own] = N.x;
@@ -693,7 +753,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_ds(const __grid_constant_
   const int gt = rank * T + t, GT = CS * T;
   extern __shared__ __align__(16) unsigned char ds_raw[];
   DsSmem S;
-  S.xs[0] = reinterpret_cast<float2 *>(ds_raw);
+  S.bar = reinterpret_cast<unsigned long long *>(ds_raw);
+  S.mode = a.ds_mode;
+  S.uses[0] = S.uses[1] = 0u;
+  S.expect = 0u;
+  S.xs[0] = reinterpret_cast<float2 *>(ds_raw + 16);
   S.xs[1] = S.xs[0] + DS_XS;
   S.rs = reinterpret_cast<double2 *>(S.xs[1] + DS_XS);
 #pragma unroll
@@ -703,7 +767,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_ds(const __grid_constant_
   }
   // halo rows outside the domain are never written: they are read with zero coefficients and must hold finite numbers
   for (int i = t; i < 2 * DS_XS; i += T) S.xs[0][i] = make_float2(0.f, 0.f);
-  cluster.sync();                               // nobody pushes into a block that is still being cleared
+  if (S.mode == 2 && t == 0) {                  // one pending arrival each: the CTA's own expect_tx
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ds_smem_u32(S.bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ds_smem_u32(S.bar + 1)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cluster.sync();                               // nobody pushes into a block that is still being cleared / whose barriers do not exist yet
   int lsmall = 0;                               // cluster levels = tail levels 0 .. lsmall-1
   while (lsmall + 1 < a.n && (a.lv[lsmall].nx + 1) * (a.lv[lsmall].ny + 1) > TAIL_SMALL) ++lsmall;
   double2 b = make_double2(0.0, 0.0);
@@ -889,10 +958,15 @@ int tail_ds_cluster_size(const topo_handle *h) {
   }
   return cs > 0 ? cs : 0;
 }
+// TOPO_TAIL_DS: 0 (default) k_tail, 1 k_tail_ds with cluster barriers, 2 k_tail_ds with the neighbour hand-over
+int tail_ds_mode() {
+  static const int mode = getenv("TOPO_TAIL_DS") ? atoi(getenv("TOPO_TAIL_DS")) : 0;
+  return (mode == 1 || mode == 2) ? mode : 0;
+}
 // Does the tail starting at level `tail` run in k_tail_ds?  Every cluster level must split into blocks of whole node
 // rows, one node per thread, that fit the shared-memory plan; rows[] receives the rows per CTA of each cluster level.
 bool tail_ds_plan(const topo_handle *h, int tail, int *rows) {
-  static const bool want = getenv("TOPO_TAIL_DS") && atoi(getenv("TOPO_TAIL_DS")) != 0;
+  static const bool want = tail_ds_mode() != 0;
   if (!want || h->dist.on || h->tail_dbg != nullptr) return false;
   const int L = h->n_levels;
   int ncl = 0;
@@ -961,6 +1035,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (ds) {
+    ta.ds_mode = tail_ds_mode();
     cfg.dynamicSmemBytes = DS_SMEM_BYTES;
     KL(h, "k_tail_ds", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail_ds, ta)));
   } else {
