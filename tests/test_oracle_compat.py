@@ -64,3 +64,40 @@ def test_strain_nodes_constant_strain_patch():
     assert np.allclose(E_n, [0.01, -0.02, 0.0], atol=1e-15)
     c = 10/(1 - 0.25**2)
     assert np.allclose(S_n[:, 0], c*(0.01 - 0.25*0.02)) and np.allclose(S_n[:, 2], 0, atol=1e-14)
+
+
+def test_beam_convergence_error_table():
+    """reference examples/beam_convergence: the notebook's mesh-refinement loop (rect_grid, DME, assembler, loadasem,
+    solve, complete_disp, scipy griddata to the next mesh) run on the stand-in reproduces error_vs_h.txt: iterations
+    2-3 to all six printed digits, 4-6 to 4e-4 (there the difference is how scipy's griddata breaks the ties of the
+    degenerate Delaunay triangulation of a regular grid, not the finite-element arithmetic)."""
+    from scipy.interpolate import griddata
+    published = {2: 0.0489864, 3: 0.107604, 4: 0.0427641, 5: 0.0277539, 6: 0.01599}     # error_vs_h.txt rows 2-6
+    P, E, nu, L, h = -50, 1000, 0.3, 24, 8
+    mats = np.array([[E, nu]])
+    u_i = v_i = None
+    for cont in range(1, 7):
+        nx, ny = 3*2**(cont - 1), 2**(cont - 1)
+        x, y, els = pre.rect_grid(L, h, nx, ny)
+        nodes = np.zeros(((nx + 1)*(ny + 1), 5))
+        nodes[:, 0] = range((nx + 1)*(ny + 1))
+        nodes[:, 1] = x
+        nodes[:, 2] = y
+        nodes[x == L/2, 3] = -1
+        nodes[nx*(ny//2 + 1) - 1, 4] = -1
+        loads = np.zeros((ny + 1, 3))
+        loads[:, 0] = nodes[x == -L/2, 0]
+        loads[:, 2] = P/ny
+        assem_op, bc, neq = ass.DME(nodes[:, -2:], els)
+        K, _ = ass.assembler(els, mats, nodes[:, :3], neq, assem_op)
+        u = spsolve(K, ass.loadasem(loads, bc, neq))
+        UC = pos.complete_disp(bc, nodes, u)
+        if cont > 1:
+            err = np.linalg.norm(np.column_stack([u_i, v_i]) - UC)/np.linalg.norm(UC)
+            if cont <= 3:
+                assert "%g" % err == "%g" % published[cont], (cont, err)
+            else:
+                assert abs(err - published[cont]) <= 1e-3*published[cont], (cont, err)
+        xn, yn, _ = pre.rect_grid(L, h, 2*nx, 2*ny)
+        u_i = griddata((x, y), UC[:, 0], (xn, yn))
+        v_i = griddata((x, y), UC[:, 1], (xn, yn))
