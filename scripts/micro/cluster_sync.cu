@@ -10,7 +10,6 @@
 //       the pattern a row-block smoother needs (a block only reads its two neighbours' halo rows).
 // (C) checks the payload (every value carries the iteration number and the sender's rank).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o cluster_sync cluster_sync.cu        Run: ./cluster_sync [iterations]
-// NOT YET RUN ON A GPU (written when the round's GPU budget was spent; it assembles for sm_100a).
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -66,16 +65,16 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+// bounded: a protocol error must end the kernel (flag + early exit), never hang or fault the device
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
 }
 // 8 bytes into a peer's shared memory; the peer's mbarrier is credited with them when they have landed
 __device__ __forceinline__ void st_async_b64(unsigned remote_addr, unsigned long long v, unsigned remote_bar) {
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(THREADS) k_neighbour(int iters, unsigned long 
       if (has_lo) st_async_b64(mapa(smem_u32(&halo[p][1][t]), rank - 1), v, mapa(smem_u32(&bar[p]), rank - 1));   // I am "above" my lower neighbour
       if (has_hi) st_async_b64(mapa(smem_u32(&halo[p][0][t]), rank + 1), v, mapa(smem_u32(&bar[p]), rank + 1));   // and "below" the upper one
     }
-    mbar_wait(&bar[p], phase);
+    if (!mbar_wait(&bar[p], phase)) { if (t == 0) atomicAdd(errors, 1 << 20); break; }   // gave up: report, leave
     if (t < NPR) {                                                    // payload of both neighbours for THIS iteration
       if (has_lo && halo[p][0][t] != (((unsigned long long)(unsigned)it << 32) | (unsigned)((rank - 1) * 1024 + t))) ++bad;
       if (has_hi && halo[p][1][t] != (((unsigned long long)(unsigned)it << 32) | (unsigned)((rank + 1) * 1024 + t))) ++bad;

@@ -159,6 +159,23 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
         for (int j = 0; j < 8; ++j) A[i * 8 + j] -= l[i] * l[j];
     }
   }
+  {
+    auto env_i = [](const char *n, long long d) { const char *v = getenv(n); return v ? atoll(v) : d; };
+    TopoKnobs &k = h->knobs;
+    k.fine_waves = getenv("TOPO_FINE_WAVES") ? atof(getenv("TOPO_FINE_WAVES")) : 1.0;
+    k.fine_nc_mask = (int)env_i("TOPO_FINE_NC_MASK", 0);
+    k.sym_min = env_i("TOPO_SYM_MIN", 100000);
+    k.nu_coarse_maxlvl = (int)env_i("TOPO_NU_COARSE_MAXLVL", 99);
+    k.tail_cluster_max = (int)env_i("TOPO_TAIL_CLUSTER", 16);
+    k.unfused_min = (int)env_i("TOPO_UNFUSED_MIN", 200000);
+    k.fuse_prolong = getenv("TOPO_FUSE_PROLONG") ? 1 : 0;
+    k.oc_ctas_per_sm = (int)std::max<long long>(1, env_i("TOPO_OC_CTAS_PER_SM", 2));
+    k.oc_no_probe = getenv("TOPO_OC_NO_PROBE") ? 1 : 0;
+    k.coarsest_nodes = (int)env_i("TOPO_COARSEST_NODES", 48);
+    k.no_l2persist = getenv("TOPO_NO_L2PERSIST") ? 1 : 0;
+    k.tail_ds = (int)env_i("TOPO_TAIL_DS", 0);
+    if (k.tail_ds != 1 && k.tail_ds != 2) k.tail_ds = 0;
+  }
   h->omega = getenv("TOPO_OMEGA") ? atof(getenv("TOPO_OMEGA")) : 0.7;
   h->nu_pre = 1;
   h->nu_post = 1;
@@ -210,8 +227,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * (size_t)h->ne;
   CUDA_TRY(cudaMalloc(&h->nodal, sizeof(double) * (size_t)h->nn));
   CUDA_TRY(cudaMalloc(&h->dinv_f, sizeof(float2) * (size_t)h->nn));
-  CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn + 64));          // + slack: the stage-1 kernel reads aligned words
-  CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn + 64, h->stream));
+  CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn + 128));         // + slack: the stage-1 kernel copies up to 68 bytes of aligned words from the last node on
+  CUDA_TRY(cudaMemsetAsync(h->fixed, 0, (size_t)h->nn + 128, h->stream));
   CUDA_TRY(cudaMalloc(&h->keep, (size_t)h->ne));
   CUDA_TRY(cudaMemsetAsync(h->keep, 1, (size_t)h->ne, h->stream));
   CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * TOPO_RED_SLOTS * TOPO_MAX_PARTIAL_BLOCKS));

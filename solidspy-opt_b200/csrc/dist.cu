@@ -134,7 +134,7 @@ extern "C" int topo_dist_init(topo_t *h, int rank, int world, int K_request) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   const int ny_global = h->ny * world;
   // K: the first level of the GLOBAL hierarchy small enough for the tail kernel (or the coarsest one)
-  const int coarsest_max_nodes = getenv("TOPO_COARSEST_NODES") ? atoi(getenv("TOPO_COARSEST_NODES")) : 48;
+  const int coarsest_max_nodes = h->knobs.coarsest_nodes;
   int K = 0;
   {
     int nx = h->nx, ny = ny_global, l = 0;

@@ -470,7 +470,7 @@ int launch_fine_nc(topo_handle *h, FineArgs &a) {
     resident = std::max(1, occ);
   }
   // chunk rows so that one wave of CTAs covers the mesh (TOPO_FINE_WAVES: more, shorter chunks -- experiment knob)
-  static const double waves = getenv("TOPO_FINE_WAVES") ? atof(getenv("TOPO_FINE_WAVES")) : 1.0;
+  const double waves = h->knobs.fine_waves;
   const int bx = div_up(h->nx + 1, 4 * Geo<NC>::WC);
   const int chunks = std::max(1, (int)(waves * 148 * resident) / bx);
   a.rows_per_chunk = std::max(8, div_up(h->ny + 1, chunks));
@@ -503,7 +503,7 @@ int launch_fine(topo_handle *h, FineArgs &a) {
   // node columns per lane: 2 for the plain product on wide meshes (overhead instructions amortised over two
   // nodes), 1 for the fused kinds (measured: they lose more from the lower occupancy of 64-column strips than
   // they gain); TOPO_FINE_NC_MASK (bit KIND set = two columns for that kind) is the experiment knob
-  static const int nc_mask = getenv("TOPO_FINE_NC_MASK") ? atoi(getenv("TOPO_FINE_NC_MASK")) : 0;
+  const int nc_mask = h->knobs.fine_nc_mask;
   const int nc = (KIND == FK_APPLY) ? h->fine_nc : (((nc_mask >> KIND) & 1) && h->nx + 1 >= 1024 ? 2 : 1);
   if (nc == 2) return launch_fine_nc<KIND, 2>(h, a);
   return launch_fine_nc<KIND, 1>(h, a);

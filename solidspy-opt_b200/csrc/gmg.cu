@@ -288,7 +288,7 @@ int topo_gmg_plan(topo_handle *h) {
   // a dense inverse (<= 96 DOFs), which is both cheaper and more accurate than smoothing three more tiny levels.
   // Row-slab mode: levels < K halve the slab (its height is a multiple of 2^K), level K and deeper have the
   // dimensions of the GLOBAL hierarchy (they are replicated on every rank).
-  const int coarsest_max_nodes = getenv("TOPO_COARSEST_NODES") ? atoi(getenv("TOPO_COARSEST_NODES")) : 48;
+  const int coarsest_max_nodes = h->knobs.coarsest_nodes;
   const bool slab = h->dist.on;
   while (h->n_levels < TOPO_MAX_LEVELS) {
     const int l = h->n_levels;
@@ -363,7 +363,7 @@ int topo_gmg_plan(topo_handle *h) {
     cudaDeviceGetAttribute(&dev_max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
     const size_t win_bytes = tot - persist_off;
     const size_t want = std::min<size_t>(std::min<size_t>(win_bytes, (size_t)16 << 20), (size_t)std::max(dev_max_persist, 0));
-    if (want > 0 && dev_max_window > 0 && !getenv("TOPO_NO_L2PERSIST")) {
+    if (want > 0 && dev_max_window > 0 && !h->knobs.no_l2persist) {
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
       cudaStreamAttrValue attr = {};
       attr.accessPolicyWindow.base_ptr = p + persist_off;

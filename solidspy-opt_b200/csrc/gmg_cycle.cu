@@ -315,6 +315,7 @@ struct TailArgs {
   double omega;
   int nu[TAIL_MAX];            // smoothing sweeps (pre = post) per tail level
   const int *done;
+  int *err;                    // SolverScalars::tail_error
   unsigned long long *dbg;     // optional: globaltimer stamps at stage boundaries (thread 0 of CTA 0)
   int ds_rows[TAIL_MAX];       // k_tail_ds: node rows per CTA on each cluster level
   int ds_mode;                 // k_tail_ds: 1 = cluster barrier after every sweep, 2 = neighbour hand-over (st.async + mbarrier)
@@ -519,6 +520,7 @@ struct DsSmem {
   int mode;                        // 1: cluster.sync() after every sweep, 2: neighbour hand-over
   unsigned uses[2];                // completed phases of each mbarrier (same sequence on every thread of the cluster)
   unsigned expect;                 // bytes this CTA receives per sweep on the current level
+  int *err;                        // raised when a hand-over wait gives up
   float2 *xs[2];                   // iterate copies incl. halo rows (local row 0 = row below the block)
   double2 *rs;                     // residual of the block's own nodes (read remotely by the restriction)
   double2 *xd[DS_MAXLV], *bd[DS_MAXLV];   // fp64 iterate and right-hand side of the own nodes, per cluster level
@@ -564,15 +566,17 @@ __device__ __forceinline__ unsigned ds_mapa(unsigned local_addr, unsigned rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void ds_mbar_wait(unsigned long long *bar, unsigned parity) {
+// bounded: a protocol error must neither hang nor fault the device -- the wait gives up, raises *err (the solver's
+// tail_error flag, checked by the host after the solve) and the kernel runs on to its end with wrong numbers
+__device__ __forceinline__ void ds_mbar_wait(unsigned long long *bar, unsigned parity, int *err) {
   const unsigned addr = ds_smem_u32(bar);
-  for (unsigned spin = 0;; ++spin) {
+  for (unsigned spin = 0; spin < (1u << 20); ++spin) {
     unsigned ok;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     if (ok) return;
-    if (spin > (1u << 24)) __trap();          // a protocol error must not hang the device
   }
+  if (threadIdx.x == 0) atomicExch(err, 1);
 }
 // own value into the local block and into the neighbours' halo rows of iterate buffer b
 __device__ __forceinline__ void ds_publish(cg::cluster_group &cl, const DsSmem &S, int b, const DsNode &d, int rank, const double2 &x) {
@@ -598,7 +602,7 @@ __device__ __forceinline__ void ds_publish(cg::cluster_group &cl, const DsSmem &
 // iterate buffer b is complete (own values and both halo rows) and every thread of the CTA may read it
 __device__ __forceinline__ void ds_handover(cg::cluster_group &cl, DsSmem &S, int b) {
   if (S.mode == 2) {
-    ds_mbar_wait(S.bar + b, S.uses[b] & 1u);
+    ds_mbar_wait(S.bar + b, S.uses[b] & 1u, S.err);
     S.uses[b] += 1;
     __syncthreads();
   } else {
@@ -757,6 +761,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_ds(const __grid_constant_
   S.mode = a.ds_mode;
   S.uses[0] = S.uses[1] = 0u;
   S.expect = 0u;
+  S.err = a.err;
   S.xs[0] = reinterpret_cast<float2 *>(ds_raw + 16);
   S.xs[1] = S.xs[0] + DS_XS;
   S.rs = reinterpret_cast<double2 *>(S.xs[1] + DS_XS);
@@ -886,14 +891,13 @@ const char *lvl_name(const char *what, int l) {
   return names[what[0] == 'd' ? 0 : 1][l];
 }
 
-LevelView view_of(const GmgLevel &G) {
+LevelView view_of(const topo_handle *h, const GmgLevel &G) {
   LevelView v;
   v.st = G.st; v.dinv = G.dinv; v.x = G.x; v.x2 = G.x2; v.b = G.b; v.r = G.r; v.nx = G.nx; v.ny = G.ny;
   v.wf = v.wl = 1.0;
   // levels whose stencil stream is what bounds them (TOPO_SYM_MIN nodes and more; default 100 000) read the symmetric
   // half only: 2048x1024 8.9 -> 8.6 ms per design iteration, 8192x4096 66.8 -> 64.3 ms, identical trajectories
-  static const int64_t sym_min = getenv("TOPO_SYM_MIN") ? atoll(getenv("TOPO_SYM_MIN")) : 100000;
-  v.sym = G.nn >= sym_min ? 1 : 0;
+  v.sym = G.nn >= h->knobs.sym_min ? 1 : 0;
   return v;
 }
 
@@ -903,11 +907,11 @@ int tail_nu(const topo_handle *h, int l) {
   return h->levels[l].nn > TAIL_SMALL ? h->nu_tail_big : h->nu_tail_small;
 }
 int nu_pre_of(const topo_handle *h, int l) {
-  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
+  const int nuc_max = h->knobs.nu_coarse_maxlvl;
   return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_pre;
 }
 int nu_post_of(const topo_handle *h, int l) {
-  const int nuc_max = getenv("TOPO_NU_COARSE_MAXLVL") ? atoi(getenv("TOPO_NU_COARSE_MAXLVL")) : 99;
+  const int nuc_max = h->knobs.nu_coarse_maxlvl;
   return (h->nu_coarse > 0 && l <= nuc_max) ? h->nu_coarse : h->nu_post;
 }
 // first level handled by the tail kernel (row-slab mode: the first global level)
@@ -919,10 +923,9 @@ int tail_start(const topo_handle *h) {
 }
 // largest cluster the device schedules for the tail kernels (16 needs the non-portable size; else 8, 4, 2, 1)
 template <class Kern>
-int probe_cluster_size(Kern kern, size_t dyn_smem) {
+int probe_cluster_size(Kern kern, size_t dyn_smem, int cs_max) {
   int cluster_size = 1;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-    static const int cs_max = getenv("TOPO_TAIL_CLUSTER") ? atoi(getenv("TOPO_TAIL_CLUSTER")) : 16;
     for (int cs : {16, 8, 4, 2}) {
       if (cs > cs_max) continue;
       cudaLaunchConfig_t q = {};
@@ -941,7 +944,7 @@ int probe_cluster_size(Kern kern, size_t dyn_smem) {
 int tail_cluster_size(const topo_handle *h) {
   static int cs_dev[TOPO_MAX_DEVICES] = {};
   int &cs = cs_dev[topo_dev_slot(h)];
-  if (cs == 0) cs = probe_cluster_size(k_tail, 0);
+  if (cs == 0) cs = probe_cluster_size(k_tail, 0, h->knobs.tail_cluster_max);
   return cs;
 }
 // k_tail_ds (TOPO_TAIL_DS=1): cluster size it can be launched with on this device, 0 = not available
@@ -951,7 +954,7 @@ int tail_ds_cluster_size(const topo_handle *h) {
   if (cs == 0) {
     cs = -1;
     if (cudaFuncSetAttribute(k_tail_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_SMEM_BYTES) == cudaSuccess) {
-      const int c = probe_cluster_size(k_tail_ds, DS_SMEM_BYTES);
+      const int c = probe_cluster_size(k_tail_ds, DS_SMEM_BYTES, h->knobs.tail_cluster_max);
       if (c >= 2) cs = c;
     }
     cudaGetLastError();
@@ -959,14 +962,11 @@ int tail_ds_cluster_size(const topo_handle *h) {
   return cs > 0 ? cs : 0;
 }
 // TOPO_TAIL_DS: 0 (default) k_tail, 1 k_tail_ds with cluster barriers, 2 k_tail_ds with the neighbour hand-over
-int tail_ds_mode() {
-  static const int mode = getenv("TOPO_TAIL_DS") ? atoi(getenv("TOPO_TAIL_DS")) : 0;
-  return (mode == 1 || mode == 2) ? mode : 0;
-}
+int tail_ds_mode(const topo_handle *h) { return h->knobs.tail_ds; }
 // Does the tail starting at level `tail` run in k_tail_ds?  Every cluster level must split into blocks of whole node
 // rows, one node per thread, that fit the shared-memory plan; rows[] receives the rows per CTA of each cluster level.
 bool tail_ds_plan(const topo_handle *h, int tail, int *rows) {
-  static const bool want = tail_ds_mode() != 0;
+  const bool want = tail_ds_mode(h) != 0;
   if (!want || h->dist.on || h->tail_dbg != nullptr) return false;
   const int L = h->n_levels;
   int ncl = 0;
@@ -1005,13 +1005,14 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
     topo_set_error("multigrid tail has %d levels (max %d)", ta.n, TAIL_MAX);
     return TOPO_EINVAL;
   }
-  for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h->levels[l]);
+  for (int l = tail; l < L; ++l) ta.lv[l - tail] = view_of(h, h->levels[l]);
   ta.r_parent = r_parent; ta.pnx = pnx; ta.pny = pny; ta.parent_f32 = parent_f32;
   ta.coarse_inv = h->coarse_inv;
   ta.coarse_n = h->coarse_n;
   ta.omega = h->omega;
   for (int l = tail; l < L; ++l) ta.nu[l - tail] = tail_nu(h, l);
   ta.done = &h->sc->done;
+  ta.err = &h->sc->tail_error;
   ta.dbg = h->tail_dbg;
   const int cluster_size = tail_cluster_size(h);
   if (h->inv_pending) {     // join the side stream that inverts the coarsest operator (first tail launch of a solve)
@@ -1035,7 +1036,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (ds) {
-    ta.ds_mode = tail_ds_mode();
+    ta.ds_mode = tail_ds_mode(h);
     cfg.dynamicSmemBytes = DS_SMEM_BYTES;
     KL(h, "k_tail_ds", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail_ds, ta)));
   } else {
@@ -1070,7 +1071,7 @@ __global__ void k_dist_assemble_bK(const double2 *__restrict__ recv0, const doub
 }
 
 LevelView dist_view(const topo_handle *h, int l) {
-  LevelView v = view_of(h->levels[l]);
+  LevelView v = view_of(h, h->levels[l]);
   if (h->dist.on && l < h->dist.K) { v.wf = h->dist.w_first; v.wl = h->dist.w_last; }
   return v;
 }
@@ -1099,7 +1100,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   }
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
-    LevelView V = view_of(F);
+    LevelView V = view_of(h, F);
     KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down<true> : k_lvl_down<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
     for (int s = 1; s < nu_pre_of(h, l); ++s) {
       KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
@@ -1115,8 +1116,8 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   else TOPO_TRY(launch_tail(h, tail, h->levels[tail - 1].r, h->levels[tail - 1].nx, h->levels[tail - 1].ny));
   for (int l = tail - 1; l >= 1; --l) {
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
-    LevelView V = view_of(F);
-    static const int unfused_min = getenv("TOPO_UNFUSED_MIN") ? atoi(getenv("TOPO_UNFUSED_MIN")) : 200000;
+    LevelView V = view_of(h, F);
+    const int unfused_min = h->knobs.unfused_min;
     if (F.nn > unfused_min) {
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel

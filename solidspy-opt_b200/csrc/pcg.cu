@@ -233,7 +233,7 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
       CUDA_TRY(cudaGetLastError());
     }
   } else {
-    const bool fuse_prolong = getenv("TOPO_FUSE_PROLONG") != nullptr;
+    const bool fuse_prolong = h->knobs.fuse_prolong != 0;
     // one PCG iteration reading the buffers of parity `par` and writing those of parity par^1
     auto iteration = [&](int par) -> int {
       TOPO_TRY(topo_fine_pcg_matvec(h, h->z, pb[par], pb[par ^ 1], h->Ap));
@@ -307,6 +307,10 @@ extern "C" int topo_solve(topo_t *h, int precond, double rtol, int maxit, int wa
   if (iters) *iters = hs->iters;
   const double rel = (hs->bb > 0.0) ? std::sqrt(hs->rr / hs->bb) : (hs->rr == 0.0 ? 0.0 : INFINITY);
   if (relres) *relres = rel;
+  if (hs->tail_error) {
+    topo_set_error("multigrid tail: a hand-over between thread blocks timed out (results invalid)");
+    return TOPO_ECUDA;
+  }
   if (!(hs->rr == hs->rr)) {
     topo_set_error("PCG produced NaN (singular system?)");
     return TOPO_ENOCONV;

@@ -253,10 +253,7 @@ __device__ __forceinline__ void oc_decide_probe(OcState *oc, const double *v, do
   oc_fastforward(oc);
 }
 // grid of the multi-candidate pass: a few CTAs per SM (16 partial sums per CTA are folded by the last block)
-static int oc_multi_blocks() {
-  static const int per_sm = getenv("TOPO_OC_CTAS_PER_SM") ? atoi(getenv("TOPO_OC_CTAS_PER_SM")) : 2;
-  return 148 * std::max(1, per_sm);
-}
+static int oc_multi_blocks(const topo_handle *h) { return 148 * h->knobs.oc_ctas_per_sm; }
 __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho, const double *__restrict__ amp,
                                                  int64_t ne, double move, double margin, double *partials,
                                                  unsigned int *ticket, double *out, OcState *oc, int defer,
@@ -472,14 +469,14 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
   const int hard_cap = 700;                // the bracket [0,1e9] underflows after ~1100 halvings = 275 rounds
   // with a multiplier from the previous design iteration the probe pass brackets the root within a factor 2 and
   // ~3 fast passes finish the bisection (instead of ~23): poll after 4 rounds, else after 12
-  const bool probe = h->oc_lam_prev > 0.0 && !getenv("TOPO_OC_NO_PROBE");
+  const bool probe = h->oc_lam_prev > 0.0 && !h->knobs.oc_no_probe;
   if (probe)
-    KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks()), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+    KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks(h)), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
                                                                       h->red_out, h->oc, 0, h->oc_lam_prev));
   while (rounds < hard_cap) {
     const int batch = probe ? 4 : 12;
     for (int i = 0; i < batch; ++i) {
-      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks()), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks(h)), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
                                                         h->red_out, h->oc, 0, 0.0));
       KL(h, "k_oc_step", k_oc_step<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, 1, h->partials, h->ticket,
                                                       h->red_out, h->oc, 0));
@@ -534,12 +531,12 @@ extern "C" int topo_dist_oc(topo_t *h, int op, double move, double value, long l
       KL(h, "k_oc_prep", k_oc_prep<<<nb, ET, 0, st>>>(h->rho, h->dc, amp, h->ne));
       break;
     case 1:
-      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks()), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks(h)), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
                                                                         h->red_out, h->oc, 1, 0.0));
       break;
     case 2: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 0, 0.0)); break;
     case 9:                                   // probe pass around `value` (the previous multiplier) -> all-reduce 16, op 10
-      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks()), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
+      KL(h, "k_oc_multi", k_oc_multi<<<std::min(nb, oc_multi_blocks(h)), ET, 0, st>>>(h->rho, amp, h->ne, move, margin, h->partials, h->ticket,
                                                                         h->red_out, h->oc, 1, value));
       break;
     case 10: KL(h, "k_oc_decide", k_oc_decide<<<1, 1, 0, st>>>(h->oc, h->red_out, margin, 4, value)); break;

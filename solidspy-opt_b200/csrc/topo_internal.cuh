@@ -49,7 +49,7 @@ struct SolverScalars {
   int iters;         // PCG iterations completed
   int done;          // 1 once rr <= tol2*bb (kernels become no-ops)
   int maxit;
-  int pad;
+  int tail_error;    // a bounded hand-over wait inside the tail kernel gave up (results invalid)
 };
 
 struct OcState {
@@ -128,8 +128,26 @@ struct DistState {
   P2PCounters *p2p_cnt;
 };
 
+// Experiment knobs (environment variables): read ONCE per handle in topo_create, never in a
+// launch path.  Defaults are what every number in DESIGN.md / profiles/ was measured with.
+struct TopoKnobs {
+  double fine_waves;        // TOPO_FINE_WAVES      waves of CTAs the fine-grid row chunks are cut for (1)
+  int fine_nc_mask;         // TOPO_FINE_NC_MASK    bit k: two node columns per lane for fine-grid kind k (0)
+  long long sym_min;        // TOPO_SYM_MIN         levels with at least this many nodes read the symmetric stencil half (100000)
+  int nu_coarse_maxlvl;     // TOPO_NU_COARSE_MAXLVL
+  int tail_cluster_max;     // TOPO_TAIL_CLUSTER    largest cluster tried for the tail kernel (16)
+  int unfused_min;          // TOPO_UNFUSED_MIN     levels above this many nodes: separate prolongation + smoothing (200000)
+  int fuse_prolong;         // TOPO_FUSE_PROLONG
+  int oc_ctas_per_sm;       // TOPO_OC_CTAS_PER_SM  (2)
+  int oc_no_probe;          // TOPO_OC_NO_PROBE
+  int coarsest_nodes;       // TOPO_COARSEST_NODES  first level solved densely (48)
+  int no_l2persist;         // TOPO_NO_L2PERSIST
+  int tail_ds;              // TOPO_TAIL_DS         0: k_tail, 1: k_tail_ds with cluster barriers, 2: with neighbour hand-overs
+};
+
 struct topo_handle {
   int device;
+  TopoKnobs knobs;
   int nx, ny;
   int64_t nn, ne;
   KeParam ke;

@@ -1,0 +1,224 @@
+"""Parity AT THE SIZES THE NUMBERS ARE QUOTED ON (BASELINE.json configs[1..4]; config 5 = the slab run is checked inside
+``bench.py`` as ``strong.slab_parity_ok`` because it needs 8 GPUs).
+
+The oracle at these sizes:
+  * K(rho)u        -- ``t1.apply_K``: the element-by-element contraction of the COO triplets ``sparse_assem`` would sum
+                      (reference solver.py:394-408, optimize.py:455), no assembled matrix; assembled CSR for the thin
+                      wide meshes that select the two-columns-per-lane kernel (nx + 1 >= 1024);
+  * config 2 / 3   -- goldens computed in the build container by ``oracle/gen_golden_sized.py`` with the CPU restatement
+                      (numpy assembly + SuperLU): 480x160 MBB r = 2.5 (6 design iterations), BESO 1024x512 (two removals);
+  * config 4       -- at 2048x1024 the solve is checked through the residual of the ORACLE operator, ||f - K_ref u_gpu||
+                      <= 1.5e-9 ||f||, and the stages after it (sensitivity, filter, OC) are recomputed with the oracle from
+                      the GPU's displacements and compared value by value.
+Tolerances: sets / counts / bisection steps bit-exact; compliance and density 1e-6 (north_star); stage values 1e-12."""
+import numpy as np
+import pytest
+
+import gmg_proto
+import t1
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+E0, NU = 206.8e9, 0.28
+
+
+@pytest.fixture(scope="module")
+def capi(lib_built):
+    from solidspy_opt import _capi
+    _capi.device_count()
+    return _capi
+
+
+def _cantilever_cons(nx, ny, scattered=0, seed=0):
+    nn = (nx + 1)*(ny + 1)
+    cons = np.zeros((nn, 2), dtype=np.int8)
+    cons[::nx + 1] = -1
+    if scattered:
+        rng = np.random.default_rng(seed)
+        pick = rng.choice(nn, size=scattered, replace=False)
+        cons[pick, rng.integers(0, 2, pick.size)] = -1
+    return cons
+
+
+# ---- stage 1 on the kernel variant the headline meshes select (two node columns per lane, nx + 1 >= 1024) ----------------
+@pytest.mark.parametrize("nx,ny", [(1023, 2), (1100, 3), (2050, 3), (4100, 9), (1024, 40)])
+def test_wide_matvec_matches_assembled_matrix(capi, nx, ny):
+    rng = np.random.default_rng(nx + ny)
+    ke = t1.kloc_closed_form(E0, NU)
+    cons = _cantilever_cons(nx, ny, scattered=(nx*ny)//20, seed=nx)
+    scale = 1e-9 + rng.uniform(0, 1, nx*ny)**3
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        y = t.matvec(u).reshape(-1)
+    free = (cons.reshape(-1) == 0).astype(float)
+    K = gmg_proto.full_K(nx, ny, scale, ke)
+    ref = free*(K @ (free*u))
+    assert np.abs(y - ref).max() <= 1e-13*np.abs(ref).max()
+    assert np.all(y[free == 0] == 0.0)
+
+
+def test_matvec_2048x1024_matches_oracle(capi):
+    """The plain product on the headline mesh, every DOF, against the oracle's element-by-element product."""
+    nx, ny = 2048, 1024
+    rng = np.random.default_rng(1)
+    ke = t1.kloc_closed_form(E0, NU)
+    cons = _cantilever_cons(nx, ny, scattered=5000, seed=2)
+    free = (cons.reshape(-1) == 0).astype(float)
+    scale = 1e-9 + rng.uniform(0, 1, nx*ny)**3
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        y = t.matvec(u).reshape(-1)
+    ref = t1.apply_K(nx, ny, scale, ke, u, free)
+    assert np.abs(y - ref).max() <= 1e-13*np.abs(ref).max()
+    assert np.all(y[free == 0] == 0.0)
+
+
+def test_matvec_8192x4096_bands_match_oracle(capi):
+    """Config-5 mesh on ONE GPU (67 M DOFs, indices beyond 2^25, many row chunks): node-row bands at the bottom, the
+    top, and across the middle against the oracle."""
+    nx, ny = 8192, 4096
+    rng = np.random.default_rng(3)
+    ke = t1.kloc_closed_form(E0, NU)
+    cons = _cantilever_cons(nx, ny, scattered=20000, seed=4)
+    free = (cons.reshape(-1) == 0).astype(float)
+    scale = 1e-9 + rng.uniform(0, 1, nx*ny)**3
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(cons)
+        t.set(capi.F_SCALE, scale)
+        y = t.matvec(u).reshape(ny + 1, -1)
+    ymax = np.abs(y).max()
+    for r0, r1 in ((0, 5), (ny - 5, ny), (2040, 2056), (1021, 1030), (3333, 3340)):
+        ref = t1.apply_K(nx, ny, scale, ke, u, free, rows=(r0, r1)).reshape(r1 - r0 + 1, -1)
+        assert np.abs(y[r0:r1 + 1] - ref).max() <= 1e-13*ymax, (r0, r1)
+
+
+# ---- config 2: SIMP MBB 480x160, density filter r = 2.5 ------------------------------------------------------------------
+def test_simp_mbb_480x160_config2(capi):
+    from solidspy_opt.optimize import SIMP_from_model
+    g = golden("simp_mbb_480x160")
+    nx, ny, niter = int(g["nx"]), int(g["ny"]), int(g["niter"])
+    nodes, mats, els, loads, _ = t1.beam(L=nx, H=ny, nx=nx, ny=ny, dirs=np.array([[0, -1]]), positions=np.array([[ny, 1]]))
+    cons = np.zeros((nodes.shape[0], 2))
+    cons[np.arange(nodes.shape[0]) % (nx + 1) == 0, 0] = -1
+    cons[nx, 1] = -1
+    data = {"nodes": nodes[:, :3], "cons": cons, "elements": els, "mats": np.array([[E0, NU]]),
+            "loads": np.array([[int(g["load_node"]), 0.0, -1.0]])}
+    hist = {"keep_rho": True}
+    rho = SIMP_from_model(data, niter, 3, r_min=float(g["r_min"]), history=hist, verbose=False)
+    assert len(hist["compliance"]) == niter
+    assert np.allclose(hist["compliance"], g["compliance"], rtol=1e-6, atol=0)
+    assert np.allclose(hist["g"], g["g"], rtol=0, atol=1e-5)
+    assert np.abs(hist["rho"][0] - g["rho_first"]).max() <= 1e-6
+    assert np.abs(rho - g["rho_final"]).max() <= 1e-6
+
+
+# ---- config 3: BESO 1024x512, two removals ------------------------------------------------------------------------------
+def test_beso_1024x512_config3_removal_sets(capi):
+    from solidspy_opt.optimize import BESO
+    g = golden("beso_1024x512")
+    nx, ny, niter = int(g["nx"]), int(g["ny"]), int(g["niter"])
+    hist = {}
+    ELS, nodes = BESO(nx, ny, nx, ny, g["dirs"], g["positions"], niter, float(g["t"]), float(g["ER"]), float(g["volfrac"]),
+                      history=hist, verbose=False)
+    kept_ref = np.unpackbits(g["kept_bits"], axis=1)[:, :nx*ny].astype(bool)
+    assert len(hist["kept_ids"]) == niter
+    for k in range(niter):
+        got = np.zeros(nx*ny, dtype=bool)
+        got[hist["kept_ids"][k]] = True
+        assert np.array_equal(got, kept_ref[k]), "removal %d: %d elements differ" % (k, np.count_nonzero(got != kept_ref[k]))
+    assert np.array_equal(hist["n_protected"], g["n_protected"])
+    assert np.allclose(hist["alpha"], g["alpha"], rtol=1e-9, atol=0)
+    assert np.allclose(hist["C"], g["C"], rtol=1e-6, atol=0)
+    cons_ref = np.unpackbits(g["cons_bits"])[:niter*2*(nx + 1)*(ny + 1)].reshape(niter, -1, 2).astype(bool)
+    assert np.array_equal(np.array(hist["cons"]) != 0, cons_ref)
+    assert ELS.shape[0] == int(g["n_els_final"])
+    assert hist.get("jacobi_restarts", 0) == 0
+
+
+# ---- config 4: one design iteration at 2048x1024, stage by stage against the oracle -------------------------------------
+def test_simp_2048x1024_config4_stages_vs_oracle(capi):
+    from solidspy_opt.Utils.beams import beam
+    from solidspy_opt.optimize import kloc_simp
+    nx, ny = 2048, 1024
+    nodes, mats, els, loads, _ = beam(L=float(nx), H=float(ny), nx=nx, ny=ny, dirs=np.array([[0, -1]]),
+                                      positions=np.array([[ny//4, 1]]), n=1)
+    ke = kloc_simp(mats[0, 0], mats[0, 1])
+    assert np.array_equal(ke, t1.kloc_closed_form(mats[0, 0], mats[0, 1]))
+    free = (nodes[:, 3:5].reshape(-1) == 0).astype(float)
+    penal, emin, emax, rmin = 3.0, 1e-9, 1.0, 4.0
+    params = capi.SimpParams(penal=penal, emin=emin, emax=emax, rmin=rmin, dx=1.0, dy=1.0, move=0.2, rtol=1e-9,
+                             precond=capi.PRECOND_GMG, maxit=5000, warm=1)
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(nodes[:, 3:5])
+        t.set_loads(loads)
+        t.fill(capi.F_RHO, 0.5)
+        g = 0.0
+        for _ in range(3):                                   # three iterations: the checked one starts from a non-uniform design
+            rho_in, g_in = t.get(capi.F_RHO), g
+            g, res = t.simp_step(params, g)
+        u = t.get(capi.F_U).reshape(-1)
+        f = t.get(capi.F_LOAD).reshape(-1)
+        scale = t.get(capi.F_SCALE)
+        dc_gpu = t.get(capi.F_DC)
+        rho_gpu = t.get(capi.F_RHO)
+    assert res.status == capi.OK and res.equilibrium_ok
+    # stage 2: the GPU's displacements solve the ORACLE's system
+    assert np.array_equal(scale, emin + rho_in**penal*(emax - emin))
+    r = f - t1.apply_K(nx, ny, scale, ke, u, free)
+    assert np.linalg.norm(r) <= 1.5e-9*np.linalg.norm(f), np.linalg.norm(r)/np.linalg.norm(f)
+    assert np.all(u[free == 0] == 0.0)
+    assert res.compliance == pytest.approx(f @ u, rel=1e-12)
+    # stage 3: sensitivity + objective from those displacements
+    s = t1.element_energy(u.reshape(-1, 2), els, ke)
+    assert res.objective == pytest.approx((scale*s).sum(), rel=1e-10)
+    assert res.objective == pytest.approx(res.compliance, rel=1e-7)                  # u^T K u = f.u up to the solve's residual
+    dc = (-penal*rho_in**(penal - 1)*(emax - emin))*s
+    # stage 4: filter, OC (same bisection path, same densities)
+    dcf = t1.sensitivity_filter_simp(nx, ny, 1.0, 1.0, rmin, rho_in, dc)
+    assert np.allclose(dc_gpu, dcf, rtol=1e-11, atol=1e-12*np.abs(dcf).max())
+    rho_ref, g_ref, n_ref = t1.optimality_criteria(rho_in, dcf, g_in)
+    assert res.oc_steps == n_ref
+    assert np.abs(rho_gpu - rho_ref).max() <= 1e-9
+    assert g == pytest.approx(g_ref, abs=1e-6)
+    assert res.change == pytest.approx(np.abs(rho_ref - rho_in).max(), rel=1e-9)
+
+
+# ---- a13: the equilibrium guard says NO when the oracle's says no -------------------------------------------------------
+@pytest.mark.parametrize("perturb", ["none", "scale_1e7", "nan", "one_dof"])
+def test_equilibrium_guard_agrees_with_oracle(capi, perturb):
+    """np.allclose(K u / K.max(), f / K.max()) (optimize.py:72,172,286,455) on displacements that do / do not solve
+    the system: the device guard and the oracle's take the same decision."""
+    nx, ny = 40, 24
+    rng = np.random.default_rng(9)
+    nodes, mats, els, loads, _ = t1.beam(L=nx, H=ny, nx=nx, ny=ny, dirs=np.array([[0, -1]]), positions=np.array([[7, 1]]))
+    ke = t1.kloc_closed_form(E0, NU)
+    scale = 1e-9 + rng.uniform(0.2, 1, nx*ny)**3
+    assem_op, bc, neq = t1.dme(nodes[:, -2:], els)
+    K = t1.assemble(scale, ke, assem_op, neq)
+    fv = t1.loadasem(loads, bc, neq)
+    with capi.Topo(nx, ny, ke) as t:
+        t.set_cons(nodes[:, 3:5])
+        t.set_loads(loads)
+        t.set(capi.F_SCALE, scale)
+        t.solve(capi.PRECOND_GMG, 1e-11, 2000, warm=False)
+        UC = t.get(capi.F_U).reshape(-1, 2)
+        if perturb == "scale_1e7":
+            UC = UC*1e7
+        elif perturb == "nan":
+            UC[UC.shape[0]//2, 1] = np.nan
+        elif perturb == "one_dof":
+            UC[np.argmax(np.abs(UC[:, 1])), 1] += 1.0
+        t.set(capi.F_U, UC)
+        got = t.equilibrium_ok()
+    free = bc != -1
+    u = np.zeros(neq)
+    u[bc[free]] = UC[free]
+    want = t1.equilibrium_ok(K, u, fv)
+    assert got == want
+    assert want == (perturb == "none")

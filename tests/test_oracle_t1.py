@@ -94,3 +94,20 @@ def test_filter_matches_dense_definition():
         ref = (rho*H*dc).sum(1)/(H.sum(1)*np.maximum(0.001, rho))
         got = t1.sensitivity_filter_simp(nx, ny, dx, dx, r_min, rho, dc)
         assert np.allclose(got, ref, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("nx,ny", [(7, 5), (33, 17), (1500, 3)])
+def test_apply_K_equals_assembled_matrix(nx, ny):
+    """The matrix-free product the sized GPU tests use as their checker (2048x1024, 8192x4096) is the assembled
+    matrix of ``sparse_assem`` applied to u -- whole vector and node-row bands."""
+    import gmg_proto
+    rng = np.random.default_rng(nx)
+    ke = t1.kloc_closed_form(206.8e9, 0.28)
+    scale = rng.uniform(0, 1, nx*ny)
+    u = rng.standard_normal(2*(nx + 1)*(ny + 1))
+    free = (rng.uniform(0, 1, u.size) > 0.1).astype(float)
+    ref = free*(gmg_proto.full_K(nx, ny, scale, ke) @ (free*u))
+    assert np.abs(t1.apply_K(nx, ny, scale, ke, u, free) - ref).max() <= 1e-14*np.abs(ref).max()
+    for band in ((0, 0), (0, 2), (ny, ny), (1, ny - 1), (ny - 1, ny)):
+        got = t1.apply_K(nx, ny, scale, ke, u, free, rows=band)
+        assert np.abs(got - ref[2*(nx + 1)*band[0]:2*(nx + 1)*(band[1] + 1)]).max() <= 1e-14*np.abs(ref).max()
