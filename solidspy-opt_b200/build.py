@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtopo_b200.so")
-SOURCES = ["capi.cu", "fine.cu", "pcg.cu", "gmg.cu", "gmg_cycle.cu", "simp.cu", "beso.cu", "dist.cu"]
+SOURCES = ["capi.cu", "fine.cu", "pcg.cu", "gmg.cu", "gmg_cycle.cu", "gmg_tail.cu", "simp.cu", "beso.cu", "dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -173,8 +173,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
     k.oc_no_probe = getenv("TOPO_OC_NO_PROBE") ? 1 : 0;
     k.coarsest_nodes = (int)env_i("TOPO_COARSEST_NODES", 48);
     k.no_l2persist = getenv("TOPO_NO_L2PERSIST") ? 1 : 0;
-    k.tail_ds = (int)env_i("TOPO_TAIL_DS", 0);
-    if (k.tail_ds != 1 && k.tail_ds != 2) k.tail_ds = 0;
+    k.tail_kind = (int)env_i("TOPO_TAIL_KIND", 2);
   }
   h->omega = getenv("TOPO_OMEGA") ? atof(getenv("TOPO_OMEGA")) : 0.7;
   h->nu_pre = 1;
@@ -184,6 +183,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->nu_tail_small = getenv("TOPO_NU_TAIL_SMALL") ? atoi(getenv("TOPO_NU_TAIL_SMALL")) : 12;
   h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
   h->tail_dbg = nullptr;
+  h->tail2_cache = nullptr;
+  h->tail2_cache_tail = -1;
   h->use_graph = getenv("TOPO_NO_GRAPH") ? false : true;
   h->pcg_graph_valid = false;
   h->pcg_graph_exec = nullptr;

@@ -576,7 +576,10 @@ int topo_dist_setup_global(topo_handle *h) {
   return TOPO_OK;
 }
 
+void topo_tail2_forget(topo_handle *h);
+
 void topo_gmg_free(topo_handle *h) {
+  topo_tail2_forget(h);
   for (size_t l = 1; l < h->levels.size(); ++l) cudaFree(h->levels[l].cell);
   h->levels.clear();
   cudaFree(h->lvl1_slab);

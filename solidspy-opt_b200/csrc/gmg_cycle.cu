@@ -16,133 +16,16 @@
 #include <cooperative_groups.h>
 
 #include "topo_internal.cuh"
+#include "gmg_common.cuh"
 
 namespace cg = cooperative_groups;
+
+bool topo_tail2_applicable(const topo_handle *h, int tail);
+int topo_tail2_launch(topo_handle *h, int tail, const double2 *r_parent, int pnx, int pny, int parent_f32);
 
 namespace {
 
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
-
-// ---- transfers: 1-D rules --------------------------------------------------------------------------------------
-// Coarse node I sits at fine index X = min(2I, nf).  Fine node i is a coarse node if i is even or
-// i == nf; otherwise it interpolates (1/2, 1/2) between coarse (i-1)/2 and (i+1)/2.
-__device__ __forceinline__ void restrict_taps(int I, int nf, int &X, double &wl, double &wr) {
-  X = min(2 * I, nf);
-  const bool even = (X == 2 * I);
-  wl = (even && I >= 1) ? 0.5 : 0.0;
-  wr = (even && X + 1 < nf) ? 0.5 : 0.0;
-}
-__device__ __forceinline__ void prolong_taps(int i, int nf, int &I0, int &I1, double &w0, double &w1) {
-  if ((i & 1) == 0) { I0 = I1 = i >> 1; w0 = 1.0; w1 = 0.0; }
-  else if (i == nf) { I0 = I1 = (i + 1) >> 1; w0 = 1.0; w1 = 0.0; }
-  else { I0 = (i - 1) >> 1; I1 = (i + 1) >> 1; w0 = 0.5; w1 = 0.5; }
-}
-
-template <class V2>
-__device__ __forceinline__ double2 restrict_node(const V2 *__restrict__ rf, int I, int J, int nxf, int nyf) {
-  const int nprf = nxf + 1;
-  int X, Y;
-  double wxl, wxr, wyl, wyr;
-  restrict_taps(I, nxf, X, wxl, wxr);
-  restrict_taps(J, nyf, Y, wyl, wyr);
-  const double wx[3] = {wxl, 1.0, wxr}, wy[3] = {wyl, 1.0, wyr};
-  double sx = 0.0, sy = 0.0;
-#pragma unroll
-  for (int dj = -1; dj <= 1; ++dj) {
-    if (wy[dj + 1] == 0.0) continue;
-#pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const double w = wy[dj + 1] * wx[di + 1];
-      if (w == 0.0) continue;
-      const V2 v = rf[(size_t)(Y + dj) * nprf + (X + di)];
-      sx = fma(w, (double)v.x, sx);
-      sy = fma(w, (double)v.y, sy);
-    }
-  }
-  return make_double2(sx, sy);
-}
-
-// (P xc) at fine node (i, j)
-__device__ __forceinline__ double2 prolong_node(const double2 *__restrict__ xc, int i, int j, int nxf, int nyf,
-                                                int nprc) {
-  int I0, I1, J0, J1;
-  double wx0, wx1, wy0, wy1;
-  prolong_taps(i, nxf, I0, I1, wx0, wx1);
-  prolong_taps(j, nyf, J0, J1, wy0, wy1);
-  const double2 v00 = xc[(size_t)J0 * nprc + I0];
-  double px = wy0 * wx0 * v00.x, py = wy0 * wx0 * v00.y;
-  if (wx1 != 0.0) {
-    const double2 v = xc[(size_t)J0 * nprc + I1];
-    px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
-  }
-  if (wy1 != 0.0) {
-    const double2 v = xc[(size_t)J1 * nprc + I0];
-    px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
-    if (wx1 != 0.0) {
-      const double2 w = xc[(size_t)J1 * nprc + I1];
-      px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
-    }
-  }
-  return make_double2(px, py);
-}
-
-// (row, column) of node n on a level with npr nodes per row.  Node counts stay below 2^30 (topo_create refuses
-// larger meshes), so the 32-bit division is exact -- the 64-bit one is a ~60-instruction subroutine, a third of the
-// dynamic instructions of the transfer kernels.
-__device__ __forceinline__ void rc_of(int64_t n, int npr, int &r, int &c) {
-  const unsigned un = (unsigned)n, q = un / (unsigned)npr;
-  r = (int)q;
-  c = (int)(un - q * (unsigned)npr);
-}
-
-// A x at node n of a stencil level, x of each neighbour supplied by `get(rr, cc)`.
-// sym: the operator is symmetric, so the block towards a "backward" neighbour m (W, SE, S, SW) is the transpose of
-// the block node m stores towards n.  Reading planes 4..8 only (self, E, NW, N, NE -- at n and at the four backward
-// neighbours, whose entries sit in cache lines the neighbouring threads fetch anyway) cuts the stencil stream of a
-// level from 144 to 80 B per node; the big levels are bound by exactly that stream.
-template <bool SYM, class Get>
-__device__ __forceinline__ void stencil_row(const stencil_t *__restrict__ st, int64_t nn, int64_t n, int r, int c, int nx,
-                                            int ny, Get get, double &ax, double &ay) {
-  ax = 0.0;
-  ay = 0.0;
-  const float4 *__restrict__ pl = reinterpret_cast<const float4 *>(st);
-  const int npr = nx + 1;
-#pragma unroll
-  for (int dr = -1; dr <= 1; ++dr) {
-#pragma unroll
-    for (int dc = -1; dc <= 1; ++dc) {
-      const int rr = r + dr, cc = c + dc;
-      if (rr < 0 || rr > ny || cc < 0 || cc > nx) continue;
-      const int nb = 3 * (dr + 1) + (dc + 1);
-      const double2 xv = get(rr, cc);
-      if (SYM && nb < 4) {
-        // A[n, m] = A[m, n]^T ; node m keeps A[m, n] in plane 8 - nb
-        const float4 cf = pl[(size_t)(8 - nb) * nn + (n + (int64_t)dr * npr + dc)];
-        ax = fma((double)cf.x, xv.x, ax);
-        ax = fma((double)cf.z, xv.y, ax);
-        ay = fma((double)cf.y, xv.x, ay);
-        ay = fma((double)cf.w, xv.y, ay);
-      } else {
-        // one float4 per neighbour block: (a00, a01, a10, a11), plane nb, consecutive nodes contiguous
-        const float4 cf = pl[(size_t)nb * nn + n];
-        ax = fma((double)cf.x, xv.x, ax);
-        ax = fma((double)cf.y, xv.y, ax);
-        ay = fma((double)cf.z, xv.x, ay);
-        ay = fma((double)cf.w, xv.y, ay);
-      }
-    }
-  }
-}
-
-struct LevelView {
-  const stencil_t *st;
-  const double2 *dinv;
-  double2 *x, *x2, *b, *r;
-  int nx, ny;
-  double wf, wl;       // row-slab mode: weights of node rows 0 / ny that make a distributed copy of b (else 1)
-  int sym;             // read the backward half of the stencil as transposes of the neighbours' forward blocks
-};
-__device__ __forceinline__ double row_weight(const LevelView &L, int r) { return r == 0 ? L.wf : (r == L.ny ? L.wl : 1.0); }
 
 // ---- per-node bodies shared by the multi-block kernels and the tail kernel -------------------------------
 // down: x = w dinv b ; r = b - A x   (x at neighbours recomputed from b, dinv)
@@ -302,7 +185,10 @@ __global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restr
 // cluster barrier (barrier.cluster, release/acquire: global writes of one CTA are visible to the others
 // after it) between stages; the smallest levels are finished by CTA 0 alone with __syncthreads.
 constexpr int TAIL_MAX = 16;
-constexpr int TAIL_THREADS = 768;     // 80 registers per thread: the small-level path keeps a node's operator in registers
+#ifndef TOPO_TAIL_THREADS
+#define TOPO_TAIL_THREADS 768
+#endif
+constexpr int TAIL_THREADS = TOPO_TAIL_THREADS;     // 80 registers per thread: the small-level path keeps a node's operator in registers
 constexpr int TAIL_SMALL = TAIL_THREADS;
 struct TailArgs {
   LevelView lv[TAIL_MAX];
@@ -317,8 +203,6 @@ struct TailArgs {
   const int *done;
   int *err;                    // SolverScalars::tail_error
   unsigned long long *dbg;     // optional: globaltimer stamps at stage boundaries (thread 0 of CTA 0)
-  int ds_rows[TAIL_MAX];       // k_tail_ds: node rows per CTA on each cluster level
-  int ds_mode;                 // k_tail_ds: 1 = cluster barrier after every sweep, 2 = neighbour hand-over (st.async + mbarrier)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -494,329 +378,6 @@ __device__ __noinline__ void small_up(const TailArgs &a, int l, float2 (*xs)[TAI
   __syncthreads();
 }
 
-// ---- cluster levels through distributed shared memory (EXPERIMENTAL, TOPO_TAIL_DS=1, default off) ---------------------
-// In k_tail a stage of a cluster level costs ~2.5 us whatever the level size: every sweep stores the iterate to global
-// memory, barrier.cluster's release waits for those stores to reach L2 (MEMBAR.ALL.GPU) and the next stage starts with
-// L2-latency loads of operator and iterate.  Here a cluster level is cut into blocks of node ROWS, one block per CTA and
-// one node per thread, and a phase (pre- or post-smoothing of one level) works like the small-level path: operator,
-// D^-1, b and the fp64 iterate stay in registers, the iterate travels as an fp32 copy in shared memory.  What crosses
-// CTAs goes through distributed shared memory: a thread on the first / last row of its block also writes its value
-// into the neighbouring CTA's halo row, restriction and prolongation read the residual / the coarse iterate from the
-// owner CTA's shared memory (map_shared_rank).  Global memory is touched at the ends only: the right-hand side of the
-// first tail level, the hand-over to / from the single-CTA small levels, the result of the first tail level.
-// Products A x are formed in fp32 as on the small levels (numpy prototype: identical PCG iteration counts).
-constexpr int DS_XS = 1536;        // floats2 per iterate buffer: (rows per CTA + 2 halo rows) * nodes per row
-constexpr int DS_MAXLV = 3;        // cluster levels the shared-memory plan has room for
-constexpr size_t DS_SMEM_BYTES = sizeof(float2) * 2 * DS_XS + sizeof(double2) * TAIL_THREADS * (1 + 2 * DS_MAXLV) + 16;
-// TOPO_TAIL_DS=2 (NOT YET RUN ON A GPU: written after the round's GPU budget was spent): inside a smoothing phase the
-// cluster-wide barrier is replaced by a neighbour-to-neighbour hand-over.  Halo values go out with st.async, which
-// credits the receiving CTA's mbarrier (one per iterate buffer) with their bytes; a CTA arms that mbarrier with the
-// bytes its one or two neighbours will send, waits for it and does a __syncthreads.  Why this is enough: a block
-// reads only its neighbours' halo rows; a neighbour can start the next sweep (and overwrite the halo row of the
-// buffer I am reading) only after ALL boundary-row threads of mine have pushed, and each of them reads before it
-// pushes.  Phase boundaries (residual -> restriction, result -> prolongation) keep the cluster-wide barrier.
-struct DsSmem {
-  unsigned long long *bar;         // two mbarriers, one per iterate buffer (mode 2)
-  int mode;                        // 1: cluster.sync() after every sweep, 2: neighbour hand-over
-  unsigned uses[2];                // completed phases of each mbarrier (same sequence on every thread of the cluster)
-  unsigned expect;                 // bytes this CTA receives per sweep on the current level
-  int *err;                        // raised when a hand-over wait gives up
-  float2 *xs[2];                   // iterate copies incl. halo rows (local row 0 = row below the block)
-  double2 *rs;                     // residual of the block's own nodes (read remotely by the restriction)
-  double2 *xd[DS_MAXLV], *bd[DS_MAXLV];   // fp64 iterate and right-hand side of the own nodes, per cluster level
-};
-struct DsNode {
-  int active;                      // this thread owns a node of the level
-  int g;                           // its global node index
-  int r, c;                        // its row / column
-  int loc;                         // index in the halo-extended block: (local row + 1) * npr + c
-  int own;                         // index among the block's own nodes (= thread index)
-  int push_lo, push_hi;            // where its value goes in the lower / upper neighbour's block (-1: nowhere)
-};
-__device__ __forceinline__ DsNode ds_node(const LevelView &L, int R, int rank, int t) {
-  const int npr = L.nx + 1, nrows = L.ny + 1;
-  const int r0 = min(rank * R, nrows), r1 = min(r0 + R, nrows);
-  DsNode d;
-  d.active = t < (r1 - r0) * npr;
-  const int lr = t / npr;
-  d.c = t - lr * npr;
-  d.r = r0 + lr;
-  d.g = d.r * npr + d.c;
-  d.loc = (lr + 1) * npr + d.c;
-  d.own = t;
-  d.push_lo = (d.active && lr == 0 && r0 > 0) ? (R + 1) * npr + d.c : -1;          // the lower neighbour's block is full
-  d.push_hi = (d.active && lr == r1 - r0 - 1 && r1 < nrows) ? d.c : -1;
-  return d;
-}
-__device__ __forceinline__ void ds_load(const LevelView &L, int R, const DsNode &d, SmallNode &N) {
-  const int npr = L.nx + 1, nn = npr * (L.ny + 1);
-  N.n = d.loc; N.npr = npr; N.valid = (R + 2) * npr - 1;
-  if (!d.active) return;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int rr = d.r + k / 3 - 1, cc = d.c + k % 3 - 1;
-    const bool ok = rr >= 0 && rr <= L.ny && cc >= 0 && cc <= L.nx;
-    N.st[k] = ok ? __ldg(reinterpret_cast<const float4 *>(L.st) + (size_t)k * nn + d.g) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  N.dinv = L.dinv[d.g];
-}
-__device__ __forceinline__ unsigned ds_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned ds_mapa(unsigned local_addr, unsigned rank) {      // same offset in CTA `rank`
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-// bounded: a protocol error must neither hang nor fault the device -- the wait gives up, raises *err (the solver's
-// tail_error flag, checked by the host after the solve) and the kernel runs on to its end with wrong numbers
-__device__ __forceinline__ void ds_mbar_wait(unsigned long long *bar, unsigned parity, int *err) {
-  const unsigned addr = ds_smem_u32(bar);
-  for (unsigned spin = 0; spin < (1u << 20); ++spin) {
-    unsigned ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) return;
-  }
-  if (threadIdx.x == 0) atomicExch(err, 1);
-}
-// own value into the local block and into the neighbours' halo rows of iterate buffer b
-__device__ __forceinline__ void ds_publish(cg::cluster_group &cl, const DsSmem &S, int b, const DsNode &d, int rank, const double2 &x) {
-  float2 *buf = S.xs[b];
-  if (S.mode == 2 && threadIdx.x == 0)        // arm this use of the buffer's mbarrier: my arrival + the neighbours' bytes
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ds_smem_u32(S.bar + b)), "r"(S.expect) : "memory");
-  if (!d.active) return;
-  const float2 v = make_float2((float)x.x, (float)x.y);
-  buf[d.loc] = v;
-  if (S.mode == 2) {
-    const unsigned long long bits = ((unsigned long long)__float_as_uint(v.y) << 32) | (unsigned long long)__float_as_uint(v.x);
-    if (d.push_lo >= 0)
-      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::
-                   "r"(ds_mapa(ds_smem_u32(buf + d.push_lo), rank - 1)), "l"(bits), "r"(ds_mapa(ds_smem_u32(S.bar + b), rank - 1)) : "memory");
-    if (d.push_hi >= 0)
-      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::
-                   "r"(ds_mapa(ds_smem_u32(buf + d.push_hi), rank + 1)), "l"(bits), "r"(ds_mapa(ds_smem_u32(S.bar + b), rank + 1)) : "memory");
-  } else {
-    if (d.push_lo >= 0) cl.map_shared_rank(buf, rank - 1)[d.push_lo] = v;
-    if (d.push_hi >= 0) cl.map_shared_rank(buf, rank + 1)[d.push_hi] = v;
-  }
-}
-// iterate buffer b is complete (own values and both halo rows) and every thread of the CTA may read it
-__device__ __forceinline__ void ds_handover(cg::cluster_group &cl, DsSmem &S, int b) {
-  if (S.mode == 2) {
-    ds_mbar_wait(S.bar + b, S.uses[b] & 1u, S.err);
-    S.uses[b] += 1;
-    __syncthreads();
-  } else {
-    cl.sync();
-  }
-}
-// bytes a CTA receives per sweep on a level: one halo row from each neighbour that exists
-__device__ __forceinline__ unsigned ds_expect_bytes(const LevelView &L, int R, int rank) {
-  const int npr = L.nx + 1, nrows = L.ny + 1;
-  const int r0 = min(rank * R, nrows), r1 = min(r0 + R, nrows);
-  if (r1 <= r0) return 0u;
-  return 8u * (unsigned)npr * ((r0 > 0 ? 1u : 0u) + (r1 < nrows ? 1u : 0u));
-}
-__device__ __forceinline__ void ds_sweeps(cg::cluster_group &cl, DsSmem &S, const DsNode &d, int rank, SmallNode &N,
-                                          int &cur, int nsweeps, double omega) {
-  for (int s = 0; s < nsweeps; ++s) {
-    if (d.active) {
-      float ax, ay;
-      small_apply(N, S.xs[cur], ax, ay);
-      N.x.x = fma(omega * N.dinv.x, N.b.x - (double)ax, N.x.x);
-      N.x.y = fma(omega * N.dinv.y, N.b.y - (double)ay, N.x.y);
-    }
-    ds_publish(cl, S, cur ^ 1, d, rank, N.x);
-    ds_handover(cl, S, cur ^ 1);
-    cur ^= 1;
-  }
-}
-// (P^T r)(I, J) with the fine residual in the owner CTAs' shared memory (blocks of Rf rows)
-__device__ __forceinline__ double2 ds_restrict(cg::cluster_group &cl, double2 *rs, int Rf, int I, int J, int nxf, int nyf) {
-  const int nprf = nxf + 1;
-  int X, Y;
-  double wxl, wxr, wyl, wyr;
-  restrict_taps(I, nxf, X, wxl, wxr);
-  restrict_taps(J, nyf, Y, wyl, wyr);
-  const double wx[3] = {wxl, 1.0, wxr}, wy[3] = {wyl, 1.0, wyr};
-  double sx = 0.0, sy = 0.0;
-#pragma unroll
-  for (int dj = -1; dj <= 1; ++dj) {
-    if (wy[dj + 1] == 0.0) continue;
-    const int row = Y + dj, owner = row / Rf;
-    const double2 *src = cl.map_shared_rank(rs, owner) + (row - owner * Rf) * nprf;
-#pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const double w = wy[dj + 1] * wx[di + 1];
-      if (w == 0.0) continue;
-      const double2 v = src[X + di];
-      sx = fma(w, v.x, sx);
-      sy = fma(w, v.y, sy);
-    }
-  }
-  return make_double2(sx, sy);
-}
-// (P xc)(i, j) with the coarse iterate in the owner CTAs' shared memory (blocks of Rc rows)
-__device__ __forceinline__ double2 ds_prolong(cg::cluster_group &cl, double2 *xc, int Rc, int nprc, int i, int j, int nxf, int nyf) {
-  int I0, I1, J0, J1;
-  double wx0, wx1, wy0, wy1;
-  prolong_taps(i, nxf, I0, I1, wx0, wx1);
-  prolong_taps(j, nyf, J0, J1, wy0, wy1);
-  auto at = [&](int J, int I) {
-    const int owner = J / Rc;
-    return cl.map_shared_rank(xc, owner)[(J - owner * Rc) * nprc + I];
-  };
-  const double2 v00 = at(J0, I0);
-  double px = wy0 * wx0 * v00.x, py = wy0 * wx0 * v00.y;
-  if (wx1 != 0.0) {
-    const double2 v = at(J0, I1);
-    px = fma(wy0 * wx1, v.x, px); py = fma(wy0 * wx1, v.y, py);
-  }
-  if (wy1 != 0.0) {
-    const double2 v = at(J1, I0);
-    px = fma(wy1 * wx0, v.x, px); py = fma(wy1 * wx0, v.y, py);
-    if (wx1 != 0.0) {
-      const double2 w = at(J1, I1);
-      px = fma(wy1 * wx1, w.x, px); py = fma(wy1 * wx1, w.y, py);
-    }
-  }
-  return make_double2(px, py);
-}
-// pre-smoothing of cluster level l from a zero guess (nu sweeps), residual, restriction.  `b` = right-hand side of this
-// thread's node; returns the right-hand side of its node on level l+1 when that is a cluster level too, otherwise
-// (first small level) the restricted residual goes to global memory for CTA 0.
-__device__ __noinline__ double2 ds_down(const TailArgs &a, int l, bool next_is_cluster, DsSmem &S, cg::cluster_group &cl,
-                                        int rank, int t, int gt, int GT, double2 b) {
-  const LevelView &L = a.lv[l];
-  const int R = a.ds_rows[l];
-  const DsNode d = ds_node(L, R, rank, t);
-  S.expect = ds_expect_bytes(L, R, rank);
-  SmallNode N;
-  ds_load(L, R, d, N);
-  N.b = b;
-  N.x = make_double2(a.omega * N.dinv.x * b.x, a.omega * N.dinv.y * b.y);
-  int cur = 0;
-  ds_publish(cl, S, 0, d, rank, N.x);
-  ds_handover(cl, S, 0);
-  ds_sweeps(cl, S, d, rank, N, cur, a.nu[l] - 1, a.omega);
-  if (d.active) {
-    float ax, ay;
-    small_apply(N, S.xs[cur], ax, ay);
-    S.rs[d.own] = make_double2(N.dinv.x != 0.0 ? N.b.x - (double)ax : 0.0, N.dinv.y != 0.0 ? N.b.y - (double)ay : 0.0);
-    S.xd[l][d.own] = N.x;
-    S.bd[l][d.own] = N.b;
-  }
-  cl.sync();
-  const LevelView &C = a.lv[l + 1];
-  double2 bnext = make_double2(0.0, 0.0);
-  if (next_is_cluster) {
-    const DsNode dc = ds_node(C, a.ds_rows[l + 1], rank, t);
-    if (dc.active) bnext = ds_restrict(cl, S.rs, R, dc.c, dc.r, L.nx, L.ny);
-  } else {
-    const int nprc = C.nx + 1, nnc = nprc * (C.ny + 1);
-    for (int n = gt; n < nnc; n += GT) C.b[n] = ds_restrict(cl, S.rs, R, n % nprc, n / nprc, L.nx, L.ny);
-  }
-  return bnext;
-}
-// coarse correction + nu post-smoothing sweeps of cluster level l; the result stays in xd[l] (and goes to global
-// memory for the first tail level, whose result the next kernel prolongates)
-__device__ __noinline__ void ds_up(const TailArgs &a, int l, bool next_is_cluster, DsSmem &S, cg::cluster_group &cl,
-                                   int rank, int t) {
-  const LevelView &L = a.lv[l];
-  const LevelView &C = a.lv[l + 1];
-  const int R = a.ds_rows[l];
-  const DsNode d = ds_node(L, R, rank, t);
-  S.expect = ds_expect_bytes(L, R, rank);
-  SmallNode N;
-  ds_load(L, R, d, N);
-  N.b = make_double2(0.0, 0.0);
-  N.x = make_double2(0.0, 0.0);
-  if (d.active) {
-    N.b = S.bd[l][d.own];
-    N.x = S.xd[l][d.own];
-    const double2 p = next_is_cluster ? ds_prolong(cl, S.xd[l + 1], a.ds_rows[l + 1], C.nx + 1, d.c, d.r, L.nx, L.ny)
-                                      : prolong_node(C.x, d.c, d.r, L.nx, L.ny, C.nx + 1);      // small levels leave their result in x
-    if (N.dinv.x != 0.0) N.x.x += p.x;
-    if (N.dinv.y != 0.0) N.x.y += p.y;
-  }
-  int cur = 0;
-  ds_publish(cl, S, 0, d, rank, N.x);
-  ds_handover(cl, S, 0);
-  ds_sweeps(cl, S, d, rank, N, cur, a.nu[l], a.omega);
-  if (d.active) {
-    S.xd[l][d.own] = N.x;
-    if (l == 0) L.x[d.g] = N.x;
-  }
-  cl.sync();
-}
-
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail_ds(const __grid_constant__ TailArgs a) {
-  if (a.done && *a.done) return;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
-  const int T = blockDim.x, t = threadIdx.x;
-  const int gt = rank * T + t, GT = CS * T;
-  extern __shared__ __align__(16) unsigned char ds_raw[];
-  DsSmem S;
-  S.bar = reinterpret_cast<unsigned long long *>(ds_raw);
-  S.mode = a.ds_mode;
-  S.uses[0] = S.uses[1] = 0u;
-  S.expect = 0u;
-  S.err = a.err;
-  S.xs[0] = reinterpret_cast<float2 *>(ds_raw + 16);
-  S.xs[1] = S.xs[0] + DS_XS;
-  S.rs = reinterpret_cast<double2 *>(S.xs[1] + DS_XS);
-#pragma unroll
-  for (int k = 0; k < DS_MAXLV; ++k) {
-    S.xd[k] = S.rs + TAIL_THREADS * (1 + 2 * k);
-    S.bd[k] = S.rs + TAIL_THREADS * (2 + 2 * k);
-  }
-  // halo rows outside the domain are never written: they are read with zero coefficients and must hold finite numbers
-  for (int i = t; i < 2 * DS_XS; i += T) S.xs[0][i] = make_float2(0.f, 0.f);
-  if (S.mode == 2 && t == 0) {                  // one pending arrival each: the CTA's own expect_tx
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ds_smem_u32(S.bar)) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ds_smem_u32(S.bar + 1)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  cluster.sync();                               // nobody pushes into a block that is still being cleared / whose barriers do not exist yet
-  int lsmall = 0;                               // cluster levels = tail levels 0 .. lsmall-1
-  while (lsmall + 1 < a.n && (a.lv[lsmall].nx + 1) * (a.lv[lsmall].ny + 1) > TAIL_SMALL) ++lsmall;
-  double2 b = make_double2(0.0, 0.0);
-  if (lsmall > 0) {                             // right-hand side of this thread's node on the first tail level
-    const LevelView &L0 = a.lv[0];
-    const DsNode d = ds_node(L0, a.ds_rows[0], rank, t);
-    if (d.active) {
-      if (a.r_parent == nullptr) b = L0.b[d.g];
-      else if (a.parent_f32) b = restrict_node(reinterpret_cast<const float2 *>(a.r_parent), d.c, d.r, a.pnx, a.pny);
-      else b = restrict_node(a.r_parent, d.c, d.r, a.pnx, a.pny);
-    }
-  }
-  for (int l = 0; l < lsmall; ++l) b = ds_down(a, l, l + 1 < lsmall, S, cluster, rank, t, gt, GT, b);
-  cluster.sync();                               // the first small level's right-hand side is in global memory
-  if (rank == 0) {
-    __shared__ float2 xs[2][TAIL_THREADS];
-    for (int l = lsmall; l + 1 < a.n; ++l) small_down(a, l, xs, t, T);
-    {  // coarsest: dense inverse, one warp per row (as in k_tail)
-      const LevelView &C = a.lv[a.n - 1];
-      const double *bb = reinterpret_cast<const double *>(C.b);
-      const double *dd = reinterpret_cast<const double *>(C.dinv);
-      double *xx = reinterpret_cast<double *>(C.x);
-      const int N = a.coarse_n;
-      const int lane = t & 31, warp = t >> 5, nwarp = T >> 5;
-      for (int i = warp; i < N; i += nwarp) {
-        double sacc = 0.0;
-        for (int j = lane; j < N; j += 32) sacc = fma(a.coarse_inv[i * N + j], bb[j], sacc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
-        if (lane == 0) xx[i] = dd[i] != 0.0 ? sacc : 0.0;
-      }
-    }
-    __syncthreads();
-    for (int l = a.n - 2; l >= lsmall; --l) small_up(a, l, xs, t);
-  }
-  cluster.sync();                               // the first small level's result is in global memory (its x)
-  for (int l = lsmall - 1; l >= 0; --l) ds_up(a, l, l + 1 < lsmall, S, cluster, rank, t);
-}
-
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ TailArgs a) {
   if (a.done && *a.done) return;
   cg::cluster_group cluster = cg::this_cluster();
@@ -850,7 +411,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ T
   // computed identically); the small levels are finished by CTA 0, which publishes cur[lsmall] via the rule below
   if (rank == 0) {
     __shared__ float2 xs[2][TAIL_THREADS];
-    for (l = lsmall; l + 1 < a.n; ++l) small_down(a, l, xs, t, T);
+    for (l = lsmall; l + 1 < a.n; ++l) { small_down(a, l, xs, t, T); STAMP(); }
     {  // coarsest: dense inverse, one warp per row (lanes stride the columns, shuffle reduction)
       const LevelView &C = a.lv[a.n - 1];
       const double *bb = reinterpret_cast<const double *>(C.b);
@@ -869,7 +430,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ T
     }
     __syncthreads();
     STAMP();
-    for (l = a.n - 2; l >= lsmall; --l) small_up(a, l, xs, t);
+    for (l = a.n - 2; l >= lsmall; --l) { small_up(a, l, xs, t); STAMP(); }
   }
   // small levels (and the coarsest) leave their result in x
   if (lsmall < a.n) cur[lsmall] = a.lv[lsmall].x;
@@ -947,48 +508,13 @@ int tail_cluster_size(const topo_handle *h) {
   if (cs == 0) cs = probe_cluster_size(k_tail, 0, h->knobs.tail_cluster_max);
   return cs;
 }
-// k_tail_ds (TOPO_TAIL_DS=1): cluster size it can be launched with on this device, 0 = not available
-int tail_ds_cluster_size(const topo_handle *h) {
-  static int cs_dev[TOPO_MAX_DEVICES] = {};
-  int &cs = cs_dev[topo_dev_slot(h)];
-  if (cs == 0) {
-    cs = -1;
-    if (cudaFuncSetAttribute(k_tail_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_SMEM_BYTES) == cudaSuccess) {
-      const int c = probe_cluster_size(k_tail_ds, DS_SMEM_BYTES, h->knobs.tail_cluster_max);
-      if (c >= 2) cs = c;
-    }
-    cudaGetLastError();
-  }
-  return cs > 0 ? cs : 0;
-}
-// TOPO_TAIL_DS: 0 (default) k_tail, 1 k_tail_ds with cluster barriers, 2 k_tail_ds with the neighbour hand-over
-int tail_ds_mode(const topo_handle *h) { return h->knobs.tail_ds; }
-// Does the tail starting at level `tail` run in k_tail_ds?  Every cluster level must split into blocks of whole node
-// rows, one node per thread, that fit the shared-memory plan; rows[] receives the rows per CTA of each cluster level.
-bool tail_ds_plan(const topo_handle *h, int tail, int *rows) {
-  const bool want = tail_ds_mode(h) != 0;
-  if (!want || h->dist.on || h->tail_dbg != nullptr) return false;
-  const int L = h->n_levels;
-  int ncl = 0;
-  while (tail + ncl + 1 < L && h->levels[tail + ncl].nn > TAIL_SMALL) ++ncl;
-  if (ncl < 1 || ncl > DS_MAXLV) return false;
-  const int cs = tail_ds_cluster_size(h);
-  if (cs < 2) return false;
-  for (int k = 0; k < ncl; ++k) {
-    const GmgLevel &G = h->levels[tail + k];
-    const int npr = G.nx + 1, R = (G.ny + 1 + cs - 1) / cs;
-    if (R * npr > TAIL_THREADS || (R + 2) * npr > DS_XS) return false;
-    if (rows) rows[k] = R;
-  }
-  return true;
-}
 // where the final iterate of level l lives after the cycle
 const double2 *level_result(const topo_handle *h, int l, int tail) {
   const int L = h->n_levels;
   if (l == L - 1) return h->levels[l].x;          // coarsest: dense solve writes x
   if (l >= tail) {                                 // tail levels: parity of the pointer swaps (see k_tail)
     if (h->levels[l].nn <= TAIL_SMALL) return h->levels[l].x;      // small levels keep their iterate in x
-    if (tail_ds_plan(h, tail, nullptr)) return h->levels[l].x;     // k_tail_ds writes the first tail level's result to x
+    if (topo_tail2_applicable(h, tail)) return h->levels[l].x;     // k_tail2 writes the first tail level's result to x
     const int nu = tail_nu(h, l);
     const int swaps = (nu > 1 ? nu - 1 : 0) + nu;
     return (swaps & 1) ? h->levels[l].x2 : h->levels[l].x;
@@ -1023,9 +549,9 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
       h->inv_pending = false;
     }
   }
+  if (topo_tail2_applicable(h, tail)) return topo_tail2_launch(h, tail, r_parent, pnx, pny, parent_f32);
   const bool big_tail = h->levels[tail].nn > TAIL_SMALL;
-  const bool ds = big_tail && tail_ds_plan(h, tail, ta.ds_rows);
-  const int cs = ds ? tail_ds_cluster_size(h) : (big_tail ? cluster_size : 1);
+  const int cs = big_tail ? cluster_size : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs);
   cfg.blockDim = dim3(TAIL_THREADS);
@@ -1035,13 +561,7 @@ int launch_tail(topo_handle *h, int tail, const double2 *r_parent, int pnx, int 
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (ds) {
-    ta.ds_mode = tail_ds_mode(h);
-    cfg.dynamicSmemBytes = DS_SMEM_BYTES;
-    KL(h, "k_tail_ds", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail_ds, ta)));
-  } else {
-    KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
-  }
+  KL(h, "k_tail", CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tail, ta)));
   return TOPO_OK;
 }
 

@@ -142,7 +142,7 @@ struct TopoKnobs {
   int oc_no_probe;          // TOPO_OC_NO_PROBE
   int coarsest_nodes;       // TOPO_COARSEST_NODES  first level solved densely (48)
   int no_l2persist;         // TOPO_NO_L2PERSIST
-  int tail_ds;              // TOPO_TAIL_DS         0: k_tail, 1: k_tail_ds with cluster barriers, 2: with neighbour hand-overs
+  int tail_kind;            // TOPO_TAIL_KIND       2: shared-memory tail k_tail2 where its plan fits (default), 0: generic k_tail
 };
 
 struct topo_handle {
@@ -203,6 +203,8 @@ struct topo_handle {
   int nu_tail_big, nu_tail_small;   // sweeps on tail levels with > / <= 1024 nodes
   unsigned long long *tail_dbg;   // device buffer for k_tail stage stamps (nullptr = off)
   int tail_max_nodes;
+  void *tail2_cache;       // gmg_tail.cu: the plan of the shared-memory tail kernel (nullptr: not computed yet)
+  int tail2_cache_tail;
   bool use_graph, pcg_graph_valid;
   cudaGraphExec_t pcg_graph_exec;
   int last_pcg_iters;          // iterations of the previous multigrid-PCG solve (sizes the first batch of the next)
