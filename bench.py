@@ -4,20 +4,30 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx 2048 --ny 1024]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE SIMP design iteration of the cantilever (reference optimize.py:420-456: SIMP
-interpolation, K(rho)u = f solve, compliance, sensitivity, filter, OC update, equilibrium guard) on the
-2048x1024 quad4 mesh (BASELINE.json configs[3], the configuration the metric is quoted on).  The steps
-are consecutive iterations of the real optimisation started from rho = 0.5 (no cached results, nothing
-skipped): W warm-up iterations, then K timed ones.
+A "step" is ONE SIMP design iteration of the cantilever (reference optimize.py:420-456: SIMP interpolation,
+K(rho)u = f solve, compliance, sensitivity, filter, OC update, equilibrium guard) on the 2048x1024 quad4 mesh
+(BASELINE.json configs[3], the configuration the metric is quoted on).  The steps are consecutive iterations of the
+real optimisation started from rho = 0.5 (no cached results, nothing skipped): W warm-up iterations, then K timed.
 
-Prints ONE JSON line (rank 0).  Keys: see the task contract; `value` = design iterations/s with all
-state resident in HBM, `e2e` = the same through topo_simp_step_host with pinned HOST density buffers
-(upload + download inside the timed region), `roofline` = achieved algorithmic HBM GB/s of the stage-1
-kernel (matrix-free K(rho)u) measured with CUDA events around its launches inside the timed steps,
-`cpu_baseline` = the numpy/scipy oracle (T1 port of the reference) timed on this box's host cores.
+ONE JSON line on rank 0.  Besides the contract keys:
+  value / e2e        design iterations/s with the state resident in HBM / through topo_simp_step_host with pinned HOST
+                     density buffers (upload + download inside the timed region); e2e.simp_call = the drop-in
+                     SIMP(...) call itself, mesh set-up and handle creation included
+  late               the same metric over design iterations 100..119 of the same run (PCG iteration counts grow as the
+                     design turns 0/1)
+  roofline           the kernel with the largest share of the step (CUDA-event brackets inside an instrumented pass) +
+                     `kernels`: achieved algorithmic GB/s and fraction of the measured HBM peak for EVERY kernel of
+                     the step, + the plain product K(rho)u in isolation (L2-assisted on this mesh) and beyond L2
+  cpu_baseline       oracle/t1.py (numpy + SuperLU port of the reference) on a bounded sample (512x256, >= 3 timed
+                     iterations after one warm-up), extrapolated by element count and labelled so
+  same_config_sample this GPU path on the SAME meshes the CPU arm can run (512x256 and the reference's own 60x60): two
+                     measured numbers a reader can divide
+  beso_1024x512      BASELINE configs[2] through the drop-in BESO()
+  strong             LAST KEY: BASELINE configs[4] (8192x4096) -- one GPU against row slabs over all N ranks, with the
+                     slab solution checked against the oracle's operator (slab_parity_ok)
 
---impl reference times that CPU path alone (the reference itself is pure Python + an un-vendored
-dependency and its source tree does not exist on the GPU box; oracle/t1.py is its verified port).
+--impl reference times the CPU path alone (the reference is pure Python + an un-vendored dependency and its source
+tree does not exist on the GPU box; oracle/t1.py is its verified port): the mesh that actually runs is in `config`.
 """
 import argparse
 import json
@@ -111,70 +121,140 @@ class _StampedHistory(dict):
         return super().setdefault(key, default)
 
 
-def cpu_port_rate(nx, ny, budget_s=20.0, steps=2, warmup=0):
-    """Design iterations/s of the oracle port (numpy + SuperLU, single thread like the reference) on a
-    bounded sample: the same cantilever at (nx/4 x ny/4) -- SuperLU cannot factor the full 2048x1024
-    system (MemoryError at 4.2 M equations) -- scaled to the full mesh by the element
-    ratio (linear scaling: optimistic for the CPU, a sparse direct solve grows faster than that).
-    One probe iteration sizes the run; then `warmup` untimed + up to `steps` timed consecutive design iterations
-    from rho = 0.5, as many as fit the time budget (the numbers that actually ran are in the returned dict)."""
+
+SAMPLE_MESH = (512, 256)          # largest mesh SuperLU factors within the CPU arm's time budget
+
+
+def cpu_port_rate(nx, ny, budget_s=None, steps=3, warmup=1):
+    """Design iterations/s of the oracle port (numpy + SuperLU, single thread like the reference) on a bounded sample:
+    the same cantilever at SAMPLE_MESH -- SuperLU cannot factor the full 2048x1024 system (MemoryError at 4.2 M
+    equations).  `warmup` untimed + up to `steps` timed consecutive design iterations from
+    rho = 0.5 (budget_s = None: exactly those; else as many of them as a one-iteration probe says fit the budget;
+    the numbers that actually ran are in the returned dict).  `value` is the MEASURED rate on the sample mesh;
+    `value_extrapolated` scales it to (nx, ny) by element count (optimistic for the CPU: a sparse direct solve grows
+    faster than linearly)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import t1
-    sx, sy = max(nx//4, 8), max(ny//4, 4)
+    sx, sy = min(nx, SAMPLE_MESH[0]), min(ny, SAMPLE_MESH[1])
     dirs, pos = np.array([[0, -1]]), np.array([[sy//4, 1]])
-    ts = time.perf_counter()
-    t1.simp(sx, sy, sx, sy, dirs, pos, 1, 3)
-    probe = time.perf_counter() - ts
-    fit = int((budget_s - probe)/max(probe, 1e-9))
-    n_warm = max(0, min(warmup, 1, fit - 1))
-    n_timed = max(1, min(steps, fit - n_warm))
-    per_it = probe
-    if fit >= 1:
-        hist = _StampedHistory()
-        ts = time.perf_counter()
-        t1.simp(sx, sy, sx, sy, dirs, pos, n_warm + n_timed, 3, history=hist)
-        stamps = [ts] + hist.stamps
-        n_timed = max(1, len(stamps) - 1 - n_warm)            # the loop may stop early (change < 0.01)
-        per_it = (stamps[-1] - stamps[n_warm])/n_timed if len(stamps) - 1 > n_warm else probe
+    if budget_s is None:                                      # fixed size: `warmup` + `steps` iterations, no probe
+        n_warm, n_timed = warmup, steps
     else:
-        n_warm, n_timed = 0, 1
+        ts = time.perf_counter()
+        t1.simp(sx, sy, sx, sy, dirs, pos, 1, 3)
+        probe = time.perf_counter() - ts
+        fit = int((budget_s - probe)/max(probe, 1e-9))
+        n_warm = max(0, min(warmup, max(1, fit - steps)))     # the timed steps come first: shrink the warm-up before them
+        n_timed = max(1, min(steps, fit - n_warm))
+    hist = _StampedHistory()
+    ts = time.perf_counter()
+    t1.simp(sx, sy, sx, sy, dirs, pos, n_warm + n_timed, 3, history=hist)
+    stamps = [ts] + hist.stamps
+    n_timed = max(1, len(stamps) - 1 - n_warm)                # the loop may stop early (change < 0.01)
+    per_it = (stamps[-1] - stamps[n_warm])/n_timed
     scale = (nx*ny)/float(sx*sy)
-    return {"value": 1.0/(per_it*scale), "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": 1.0/per_it, "unit": UNIT, "cores": 1, "kind": "port", "sample_mesh": [sx, sy],
+            "sample_s_per_iter": per_it, "sample_steps": n_timed, "sample_warmup": n_warm,
+            "extrapolated": bool(scale != 1.0), "extrapolation_factor": scale, "value_extrapolated": 1.0/(per_it*scale),
             "sample": "oracle/t1.py (numpy COO assembly + SuperLU spsolve + stencil filter + OC), %d timed design "
-                      "iteration(s) after %d warm-up of the same cantilever at %dx%d = %.3f s/iteration, scaled x%.0f by "
-                      "element count to %dx%d; host has %d cores, the reference path is single-threaded"
-                      % (n_timed, n_warm, sx, sy, per_it, scale, nx, ny, os.cpu_count() or 1),
-            "sample_s_per_iter": per_it, "sample_mesh": [sx, sy], "sample_steps": n_timed, "sample_warmup": n_warm}
+                      "iteration(s) after %d warm-up of the same cantilever at %dx%d = %.3f s/iteration MEASURED; "
+                      "value_extrapolated = that rate / %.0f (element count of %dx%d); host has %d cores, the "
+                      "reference path is single-threaded" % (n_timed, n_warm, sx, sy, per_it, scale, nx, ny,
+                                                             os.cpu_count() or 1)}
 
 
 def run_reference(args, rank, world):
+    """CPU arm: as many of the K timed design iterations (after the warm-up) of the bounded sample as fit the budget."""
     if rank != 0:
         return
-    cb = cpu_port_rate(args.nx, args.ny, budget_s=120.0, steps=args.steps, warmup=args.warmup)
-    v = cb["value"]
+    cb = cpu_port_rate(args.nx, args.ny, budget_s=240.0, steps=args.steps, warmup=args.warmup)
+    v = cb["value_extrapolated"]
+    sx, sy = cb["sample_mesh"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3/v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": cb["sample_steps"], "warmup": cb["sample_warmup"], "ms_per_step": 1e3*cb["sample_s_per_iter"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "extrapolated": cb["extrapolated"],
             "config": {"workload": "SIMP cantilever %dx%d quad4 (BASELINE configs[3]), p=3, r_min=4 elements, consecutive "
-                                   "design iterations from rho=0.5; CPU arm: bounded sample, see cpu_baseline.sample"
-                                   % (args.nx, args.ny), "nx": args.nx, "ny": args.ny},
+                                   "design iterations from rho=0.5" % (args.nx, args.ny), "nx": args.nx, "ny": args.ny,
+                       "mesh_that_ran": [sx, sy], "extrapolated": cb["extrapolated"],
+                       "extrapolation_factor": cb["extrapolation_factor"],
+                       "note": "ms_per_step and value_sample_mesh are MEASURED on mesh_that_ran (SuperLU cannot factor "
+                               "%dx%d); value = value_sample_mesh / extrapolation_factor.  The GPU arm reports its own "
+                               "rate on mesh_that_ran as same_config_sample" % (args.nx, args.ny)},
+            "value_sample_mesh": cb["value"],
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cantilever(nx, ny):
+    """cons, loads of the bench cantilever: clamped on x = -L/2, unit load at the right edge, quarter height
+    (beams.py:84 with positions = [[ny//4, 1]])."""
+    cons = np.zeros(((nx + 1)*(ny + 1), 2), dtype=np.int8)
+    cons[::nx + 1] = -1
+    return cons, np.array([[(nx + 1)*(ny//4) - 1, 0.0, -1.0]])
+
+
+def algorithmic_bytes(levels, tail_max=10000):
+    """ALGORITHMIC bytes per launch of every kernel of a design iteration (fp64): what the
+    kernel must move if every operand crossed HBM exactly once.  nodal vectors 16 B/node (the preconditioner-internal
+    x^, res, D^-1 copy: 8), element fields 8 B/element, BC flags 1 B/node, level stencils 144 B/node in fp32 (80 where
+    the symmetric half is read: levels of >= 100 000 nodes).  Names that cover several levels (k_restrict, ...) get the
+    mean over their launches of one V-cycle / one set-up."""
+    nn = [(a + 1)*(b + 1) for a, b in levels]
+    nc = [a*b for a, b in levels]
+    ne = nc[0]
+    L = len(levels)
+    tail = L - 1
+    while tail > 1 and nn[tail - 1] <= tail_max:
+        tail -= 1
+    st = [0] + [80 if nn[l] >= 100000 else 144 for l in range(1, L)]
+    out = {"k_fine<apply>": 32*nn[0] + 8*ne, "k_fine<resid>": 49*nn[0] + 8*ne, "k_fine<pcg_matvec>": 64*nn[0] + 8*ne,
+           "k_fine<pcg_matvec_jacobi>": 80*nn[0] + 8*ne, "k_fine<update_resid0>": 120*nn[0] + 8*ne,
+           "k_fine<smooth_dot>": 48*nn[0] + 8*ne, "k_fine<smooth>": 64*nn[0] + 8*ne,
+           "k_simp_scale": 16*ne, "k_simp_sens": 16*nn[0] + 24*ne, "k_filter": 24*ne, "k_oc_prep": 24*ne,
+           "k_oc_multi": 16*ne, "k_oc_step": 16*ne, "k_oc_final_gt": 16*ne, "k_oc_apply": 24*ne,
+           "k_build_diag": 8*ne + 25*nn[0], "k_equilibrium": 32*nn[0], "k_dot": 32*nn[0], "k_mask2": 33*nn[0],
+           "k_prolong_add_fine": 17*nn[0] + 16*nn[1] if L > 1 else 0}
+    if L > 1:
+        r = [8*nn[0] + 16*nn[1]] + [16*nn[l] + 16*nn[l + 1] for l in range(1, tail - 1)]
+        out["k_restrict"] = sum(r)/max(len(r), 1)
+        for l in range(1, tail):
+            out["k_lvl_down L%d" % l] = (st[l] + 64)*nn[l]
+            fused = nn[l] <= 200000
+            out["k_lvl_up L%d" % l] = (st[l] + 64)*nn[l] + (16*nn[l + 1] if fused else 0)
+        pro = [48*nn[l] + 16*nn[l + 1] for l in range(1, tail) if nn[l] > 200000]
+        if pro:
+            out["k_lvl_prolong"] = sum(pro)/len(pro)
+        t_bytes = 16*nn[tail - 1] if tail > 1 else 8*nn[0]
+        for l in range(tail, L):
+            t_bytes += (2*(144 + 16) if l < L - 1 else 16)*nn[l]
+        t_bytes += 16*nn[tail] + 8*(2*nn[L - 1])**2
+        out["k_tail2"] = out["k_tail"] = t_bytes
+        out["k_cells_level1"] = 8*ne + nn[0] + 512*nc[1]
+        co = [512*nc[l - 1] + 512*nc[l] for l in range(2, L)]
+        if co:
+            out["k_cells_coarsen"] = sum(co)/(4.0*len(co))                 # four launches (one per component pair) per level
+        cs = [512*nc[l] + 160*nn[l] for l in range(1, L)]
+        out["k_cells_to_stencil"] = sum(cs)/len(cs)
+        out["k_coarse_invert"] = 144*nn[L - 1] + 8*(2*nn[L - 1])**2
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--ny", type=int, default=1024)
     ap.add_argument("--rtol", type=float, default=1e-9)
     ap.add_argument("--precond", default="gmg", choices=["gmg", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-slab-simp", action="store_true", help="skip the 8192x4096 row-slab design-iteration measurement")
+    ap.add_argument("--no-slab-simp", action="store_true", help="skip the 8192x4096 strong-scaling block and the side measurements")
+    ap.add_argument("--no-late", action="store_true", help="skip the late-window trajectory (design iterations 100..119)")
+    ap.add_argument("--strong-steps", type=int, default=6)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -193,164 +273,111 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-
-    nx, ny = args.nx, args.ny
-    nn, ne = (nx + 1)*(ny + 1), nx*ny
-    # ---- model: cantilever clamped on x = -L/2, unit load at the right edge, quarter height --------
-    cons = np.zeros((nn, 2), dtype=np.int8)
-    cons[::nx + 1] = -1
-    load_node = (nx + 1)*(ny//4) - 1                       # beams.py:84 with positions = [[ny//4, 1]]
-    loads = np.array([[load_node, 0.0, -1.0]])
-    topo = _capi.Topo(nx, ny, kloc_simp(206.8e9, 0.28), device=local_rank)
-    topo.set_cons(cons)
-    topo.set_loads(loads)
-    params = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=4.0, dx=1.0, dy=1.0, move=0.2, rtol=args.rtol,
-                              precond=_capi.PRECOND_GMG if args.precond == "gmg" else _capi.PRECOND_JACOBI,
-                              maxit=100000, warm=1)
+    ke = kloc_simp(206.8e9, 0.28)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def trajectory(n_steps, host_io, profile=False):
-        """rho = 0.5, then n_steps consecutive design iterations; returns per-step results."""
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def simp_params(rtol=None):
+        return _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=4.0, dx=1.0, dy=1.0, move=0.2,
+                                rtol=args.rtol if rtol is None else rtol,
+                                precond=_capi.PRECOND_GMG if args.precond == "gmg" else _capi.PRECOND_JACOBI,
+                                maxit=100000, warm=1)
+
+    nx, ny = args.nx, args.ny
+    nn, ne = (nx + 1)*(ny + 1), nx*ny
+    cons, loads = cantilever(nx, ny)
+    topo = _capi.Topo(nx, ny, ke, device=local_rank)
+    topo.set_cons(cons)
+    topo.set_loads(loads)
+    params = simp_params()
+
+    def trajectory(t, n_warm, n_timed, host_io=False, profile=False, sync=True):
+        """rho = 0.5, then n_warm + n_timed consecutive design iterations on handle t; device time of the timed ones."""
         out = []
         g = 0.0
+        n_e = t.nx*t.ny
         if host_io:
-            a = torch.full((ne,), 0.5, dtype=torch.float64).pin_memory().numpy()
-            b = torch.empty((ne,), dtype=torch.float64).pin_memory().numpy()
+            a = torch.full((n_e,), 0.5, dtype=torch.float64).pin_memory().numpy()
+            b = torch.empty((n_e,), dtype=torch.float64).pin_memory().numpy()
         else:
-            topo.fill(_capi.F_RHO, 0.5)
-        topo.set(_capi.F_U, np.zeros(2*nn))
-        for i in range(n_steps):
-            if i == args.warmup:
-                barrier()
+            t.fill(_capi.F_RHO, 0.5)
+        t.set(_capi.F_U, np.zeros(2*(t.nx + 1)*(t.ny + 1)))
+        for i in range(n_warm + n_timed):
+            if i == n_warm:
+                if sync:
+                    barrier()
                 if profile:
-                    topo.profile_matvec(True)
-                l0 = topo.timing().kernel_launches
-                topo.timer_start()
+                    t.profile_matvec(True)
+                l0 = t.timing().kernel_launches
+                t.timer_start()
                 t0 = time.perf_counter()
             if host_io:
-                g, res = topo.simp_step(params, g, rho_in=a, rho_out=b)
+                g, res = t.simp_step(params, g, rho_in=a, rho_out=b)
                 a, b = b, a
             else:
-                g, res = topo.simp_step(params, g)
+                g, res = t.simp_step(params, g)
             out.append((res.compliance, res.change, res.cg_iters, res.oc_steps, res.relres, res.status))
-        ms = topo.timer_stop()
-        barrier()
+        ms = t.timer_stop()
+        if sync:
+            barrier()
         wall_ms = (time.perf_counter() - t0)*1e3
-        launches = topo.timing().kernel_launches - l0
-        return out, ms, wall_ms, launches
+        return out, ms, wall_ms, t.timing().kernel_launches - l0
 
-    total = args.warmup + args.steps
+    W, K = args.warmup, args.steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    res_dev, ms_dev, wall_dev, launches = trajectory(total, host_io=False)
+    res_dev, ms_dev, wall_dev, launches = trajectory(topo, W, K)
     clocks = sampler.stop()
-    res_e2e, ms_e2e, wall_e2e, _ = trajectory(total, host_io=True)
-    # third pass over the same steps with every kernel launch bracketed by CUDA events (this disables the
-    # CUDA-graph replay, so it is NOT the pass `value` comes from): per-kernel durations inside real steps
-    _, ms_prof, _, _ = trajectory(total, host_io=False, profile=True)
-    n_mv, mv_ms = topo.profile_read()
+    res_e2e, ms_e2e, wall_e2e, _ = trajectory(topo, W, K, host_io=True)
+    # third pass over the same steps with every kernel launch bracketed by CUDA events (this disables the CUDA-graph
+    # replay, so it is NOT the pass `value` comes from): per-kernel durations inside real steps
+    _, ms_prof, _, _ = trajectory(topo, W, K, profile=True)
     report = topo.profile_report()
     topo.profile_matvec(False)
+    levels = topo.gmg_levels()
+    ms_dev_max, ms_e2e_max = allmax(ms_dev), allmax(ms_e2e)
 
-    def slab_matvec():
-        """Stage 1 on the 8192x4096 mesh (BASELINE configs[4]) split into row slabs over all ranks: halo exchange of
-        the interface node rows over NCCL after every product (solidspy_opt.distributed).  Strong scaling."""
-        from solidspy_opt.distributed import SlabSolver, TopoBackend, slab_rows
-        bx, by = 8192, 4096
-        e0, e1 = slab_rows(by, world, rank)
-        nyl = e1 - e0
-        cons_l = np.zeros(((bx + 1)*(nyl + 1), 2), dtype=np.int8)
-        cons_l[::bx + 1] = -1
-        be = TopoBackend(bx, nyl, kloc_simp(206.8e9, 0.28), cons_l, np.full(bx*nyl, 0.125), local_rank)
-        S = SlabSolver(be, rank, world, dist if world > 1 else None)
-        a, b = be.zeros(), be.empty()
-        a.normal_()
-        a[:, 0, :] = 0
-        for _ in range(5):
-            S.matvec(a, b)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 30
-        ev0.record()
-        for _ in range(reps):
-            S.matvec(a, b)
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = allmax(ev0.elapsed_time(ev1)/reps)
-        be.topo.close()
-        bn, bne = (bx + 1)*(by + 1), bx*by
-        gbs = (32*bn + 8*bne)/(ms*1e-3)/1e9
-        return {"mesh": [bx, by], "ms_per_matvec": ms, "algorithmic_gbs_all_gpus": gbs, "per_gpu_gbs": gbs/world,
-                "halo_bytes_per_rank_per_matvec": S.halo_bytes_per_exchange, "scaling": "strong",
-                "note": "row slabs, one interface node row exchanged each way per product (NCCL P2P), host-driven"}
+    side = rank == 0 and world == 1 and not args.no_slab_simp
+    late = None
+    if side and not args.no_late:
+        # the same optimisation carried on: iterations 100..119 (the PCG iteration count grows with the 0/1 contrast)
+        r_l, ms_l, _, _ = trajectory(topo, 100, 20, sync=False)
+        late = {"steps": [100, 119], "value": 20/(ms_l*1e-3), "unit": UNIT, "ms_per_step": ms_l/20,
+                "cg_iters": [r[2] for r in r_l[100:]], "cg_iters_max_0_to_119": max(r[2] for r in r_l),
+                "all_converged": all(r[5] == 0 for r in r_l), "compliance_last": r_l[-1][0]}
+    mv_iso_ms = topo.matvec_device(50) if rank == 0 else None
+    topo.close()
 
-    def slab_simp(n_warm=3, n_timed=5):
-        """The WHOLE design iteration on the 8192x4096 mesh (BASELINE configs[4]) split into row slabs, one per rank:
-        multigrid-PCG, sensitivity, filter and OC with NCCL halo sums / gathers / all-reduces between the library's
-        segments (solidspy_opt.distributed.SlabSimp).  Strong scaling: rank 0 also times the same steps on ONE GPU
-        with the ordinary single-handle path.  Device time (CUDA events), max over ranks."""
-        from solidspy_opt.distributed import SlabSimp
-        bx, by = 8192, 4096
-        ke = kloc_simp(206.8e9, 0.28)
-        cons_b = np.zeros((by + 1, bx + 1, 2), dtype=np.int8)
-        cons_b[:, 0, :] = -1
-        loads_b = np.array([[(bx + 1)*(by//4) - 1, 0.0, -1.0]])
-        out = {"mesh": [bx, by], "n_gpus": world, "scaling": "strong", "steps": n_timed, "warmup": n_warm}
-        single_ms = None
-        if rank == 0:
-            with _capi.Topo(bx, by, ke, device=local_rank) as big:
-                big.set_cons(cons_b.reshape(-1, 2))
-                big.set_loads(loads_b)
-                big.fill(_capi.F_RHO, 0.5)
-                pb = _capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=4.0, dx=1.0, dy=1.0, move=0.2, rtol=args.rtol,
-                                      precond=_capi.PRECOND_GMG, maxit=100000, warm=1)
-                g, its1 = 0.0, []
-                for i in range(n_warm + n_timed):
-                    if i == n_warm:
-                        big.timer_start()
-                    g, r = big.simp_step(pb, g)
-                    if i >= n_warm:
-                        its1.append(r.cg_iters)
-                single_ms = big.timer_stop()/n_timed
-                out["single_gpu"] = {"ms_per_step": single_ms, "it_per_s": 1e3/single_ms, "cg_iters": its1,
-                                     "compliance_last": r.compliance}
-        if world > 1:
-            sim = SlabSimp(bx, by, ke, cons_b, loads_b, rmin=4.0, dist=dist, device=local_rank, rtol=args.rtol,
-                           maxit=100000, use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0",
-                   transport=os.environ.get("TOPO_DIST_TRANSPORT", "p2p"))
-            g, its, stage = 0.0, [], {}
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for i in range(n_warm + n_timed):
-                if i == n_warm:
-                    barrier()
-                    c0 = sim.collectives
-                    with torch.cuda.stream(sim.stream):
-                        ev0.record()
-                g, r = sim.step(g)
-                if i >= n_warm:
-                    its.append(r["cg_iters"])
-                    for k, v in r["stage_ms"].items():
-                        stage[k] = stage.get(k, 0.0) + v/n_timed
-            with torch.cuda.stream(sim.stream):
-                ev1.record()
-            barrier()
-            ms = allmax(ev0.elapsed_time(ev1)/n_timed)
-            out.update(ms_per_step=ms, it_per_s=1e3/ms, cg_iters=its, stage_ms=stage, first_global_level=sim.K,
-                       cuda_graph=bool(sim.use_graph), graph_error=sim.graph_error, compliance_last=r["compliance"],
-                       transport="peer memory (CUDA IPC over NVLink) for the PCG loop, NCCL for set-up" if sim.p2p else "NCCL",
-                       p2p_error=sim.p2p_error,
-                       host_collective_calls_per_step=(sim.collectives - c0)/n_timed,
-                       note="one slab of %d element rows per GPU; accumulated vectors, halo sums of interface node rows, "
-                            "level-%d operator gathered and solved redundantly; NCCL via torch.distributed, one pair "
-                            "of PCG iterations (kernels + collectives) per CUDA graph" % (by//world, sim.K))
-            if single_ms is not None:
-                out["speedup_vs_single_gpu"] = single_ms/ms
-            sim.close()
-        return out
+    def gpu_rate_on(mx, my, n_warm=3, n_timed=10):
+        """this GPU path on a mesh the CPU arm can run: device-resident and with host density buffers"""
+        c2, l2 = cantilever(mx, my)
+        with _capi.Topo(mx, my, ke, device=local_rank) as t:
+            t.set_cons(c2)
+            t.set_loads(l2)
+            r1, ms1, _, _ = trajectory(t, n_warm, n_timed, sync=False)
+            r2, ms2, _, _ = trajectory(t, n_warm, n_timed, host_io=True, sync=False)
+        return {"mesh": [mx, my], "value": n_timed/(ms1*1e-3), "e2e": n_timed/(ms2*1e-3), "unit": UNIT, "steps": n_timed,
+                "warmup": n_warm, "cg_iters": [r[2] for r in r1[n_warm:]], "compliance_last": r1[-1][0]}
+
+    def simp_call():
+        """the drop-in entry point itself: beam() set-up, handle creation, W + K design iterations, rho back on the host"""
+        from solidspy_opt.optimize import SIMP
+        t0 = time.perf_counter()
+        rho = SIMP(float(nx), float(ny), nx, ny, np.array([[0, -1]]), np.array([[ny//4, 1]]), W + K, 3, verbose=False,
+                   device=local_rank, rtol=args.rtol)
+        dt = time.perf_counter() - t0
+        return {"design_iterations": W + K, "wall_s": dt, "value_incl_setup": (W + K)/dt, "unit": UNIT,
+                "rho_mean": float(rho.mean())}
 
     def beso_config3():
         """BASELINE configs[2]: BESO cantilever 1024x512 (strain-energy sensitivity, node/element smoothing, device
@@ -367,102 +394,175 @@ def main():
             samples.append((w[-1] - w[2])/(len(w) - 3))
         per = min(samples)
         return {"mesh": [bx, by], "ms_per_design_iteration": per*1e3, "design_iterations_per_s": 1.0/per,
-                "elements_kept": int(ELS.shape[0]),
-                "samples_ms": [round(v*1e3, 3) for v in samples],
-                "note": "ER = 5 %, volfrac 0.5, GMG-PCG rtol 1e-12 (strict removal thresholds); removal sets are "
-                        "bit-identical to the reference on its fixtures (tests/test_gpu_parity.py)"}
+                "elements_kept": int(ELS.shape[0]), "samples_ms": [round(v*1e3, 3) for v in samples],
+                "jacobi_restarts": hist.get("jacobi_restarts", 0)}
 
-    def allmax(x):
+    def strong_block(n_warm=3, n_timed=args.strong_steps):
+        """BASELINE configs[4]: the WHOLE design iteration on 8192x4096 -- rank 0 alone on one GPU, then on row slabs over
+        all ranks (multigrid-PCG, sensitivity, filter, OC; peer-memory halo sums / gathers / all-reduces inside the PCG
+        loop).  Device time (CUDA events), max over ranks.  slab_parity_ok: the slab displacements solve the ORACLE's
+        system (||f - K_ref u|| <= 2e-9 ||f||, operator applied element by element on the host, interface rows summed
+        over ranks) AND the compliance history equals the single-GPU one to 1e-6 (north_star's bar)."""
+        from solidspy_opt.distributed import SlabSimp
+        bx, by = 8192, 4096
+        cons_b, loads_b = cantilever(bx, by)
+        pb = simp_params()
+        out = {"mesh": [bx, by], "n_gpus": world, "steps": n_timed, "warmup": n_warm}
+        comp1 = None
+        if rank == 0:
+            with _capi.Topo(bx, by, ke, device=local_rank) as big:
+                big.set_cons(cons_b)
+                big.set_loads(loads_b)
+                big.fill(_capi.F_RHO, 0.5)
+                g, its1, comp1 = 0.0, [], []
+                for i in range(n_warm + n_timed):
+                    if i == n_warm:
+                        big.timer_start()
+                    g, r = big.simp_step(pb, g)
+                    comp1.append(r.compliance)
+                    if i >= n_warm:
+                        its1.append(r.cg_iters)
+                single_ms = big.timer_stop()/n_timed
+                mv_ms = big.matvec_device(20)                # the plain product where nothing fits in L2 (1.34 GB per launch)
+            mv_bytes = 32*(bx + 1)*(by + 1) + 8*bx*by
+            out.update(single_gpu_ms_per_step=single_ms, single_gpu_it_per_s=1e3/single_ms, single_gpu_cg_iters=its1,
+                       single_gpu_matvec={"avg_launch_us": mv_ms*1e3, "algorithmic_bytes": mv_bytes,
+                                          "achieved_gbs": mv_bytes/(mv_ms*1e-3)/1e9})
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            return out
+        sim = SlabSimp(bx, by, ke, cons_b.reshape(by + 1, bx + 1, 2), loads_b, rmin=4.0, dist=dist, device=local_rank,
+                       rtol=args.rtol, maxit=100000, use_graph=os.environ.get("TOPO_DIST_GRAPH", "1") != "0",
+                       transport=os.environ.get("TOPO_DIST_TRANSPORT", "p2p"))
+        g, its, comp, stage = 0.0, [], [], {}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(n_warm + n_timed):
+            if i == n_warm:
+                barrier()
+                with torch.cuda.stream(sim.stream):
+                    ev0.record()
+            g, r = sim.step(g)
+            comp.append(r["compliance"])
+            if i >= n_warm:
+                its.append(r["cg_iters"])
+                for k, v in r["stage_ms"].items():
+                    stage[k] = stage.get(k, 0.0) + v/n_timed
+        with torch.cuda.stream(sim.stream):
+            ev1.record()
+        barrier()
+        ms = allmax(ev0.elapsed_time(ev1)/n_timed)
+        # ---- parity of the slab solution against the oracle's operator (host, numpy): the state after the last step's
+        # solve is gone (OC moved rho), so solve once more on the final design and check THAT solution
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import t1
+        t = sim.slabs[0]
+        with torch.cuda.stream(sim.stream):
+            t.simp_scale(3.0, 1e-9, 1.0)
+            sim.setup()
+            it_chk, rel_chk = sim.solve(True)
+        sim.stream.synchronize()
+        nyl = sim.nyl
+        u = t.get(_capi.F_U).reshape(-1)
+        f = t.get(_capi.F_LOAD).reshape(nyl + 1, -1).copy()
+        scale = t.get(_capi.F_SCALE)
+        free = (cons_b.reshape(by + 1, -1)[rank*nyl:(rank + 1)*nyl + 1].reshape(-1) == 0).astype(float)
+        y = t1.apply_K(bx, nyl, scale, ke, u, free).reshape(nyl + 1, -1)        # partial sums on the interface rows
+        edge = torch.tensor(np.stack([y[0], y[-1]]), device="cuda")
+        edges = [torch.empty_like(edge) for _ in range(world)]
+        dist.all_gather(edges, edge)
+        if rank > 0:
+            y[0] += edges[rank - 1][1].cpu().numpy()
+        if rank < world - 1:
+            y[-1] += edges[rank + 1][0].cpu().numpy()
+        own = slice(0, nyl + 1) if rank == world - 1 else slice(0, nyl)            # the lower slab owns a shared row
+        sums = torch.tensor([((f[own] - y[own])**2).sum(), (f[own]**2).sum()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sums)
+        resid = float(torch.sqrt(sums[0]/sums[1]).item())
+        sim.close()
+        out.update(slab_ms_per_step=ms, slab_it_per_s=1e3/ms, slab_cg_iters=its, slab_stage_ms={k: round(v, 3) for k, v in stage.items()},
+                   first_global_level=sim.K, cuda_graph=bool(sim.use_graph),
+                   transport="peer memory (CUDA IPC over NVLink)" if sim.p2p else "NCCL", slab_oracle_residual=resid)
+        if rank == 0:
+            rel = max(abs(a - b)/abs(b) for a, b in zip(comp, comp1))
+            out.update(speedup=out["single_gpu_ms_per_step"]/ms, compliance_rel_diff_vs_single_gpu=rel,
+                       cg_iters_equal=bool(its == out["single_gpu_cg_iters"]),
+                       slab_parity_ok=bool(resid <= 2e-9 and rel <= 1e-6))
+        return out
 
-    ms_dev_max, ms_e2e_max = allmax(ms_dev), allmax(ms_e2e)
-    slab = slab_matvec()
-    slab_full = slab_simp() if not args.no_slab_simp else None
-    beso3 = None
-    if rank == 0 and world == 1 and not args.no_slab_simp:
-        try:
-            beso3 = beso_config3()
-        except Exception as exc:                      # never lose the headline line over the side measurement
-            beso3 = {"error": repr(exc)}
+    strong = strong_block() if not args.no_slab_simp else None
+    extras = {}
+    if side:
+        for name, fn in (("same_512x256", lambda: gpu_rate_on(*SAMPLE_MESH)), ("same_60x60", lambda: gpu_rate_on(60, 60)),
+                         ("simp_call", simp_call), ("beso", beso_config3 if world == 1 else (lambda: None))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:                      # never lose the headline line over a side measurement
+                extras[name] = {"error": repr(exc)}
     if rank == 0:
         peak, peak_src = measured_peak()
-        # ALGORITHMIC bytes per launch of each variant of the stage-1 kernel (fp64):
-        # nodal vectors are 16 B/node, element scales 8 B/element, BC flags 1 B/node
-        alg = {"k_fine<apply>": 32*nn + 8*ne, "k_fine<resid>": 48*nn + 8*ne + nn,
-               "k_fine<pcg_matvec>": 64*nn + 8*ne + nn, "k_fine<pcg_matvec_jacobi>": 80*nn + 8*ne + nn,
-               # x^, res and the D^-1 copy of the fused passes are float2 (8 B/node): update reads p, Ap, u, r (64) +
-               # D^-1 (8) and writes u, r (32) + x^, res (16); smooth_dot reads x^ (8), r (16), D^-1 (8), writes z (16)
-               "k_fine<update_resid0>": 120*nn + 8*ne, "k_fine<smooth_dot>": 48*nn + 8*ne,
-               "k_fine<smooth>": 64*nn + 8*ne}
-        fine = [(nm, n, ms) for nm, n, ms in report if nm in alg]
-        kernels = [{"kernel": nm, "launches": n, "avg_launch_us": ms*1e3/n, "algorithmic_bytes": alg[nm],
-                    "achieved_gbs": alg[nm]/(ms*1e-3/n)/1e9, "frac": alg[nm]/(ms*1e-3/n)/1e9/peak,
-                    "share_of_step": ms/ms_prof} for nm, n, ms in fine]
-        dom = max(kernels, key=lambda k: k["share_of_step"]) if kernels else None
-        mv_iso_ms = topo.matvec_device(50)
+        alg = algorithmic_bytes(levels)
+        rows = []
+        for nm, n, ms in report:
+            row = {"kernel": nm, "launches_per_step": round(n/K, 2), "avg_us": round(ms*1e3/n, 2),
+                   "ms_per_step": round(ms/K, 4), "share": round(ms/ms_prof, 4)}
+            if alg.get(nm):
+                gbs = alg[nm]/(ms*1e-3/n)/1e9
+                row.update(algorithmic_mb=round(alg[nm]/1e6, 2), gbs=round(gbs, 1), frac=round(gbs/peak, 4))
+            rows.append(row)
+        dom = next((r for r in rows if "gbs" in r), None)
+        traffic = {"k_fine<update_resid0>": (189564160 + 73890560, "profiles/r1_ncu_k_fine_update_resid0.txt")}
         mv_iso = (32*nn + 8*ne)/(mv_iso_ms*1e-3)/1e9
-        timed = res_dev[args.warmup:]
+        timed = res_dev[W:]
         line = {
-            "metric": METRIC, "value": world*args.steps/(ms_dev_max*1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev_max/args.steps,
-            "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "SIMP cantilever %dx%d quad4 (BASELINE configs[3]), p=3, r_min=4 elements, "
-                                   "GMG-PCG rtol %.0e, consecutive design iterations from rho=0.5" % (nx, ny, args.rtol),
+            "metric": METRIC, "value": world*K/(ms_dev_max*1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev_max/K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "SIMP cantilever %dx%d quad4 (BASELINE configs[3]), p=3, r_min=4 elements, GMG-PCG rtol "
+                                   "%.0e, consecutive design iterations from rho=0.5" % (nx, ny, args.rtol),
                        "nx": nx, "ny": ny, "precond": args.precond,
-                       "parallelism": "1 mesh per GPU" if world == 1 else "%d independent replicas (one mesh per GPU)" % world,
+                       "parallelism": "1 mesh per GPU" if world == 1 else
+                                      "%d independent replicas of the headline mesh (one per GPU, no communication); the "
+                                      "partitioned run is the `strong` block" % world,
                        "l2": "working set per step (>1 GB of vectors and multigrid operators) exceeds the 126 MB L2"},
-            "e2e": {"value": world*args.steps/(ms_e2e_max*1e-3), "unit": UNIT, "h2d_bytes_per_step": 8*ne,
-                    "d2h_bytes_per_step": 8*ne, "ms_per_step": ms_e2e_max/args.steps},
+            "e2e": {"value": world*K/(ms_e2e_max*1e-3), "unit": UNIT, "h2d_bytes_per_step": 8*ne, "d2h_bytes_per_step": 8*ne,
+                    "ms_per_step": ms_e2e_max/K, "api": "topo_simp_step_host (C ABI, pinned host density buffers)",
+                    "simp_call": extras.get("simp_call")},
             "gpu_launches": int(launches),
-            "slab_matvec": slab,
-            "slab_simp": slab_full,
-            "beso_1024x512": beso3,
             "clocks": clocks,
+            "late": late,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"] if dom else None,
-                         "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
+                         "achieved": dom["gbs"] if dom else None, "peak": peak, "unit": "GB/s",
                          "frac": dom["frac"] if dom else None,
-                         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-                         # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_k_fine_update_resid0.txt);
-                         # only meaningful for the mesh and kernel it was captured on
-                         "traffic": (189564160 + 73890560) if (dom and dom["kernel"] == "k_fine<update_resid0>"
-                                                                and (nx, ny) == (2048, 1024)) else None,
-                         "traffic_source": "profiles/r1_ncu_k_fine_update_resid0.txt",
-                         "peak_source": peak_src,
-                         "avg_launch_us": dom["avg_launch_us"] if dom else None,
-                         "launches_timed": dom["launches"] if dom else 0,
-                         "algorithmic_bytes_per_launch": dom["algorithmic_bytes"] if dom else None,
-                         "share_of_step": dom["share_of_step"] if dom else None,
-                         "frac_of_nominal_8TBs": (dom["achieved_gbs"]/8000.0) if dom else None,
-                         "note": "dominant kernel of the step = the stage-1 kernel variant with the largest share; "
-                                 "durations are CUDA-event brackets of its launches inside a separate instrumented "
-                                 "pass over the same steps (CUDA-graph replay off)",
-                         "stage1_variants": kernels,
+                         "traffic": traffic.get(dom["kernel"], (None, None))[0] if dom and (nx, ny) == (2048, 1024) else None,
+                         "traffic_source": traffic.get(dom["kernel"], (None, None))[1] if dom else None,
+                         "peak_source": peak_src, "avg_launch_us": dom["avg_us"] if dom else None,
+                         "launches_timed": int(round(dom["launches_per_step"]*K)) if dom else 0,
+                         "algorithmic_bytes_per_launch": alg.get(dom["kernel"]) if dom else None,
+                         "share_of_step": dom["share"] if dom else None,
+                         "frac_of_nominal_8TBs": (dom["gbs"]/8000.0) if dom else None,
+                         "note": "kernel = the one with the largest share of the step, whatever it is; durations are "
+                                 "CUDA-event brackets inside a separate instrumented pass over the same steps (CUDA-graph "
+                                 "replay off); `kernels` lists every kernel of the step the same way",
+                         "kernels": rows[:24],
                          "matvec_isolated": {"kernel": "k_fine<apply> (plain y = K(rho) u)", "avg_launch_us": mv_iso_ms*1e3,
                                              "algorithmic_bytes": 32*nn + 8*ne, "achieved_gbs": mv_iso,
                                              "frac": mv_iso/peak, "launches": 50,
-                                             "note": "repeated launches on this mesh: its 84 MB fit the 126 MB L2, so part of the "
-                                                     "traffic never reaches HBM (ncu: 56 MB of DRAM traffic per launch)"},
-                         # the same kernel where nothing fits in L2 (1.34 GB per launch): the honest HBM-streaming figure
-                         "matvec_beyond_l2": ({"mesh": slab["mesh"], "avg_launch_us": slab["ms_per_matvec"]*1e3,
-                                               "algorithmic_bytes": 32*(slab["mesh"][0] + 1)*(slab["mesh"][1] + 1) + 8*slab["mesh"][0]*slab["mesh"][1],
-                                               "achieved_gbs": slab["algorithmic_gbs_all_gpus"],
-                                               "frac": slab["algorithmic_gbs_all_gpus"]/peak} if world == 1 else None)},
+                                             "note": "repeated launches on this mesh: its 84 MB fit the 126 MB L2"},
+                         "matvec_beyond_l2": (dict(strong["single_gpu_matvec"], mesh=strong["mesh"],
+                                                   frac=strong["single_gpu_matvec"]["achieved_gbs"]/peak)
+                                              if strong and "single_gpu_matvec" in strong else None)},
             "detail": {"cg_iters": [r[2] for r in timed], "oc_steps": [r[3] for r in timed],
                        "compliance_first_last": [timed[0][0], timed[-1][0]],
                        "max_relres": max(r[4] for r in timed), "all_converged": all(r[5] == 0 for r in timed),
-                       "wall_ms_per_step": wall_dev/args.steps,
-                       "kernel_ms_per_step": {name: round(ms/args.steps, 4) for name, n, ms in report[:14]}},
+                       "wall_ms_per_step": wall_dev/K, "instrumented_pass_ms_per_step": ms_prof/K},
+            "beso_1024x512": extras.get("beso"),
+            "same_config_sample": {"gpu_512x256": extras.get("same_512x256"), "gpu_60x60": extras.get("same_60x60"),
+                                   "note": "the CPU arm (bench.py --impl reference / cpu_baseline) MEASURES the oracle port on "
+                                           "512x256; divide gpu_512x256.e2e by its value_sample_mesh for a like-for-like ratio"},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_port_rate(nx, ny)
+        line["strong"] = strong                                   # LAST key: survives any truncation of the line's head
         print(json.dumps(line), flush=True)
-    topo.close()
     if world > 1:
         dist.destroy_process_group()
 
