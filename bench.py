@@ -355,6 +355,8 @@ def main():
         late = {"steps": [100, 119], "value": 20/(ms_l*1e-3), "unit": UNIT, "ms_per_step": ms_l/20,
                 "cg_iters": [r[2] for r in r_l[100:]], "cg_iters_max_0_to_119": max(r[2] for r in r_l),
                 "all_converged": all(r[5] == 0 for r in r_l), "compliance_last": r_l[-1][0]}
+    if rank == 0:
+        topo.matvec_device(3)
     mv_iso_ms = topo.matvec_device(50) if rank == 0 else None
     topo.close()
 
@@ -423,6 +425,7 @@ def main():
                     if i >= n_warm:
                         its1.append(r.cg_iters)
                 single_ms = big.timer_stop()/n_timed
+                big.matvec_device(3)                         # one-time launch set-up of this kernel variant outside the timing
                 mv_ms = big.matvec_device(20)                # the plain product where nothing fits in L2 (1.34 GB per launch)
             mv_bytes = 32*(bx + 1)*(by + 1) + 8*bx*by
             out.update(single_gpu_ms_per_step=single_ms, single_gpu_it_per_s=1e3/single_ms, single_gpu_cg_iters=its1,
