@@ -221,11 +221,12 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   for (size_t i = 0; i < nvec; ++i) *vecs[i] = slab + i * (size_t)h->nn;
   double *eslab = nullptr;
   const size_t nev = 7;
-  CUDA_TRY(cudaMalloc(&eslab, sizeof(double) * (size_t)h->ne * nev));
-  CUDA_TRY(cudaMemsetAsync(eslab, 0, sizeof(double) * (size_t)h->ne * nev, h->stream));
+  const size_t ne_pad = ((size_t)h->ne + 1) & ~(size_t)1;        // every element field 16-byte aligned (double2 loads)
+  CUDA_TRY(cudaMalloc(&eslab, sizeof(double) * ne_pad * nev));
+  CUDA_TRY(cudaMemsetAsync(eslab, 0, sizeof(double) * ne_pad * nev, h->stream));
   h->slab_elem = eslab;
   double **evs[nev] = {&h->rho, &h->rho_new, &h->dc, &h->dc2, &h->scale, &h->sens, &h->sens_prev};
-  for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * (size_t)h->ne;
+  for (size_t i = 0; i < nev; ++i) *evs[i] = eslab + i * ne_pad;
   CUDA_TRY(cudaMalloc(&h->nodal, sizeof(double) * (size_t)h->nn));
   CUDA_TRY(cudaMalloc(&h->dinv_f, sizeof(float2) * (size_t)h->nn));
   CUDA_TRY(cudaMalloc(&h->fixed, (size_t)h->nn + 128));         // + slack: the stage-1 kernel copies up to 68 bytes of aligned words from the last node on
@@ -233,8 +234,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   CUDA_TRY(cudaMalloc(&h->keep, (size_t)h->ne));
   CUDA_TRY(cudaMemsetAsync(h->keep, 1, (size_t)h->ne, h->stream));
   CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * TOPO_RED_SLOTS * TOPO_MAX_PARTIAL_BLOCKS));
-  CUDA_TRY(cudaMalloc(&h->ticket, sizeof(unsigned int)));
-  CUDA_TRY(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream));
+  CUDA_TRY(cudaMalloc(&h->ticket, 4 * sizeof(unsigned int)));          // [1]: second reduction of a kernel that folds twice
+  CUDA_TRY(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned int), h->stream));
   CUDA_TRY(cudaMalloc(&h->red_out, sizeof(double) * 16));
   CUDA_TRY(cudaMemsetAsync(h->red_out, 0, sizeof(double) * 16, h->stream));
   CUDA_TRY(cudaMalloc(&h->sc, sizeof(SolverScalars)));

@@ -34,29 +34,41 @@ __global__ void k_simp_scale(const double *__restrict__ rho, double *__restrict_
 // (free end of a long cantilever: |u|^2 |ke| eps exceeds the true energy on fine meshes) and then turns
 // NEGATIVE at random, which np.sqrt(-dc/lmid) converts into NaN densities (solver.py:441).  Same value to
 // rounding where the reference is accurate; non-negative everywhere.
-__global__ void __launch_bounds__(ET) k_simp_sens(const __grid_constant__ KeParam lf, const double2 *__restrict__ u,
-                                                  const double *__restrict__ rho, const double *__restrict__ scale,
-                                                  double *__restrict__ dc, int nx, int ny, double penal, double emin,
-                                                  double emax, double *partials, unsigned int *ticket, double *out) {
-  const int64_t ne = (int64_t)nx * ny;
+// A thread marches up a column of elements: the two upper nodes of an element are the lower
+// nodes of the next one, so a row costs two 16-byte loads instead of four, there is no 64-bit index division, and only
+// the `rank` non-zero rows of the factor are evaluated (5 for the plane-stress quad4: three rigid-body modes).
+__global__ void __launch_bounds__(ET) k_simp_sens_march(const __grid_constant__ KeParam lf, int rank, const double2 *__restrict__ u,
+                                                        const double *__restrict__ rho, const double *__restrict__ scale,
+                                                        double *__restrict__ dc, int nx, int ny, int rows_per_chunk, double penal,
+                                                        double emin, double emax, double *partials, unsigned int *ticket,
+                                                        double *out) {
   const int npr = nx + 1;
+  const int c = blockIdx.x * ET + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, ny);
   double v[1] = {0.0};
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(e / nx), c = (int)(e - (int64_t)r * nx);
-    const double2 *p = u + (size_t)r * npr + c;
-    const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + npr + 1), q3 = __ldg(p + npr);
-    const double d[6] = {q1.x - q0.x, q1.y - q0.y, q2.x - q0.x, q2.y - q0.y, q3.x - q0.x, q3.y - q0.y};
-    double s = 0.0;
+  if (c < nx && r0 < r1) {
+    const double2 *p = u + (size_t)r0 * npr + c;
+    double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+    size_t e = (size_t)r0 * nx + c;
+    for (int r = r0; r < r1; ++r, p += npr, e += nx) {
+      const double2 q3 = __ldg(p + npr), q2 = __ldg(p + npr + 1);
+      const double d[6] = {q1.x - q0.x, q1.y - q0.y, q2.x - q0.x, q2.y - q0.y, q3.x - q0.x, q3.y - q0.y};
+      double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      double t = 0.0;
+      for (int k = 0; k < 8; ++k) {
+        if (k < rank) {
+          double t = 0.0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) t = fma(lf.k[8 * k + 2 + i], d[i], t);
-      s = fma(t, t, s);
+          for (int i = 0; i < 6; ++i) t = fma(lf.k[8 * k + 2 + i], d[i], t);
+          s = fma(t, t, s);
+        }
+      }
+      const double rh = rho[e];
+      dc[e] = (-penal * powp(rh, penal - 1.0) * (emax - emin)) * s;
+      v[0] = fma(scale[e], s, v[0]);
+      q0 = q3;
+      q1 = q2;
     }
-    const double rh = rho[e];
-    dc[e] = (-penal * powp(rh, penal - 1.0) * (emax - emin)) * s;
-    v[0] = fma(scale[e], s, v[0]);
   }
   grid_reduce<1>(v, partials, ticket, out);
 }
@@ -119,6 +131,85 @@ __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ FilterTa
     }
     const size_t e = (size_t)gy * nx + gx;
     out[e] = num / (den * np_max(0.001, rho[e]));
+  }
+}
+
+// Same filter for the common square stencils (hx == hy == H known at compile time: H = 3 for the reference's r_min = 4
+// element widths, 2 for r = 2.5, 1 for r = 1.5).  The generic kernel spends ~500 instructions per element on the tap
+// loop (weight fetched through a dynamic constant index, a branch and the domain test for the denominator per tap:
+// 0.45 TB/s = 7 % of the HBM roofline in ncu); here a thread owns FB vertically adjacent elements, reads each tile
+// column segment once for all of them ((2H+1)(FB+2H) LDS.64 instead of FB (2H+1)^2), keeps the (H+1)^2 distinct weights
+// in registers, and the denominator is the constant sum of all weights except in the frame of H elements along the
+// mesh boundary, where it is summed tap by tap as before.
+template <int H, int FB>
+__global__ void __launch_bounds__(256) k_filter_sq(const __grid_constant__ FilterTaps taps, const double *__restrict__ rho,
+                                                   const double *__restrict__ dc, double *__restrict__ out, int nx, int ny,
+                                                   const double *__restrict__ ghost_lo, const double *__restrict__ ghost_hi) {
+  constexpr int W = 2 * H + 1, TW = FT + 2 * H, TH = 8 * FB + 2 * H;      // block (32, 8): FT columns x 8*FB rows
+  __shared__ double tile[TH * TW];
+  const int x0 = blockIdx.x * FT, y0 = blockIdx.y * (8 * FB);
+  for (int t = threadIdx.y * 32 + threadIdx.x; t < TW * TH; t += 256) {
+    const int ty = t / TW, tx = t - ty * TW;
+    const int gx = x0 + tx - H, gy = y0 + ty - H;
+    double q = 0.0;
+    if (gx >= 0 && gx < nx) {
+      if (gy >= 0 && gy < ny) {
+        const size_t e = (size_t)gy * nx + gx;
+        q = rho[e] * dc[e];
+      } else if (gy < 0 && ghost_lo != nullptr) {
+        q = ghost_lo[(size_t)(gy + H) * nx + gx];
+      } else if (gy >= ny && ghost_hi != nullptr) {
+        q = ghost_hi[(size_t)(gy - ny) * nx + gx];
+      }
+    }
+    tile[t] = q;
+  }
+  // weights by (|dj|, |di|); taps outside the radius carry 0 (the generic kernel skips them: same sums)
+  double w[H + 1][H + 1];
+  double wsum = 0.0;
+#pragma unroll
+  for (int a = 0; a <= H; ++a)
+#pragma unroll
+    for (int b = 0; b <= H; ++b) {
+      const double v = taps.w[(a + H) * W + b + H];
+      w[a][b] = v > 0.0 ? v : 0.0;
+      wsum += w[a][b] * ((a == 0 ? 1.0 : 2.0) * (b == 0 ? 1.0 : 2.0));
+    }
+  __syncthreads();
+  const int gx = x0 + threadIdx.x;
+  const int ly0 = threadIdx.y * FB, gy0 = y0 + ly0;
+  if (gx >= nx || gy0 >= ny) return;
+  double num[FB];
+#pragma unroll
+  for (int k = 0; k < FB; ++k) num[k] = 0.0;
+#pragma unroll
+  for (int di = -H; di <= H; ++di) {
+    double col[FB + 2 * H];
+#pragma unroll
+    for (int i = 0; i < FB + 2 * H; ++i) col[i] = tile[(ly0 + i) * TW + threadIdx.x + H + di];
+#pragma unroll
+    for (int k = 0; k < FB; ++k)
+#pragma unroll
+      for (int dj = -H; dj <= H; ++dj) num[k] = fma(w[dj < 0 ? -dj : dj][di < 0 ? -di : di], col[k + H + dj], num[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < FB; ++k) {
+    const int gy = gy0 + k;
+    if (gy >= ny) break;
+    double den = wsum;
+    const bool lo_open = ghost_lo != nullptr, hi_open = ghost_hi != nullptr;
+    if (gx < H || gx >= nx - H || (gy < H && !lo_open) || (gy >= ny - H && !hi_open)) {     // frame: truncated stencil
+      den = 0.0;
+      for (int dj = -H; dj <= H; ++dj) {
+        const bool rowok = (gy + dj >= 0 || lo_open) && (gy + dj < ny || hi_open);
+        for (int di = -H; di <= H; ++di) {
+          const double v = taps.w[(dj + H) * W + di + H];
+          if (v > 0.0 && rowok && gx + di >= 0 && gx + di < nx) den += v;
+        }
+      }
+    }
+    const size_t e = (size_t)gy * nx + gx;
+    out[e] = num[k] / (den * np_max(0.001, rho[e]));
   }
 }
 
@@ -288,8 +379,7 @@ __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho,
   double v[OC_CAND + 1];                 // [OC_CAND]: contributions common to all candidates (+ NaN contamination)
 #pragma unroll
   for (int j = 0; j <= OC_CAND; ++j) v[j] = 0.0;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
-    const double rh = rho[e], am = amp[e];
+  auto element = [&](double rh, double am) {
     const double cl = fmax(0.0, rh - move), ch = fmin(1.0, rh + move);
     // elements clamped the same way by ALL 15 multipliers of this pass contribute a common constant
     // (exactly: a*t is monotone in t, so the clamp result is identical for every candidate)
@@ -303,7 +393,22 @@ __global__ void __launch_bounds__(ET) k_oc_multi(const double *__restrict__ rho,
 #pragma unroll
       for (int j = 0; j < OC_CAND; ++j) v[j] += fmax(cl, fmin(ch, am * tinv[j])) - rh;
     }
+  };
+  // 16-byte loads, four elements in flight per thread: at 2 CTAs per SM the plain one-element loop kept 8 KB per SM in
+  // flight and ran at 0.9 TB/s (ncu, profiles/r2_stage_kernels.md); the assignment of elements to threads is fixed, so
+  // the sums stay deterministic
+  const int64_t npair = ne >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+  const double2 *rho2 = reinterpret_cast<const double2 *>(rho), *amp2 = reinterpret_cast<const double2 *>(amp);
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; q + stride < npair; q += 2 * stride) {
+    const double2 r0 = __ldg(rho2 + q), a0 = __ldg(amp2 + q), r1 = __ldg(rho2 + q + stride), a1 = __ldg(amp2 + q + stride);
+    element(r0.x, a0.x); element(r0.y, a0.y); element(r1.x, a1.x); element(r1.y, a1.y);
   }
+  if (q < npair) {
+    const double2 r0 = __ldg(rho2 + q), a0 = __ldg(amp2 + q);
+    element(r0.x, a0.x); element(r0.y, a0.y);
+  }
+  if ((ne & 1) && blockIdx.x == 0 && threadIdx.x == 0) element(rho[ne - 1], amp[ne - 1]);
   if (grid_reduce<OC_CAND + 1>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) {
     if (probe_base > 0.0) oc_decide_probe(oc, v, margin, probe_base);
     else oc_decide_multi(oc, v, margin);
@@ -343,6 +448,30 @@ __global__ void __launch_bounds__(ET) k_oc_apply(const double *__restrict__ rho,
   if (grid_reduce<1, true>(v, partials, ticket, out) && threadIdx.x == 0 && !defer) oc->change = v[0];
 }
 
+// single-GPU path: the two kernels above in one pass (rho_new, the sum for gt and the max for change share the candidate)
+__global__ void __launch_bounds__(ET) k_oc_finish(const double *__restrict__ rho, const double *__restrict__ dc,
+                                                  double *__restrict__ rho_new, int64_t ne, double move, double *partials,
+                                                  unsigned int *ticket, double *out, OcState *oc) {
+  const double lmid = oc->lmid;
+  const int steps = oc->steps;
+  double sum = 0.0, mx = 0.0;                  // sum(rho_new - rho) for gt, max|rho_new - rho| for change
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const double rh = rho[e];
+    const double cand = steps > 0 ? oc_candidate(rh, dc[e], lmid, move) : 0.0;
+    rho_new[e] = cand;                         // zero bisection steps: the reference returns its zero-initialised rho_new
+    sum += cand - rh;
+    const double d = fabs(cand - rh);
+    mx = (d > mx || d != d) ? d : mx;
+  }
+  // two reductions with different operators: the sum first, then the max through the same deterministic machinery
+  double s[1] = {sum};
+  const bool last_sum = grid_reduce<1>(s, partials, ticket, out);
+  if (last_sum && threadIdx.x == 0 && steps > 0) oc->gt = oc->g + s[0];
+  double m[1] = {mx};
+  const bool last_max = grid_reduce<1, true>(m, partials + TOPO_MAX_PARTIAL_BLOCKS, ticket + 1, out + 1);
+  if (last_max && threadIdx.x == 0) oc->change = m[0];
+}
+
 // row-slab mode: decisions from the all-reduced sums in red[]
 __global__ void k_oc_decide(OcState *oc, const double *red, double margin, int kind, double probe_base) {
   if (kind == 0 || kind == 4) {        // fast pass / probe pass (16 sums)
@@ -376,8 +505,19 @@ extern "C" int topo_simp_scale(topo_t *h, double penal, double emin, double emax
 extern "C" int topo_simp_sensitivity(topo_t *h, double penal, double emin, double emax, double *objective) {
   if (!h) return TOPO_EINVAL;
   CUDA_TRY(cudaSetDevice(h->device));
-  KL(h, "k_simp_sens", k_simp_sens<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->ke_factor, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, penal, emin,
-                                                      emax, h->partials, h->ticket, h->red_out));
+  {
+    int rank = 0;                                // rows of the pivoted Cholesky factor (zero rows beyond the rank)
+    for (int k = 0; k < 8; ++k) {
+      bool nz = false;
+      for (int i = 0; i < 8; ++i) nz = nz || h->ke_factor.k[8 * k + i] != 0.0;
+      if (nz) rank = k + 1;
+    }
+    const int bx = div_up(h->nx, ET);
+    const int rows = std::max(8, div_up(h->ny, std::max(1, 4096 / bx)));
+    dim3 grid(bx, div_up(h->ny, rows));
+    KL(h, "k_simp_sens", k_simp_sens_march<<<grid, ET, 0, h->stream>>>(h->ke_factor, rank, h->u, h->rho, h->scale, h->dc, h->nx, h->ny, rows,
+                                                                        penal, emin, emax, h->partials, h->ticket, h->red_out));
+  }
   CUDA_TRY(cudaGetLastError());
   if (objective) {
     CUDA_TRY(cudaMemcpyAsync(objective, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -412,7 +552,16 @@ extern "C" int topo_filter_sensitivity(topo_t *h, double rmin, double dx, double
     glo = h->dist.has_lo ? h->dist.filt_recv_lo : nullptr;
     ghi = h->dist.has_hi ? h->dist.filt_recv_hi : nullptr;
   }
-  KL(h, "k_filter", k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
+  constexpr int FB = 4;
+  dim3 gsq(div_up(h->nx, FT), div_up(h->ny, 8 * FB));
+  if (taps.hx == taps.hy && taps.hx == 3)
+    KL(h, "k_filter", k_filter_sq<3, FB><<<gsq, block, 0, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
+  else if (taps.hx == taps.hy && taps.hx == 2)
+    KL(h, "k_filter", k_filter_sq<2, FB><<<gsq, block, 0, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
+  else if (taps.hx == taps.hy && taps.hx == 1)
+    KL(h, "k_filter", k_filter_sq<1, FB><<<gsq, block, 0, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
+  else
+    KL(h, "k_filter", k_filter<<<grid, block, smem, h->stream>>>(taps, h->rho, h->dc, h->dc2, h->nx, h->ny, glo, ghi));
   CUDA_TRY(cudaGetLastError());
   std::swap(h->dc, h->dc2);
   return TOPO_OK;
@@ -486,10 +635,8 @@ extern "C" int topo_oc_update(topo_t *h, double move, double *g, double *change,
     CUDA_TRY(cudaStreamSynchronize(st));
     if (hs->done) break;
   }
-  KL(h, "k_oc_final_gt", k_oc_final_gt<<<nb, ET, 0, st>>>(h->rho, h->dc, h->ne, move, h->partials, h->ticket,
-                                                          h->red_out, h->oc, 0));
-  KL(h, "k_oc_apply", k_oc_apply<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket,
-                                                    h->red_out, h->oc, 0));
+  KL(h, "k_oc_finish", k_oc_finish<<<nb, ET, 0, st>>>(h->rho, h->dc, h->rho_new, h->ne, move, h->partials, h->ticket,
+                                                      h->red_out, h->oc));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(hs, h->oc, sizeof(OcState), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(h->ev1, st));
