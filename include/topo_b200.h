@@ -148,6 +148,9 @@ int topo_beso_filter(topo_t *h, const double w4[4], const double w2x[2], const d
  * sens  <- sensitivity_filter(nodal) (solver.py:212-243, including its division by the max). */
 int topo_beso_nodes(topo_t *h, const double w4[4], const double w2x[2], const double w2y[2]);
 int topo_beso_elements(topo_t *h, const double we[4]);
+/* sensitivity_filter for ANY r_min (solver.py:212-243): the nodes within r_min of an element centre, cut off at the mesh
+ * boundary, weighted (1 - r/sum r)/(count - 1) and normalised, then divided by the max; dx, dy: element size. */
+int topo_beso_elements_radius(topo_t *h, double r_min, double dx, double dy);
 /* alpha = sort(sens)[::-1][k] over ALL N_e values (optimize.py:323-325): device radix select. */
 int topo_rank_select(topo_t *h, int64_t k, double *alpha);
 /* BESO: keep = sens > alpha; keep |= protect_els(removed) ; del_node  (optimize.py:328-331,
@@ -157,6 +160,11 @@ int topo_beso_apply(topo_t *h, double alpha, const int64_t *protect_nodes, int n
 /* ESO: delete present elements with sens < rr unless protected; scale_e <- 0, keep_e <- 0;
  * del_nodeESO (optimize.py:189-196, solver.py:318-362). */
 int topo_eso_apply(topo_t *h, double rr, const int64_t *protect_nodes, int n_protect, int64_t *n_kept);
+/* Number of present elements (keep = 1) that no chain of node-sharing present elements connects to an element touching
+ * one of `support_nodes`: a floating part.  That is what turns the reference's stiffness matrix singular once ESO has
+ * cut a piece loose (spsolve at optimize.py:84,181 fills the solution with NaN when SuperLU meets an exactly zero pivot,
+ * the guard :72,:172 then ends the loop); the host loop uses it for its `stop_on_island` option. */
+int topo_floating_elements(topo_t *h, const int64_t *support_nodes, int n_support, int64_t *n_floating);
 /* sens_prev <- sens (optimize.py:344) */
 int topo_beso_save_history(topo_t *h);
 /* ESO_stress criterion: nodal stress averaging over present elements + element average + von Mises,

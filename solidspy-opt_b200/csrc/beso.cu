@@ -101,6 +101,52 @@ __global__ void __launch_bounds__(ET) k_beso_els(const __grid_constant__ BesoW W
   grid_reduce<1, true>(v, partials, ticket, out);
 }
 
+// sensitivity_filter (solver.py:212-243) for ANY radius: the nodes within r_min of an element centre are a fixed set of
+// offsets on the uniform grid, cut off at the mesh boundary.  Per element, over the offsets that exist:
+//   m = count, R = sum r, w = (1 - r/R)/(m - 1), out = sum(w s)/sum(w)        (the reference's expressions, :236-238)
+constexpr int BR_MAX = 9;              // node offsets -BR_MAX+1 .. BR_MAX around the element's lower-left node
+struct BesoTaps {
+  int lo, hi;                          // offsets lo..hi in both directions
+  double r[2 * BR_MAX][2 * BR_MAX];    // distance node (dj, di) -> element centre; < 0: outside the radius
+};
+__global__ void __launch_bounds__(ET) k_beso_els_radius(const __grid_constant__ BesoTaps T, const double *__restrict__ nodal,
+                                                        double *__restrict__ s, int nx, int ny, double *partials,
+                                                        unsigned int *ticket, double *out) {
+  const int64_t ne = (int64_t)nx * ny;
+  const int npr = nx + 1;
+  double v[1] = {-1.0 / 0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / nx), c = (int)(e - (int64_t)r * nx);
+    int m = 0;
+    double R = 0.0;
+    for (int dj = T.lo; dj <= T.hi; ++dj) {
+      if (r + dj < 0 || r + dj > ny) continue;
+      for (int di = T.lo; di <= T.hi; ++di) {
+        const double d = T.r[dj - T.lo][di - T.lo];
+        if (d < 0.0 || c + di < 0 || c + di > nx) continue;
+        ++m;
+        R += d;
+      }
+    }
+    const double f = 1.0 / (double)(m - 1);
+    double num = 0.0, den = 0.0;
+    for (int dj = T.lo; dj <= T.hi; ++dj) {
+      if (r + dj < 0 || r + dj > ny) continue;
+      for (int di = T.lo; di <= T.hi; ++di) {
+        const double d = T.r[dj - T.lo][di - T.lo];
+        if (d < 0.0 || c + di < 0 || c + di > nx) continue;
+        const double w = f * (1.0 - d / R);
+        num = fma(w, nodal[(size_t)(r + dj) * npr + (c + di)], num);
+        den += w;
+      }
+    }
+    const double val = num / den;
+    s[e] = val;
+    v[0] = fmax(v[0], val);
+  }
+  grid_reduce<1, true>(v, partials, ticket, out);
+}
+
 // s <- s / max1 ; if avg: s <- (s + prev)/2 ; reduce max of the result
 __global__ void __launch_bounds__(ET) k_beso_hist(double *__restrict__ s, const double *__restrict__ prev,
                                                   const double *__restrict__ max1, int avg, int64_t ne,
@@ -323,6 +369,63 @@ __global__ void __launch_bounds__(ET) k_vonmises(const double *__restrict__ sn, 
   grid_reduce<1, true>(v, partials, ticket, out);
 }
 
+// ---- floating parts: present elements that no chain of node-sharing present elements ties to a support ----------------
+// (what makes the reference's direct solve singular once ESO has cut a piece loose: optimize.py:84 / :181 + the guard
+// :72 / :172).  Flood fill over the element grid: seeds = present elements touching a support node; a tile of 32 x 32
+// elements is iterated to its local fixed point in shared memory, the host repeats the pass until no tile changed.
+constexpr int IT = 32;
+__global__ void __launch_bounds__(ET) k_island_seed(const uint8_t *__restrict__ keep, const uint8_t *__restrict__ support,
+                                                    uint8_t *__restrict__ reach, int nx, int ny) {
+  const int64_t ne = (int64_t)nx * ny;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / nx), c = (int)(e - (int64_t)r * nx);
+    reach[e] = (keep[e] && touches(support, r, c, nx + 1)) ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(IT * 8) k_island_sweep(const uint8_t *__restrict__ keep, uint8_t *__restrict__ reach, int nx,
+                                                         int ny, int *changed) {
+  __shared__ uint8_t k[IT + 2][IT + 2], m[IT + 2][IT + 2];
+  __shared__ int s_any;
+  const int x0 = blockIdx.x * IT, y0 = blockIdx.y * IT;
+  for (int t = threadIdx.y * IT + threadIdx.x; t < (IT + 2) * (IT + 2); t += IT * 8) {
+    const int ty = t / (IT + 2), tx = t - ty * (IT + 2);
+    const int gx = x0 + tx - 1, gy = y0 + ty - 1;
+    const bool in = gx >= 0 && gx < nx && gy >= 0 && gy < ny;
+    k[ty][tx] = in ? keep[(size_t)gy * nx + gx] : 0;
+    m[ty][tx] = in ? reach[(size_t)gy * nx + gx] : 0;
+  }
+  bool mine = false;
+  for (int sweep = 0; sweep < 2 * IT; ++sweep) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_any = 0;
+    __syncthreads();
+    bool got = false;
+    for (int ly = threadIdx.y; ly < IT; ly += 8) {
+      const int ty = ly + 1, tx = threadIdx.x + 1;
+      if (k[ty][tx] && !m[ty][tx]) {
+        const int nb = m[ty - 1][tx - 1] | m[ty - 1][tx] | m[ty - 1][tx + 1] | m[ty][tx - 1] | m[ty][tx + 1] | m[ty + 1][tx - 1] |
+                       m[ty + 1][tx] | m[ty + 1][tx + 1];
+        if (nb) { m[ty][tx] = 1; got = true; }           // (a neighbour set in this very sweep only speeds the fill up)
+      }
+    }
+    if (got) { s_any = 1; mine = true; }
+    __syncthreads();
+    if (!s_any) break;
+  }
+  for (int ly = threadIdx.y; ly < IT; ly += 8) {
+    const int gx = x0 + threadIdx.x, gy = y0 + ly;
+    if (gx < nx && gy < ny && m[ly + 1][threadIdx.x + 1]) reach[(size_t)gy * nx + gx] = 1;
+  }
+  if (mine) *changed = 1;
+}
+__global__ void __launch_bounds__(ET) k_island_count(const uint8_t *__restrict__ keep, const uint8_t *__restrict__ reach, int64_t ne,
+                                                     double *partials, unsigned int *ticket, double *out) {
+  double v[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x)
+    v[0] += (keep[e] && !reach[e]) ? 1.0 : 0.0;
+  grid_reduce<1>(v, partials, ticket, out);
+}
+
 int build_prot(topo_handle *h, const int64_t *protect_nodes, int n_protect, uint8_t **prot_out) {
   // protection bitmap lives in the first nn bytes of h->nodal's tail buffer (h->tmp reinterpret)
   uint8_t *prot = reinterpret_cast<uint8_t *>(h->tmp2);
@@ -402,6 +505,35 @@ extern "C" int topo_beso_elements(topo_t *h, const double we[4]) {
   return TOPO_OK;
 }
 
+extern "C" int topo_beso_elements_radius(topo_t *h, double r_min, double dx, double dy) {
+  if (!h || !(r_min > 0.0) || !(dx > 0.0) || !(dy > 0.0)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  BesoTaps T;
+  T.lo = -BR_MAX + 1;
+  T.hi = BR_MAX;
+  bool edge_hit = false;
+  int count = 0;
+  for (int dj = T.lo; dj <= T.hi; ++dj)
+    for (int di = T.lo; di <= T.hi; ++di) {
+      const double x = (di - 0.5) * dx, y = (dj - 0.5) * dy;
+      const double d = std::sqrt(x * x + y * y);
+      const bool in = d < r_min;
+      T.r[dj - T.lo][di - T.lo] = in ? d : -1.0;
+      count += in ? 1 : 0;
+      if (in && (dj == T.lo || dj == T.hi || di == T.lo || di == T.hi)) edge_hit = true;
+    }
+  if (edge_hit || count < 2) {
+    topo_set_error("topo_beso_elements_radius: radius %.3g must cover at least 2 nodes and at most %d node columns/rows", r_min,
+                   2 * BR_MAX - 2);
+    return TOPO_EINVAL;
+  }
+  KL(h, "k_beso_els_radius", k_beso_els_radius<<<el_blocks(h->ne), ET, 0, h->stream>>>(T, h->nodal, h->sens, h->nx, h->ny, h->partials,
+                                                                                       h->ticket, h->red_out));
+  KL(h, "k_div_scalar", k_div_scalar<<<el_blocks(h->ne), ET, 0, h->stream>>>(h->sens, h->red_out, h->ne));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
 extern "C" int topo_rank_select(topo_t *h, int64_t k, double *alpha) {
   if (!h || !alpha || k < 0 || k >= h->ne) {
     topo_set_error("topo_rank_select: rank %lld outside [0, %lld)", (long long)k, h ? (long long)h->ne : 0ll);
@@ -463,6 +595,34 @@ extern "C" int topo_eso_apply(topo_t *h, double rr, const int64_t *protect_nodes
   CUDA_TRY(cudaStreamSynchronize(st));
   if (n_kept) *n_kept = (int64_t)cnt;
   return after_cons_change(h);
+}
+
+extern "C" int topo_floating_elements(topo_t *h, const int64_t *support_nodes, int n_support, int64_t *n_floating) {
+  if (!h || !n_floating || (n_support > 0 && !support_nodes)) return TOPO_EINVAL;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  uint8_t *support = nullptr;
+  TOPO_TRY(build_prot(h, support_nodes, n_support, &support));        // node bitmap in tmp2
+  uint8_t *reach = reinterpret_cast<uint8_t *>(h->rho_new);           // scratch: nobody reads rho_new between calls
+  int *changed = reinterpret_cast<int *>(h->red_out + 8);
+  KL(h, "k_island_seed", k_island_seed<<<el_blocks(h->ne), ET, 0, st>>>(h->keep, support, reach, h->nx, h->ny));
+  dim3 grid(div_up(h->nx, IT), div_up(h->ny, IT)), block(IT, 8);
+  const int max_pass = 4 * (div_up(h->nx, IT) + div_up(h->ny, IT)) + 8;   // a path can wind, but every pass advances >= one tile
+  for (int pass = 0; pass < max_pass * 8; ++pass) {
+    CUDA_TRY(cudaMemsetAsync(changed, 0, sizeof(int), st));
+    KL(h, "k_island_sweep", k_island_sweep<<<grid, block, 0, st>>>(h->keep, reach, h->nx, h->ny, changed));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!flag) break;
+  }
+  KL(h, "k_island_count", k_island_count<<<el_blocks(h->ne), ET, 0, st>>>(h->keep, reach, h->ne, h->partials, h->ticket, h->red_out));
+  CUDA_TRY(cudaGetLastError());
+  double cnt = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *n_floating = (int64_t)cnt;
+  return TOPO_OK;
 }
 
 extern "C" int topo_beso_save_history(topo_t *h) {

@@ -60,6 +60,15 @@ __global__ void k_fixed_to_cons(const uint8_t *fixed, int8_t *cons, int64_t nn) 
 
 inline int nblk(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 8); }
 
+// warm start by extrapolation along the design trajectory: u <- u + theta (u - u_prev), u_prev <- u (have = 0: copy only)
+__global__ void k_extrapolate(double2 *__restrict__ u, double2 *__restrict__ up, int64_t nn, double theta, int have) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 a = u[n], b = up[n];
+    up[n] = a;
+    if (have) u[n] = make_double2(fma(theta, a.x - b.x, a.x), fma(theta, a.y - b.y, a.y));
+  }
+}
+
 struct FieldRef {
   void *ptr;
   size_t bytes;
@@ -174,6 +183,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
     k.coarsest_nodes = (int)env_i("TOPO_COARSEST_NODES", 48);
     k.no_l2persist = getenv("TOPO_NO_L2PERSIST") ? 1 : 0;
     k.tail_kind = (int)env_i("TOPO_TAIL_KIND", 2);
+    k.extrap = getenv("TOPO_EXTRAP") ? atof(getenv("TOPO_EXTRAP")) : 0.0;
   }
   h->omega = getenv("TOPO_OMEGA") ? atof(getenv("TOPO_OMEGA")) : 0.7;
   h->nu_pre = 1;
@@ -183,6 +193,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   h->nu_tail_small = getenv("TOPO_NU_TAIL_SMALL") ? atoi(getenv("TOPO_NU_TAIL_SMALL")) : 12;
   h->tail_max_nodes = getenv("TOPO_TAIL_MAX") ? atoi(getenv("TOPO_TAIL_MAX")) : 10000;
   h->tail_dbg = nullptr;
+  h->u_prev = nullptr;
+  h->u_prev_valid = false;
   h->tail2_cache = nullptr;
   h->tail2_cache_tail = -1;
   h->use_graph = getenv("TOPO_NO_GRAPH") ? false : true;
@@ -272,6 +284,7 @@ extern "C" int topo_destroy(topo_t *h) {
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   cudaFree(h->nodal);
   cudaFree(h->dinv_f);
+  cudaFree(h->u_prev);
   cudaFree(h->fixed);
   cudaFree(h->keep);
   cudaFree(h->partials);
@@ -434,6 +447,11 @@ extern "C" int topo_simp_step(topo_t *h, const topo_simp_params *p, double *g_in
   CUDA_TRY(cudaEventRecord(h->evs[1], st));
   // the multigrid attempt is capped; a stalled solve restarts from its last iterate with the Jacobi preconditioner
   // (converges on any SPD system) -- a safety net: SIMP designs keep Emin > 0 and have not needed it in any run
+  if (h->knobs.extrap != 0.0 && p->warm) {
+    if (!h->u_prev) CUDA_TRY(cudaMalloc(&h->u_prev, sizeof(double2) * (size_t)h->nn));
+    KL(h, "k_extrapolate", k_extrapolate<<<nblk(h->nn), 256, 0, st>>>(h->u, h->u_prev, h->nn, h->knobs.extrap, h->u_prev_valid ? 1 : 0));
+    h->u_prev_valid = true;
+  }
   const int gmg_cap = 4000;
   const bool gmg = p->precond == TOPO_PRECOND_GMG;
   int s = topo_solve(h, p->precond, p->rtol, gmg ? std::min(p->maxit, gmg_cap) : p->maxit, p->warm, &res->cg_iters, &res->relres);

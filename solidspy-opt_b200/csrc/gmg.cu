@@ -98,6 +98,194 @@ __global__ void __launch_bounds__(128) k_cells_level1(const __grid_constant__ Ke
   for (int k = 0; k < 64; ++k) cell[(size_t)k * ncell + t] = acc[k];
 }
 
+// ---- level 1 and level 2 WITHOUT the level-1 cell array --------------------------------------------------------
+// k_cells_level1 writes 64 doubles per level-1 cell (268 MB on 2048x1024, 4.3 GB on 8192x4096) that are read exactly
+// twice: by the level-1 stencil gather and by the level-2 coarsening.  The two kernels below produce those two results
+// straight from the element scales, evaluating each level-1 cell entry they need with the SAME fma chain over the
+// cell's children (so stencils and level-2 cells are bit-identical to the two-step path): 0.45 -> 0.1 ms of the
+// multigrid set-up per design iteration, and the array is no longer allocated.
+// entry (i, j) of (m o P_v)^T ke (m o P_v) (the rare children that touch constrained DOFs)
+__device__ __noinline__ double masked_entry(const KeParam &ke, int v, unsigned freebits, int i, int j) {
+  const int A = i >> 1, d = i & 1, B = j >> 1, e = j & 1;
+  double t = 0.0;
+  for (int a = 0; a < 4; ++a) {
+    const double wa = c_pw.w[v][a][A];
+    if (wa == 0.0 || !((freebits >> (2 * a + d)) & 1u)) continue;
+    for (int b = 0; b < 4; ++b) {
+      const double wb = c_pw.w[v][b][B];
+      if (wb == 0.0 || !((freebits >> (2 * b + e)) & 1u)) continue;
+      t = fma(wa * wb, ke.k[(2 * a + d) * 8 + 2 * b + e], t);
+    }
+  }
+  return t;
+}
+// NE entries of level-1 cell (I, J), entry q at matrix index idx(q): acc[q] = sum over the cell's children in
+// (cy, cx) order, exactly as k_cells_level1 accumulates them
+// scales and constraint bits of the (up to) four children of level-1 cell (I, J): ALL loads are issued before anything
+// depends on them (with the loads inside the child loop a thread paid one L2 round trip per child, 140 us per launch)
+struct L1Children {
+  double s[4];          // child (cy, cx) at 2*cy + cx; 0 where the child does not exist
+  unsigned fb[4];       // fixed bits of its 8 DOFs (0xff: skip -- missing child or fully constrained)
+  int v[4];             // interpolation variant
+  bool full;            // 2 x 2 children: variant of child c is 3*(c>>1) + (c&1), a compile-time constant-bank address
+};
+__device__ __forceinline__ void level1_load(const double *__restrict__ scale, const uint8_t *__restrict__ fixed, int nxf,
+                                            int nyf, int I, int J, bool cell_ok, L1Children &ch) {
+  const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
+  ch.full = (sx == 2 && sy == 2);
+  unsigned f[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const bool ok = cell_ok && i <= sx && j <= sy;
+      f[j][i] = ok ? (unsigned)__ldg(fixed + (size_t)(2 * J + j) * (nxf + 1) + (2 * I + i)) : 3u;
+    }
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) {
+      const bool ok = cell_ok && cx < sx && cy < sy;
+      ch.s[2 * cy + cx] = ok ? __ldg(scale + (size_t)(2 * J + cy) * nxf + (2 * I + cx)) : 0.0;
+      ch.fb[2 * cy + cx] = ok ? ((f[cy][cx] & 3u) | ((f[cy][cx + 1] & 3u) << 2) | ((f[cy + 1][cx + 1] & 3u) << 4) |
+                                 ((f[cy + 1][cx] & 3u) << 6)) : 0xffu;
+      ch.v[2 * cy + cx] = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
+    }
+}
+// NE entries of a level-1 cell, entry q at matrix index idx(q): acc[q] = sum over the cell's children in (cy, cx)
+// order, exactly as k_cells_level1 accumulates them
+template <int NE, class Idx>
+__device__ __forceinline__ void level1_entries(const KeParam &ke, const L1Children &ch, Idx idx, double (&acc)[NE]) {
+#pragma unroll
+  for (int q = 0; q < NE; ++q) acc[q] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double s = ch.s[c];
+    const unsigned fixedbits = ch.fb[c];
+    const int v = ch.v[c];
+    if (fixedbits == 0u) {
+      // (a run-time variant index makes every coefficient an indexed constant load: 256 per thread, the whole cost of
+      // the first version; cells with all four children address the table at compile time)
+      if (ch.full) {
+#pragma unroll
+        for (int q = 0; q < NE; ++q) acc[q] = fma(s, c_g.g[3 * (c >> 1) + (c & 1)][idx(q)], acc[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NE; ++q) acc[q] = fma(s, c_g.g[v][idx(q)], acc[q]);
+      }
+    } else if (fixedbits != 0xffu) {
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {                   // (unrolled: a dynamic index would move acc[] to local memory)
+        const int k = idx(q);
+        acc[q] += s * masked_entry(ke, v, (~fixedbits) & 0xffu, k >> 3, k & 7);
+      }
+    }
+  }
+}
+
+// level-1 node stencil (and D^-1) from the element scales: per adjacent cell the two matrix rows of this node
+__global__ void __launch_bounds__(128) k_stencil_level1(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
+                                                        const uint8_t *__restrict__ fixed, stencil_t *__restrict__ st,
+                                                        double2 *__restrict__ dinv, int nxf, int nyf, int nx, int ny) {
+  const int npr = nx + 1;
+  const int64_t nn = (int64_t)npr * (ny + 1);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
+  double s[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) s[k] = 0.0;
+  const int cro[4] = {0, 0, -1, -1}, cco[4] = {0, -1, -1, 0};
+  L1Children ch[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cr = r + cro[q], cc = c + cco[q];
+    level1_load(scale, fixed, nxf, nyf, cc, cr, !(cr < 0 || cr >= ny || cc < 0 || cc >= nx), ch[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cr = r + cro[q], cc = c + cco[q];
+    if (cr < 0 || cr >= ny || cc < 0 || cc >= nx) continue;
+    const int a = q;                                     // local index of this node in that cell
+    double part[16];                                     // rows 2a, 2a+1 of the cell matrix
+    level1_entries<16>(ke, ch[q], [a](int t) { return (2 * a + (t >> 3)) * 8 + (t & 7); }, part);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int dr = cr + ly(b) - r, dc = cc + lx(b) - c;
+      const int nb = 3 * (dr + 1) + (dc + 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) s[4 * nb + 2 * i + j] += part[i * 8 + 2 * b + j];
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < 9; ++nb)
+    reinterpret_cast<float4 *>(st)[(size_t)nb * nn + n] =
+        make_float4((float)s[4 * nb], (float)s[4 * nb + 1], (float)s[4 * nb + 2], (float)s[4 * nb + 3]);
+  const double dx = (double)(stencil_t)s[4 * 4 + 0], dy = (double)(stencil_t)s[4 * 4 + 3];
+  dinv[n] = make_double2(dx > 0.0 ? 1.0 / dx : 0.0, dy > 0.0 ? 1.0 / dy : 0.0);
+}
+
+// level-2 cells from the element scales: k_cells_coarsen with the child (level-1) cell entries computed on the fly
+__global__ void __launch_bounds__(128) k_cells_level2(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
+                                                      const uint8_t *__restrict__ fixed, double *__restrict__ ccell, int nx0,
+                                                      int ny0, int nxf, int nyf, int nxc, int nyc) {
+  const int64_t ncc = (int64_t)nxc * nyc;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncc) return;
+  const int d = blockIdx.y >> 1, e = blockIdx.y & 1;
+  const int J = (int)(t / nxc), I = (int)(t - (int64_t)J * nxc);
+  const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
+  double acc[4][4];
+#pragma unroll
+  for (int A = 0; A < 4; ++A)
+#pragma unroll
+    for (int B = 0; B < 4; ++B) acc[A][B] = 0.0;
+  L1Children ch[4];
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) level1_load(scale, fixed, nx0, ny0, 2 * I + cx, 2 * J + cy, cx < sx && cy < sy, ch[2 * cy + cx]);
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) {
+      if (cx >= sx || cy >= sy) continue;
+      const int v = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
+      double m16[16];                                    // M[a][b] = child cell entry (2a+d, 2b+e)
+      level1_entries<16>(ke, ch[2 * cy + cx], [d, e](int q) { return (2 * (q >> 2) + d) * 8 + 2 * (q & 3) + e; }, m16);
+      double W[4][4], T[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int A = 0; A < 4; ++A) W[a][A] = c_pw.w[v][a][A];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int B = 0; B < 4; ++B) {
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s = fma(m16[4 * a + b], W[b][B], s);
+          T[a][B] = s;
+        }
+#pragma unroll
+      for (int A = 0; A < 4; ++A)
+#pragma unroll
+        for (int B = 0; B < 4; ++B) {
+          double s = acc[A][B];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) s = fma(W[a][A], T[a][B], s);
+          acc[A][B] = s;
+        }
+    }
+  }
+#pragma unroll
+  for (int A = 0; A < 4; ++A)
+#pragma unroll
+    for (int B = 0; B < 4; ++B) ccell[(size_t)((2 * A + d) * 8 + 2 * B + e) * ncc + t] = acc[A][B];
+}
+
 // ---- generic Galerkin coarsening of cell matrices ---------------------------------------------------
 // K_C = sum_children P^T K_c P.  P couples equal displacement components only, so for each component pair
 // (d,e) the 4x4 node block M_c[a][b] = K_c[2a+d][2b+e] transforms independently: K_C^{de} += W^T M_c W with
@@ -308,7 +496,9 @@ int topo_gmg_plan(topo_handle *h) {
     L.ny = h->lvl_ny[l];
     L.nn = (L.nx + 1) * (L.ny + 1);
     L.ncell = L.nx * L.ny;
-    CUDA_TRY(cudaMalloc(&L.cell, sizeof(double) * 64 * (size_t)L.ncell));
+    // level-1 cells are never stored (k_stencil_level1 / k_cells_level2 work from the element scales)
+    // (row-slab mode with K == 1: level 1 is the first global level and its gathered cells live here)
+    if (l >= 2 || (h->dist.on && h->dist.K == 1)) CUDA_TRY(cudaMalloc(&L.cell, sizeof(double) * 64 * (size_t)L.ncell));
   }
   // Per-cycle data of the levels: level 1 gets its own allocation; levels >= 2 (and the coarsest dense
   // inverse) share ONE slab so that a single L2 persisting access-policy window can cover them -- the
@@ -450,11 +640,12 @@ int topo_gmg_setup(topo_handle *h) {
   }
   cudaStream_t st = h->stream;
   TOPO_TRY(upload_gtable(h));
-  {
-    GmgLevel &L = h->levels[1];
-    KL(h, "k_cells_level1", k_cells_level1<<<blocks_for(L.ncell), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.cell, h->nx, h->ny, L.nx, L.ny));
+  if (h->n_levels > 2) {
+    GmgLevel &F = h->levels[1], &C = h->levels[2];
+    dim3 grid(blocks_for(C.ncell), 4);
+    KL(h, "k_cells_level2", k_cells_level2<<<grid, 128, 0, st>>>(h->ke, h->scale, h->fixed, C.cell, h->nx, h->ny, F.nx, F.ny, C.nx, C.ny));
   }
-  for (int l = 2; l < h->n_levels; ++l) {
+  for (int l = 3; l < h->n_levels; ++l) {
     GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
     dim3 grid(blocks_for(C.ncell), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
@@ -462,7 +653,8 @@ int topo_gmg_setup(topo_handle *h) {
   // coarsest level first: its dense inverse (side stream) then overlaps the stencils of the other levels
   for (int l = h->n_levels - 1; l >= 1; --l) {
     GmgLevel &L = h->levels[l];
-    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+    if (l == 1) KL(h, "k_stencil_level1", k_stencil_level1<<<blocks_for(L.nn), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.st, L.dinv, h->nx, h->ny, L.nx, L.ny));
+    else KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
     if (l == h->n_levels - 1) TOPO_TRY(invert_coarsest(h));
   }
   h->gmg_valid = true;
@@ -512,19 +704,24 @@ int topo_dist_setup_local(topo_handle *h) {
   const int K = D.K;
   auto local_cells = [&](int l) -> double * { return l == K ? D.cellK_send : h->levels[l].cell; };
   auto local_ny = [&](int l) { return h->ny >> l; };
-  {
+  if (K == 1) {                                   // the level-1 cells ARE the gathered block
     const int nxc = h->lvl_nx[1], nyc = local_ny(1);
     KL(h, "k_cells_level1", k_cells_level1<<<blocks_for((int64_t)nxc * nyc), 128, 0, st>>>(h->ke, h->scale, h->fixed, local_cells(1), h->nx, h->ny,
                                                                                             nxc, nyc));
+  } else {
+    const int nxf = h->lvl_nx[1], nyf = local_ny(1), nxc = h->lvl_nx[2], nyc = local_ny(2);
+    dim3 grid(blocks_for((int64_t)nxc * nyc), 4);
+    KL(h, "k_cells_level2", k_cells_level2<<<grid, 128, 0, st>>>(h->ke, h->scale, h->fixed, local_cells(2), h->nx, h->ny, nxf, nyf, nxc, nyc));
   }
-  for (int l = 2; l <= K; ++l) {
+  for (int l = 3; l <= K; ++l) {
     const int nxf = h->lvl_nx[l - 1], nyf = local_ny(l - 1), nxc = h->lvl_nx[l], nyc = local_ny(l);
     dim3 grid(blocks_for((int64_t)nxc * nyc), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(local_cells(l - 1), local_cells(l), nxf, nyf, nxc, nyc));
   }
   for (int l = 1; l < K; ++l) {
     GmgLevel &L = h->levels[l];
-    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+    if (l == 1) KL(h, "k_stencil_level1", k_stencil_level1<<<blocks_for(L.nn), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.st, L.dinv, h->nx, h->ny, L.nx, L.ny));
+    else KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
   }
   long long off = 0;
   for (int l = 0; l < K; ++l) {

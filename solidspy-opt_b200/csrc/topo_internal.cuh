@@ -142,6 +142,7 @@ struct TopoKnobs {
   int oc_no_probe;          // TOPO_OC_NO_PROBE
   int coarsest_nodes;       // TOPO_COARSEST_NODES  first level solved densely (48)
   int no_l2persist;         // TOPO_NO_L2PERSIST
+  double extrap;            // TOPO_EXTRAP          initial guess of a warm solve: u + extrap*(u - u_previous_design) (0: off)
   int tail_kind;            // TOPO_TAIL_KIND       2: shared-memory tail k_tail2 where its plan fits (default), 0: generic k_tail
 };
 
@@ -162,6 +163,8 @@ struct topo_handle {
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
+  double2 *u_prev;     // displacements of the previous design iteration (allocated on first use; TOPO_EXTRAP)
+  bool u_prev_valid;
   float2 *dinv_f;      // fp32 copy of dinv for the fused multigrid-PCG passes (tmp = res and tmp2 = x^ hold float2 there)
   double *rho, *rho_new, *dc, *dc2, *scale, *sens, *sens_prev, *nodal;
   uint8_t *fixed, *keep;

@@ -189,7 +189,7 @@ def beso_weights(nodes, els, nx, ny, r_min):
     r = np.linalg.norm(nodes[cand, 1:3] - c0, axis=1)
     om = r < r_min
     if not np.array_equal(cand[om], np.sort(els[0, -4:])):
-        raise NotImplementedError("BESO filter radius must select exactly the 4 corner nodes of an element")
+        return w4, w2x, w2y, None                 # a wider (or narrower) radius: no 4-corner weights, see sensitivity_filter
     we = 1/(om.sum() - 1)*(1 - r[om]/r[om].sum())
     return w4, w2x, w2y, we
 
@@ -335,12 +335,17 @@ def sensitivity_nodes(nodes, adj_nodes, centers, sensi_els):
 
 
 def sensitivity_filter(nodes, centers, sensi_nodes, r_min):
-    """Reference signature (:212-243) for radii that select the 4 corner nodes of each element
-    (device kernel)."""
+    """Reference signature (:212-243), any ``r_min`` (device kernels).  The radius the optimisers use (one element
+    width, optimize.py:264: exactly the 4 corner nodes) runs the kernel whose operation order reproduces the reference
+    bit for bit; other radii run the general stencil (nodes within ``r_min`` of the element centre, cut off at the mesh
+    boundary; 1e-13 relative to the reference's summation order)."""
     nodes = np.asarray(nodes)
-    nx, ny, _, _ = grid_shape_from_nodes(nodes)
+    nx, ny, dx, dy = grid_shape_from_nodes(nodes)
     _, _, _, we = beso_weights(nodes, _unit_els(nx, ny), nx, ny, r_min)
     t = _scratch_topo(nx, ny)
     t.set(_capi.F_NODAL, sensi_nodes)
-    t.beso_elements(we)
+    if we is not None:
+        t.beso_elements(we)
+    else:
+        t.beso_elements_radius(r_min, dx, dy)
     return t.get(_capi.F_SENS)

@@ -23,7 +23,7 @@ SYMBOLS = [
     "topo_set_cons", "topo_set_loads", "topo_set", "topo_get", "topo_fill", "topo_matvec",
     "topo_matvec_device", "topo_solve", "topo_compliance", "topo_equilibrium_check", "topo_simp_scale",
     "topo_simp_sensitivity", "topo_filter_sensitivity", "topo_oc_update", "topo_simp_step",
-    "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_rank_select",
+    "topo_simp_step_host", "topo_energy_sensitivity", "topo_beso_filter", "topo_beso_nodes", "topo_beso_elements", "topo_beso_elements_radius", "topo_floating_elements", "topo_rank_select",
     "topo_beso_apply", "topo_eso_apply", "topo_beso_save_history", "topo_vonmises_sensitivity", "topo_strain_nodes",
     "topo_get_timing", "topo_gmg_info", "topo_set_gmg", "topo_timer_start", "topo_timer_stop",
     "topo_profile_matvec", "topo_profile_read", "topo_profile_report", "topo_set_stream", "topo_matvec_dev",
@@ -108,10 +108,12 @@ def load_library():
         "topo_beso_filter": [vp, dp, dp, dp, dp, C.c_int],
         "topo_beso_nodes": [vp, dp, dp, dp],
         "topo_beso_elements": [vp, dp],
+        "topo_beso_elements_radius": [vp, C.c_double, C.c_double, C.c_double],
         "topo_rank_select": [vp, C.c_int64, dp],
         "topo_beso_apply": [vp, C.c_double, C.c_void_p, C.c_int, i64p, i64p],
         "topo_eso_apply": [vp, C.c_double, C.c_void_p, C.c_int, i64p],
         "topo_beso_save_history": [vp],
+        "topo_floating_elements": [vp, C.c_void_p, C.c_int, i64p],
         "topo_vonmises_sensitivity": [vp, C.c_double, C.c_double, C.c_double, C.c_double],
         "topo_strain_nodes": [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p],
         "topo_get_timing": [vp, C.POINTER(Timing)],
@@ -333,6 +335,9 @@ class Topo:
         d = _dbl(we, 4)
         _check(self.lib.topo_beso_elements(self.h, d.ctypes.data_as(C.POINTER(C.c_double))))
 
+    def beso_elements_radius(self, r_min, dx, dy):
+        _check(self.lib.topo_beso_elements_radius(self.h, float(r_min), float(dx), float(dy)))
+
     def rank_select(self, k):
         a = C.c_double(0)
         _check(self.lib.topo_rank_select(self.h, int(k), C.byref(a)))
@@ -349,6 +354,12 @@ class Topo:
         nk = C.c_int64(0)
         _check(self.lib.topo_eso_apply(self.h, float(rr), p.ctypes.data, p.size, C.byref(nk)))
         return nk.value
+
+    def floating_elements(self, support_nodes):
+        ids = np.ascontiguousarray(support_nodes, dtype=np.int64)
+        n = C.c_int64(0)
+        _check(self.lib.topo_floating_elements(self.h, ids.ctypes.data, int(ids.size), C.byref(n)))
+        return int(n.value)
 
     def beso_save_history(self):
         _check(self.lib.topo_beso_save_history(self.h))

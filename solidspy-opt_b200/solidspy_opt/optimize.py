@@ -328,9 +328,22 @@ def _finish_fields(fields, plot, history, elsI, ELS, nodes):
 
 
 def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit, device,
-         history, verbose, model=None, plot=False):
+         history, verbose, model=None, plot=False, stop_on_island=False):
+    """Shared body of ESO_stiff / ESO_stress.
+
+    ``stop_on_island``: what happens once a removal cuts a piece of the structure loose (a group of present elements no
+    longer tied to a support) is NOT defined by the reference's algorithm but by its direct solver: the stiffness
+    matrix is singular, and ``spsolve`` either meets an exactly zero pivot -- the solution is NaN, nothing is removed
+    in that pass and the guard (:72 / :172) ends the loop, as in the reference fixture eso_stress c2 -- or rounding
+    leaves a tiny pivot, a finite solution comes back and the loop carries on (the untouched reference on 96x40 and
+    60x24, ``tests/test_oracle_t1.py``).  The PCG solve here always returns the finite solution of the consistent
+    system (default, False); True reproduces the NaN path: the floating part is detected on the device
+    (``topo_floating_elements``) and the loop ends exactly as the reference's does after a NaN solve."""
     nodes, mats, els, loads, BC, topo, protect = _setup_eso(length, height, nx, ny, dirs, positions, device, model)
     fields = _want_fields(plot, history)
+    support = np.flatnonzero((nodes[:, 3:5] == -1).any(axis=1)).astype(np.int64)
+    want_floating = stop_on_island or (history is not None and history.get("keep_floating", False))
+    island = False
     with topo:
         eq_ok = _solve(topo, precond, rtol, maxit, None)                           # :56-61 / :156-161
         _store_fields(fields, topo, mats, length/nx, height/ny, "I", present_only=True)    # :62-63 / :162-163
@@ -349,6 +362,15 @@ def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
                     print('hollaa')                                                # :73
                 break
             ELS_mask = mask                                                        # :76 / :192
+            if island and stop_on_island:
+                # the reference's solve returns NaN on this (singular) system: every comparison with NaN is False, so
+                # nothing is removed, and the guard ends the loop at the top of the next pass
+                eq_ok = False
+                if history is not None:
+                    history.setdefault("els_ids", []).append(np.flatnonzero(mask))
+                    history.setdefault("cons", []).append(topo.get_cons())
+                RR += ER
+                continue
             eq_ok = _solve(topo, precond, rtol, maxit, history)
             _store_fields(fields, topo, mats, length/nx, height/ny, "", present_only=True)     # :85-86 / :182-183
             if kind == "stiff":
@@ -359,6 +381,11 @@ def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
                 topo.vonmises_sensitivity(mats[0, 0], mats[0, 1], length/nx, height/ny)   # :86-92
             topo.eso_apply(RR, protect)                                            # :93-97 / :189-196
             mask = topo.get(_capi.F_KEEP).astype(bool)
+            if want_floating:
+                n_float = topo.floating_elements(support)
+                island = n_float > 0
+                if history is not None:
+                    history.setdefault("floating", []).append(n_float)
             if history is not None:
                 history.setdefault("els_ids", []).append(np.flatnonzero(mask))
                 history.setdefault("cons", []).append(topo.get_cons())
@@ -370,19 +397,19 @@ def _eso(kind, length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, 
 
 
 def ESO_stiff(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False, *, precond="gmg",
-              rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+              rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, stop_on_island=False):
     """Stiffness-based ESO (reference optimize.py:116-210).  As in the reference, ``niter``, ``RR`` and
-    ``ER`` are overridden by 200, 0.005, 0.05 (:165-167).  Returns ``(ELS, nodes)``."""
+    ``ER`` are overridden by 200, 0.005, 0.05 (:165-167).  Returns ``(ELS, nodes)``.  ``stop_on_island``: see ``_eso``."""
     return _eso("stiff", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
-                device, history, verbose, plot=plot)
+                device, history, verbose, plot=plot, stop_on_island=stop_on_island)
 
 
 def ESO_stress(length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, plot=False, *, precond="gmg",
-               rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True):
+               rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT, device=0, history=None, verbose=True, stop_on_island=False):
     """Stress-based ESO (reference optimize.py:16-111): von Mises of element-averaged nodal stresses.
-    Returns ``(ELS, nodes)``."""
+    Returns ``(ELS, nodes)``.  ``stop_on_island``: see ``_eso``."""
     return _eso("stress", length, height, nx, ny, dirs, positions, niter, RR, ER, volfrac, precond, rtol, maxit,
-                device, history, verbose, plot=plot)
+                device, history, verbose, plot=plot, stop_on_island=stop_on_island)
 
 
 def BESO_from_model(data, niter, t, ER, volfrac, **kw):
@@ -393,16 +420,16 @@ def BESO_from_model(data, niter, t, ER, volfrac, **kw):
 
 
 def ESO_stiff_from_model(data, niter, RR, ER, volfrac, *, precond="gmg", rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT,
-                         device=0, history=None, verbose=True):
+                         device=0, history=None, verbose=True, stop_on_island=False):
     """``ESO_stiff`` on a dict model (niter/RR/ER are overridden exactly as in the reference, :165-167)."""
     L, H, nx, ny, model = _model_arrays(data)
     return _eso("stiff", L, H, nx, ny, None, None, niter, RR, ER, volfrac, precond, rtol, maxit, device, history,
-                verbose, model)
+                verbose, model, stop_on_island=stop_on_island)
 
 
 def ESO_stress_from_model(data, niter, RR, ER, volfrac, *, precond="gmg", rtol=DEFAULT_RTOL_ESO, maxit=DEFAULT_MAXIT,
-                          device=0, history=None, verbose=True):
+                          device=0, history=None, verbose=True, stop_on_island=False):
     """``ESO_stress`` on a dict model."""
     L, H, nx, ny, model = _model_arrays(data)
     return _eso("stress", L, H, nx, ny, None, None, niter, RR, ER, volfrac, precond, rtol, maxit, device, history,
-                verbose, model)
+                verbose, model, stop_on_island=stop_on_island)

@@ -216,6 +216,57 @@ def test_eso_removal_sets_match_reference(capi, kind, case):
         assert np.array_equal(nodes, g["nodes"])
 
 
+def _floating_count(nx, ny, ids, support_nodes):
+    """Host check of topo_floating_elements: present elements in node-connected components without a support node."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    ids = np.asarray(ids)
+    n0 = ids + ids//nx
+    en = np.stack([n0, n0 + 1, n0 + nx + 2, n0 + nx + 1], 1)
+    E = len(ids)
+    A = coo_matrix((np.ones(4*E), (np.repeat(np.arange(E), 4), en.ravel())), shape=(E, (nx + 1)*(ny + 1))).tocsr()
+    nc, lab = connected_components(A @ A.T, directed=False)
+    sup = np.zeros((nx + 1)*(ny + 1), bool)
+    sup[support_nodes] = True
+    ok = np.zeros(nc, bool)
+    np.logical_or.at(ok, lab, sup[en].any(axis=1))
+    return int(np.count_nonzero(~ok[lab]))
+
+
+def test_eso_stop_on_island_reproduces_the_reference_nan_path(capi):
+    """Reference fixture eso_stress c2: the fifth removal cuts 10 elements loose, SuperLU meets a zero pivot, spsolve
+    returns NaN, nothing is removed in that pass and the guard ends the loop (optimize.py:72,84).  With
+    ``stop_on_island=True`` the whole history and the returned (ELS, nodes) equal the reference's."""
+    import solidspy_opt.optimize as opt
+    g = golden("eso_stress_c2")
+    nx, ny = int(g["nx"]), int(g["ny"])
+    hist = {}
+    ELS, nodes = opt.ESO_stress(float(g["length"]), float(g["height"]), nx, ny, g["dirs"], g["positions"], int(g["niter"]),
+                                float(g["RR"]), float(g["ER"]), float(g["volfrac"]), history=hist, verbose=False,
+                                stop_on_island=True)
+    ids = unpack_ragged(g["ids_flat"], g["ids_off"])
+    assert len(hist["els_ids"]) == len(ids)
+    for k, (a, b) in enumerate(zip(hist["els_ids"], ids)):
+        assert np.array_equal(a, b), "removal %d" % k
+    assert np.array_equal(np.array(hist["cons"]), g["cons"])
+    assert np.array_equal(ELS, g["ELS"]) and np.array_equal(nodes, g["nodes"])
+    assert hist["floating"] == [0, 0, 0, 0, 10]
+
+
+def test_floating_elements_match_host_components(capi):
+    """The device flood fill against scipy's connected components on the present-element sets of an ESO run that cuts
+    several pieces loose (96x40 stress: the untouched reference carries on through them -- its SuperLU returns a finite
+    solution there -- so the default host loop does too and the removal sets keep matching, see the mid-size test)."""
+    import solidspy_opt.optimize as opt
+    nx, ny = 96, 40
+    hist = {"keep_floating": True}
+    opt.ESO_stress(nx, ny, nx, ny, np.array([[0, -1]]), np.array([[11, 1]]), 12, 0.005, 0.05, 0.5, history=hist, verbose=False)
+    support = np.arange(0, (nx + 1)*(ny + 1), nx + 1)
+    want = [_floating_count(nx, ny, ids, support) for ids in hist["els_ids"]]
+    assert hist["floating"] == want
+    assert max(want) > 0
+
+
 def test_rank_select_matches_sort(capi):
     rng = np.random.default_rng(2)
     nx, ny = 97, 41
@@ -268,6 +319,23 @@ def test_helper_level_api(capi):
     sn = sensitivity_nodes(nodes, None, centers, s)
     assert np.array_equal(sn, t1.sensitivity_nodes(nx, ny, s, w4, w2x, w2y))      # bit-exact operation order
     assert np.array_equal(sensitivity_filter(nodes, centers, sn, 1.0), t1.sensitivity_filter_beso(nx, ny, sn, we))
+
+
+@pytest.mark.parametrize("nx,ny,L,H,r_factor", [(24, 10, 24.0, 10.0, 1.0), (24, 10, 24.0, 10.0, 1.6), (17, 13, 34.0, 13.0, 2.3),
+                                                (9, 30, 9.0, 45.0, 3.1), (12, 12, 12.0, 12.0, 0.8)])
+def test_sensitivity_filter_any_radius(capi, nx, ny, L, H, r_factor):
+    """Helper-level API: ``sensitivity_filter`` (reference solver.py:212-243) accepts any ``r_min``; the optimisers only
+    ever pass one element width (optimize.py:264).  Radii from 0.8 to 3.1 element widths, non-square elements,
+    against the reference's loop restated literally."""
+    from solidspy_opt.Utils import beam, center_els, sensitivity_filter
+    rng = np.random.default_rng(nx*ny)
+    nodes, mats, els, loads, BC = beam(L=L, H=H, nx=nx, ny=ny, dirs=np.array([[0, -1]]), positions=np.array([[2, 1]]))
+    centers = center_els(nodes, els)
+    sn = rng.uniform(0, 1, nodes.shape[0])
+    r_min = r_factor*np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])
+    got = sensitivity_filter(nodes, centers, sn, r_min)
+    ref = t1.sensitivity_filter_any_radius(nodes, centers, sn, r_min)
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)
 
 
 # ---- full-size properties (BASELINE configs 3/4) ------------------------------------------------------
