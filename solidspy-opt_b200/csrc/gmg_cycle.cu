@@ -112,6 +112,158 @@ __device__ __forceinline__ void node_prolong_add(const LevelView &L, const doubl
   L.x[n] = xv;
 }
 
+// ---- the same bodies for the multi-block kernels: two-dimensional indexing, every load issued up front ------------------
+// ncu on the level kernels of round 1 (profiles/r2_ncu_cycle.txt): 30-40 registers, 20-30 cycles of long-scoreboard stall
+// per issued instruction, 10 % occupancy on levels 2-3 -- a thread walked its nine neighbours one after the other, each
+// behind a bounds branch, and paid an L2 round trip per neighbour.  Here the neighbour index is clamped, the loads are
+// predicated instead of branched around and all of them precede the arithmetic (missing neighbours: zero coefficient);
+// the products are accumulated in the same order as stencil_row, so results are bit-identical.
+struct Nb9 {
+  int m[9];        // neighbour node (clamped to the node itself where it does not exist)
+  bool ok[9];
+};
+__device__ __forceinline__ Nb9 nb9_of(int n, int r, int c, int nx, int ny) {
+  Nb9 q;
+  const int npr = nx + 1;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int dr = k / 3 - 1, dc = k % 3 - 1;
+    q.ok[k] = (r + dr >= 0) && (r + dr <= ny) && (c + dc >= 0) && (c + dc <= nx);
+    q.m[k] = q.ok[k] ? n + dr * npr + dc : n;
+  }
+  return q;
+}
+template <bool SYM>
+__device__ __forceinline__ void stencil_load9(const stencil_t *__restrict__ st, int nn, int n, const Nb9 &q, float4 (&cf)[9]) {
+  const float4 *__restrict__ pl = reinterpret_cast<const float4 *>(st);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (SYM && k < 4) cf[k] = q.ok[k] ? pl[(size_t)(8 - k) * nn + q.m[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    else cf[k] = pl[(size_t)k * nn + n];             // planes of missing neighbours hold zeros
+  }
+}
+template <bool SYM>
+__device__ __forceinline__ void stencil_dot9(const float4 (&cf)[9], const double2 (&xv)[9], double &ax, double &ay) {
+  ax = 0.0;
+  ay = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (SYM && k < 4) {                                // transpose of the neighbour's forward block
+      ax = fma((double)cf[k].x, xv[k].x, ax);
+      ax = fma((double)cf[k].z, xv[k].y, ax);
+      ay = fma((double)cf[k].y, xv[k].x, ay);
+      ay = fma((double)cf[k].w, xv[k].y, ay);
+    } else {
+      ax = fma((double)cf[k].x, xv[k].x, ax);
+      ax = fma((double)cf[k].y, xv[k].y, ax);
+      ay = fma((double)cf[k].z, xv[k].x, ay);
+      ay = fma((double)cf[k].w, xv[k].y, ay);
+    }
+  }
+}
+constexpr int LB_X = 64, LB_Y = 2;                     // block of the two-dimensional level kernels
+inline dim3 lvl_grid(int nx, int ny) { return dim3((unsigned)div_up(nx + 1, LB_X), (unsigned)div_up(ny + 1, LB_Y)); }
+#define LVL_RC(L)                                                  \
+  const int c = blockIdx.x * LB_X + threadIdx.x;                   \
+  const int r = blockIdx.y * LB_Y + threadIdx.y;                   \
+  if (c > (L).nx || r > (L).ny) return;                            \
+  const int npr = (L).nx + 1, nn = npr * ((L).ny + 1), n = r * npr + c
+
+// down: x = w dinv b ; r = W b - A x   (x at the neighbours recomputed from b, dinv)
+template <bool SYM>
+__global__ void __launch_bounds__(LB_X * LB_Y) k_lvl_down2(const LevelView L, double omega, const int *done) {
+  if (done && *done) return;
+  LVL_RC(L);
+  const Nb9 q = nb9_of(n, r, c, L.nx, L.ny);
+  float4 cf[9];
+  double2 bv[9], dv[9], xv[9];
+  stencil_load9<SYM>(L.st, nn, n, q, cf);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { bv[k] = L.b[q.m[k]]; dv[k] = L.dinv[q.m[k]]; }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) xv[k] = make_double2(omega * dv[k].x * bv[k].x, omega * dv[k].y * bv[k].y);
+  double ax, ay;
+  stencil_dot9<SYM>(cf, xv, ax, ay);
+  L.x[n] = xv[4];
+  const double wr = row_weight(L, r);
+  L.r[n] = make_double2(dv[4].x != 0.0 ? fma(wr, bv[4].x, -ax) : 0.0, dv[4].y != 0.0 ? fma(wr, bv[4].y, -ay) : 0.0);
+}
+// plain sweep: x2 = x + w dinv (W b - A x)
+template <bool SYM>
+__global__ void __launch_bounds__(LB_X * LB_Y) k_lvl_smooth2(const LevelView L, double omega, const int *done) {
+  if (done && *done) return;
+  LVL_RC(L);
+  const Nb9 q = nb9_of(n, r, c, L.nx, L.ny);
+  float4 cf[9];
+  double2 xv[9];
+  stencil_load9<SYM>(L.st, nn, n, q, cf);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) xv[k] = L.x[q.m[k]];
+  const double2 bv = L.b[n], dv = L.dinv[n];
+  double ax, ay;
+  stencil_dot9<SYM>(cf, xv, ax, ay);
+  const double wr = row_weight(L, r);
+  L.x2[n] = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xv[4].x), fma(omega * dv.y, fma(wr, bv.y, -ay), xv[4].y));
+}
+// up: x~ = x + mask(P xc) ; x2 = x~ + w dinv (b - A x~)   (x~ of the neighbours on the fly)
+template <bool SYM>
+__global__ void __launch_bounds__(LB_X * LB_Y) k_lvl_up2(const LevelView L, const double2 *__restrict__ xc, int cnx, double omega,
+                                                         const int *done) {
+  if (done && *done) return;
+  LVL_RC(L);
+  const Nb9 q = nb9_of(n, r, c, L.nx, L.ny);
+  float4 cf[9];
+  double2 xv[9], dn[9];
+  stencil_load9<SYM>(L.st, nn, n, q, cf);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { xv[k] = L.x[q.m[k]]; dn[k] = L.dinv[q.m[k]]; }
+  const double2 bv = L.b[n];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int rr = q.ok[k] ? r + k / 3 - 1 : r, cc = q.ok[k] ? c + k % 3 - 1 : c;
+    const double2 p = prolong_node(xc, cc, rr, L.nx, L.ny, cnx + 1);
+    xv[k] = make_double2(dn[k].x != 0.0 ? xv[k].x + p.x : 0.0, dn[k].y != 0.0 ? xv[k].y + p.y : 0.0);
+  }
+  double ax, ay;
+  stencil_dot9<SYM>(cf, xv, ax, ay);
+  L.x2[n] = make_double2(fma(omega * dn[4].x, bv.x - ax, xv[4].x), fma(omega * dn[4].y, bv.y - ay, xv[4].y));
+}
+__global__ void __launch_bounds__(LB_X * LB_Y) k_lvl_prolong2(const LevelView L, const double2 *__restrict__ xc, int cnx,
+                                                              const int *done) {
+  if (done && *done) return;
+  LVL_RC(L);
+  (void)nn;
+  const double2 dv = L.dinv[n];
+  double2 xv = L.x[n];
+  const double2 p = prolong_node(xc, c, r, L.nx, L.ny, cnx + 1);
+  if (dv.x != 0.0) xv.x += p.x;
+  if (dv.y != 0.0) xv.y += p.y;
+  L.x[n] = xv;
+}
+template <class V2>
+__global__ void __launch_bounds__(LB_X * LB_Y) k_restrict2(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf, int nyf,
+                                                           int nxc, int nyc, const int *done) {
+  if (done && *done) return;
+  const int I = blockIdx.x * LB_X + threadIdx.x, J = blockIdx.y * LB_Y + threadIdx.y;
+  if (I > nxc || J > nyc) return;
+  bc[(size_t)J * (nxc + 1) + I] = restrict_node(rf, I, J, nxf, nyf);
+}
+// fine grid: x^ += mask(P x1)   (the fine-grid x^ is a float2 array: see FK<>::F32MASK in fine.cu)
+__global__ void __launch_bounds__(LB_X * LB_Y) k_prolong_add_fine2(const double2 *__restrict__ xc, float2 *__restrict__ xf,
+                                                                   const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
+                                                                   const int *done) {
+  if (done && *done) return;
+  const int i = blockIdx.x * LB_X + threadIdx.x, j = blockIdx.y * LB_Y + threadIdx.y;
+  if (i > nxf || j > nyf) return;
+  const size_t n = (size_t)j * (nxf + 1) + i;
+  const unsigned m = fixed[n];
+  float2 acc = xf[n];
+  const double2 p = prolong_node(xc, i, j, nxf, nyf, nxc + 1);
+  if (!(m & 1u)) acc.x = (float)((double)acc.x + p.x);
+  if (!(m & 2u)) acc.y = (float)((double)acc.y + p.y);
+  xf[n] = acc;
+}
+
 // ---- multi-block kernels (large coarse levels) ------------------------------------------------------------
 template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omega, const int *done) {
@@ -616,20 +768,20 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   auto result_of = [&](int l) { return level_result(h, l, tail); };
   if (tail > 1) {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict<float2>, dim3(blocks_for(C.nn)), dim3(128), 0, reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx, C.ny, done)));
+    KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict2<float2>, lvl_grid(C.nx, C.ny), dim3(LB_X, LB_Y), 0, reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx, C.ny, done)));
   }
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(h, F);
-    KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down<true> : k_lvl_down<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+    KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down2<true> : k_lvl_down2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, om, done)));
     for (int s = 1; s < nu_pre_of(h, l); ++s) {
-      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, om, done)));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
       KL(h, "k_lvl_resid", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_resid<true> : k_lvl_resid<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, done)));
     }
     if (l + 1 < tail) {
       GmgLevel &C = h->levels[l + 1];
-      KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict<double2>, dim3(blocks_for(C.nn)), dim3(128), 0, F.r, C.b, F.nx, F.ny, C.nx, C.ny, done)));
+      KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict2<double2>, lvl_grid(C.nx, C.ny), dim3(LB_X, LB_Y), 0, F.r, C.b, F.nx, F.ny, C.nx, C.ny, done)));
     }
   }
   if (tail == 1) TOPO_TRY(launch_tail(h, tail, res_fine, h->nx, h->ny, 1));
@@ -641,22 +793,22 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     if (F.nn > unfused_min) {
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel
-      KL(h, "k_lvl_prolong", CUDA_TRY(topo_launch(h, k_lvl_prolong, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, done)));
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, om, done)));
+      KL(h, "k_lvl_prolong", CUDA_TRY(topo_launch(h, k_lvl_prolong2, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, result_of(l + 1), C.nx, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, om, done)));
     } else {
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up<true> : k_lvl_up<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, result_of(l + 1), C.nx, om, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up2<true> : k_lvl_up2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, result_of(l + 1), C.nx, om, done)));
     }
     for (int s = 1; s < nu_post_of(h, l); ++s) {     // extra sweeps alternate x2 -> x -> x2 ...
       LevelView W = V;
       if (s & 1) { W.x = F.x2; W.x2 = F.x; }
-      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, W.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, W, om, done)));
+      KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, W.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, W, om, done)));
     }
   }
   if (x1_out != nullptr) {
     *x1_out = result_of(1);          // the caller's smoothing kernel prolongates on the fly
   } else {
     GmgLevel &C = h->levels[1];
-    KL(h, "k_prolong_add_fine", CUDA_TRY(topo_launch(h, k_prolong_add_fine, dim3(blocks_for(h->nn)), dim3(128), 0, result_of(1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx, h->ny, C.nx, done)));
+    KL(h, "k_prolong_add_fine", CUDA_TRY(topo_launch(h, k_prolong_add_fine2, lvl_grid(h->nx, h->ny), dim3(LB_X, LB_Y), 0, result_of(1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx, h->ny, C.nx, done)));
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
@@ -677,8 +829,8 @@ static int dist_restrict_from(topo_handle *h, int l, const double2 *r) {
   double2 *dst = (l + 1 < D.K) ? h->levels[l + 1].b : D.bK_send;
   const int nxc = h->lvl_nx[l + 1], nyc = nyf / 2;
   const int nb = blocks_for((int64_t)(nxc + 1) * (nyc + 1));
-  if (l == 0) KL(h, "k_restrict", k_restrict<<<nb, 128, 0, h->stream>>>(rf32, dst, nxf, nyf, nxc, nyc, done));
-  else KL(h, "k_restrict", k_restrict<<<nb, 128, 0, h->stream>>>(r, dst, nxf, nyf, nxc, nyc, done));
+  if (l == 0) KL(h, "k_restrict", k_restrict2<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(rf32, dst, nxf, nyf, nxc, nyc, done));
+  else KL(h, "k_restrict", k_restrict2<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(r, dst, nxf, nyf, nxc, nyc, done));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }
@@ -690,7 +842,7 @@ int topo_dist_level_down(topo_handle *h, int l) {
   if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
   GmgLevel &F = h->levels[l];
   const LevelView V = dist_view(h, l);
-  KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down<true> : k_lvl_down<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V,
+  KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down2<true> : k_lvl_down2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V,
                                                   h->omega, &h->sc->done)));
   return dist_restrict_from(h, l, F.r);
 }
@@ -727,8 +879,8 @@ int topo_dist_level_up(topo_handle *h, int l) {
   GmgLevel &F = h->levels[l];
   const LevelView V = dist_view(h, l);
   const int *done = &h->sc->done;
-  KL(h, "k_lvl_prolong", k_lvl_prolong<<<blocks_for(F.nn), 128, 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));
-  KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth<true> : k_lvl_smooth<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V,
+  KL(h, "k_lvl_prolong", k_lvl_prolong2<<<lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));
+  KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V,
                                                 h->omega, done)));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
@@ -736,7 +888,7 @@ int topo_dist_level_up(topo_handle *h, int l) {
 
 int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine) {
   if (!h->dist.on) return TOPO_EINVAL;
-  KL(h, "k_prolong_add_fine", k_prolong_add_fine<<<blocks_for(h->nn), 128, 0, h->stream>>>(dist_coarse_result(h, 1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx,
+  KL(h, "k_prolong_add_fine", k_prolong_add_fine2<<<lvl_grid(h->nx, h->ny), dim3(LB_X, LB_Y), 0, h->stream>>>(dist_coarse_result(h, 1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx,
                                                                                            h->ny, h->lvl_nx[1], &h->sc->done));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;

@@ -341,14 +341,15 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, u
   __threadfence();
   double w[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double acc = IS_MAX ? -1.0 / 0.0 : 0.0;
-    // fixed assignment of partials to threads, fixed order inside a thread
-    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
-      double t = __ldcg(&partials[k * TOPO_MAX_PARTIAL_BLOCKS + i]);
-      acc = IS_MAX ? fmax(acc, t) : acc + t;
+  for (int k = 0; k < NV; ++k) w[k] = IS_MAX ? -1.0 / 0.0 : 0.0;
+  // fixed assignment of partials to threads, fixed order inside a thread; the slot loop is the INNER one so that a
+  // thread has NV independent L2 loads in flight (slot-outer order cost the 16-slot OC pass ~10 us of serialised loads)
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = __ldcg(&partials[k * TOPO_MAX_PARTIAL_BLOCKS + i]);
+      w[k] = IS_MAX ? fmax(w[k], t) : w[k] + t;
     }
-    w[k] = acc;
   }
   block_reduce<NV, IS_MAX>(w, s_red);
   if (threadIdx.x == 0) {
