@@ -264,35 +264,7 @@ __global__ void __launch_bounds__(LB_X * LB_Y) k_prolong_add_fine2(const double2
   xf[n] = acc;
 }
 
-// ---- multi-block kernels (large coarse levels) ------------------------------------------------------------
-template <bool SYM>
-__global__ void __launch_bounds__(128) k_lvl_down(const LevelView L, double omega, const int *done) {
-  if (done && *done) return;
-  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_down<SYM>(L, n, omega);
-}
-template <bool SYM>
-__global__ void __launch_bounds__(128) k_lvl_up(const LevelView L, const double2 *__restrict__ xc, int cnx,
-                                                double omega, const int *done) {
-  if (done && *done) return;
-  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_up<SYM>(L, xc, cnx, n, omega);
-}
-__global__ void __launch_bounds__(128) k_lvl_prolong(const LevelView L, const double2 *__restrict__ xc, int cnx, const int *done) {
-  if (done && *done) return;
-  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_prolong_add(L, xc, cnx, n);
-}
-template <bool SYM>
-__global__ void __launch_bounds__(128) k_lvl_smooth(const LevelView L, double omega, const int *done) {
-  if (done && *done) return;
-  const int64_t nn = (int64_t)(L.nx + 1) * (L.ny + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) node_smooth<SYM>(L, n, omega);
-}
+// ---- multi-block kernels (large coarse levels): the two-dimensional kernels above + the residual of an iterate ------
 template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int *done) {
   if (done && *done) return;
@@ -300,38 +272,6 @@ __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int 
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < nn) node_resid<SYM>(L, n);
 }
-template <class V2>
-__global__ void __launch_bounds__(128) k_restrict(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf,
-                                                  int nyf, int nxc, int nyc, const int *done) {
-  if (done && *done) return;
-  const int nprc = nxc + 1;
-  const int64_t nnc = (int64_t)nprc * (nyc + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnc) return;
-  int J, I;
-  rc_of(n, nprc, J, I);
-  bc[n] = restrict_node(rf, I, J, nxf, nyf);
-}
-// fine grid: x^ += mask(P x1)   (constrained DOFs stay zero)
-// (the fine-grid x^ is a float2 array: see FK<>::F32MASK in fine.cu)
-__global__ void __launch_bounds__(128) k_prolong_add_fine(const double2 *__restrict__ xc, float2 *__restrict__ xf,
-                                                          const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
-                                                          const int *done) {
-  if (done && *done) return;
-  const int nprf = nxf + 1;
-  const int64_t nnf = (int64_t)nprf * (nyf + 1);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnf) return;
-  int j, i;
-  rc_of(n, nprf, j, i);
-  const double2 p = prolong_node(xc, i, j, nxf, nyf, nxc + 1);
-  const unsigned m = fixed[n];
-  float2 acc = xf[n];
-  if (!(m & 1u)) acc.x = (float)((double)acc.x + p.x);
-  if (!(m & 2u)) acc.y = (float)((double)acc.y + p.y);
-  xf[n] = acc;
-}
-
 // ---- tail: all levels >= first in ONE launch of a thread-block cluster ------------------------------------
 // Levels with more than TAIL_SMALL nodes are worked on by every CTA of the cluster with a hardware
 // cluster barrier (barrier.cluster, release/acquire: global writes of one CTA are visible to the others
