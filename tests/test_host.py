@@ -99,6 +99,19 @@ def test_grid_introspection_rejects_unstructured_input():
         solver.grid_shape_from_els(bad)
 
 
+@pytest.mark.parametrize("L,H,nx,ny,n", [(60, 60, 60, 60, 1), (60.0, 30.0, 40, 20, 2), (7.5, 3.0, 13, 5, 1), (10, 10, 1, 1, 2)])
+def test_beam_bc_equals_beam(L, H, nx, ny, n):
+    """The lean set-up of SIMP() carries exactly beam()'s BC flags, loads and node spacing."""
+    from solidspy_opt.Utils.beams import beam, beam_bc
+    dirs, pos = np.array([[0, -2], [1, 0]]), np.array([[max(ny//3, 1), 1], [ny, 1]])
+    nodes, mats, els, loads, BC = beam(L=L, H=H, nx=nx, ny=ny, dirs=dirs, positions=pos, n=n)
+    cons, loads2, spacing = beam_bc(L, H, nx, ny, dirs, pos, n)
+    assert cons.dtype == np.int8 and np.array_equal(cons, nodes[:, 3:5])
+    assert loads2.dtype == loads.dtype and np.array_equal(loads2, loads)
+    assert spacing == np.linalg.norm(nodes[0, 1:3] - nodes[1, 1:3])
+    assert (mats[0, 0], mats[0, 1]) == (206.8e9, 0.28)
+
+
 def test_library_exports_every_declared_symbol(lib_built):
     """Every function include/topo_b200.h declares is exported by the shared library (no compute calls)."""
     header = open(os.path.join(ROOT, "include", "topo_b200.h")).read()
