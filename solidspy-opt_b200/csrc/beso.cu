@@ -183,8 +183,14 @@ __global__ void k_sel_init(unsigned long long *sel, unsigned long long k) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sel[i] = 0ull;
   if (threadIdx.x == 0) { sel[256] = 0ull; sel[257] = k; sel[258] = 0ull; }
 }
-__global__ void __launch_bounds__(ET) k_sel_hist(const double *__restrict__ s, int64_t ne, unsigned long long *sel) {
+// One pass = histogram of the current 8-bit digit over the keys that match the prefix found so far; the block that
+// draws the last ticket then picks the digit (bins walked from the largest down, as np.sort(s)[::-1][k] counts) with
+// all 256 threads -- the separate one-thread scan kernel of round 1 cost 10.9 us per pass, more than the histogram.
+__global__ void __launch_bounds__(ET) k_sel_hist(const double *__restrict__ s, int64_t ne, unsigned long long *sel,
+                                                 unsigned int *ticket, double *alpha_out) {
   __shared__ unsigned int hist[256];
+  __shared__ unsigned long long cnt[256];
+  __shared__ bool s_last;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
   const int pass = (int)sel[258];
@@ -198,25 +204,29 @@ __global__ void __launch_bounds__(ET) k_sel_hist(const double *__restrict__ s, i
   __syncthreads();
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     if (hist[i]) atomicAdd(&sel[i], (unsigned long long)hist[i]);
-}
-__global__ void k_sel_scan(unsigned long long *sel, double *alpha_out) {
-  if (threadIdx.x == 0) {
-    const int pass = (int)sel[258];
-    const int shift = 56 - 8 * pass;
-    unsigned long long k = sel[257];
-    int bin = 255;
-    for (; bin > 0; --bin) {                 // walk from the largest digit down
-      const unsigned long long cnt = sel[bin];
-      if (k < cnt) break;
-      k -= cnt;
-    }
-    sel[256] |= ((unsigned long long)bin) << shift;
-    sel[257] = k;
-    sel[258] = (unsigned long long)(pass + 1);
-    if (pass == 7) *alpha_out = dunkey(sel[256]);
-  }
+  __threadfence();
   __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sel[i] = 0ull;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int b = threadIdx.x;                       // blockDim.x == 256 == number of bins
+  cnt[b] = __ldcg(&sel[b]);
+  __syncthreads();
+  unsigned long long above = 0ull;                 // keys in larger digits
+  for (int j = b + 1; j < 256; ++j) above += cnt[j];
+  const unsigned long long k = __ldcg(&sel[257]);
+  const bool mine = (b >= 1) ? (k >= above && k < above + cnt[b]) : (k >= above);
+  __syncthreads();
+  if (mine) {
+    const unsigned long long pre = prefix | (((unsigned long long)b) << shift);
+    sel[256] = pre;
+    sel[257] = k - above;
+    sel[258] = (unsigned long long)(pass + 1);
+    if (pass == 7) *alpha_out = dunkey(pre);
+  }
+  sel[b] = 0ull;
+  if (b == 0) *ticket = 0u;
 }
 
 // ---- masks, protection, node pinning ------------------------------------------------------------------------
@@ -543,8 +553,7 @@ extern "C" int topo_rank_select(topo_t *h, int64_t k, double *alpha) {
   cudaStream_t st = h->stream;
   KL(h, "k_sel_init", k_sel_init<<<1, 256, 0, st>>>(h->sel, (unsigned long long)k));
   for (int pass = 0; pass < 8; ++pass) {
-    KL(h, "k_sel_hist", k_sel_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->ne, h->sel));
-    KL(h, "k_sel_scan", k_sel_scan<<<1, 256, 0, st>>>(h->sel, h->red_out + 2));
+    KL(h, "k_sel_hist", k_sel_hist<<<el_blocks(h->ne), ET, 0, st>>>(h->sens, h->ne, h->sel, h->ticket + 2, h->red_out + 2));
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(alpha, h->red_out + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
