@@ -62,11 +62,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -75,7 +76,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a moment before its first line: do not start the timed region before it samples"""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -87,7 +100,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        hi = (self.t_end if self.t_end is not None else time.perf_counter()) + 0.05
+        for ts, r in self.rows:
+            if ts < lo or ts > hi:
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -336,9 +353,12 @@ def main():
     W, K = args.warmup, args.steps
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
+    sampler.begin()                  # samples are kept from here to the end of the e2e pass: both passes are timed regions
     res_dev, ms_dev, wall_dev, launches = trajectory(topo, W, K)
-    clocks = sampler.stop()
     res_e2e, ms_e2e, wall_e2e, _ = trajectory(topo, W, K, host_io=True)
+    sampler.end()
+    clocks = sampler.stop()
     # third pass over the same steps with every kernel launch bracketed by CUDA events (this disables the CUDA-graph
     # replay, so it is NOT the pass `value` comes from): per-kernel durations inside real steps
     _, ms_prof, _, _ = trajectory(topo, W, K, profile=True)
