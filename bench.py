@@ -237,9 +237,10 @@ def algorithmic_bytes(levels, tail_max=10000):
         r = [8*nn[0] + 16*nn[1]] + [16*nn[l] + 16*nn[l + 1] for l in range(1, tail - 1)]
         out["k_restrict"] = sum(r)/max(len(r), 1)
         for l in range(1, tail):
-            out["k_lvl_down L%d" % l] = (st[l] + 64)*nn[l]
-            fused = nn[l] <= 200000
-            out["k_lvl_up L%d" % l] = (st[l] + 64)*nn[l] + (16*nn[l + 1] if fused else 0)
+            # tile kernels: down = parent residual in (float2 on the fine grid), stencil + D^-1 in, b + r out;
+            #               up   = stencil + b + D^-1 + coarse result in, x2 out
+            out["k_lvl_down L%d" % l] = (st[l] + 48)*nn[l] + (8*nn[0] if l == 1 else 16*nn[l - 1])
+            out["k_lvl_up L%d" % l] = (st[l] + 48)*nn[l] + 16*nn[l + 1]
         pro = [48*nn[l] + 16*nn[l + 1] for l in range(1, tail) if nn[l] > 200000]
         if pro:
             out["k_lvl_prolong"] = sum(pro)/len(pro)

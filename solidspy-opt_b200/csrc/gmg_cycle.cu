@@ -264,6 +264,111 @@ __global__ void __launch_bounds__(LB_X * LB_Y) k_prolong_add_fine2(const double2
   xf[n] = acc;
 }
 
+// ---- tile kernels for levels 1..tail-1 (single GPU, one sweep before / after the coarse correction) -------------------
+// The separate transfer kernels cost a launch each (6-10 us at these sizes) and a round trip of b / x through memory.
+// Here a block owns a TX x TY tile of nodes and first forms the smoothing INPUT of the tile and of its one-node halo ring
+// in shared memory -- going down: b = P^T r_parent (restriction on the fly) and x = w D^-1 b; going up: x~ = w D^-1 b +
+// mask(P x_coarse) -- so every transfer value is computed once per tile (+ 2(TX+TY+2) halo entries) instead of once per
+// stencil neighbour, and the nine neighbour values of the stencil product are shared-memory reads.  x = w D^-1 b is never
+// stored: the up kernel recomputes it from b and D^-1, which it reads anyway.  Same operations in the same order as
+// k_restrict2 + k_lvl_down2 / k_lvl_prolong2 + k_lvl_smooth2: results are bit-identical.
+constexpr int TLX = 32, TLY = 8;
+__device__ __forceinline__ void tile_halo_slot(int h, int &hy, int &hx) {
+  if (h < TLX + 2) { hy = 0; hx = h; }
+  else if (h < 2 * (TLX + 2)) { hy = TLY + 1; hx = h - (TLX + 2); }
+  else { const int k = h - 2 * (TLX + 2); hy = 1 + (k >> 1); hx = (k & 1) ? TLX + 1 : 0; }
+}
+constexpr int TL_HALO = 2 * (TLX + 2) + 2 * TLY;
+inline dim3 tile_grid(int nx, int ny) { return dim3((unsigned)div_up(nx + 1, TLX), (unsigned)div_up(ny + 1, TLY)); }
+
+template <bool SYM>
+__device__ __forceinline__ void tile_apply(const LevelView &L, double2 (*xs)[TLX + 2], int n, int r, int c, int nn, double &ax,
+                                           double &ay, double2 &xc) {
+  const Nb9 q = nb9_of(n, r, c, L.nx, L.ny);
+  float4 cf[9];
+  double2 xv[9];
+  stencil_load9<SYM>(L.st, nn, n, q, cf);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) xv[k] = xs[threadIdx.y + k / 3][threadIdx.x + k % 3];
+  stencil_dot9<SYM>(cf, xv, ax, ay);
+  xc = xv[4];
+}
+
+// down: b = P^T r_parent ; x = w D^-1 b (not stored) ; r = W b - A x
+template <bool SYM, class V2>
+__global__ void __launch_bounds__(TLX * TLY) k_lvl_down_t(const LevelView L, const V2 *__restrict__ rp, int pnx, int pny, double omega,
+                                                          const int *done) {
+  if (done && *done) return;
+  __shared__ double2 xs[TLY + 2][TLX + 2];
+  const int c0 = blockIdx.x * TLX, r0 = blockIdx.y * TLY;
+  const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
+  const int npr = L.nx + 1, nn = npr * (L.ny + 1), n = r * npr + c;
+  const bool own = c <= L.nx && r <= L.ny;
+  double2 bv = make_double2(0.0, 0.0), dv = bv;
+  if (own) {
+    bv = restrict_node(rp, c, r, pnx, pny);
+    dv = L.dinv[n];
+    L.b[n] = bv;
+  }
+  xs[threadIdx.y + 1][threadIdx.x + 1] = make_double2(omega * dv.x * bv.x, omega * dv.y * bv.y);
+  for (int h = threadIdx.y * TLX + threadIdx.x; h < TL_HALO; h += TLX * TLY) {
+    int hy, hx;
+    tile_halo_slot(h, hy, hx);
+    const int rr = r0 + hy - 1, cc = c0 + hx - 1;
+    double2 xv = make_double2(0.0, 0.0);
+    if (rr >= 0 && rr <= L.ny && cc >= 0 && cc <= L.nx) {
+      const double2 b2 = restrict_node(rp, cc, rr, pnx, pny), d2 = L.dinv[rr * npr + cc];
+      xv = make_double2(omega * d2.x * b2.x, omega * d2.y * b2.y);
+    }
+    xs[hy][hx] = xv;
+  }
+  __syncthreads();
+  if (!own) return;
+  double ax, ay;
+  double2 xc;
+  tile_apply<SYM>(L, xs, n, r, c, nn, ax, ay, xc);
+  const double wr = row_weight(L, r);
+  L.r[n] = make_double2(dv.x != 0.0 ? fma(wr, bv.x, -ax) : 0.0, dv.y != 0.0 ? fma(wr, bv.y, -ay) : 0.0);
+}
+
+// up: x~ = w D^-1 b + mask(P xc) ; x2 = x~ + w D^-1 (b - A x~)
+template <bool SYM>
+__global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const double2 *__restrict__ xcoarse, int cnx, double omega,
+                                                        const int *done) {
+  if (done && *done) return;
+  __shared__ double2 xs[TLY + 2][TLX + 2];
+  const int c0 = blockIdx.x * TLX, r0 = blockIdx.y * TLY;
+  const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
+  const int npr = L.nx + 1, nn = npr * (L.ny + 1), n = r * npr + c;
+  const bool own = c <= L.nx && r <= L.ny;
+  auto xtilde = [&](int rr, int cc, double2 &b2, double2 &d2) {
+    const int m = rr * npr + cc;
+    b2 = L.b[m];
+    d2 = L.dinv[m];
+    const double2 p = prolong_node(xcoarse, cc, rr, L.nx, L.ny, cnx + 1);
+    // (w d) b is rounded before the coarse correction is added, exactly like the stored x of the separate kernels
+    return make_double2(d2.x != 0.0 ? __dadd_rn(__dmul_rn(omega * d2.x, b2.x), p.x) : 0.0,
+                        d2.y != 0.0 ? __dadd_rn(__dmul_rn(omega * d2.y, b2.y), p.y) : 0.0);
+  };
+  double2 bv = make_double2(0.0, 0.0), dv = bv, x0 = bv;
+  if (own) x0 = xtilde(r, c, bv, dv);
+  xs[threadIdx.y + 1][threadIdx.x + 1] = x0;
+  for (int h = threadIdx.y * TLX + threadIdx.x; h < TL_HALO; h += TLX * TLY) {
+    int hy, hx;
+    tile_halo_slot(h, hy, hx);
+    const int rr = r0 + hy - 1, cc = c0 + hx - 1;
+    double2 xv = make_double2(0.0, 0.0), b2, d2;
+    if (rr >= 0 && rr <= L.ny && cc >= 0 && cc <= L.nx) xv = xtilde(rr, cc, b2, d2);
+    xs[hy][hx] = xv;
+  }
+  __syncthreads();
+  if (!own) return;
+  double ax, ay;
+  double2 xc;
+  tile_apply<SYM>(L, xs, n, r, c, nn, ax, ay, xc);
+  L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xc.x), fma(omega * dv.y, bv.y - ay, xc.y));
+}
+
 // ---- multi-block kernels (large coarse levels): the two-dimensional kernels above + the residual of an iterate ------
 template <bool SYM>
 __global__ void __launch_bounds__(128) k_lvl_resid(const LevelView L, const int *done) {
@@ -706,20 +811,37 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
   const int *done = &h->sc->done;
   const int tail = tail_start(h);
   auto result_of = [&](int l) { return level_result(h, l, tail); };
-  if (tail > 1) {
+  // tile kernels (restriction inside the down kernel, prolongation inside the up kernel) where a level does exactly one
+  // sweep each way; the generic kernels below remain for TOPO_NU_COARSE > 1 and for the row-slab drivers
+  auto tiled = [&](int l) { return h->knobs.lvl_tiled && nu_pre_of(h, l) == 1 && nu_post_of(h, l) == 1; };
+  if (tail > 1 && !tiled(1)) {
     GmgLevel &C = h->levels[1];
     KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict2<float2>, lvl_grid(C.nx, C.ny), dim3(LB_X, LB_Y), 0, reinterpret_cast<const float2 *>(res_fine), C.b, h->nx, h->ny, C.nx, C.ny, done)));
   }
   for (int l = 1; l < tail; ++l) {
     GmgLevel &F = h->levels[l];
     LevelView V = view_of(h, F);
+    if (tiled(l)) {
+      // (a level after a non-tiled one finds its b already restricted -- only with mixed sweep counts; recomputing it is harmless)
+      if (l == 1) {
+        KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down_t<true, float2> : k_lvl_down_t<false, float2>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, reinterpret_cast<const float2 *>(res_fine), h->nx, h->ny, om, done)));
+      } else {
+        const GmgLevel &P = h->levels[l - 1];
+        KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down_t<true, double2> : k_lvl_down_t<false, double2>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, (const double2 *)P.r, P.nx, P.ny, om, done)));
+      }
+      if (l + 1 < tail && !tiled(l + 1)) {
+        GmgLevel &C = h->levels[l + 1];
+        KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict2<double2>, lvl_grid(C.nx, C.ny), dim3(LB_X, LB_Y), 0, F.r, C.b, F.nx, F.ny, C.nx, C.ny, done)));
+      }
+      continue;
+    }
     KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down2<true> : k_lvl_down2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, om, done)));
     for (int s = 1; s < nu_pre_of(h, l); ++s) {
       KL(h, "k_lvl_smooth", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V, om, done)));
       CUDA_TRY(cudaMemcpyAsync(F.x, F.x2, sizeof(double2) * (size_t)F.nn, cudaMemcpyDeviceToDevice, st));
       KL(h, "k_lvl_resid", CUDA_TRY(topo_launch(h, V.sym ? k_lvl_resid<true> : k_lvl_resid<false>, dim3(blocks_for(F.nn)), dim3(128), 0, V, done)));
     }
-    if (l + 1 < tail) {
+    if (l + 1 < tail && !tiled(l + 1)) {
       GmgLevel &C = h->levels[l + 1];
       KL(h, "k_restrict", CUDA_TRY(topo_launch(h, k_restrict2<double2>, lvl_grid(C.nx, C.ny), dim3(LB_X, LB_Y), 0, F.r, C.b, F.nx, F.ny, C.nx, C.ny, done)));
     }
@@ -730,6 +852,10 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     GmgLevel &F = h->levels[l], &C = h->levels[l + 1];
     LevelView V = view_of(h, F);
     const int unfused_min = h->knobs.unfused_min;
+    if (tiled(l)) {
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, result_of(l + 1), C.nx, om, done)));
+      continue;
+    }
     if (F.nn > unfused_min) {
       // big level: the stencil stream dominates, a separate cheap prolongation pass beats recomputing
       // P x_c for all 9 neighbours inside the smoothing kernel
