@@ -264,6 +264,14 @@ int topo_dist_p2p_attach(topo_t *h, const void *ipc_handles /* world x 64 bytes 
 int topo_dist_p2p_xchg(topo_t *h, int phase, int what, int level);
 int topo_dist_p2p_gather(topo_t *h, int phase);              /* TOPO_G_BK; then topo_dist_vcycle_tail(h, 1) */
 int topo_dist_p2p_allreduce(topo_t *h, int phase, int what, int n, int is_max);
+/* One-launch forms for ONE slab per process (a kernel that waits for its peers must not share a stream with them):
+ * interface rows of `what` pushed, awaited and completed by one kernel, optionally with the all-reduce (sum) of the
+ * first scal_n doubles of scalar block scal_what (scal_n = 0: none) and the PCG bookkeeping that follows the
+ * (rr, rz) all-reduce (finish = 1; 2 for the initial pass; replaces topo_dist_pcg_finish; finish = 3: the scalars are
+ * reduced with max instead of sum; what = -1: scalars only);
+ * level-K pieces pushed, awaited, assembled, then the tail kernel (replaces topo_dist_p2p_gather x2 + topo_dist_vcycle_tail). */
+int topo_dist_p2p_fused(topo_t *h, int what, int level, int scal_what, int scal_n, int finish);
+int topo_dist_p2p_gather_tail(topo_t *h);
 int topo_dist_p2p_error(topo_t *h, int *error);              /* 1: a wait gave up (peer missing) */
 
 /* ---- instrumentation ----------------------------------------------------------------------- */

@@ -196,7 +196,10 @@ extern "C" int topo_dist_init(topo_t *h, int rank, int world, int K_request) {
     D.p2p_off_lo = (sizeof(P2PHeader) + 4095) & ~(size_t)4095;
     D.p2p_off_hi = D.p2p_off_lo + 2 * rowb;
     D.p2p_off_gather = D.p2p_off_hi + 2 * rowb;
-    D.p2p_bytes = D.p2p_off_gather + 2 * gb;
+    D.p2p_off_ll_lo = D.p2p_off_gather + 2 * gb;
+    D.p2p_off_ll_hi = D.p2p_off_ll_lo + 4 * rowb;          // [2 parities][2 * rowb]
+    D.p2p_off_ll_gather = D.p2p_off_ll_hi + 4 * rowb;
+    D.p2p_bytes = D.p2p_off_ll_gather + 4 * gb;
     CUDA_TRY(cudaMalloc(&D.p2p_region, D.p2p_bytes));
     CUDA_TRY(cudaMemset(D.p2p_region, 0, D.p2p_bytes));
     CUDA_TRY(cudaMalloc(&D.p2p_cnt, sizeof(P2PCounters)));
@@ -494,7 +497,15 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
   return false;
 }
 
+struct PeerTable {
+  char *p[TOPO_P2P_MAXW];
+};
 __device__ __forceinline__ P2PHeader *hdr(char *region) { return reinterpret_cast<P2PHeader *>(region); }
+__device__ __forceinline__ void rc_of_host(int64_t n, int npr, int &r, int &c) {
+  const unsigned un = (unsigned)n, q = un / (unsigned)npr;
+  r = (int)q;
+  c = (int)(un - q * (unsigned)npr);
+}
 
 // my first node row -> lower neighbour's recv_hi, my last node row -> upper neighbour's recv_lo, then the flags
 __global__ void __launch_bounds__(1024) k_p2p_push_rows(const double2 *__restrict__ row_lo, const double2 *__restrict__ row_hi,
@@ -565,9 +576,6 @@ __global__ void __launch_bounds__(1024) k_p2p_finish_rows(double2 *__restrict__ 
 }
 
 // block r: my level-K piece -> rank r's gather buffer, slot [my rank], then the flag
-struct PeerTable {
-  char *p[TOPO_P2P_MAXW];
-};
 __global__ void __launch_bounds__(1024) k_p2p_gather_push(const double2 *__restrict__ src, long long n, PeerTable peers, int my_rank,
                                                           size_t off_gather, size_t stride, P2PCounters *c) {
   const unsigned long long seq = c->gather_push + 1;
@@ -622,6 +630,185 @@ __global__ void k_p2p_scalar_reduce(double *__restrict__ vals, int n, char *regi
   }
   __syncthreads();
   if (threadIdx.x == 0) c->scal_wait = seq;
+}
+
+// ---- one-launch exchanges (one slab per process: a kernel may wait for its peers because every peer pushes before it
+// waits; with several slabs of one process on one stream the two-phase kernels above are the only safe form) -------------
+// Measured on 8 GPUs (scripts/slab_variants.py, 50 exchanges per CUDA graph): an exchange built from "payload, fence.sys,
+// release-store of a sequence number / acquire-poll, read payload" costs 13-19 us even for a 4 KB row -- thirteen of them
+// were a third of a PCG iteration.  Here every double travels as ONE 16-byte store (lo, seq, hi, seq) -- each 8-byte half
+// carries its own copy of the sequence number, the protocol of NCCL's LL primitives -- so there is no fence, no separate
+// flag and no ticket on the critical path: a thread pushes the values of its node, polls its own slot until both halves
+// show the expected number, and completes its node.  Slots are double-buffered by the parity of the sequence number and
+// a stale slot holds an OLDER number, so equality is the only test needed.
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned seq) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+}
+// bounded spin (~ seconds): a missing peer must not hang the GPU
+__device__ __forceinline__ bool ll_load(const uint4 *src, unsigned seq, double &v, unsigned int *error) {
+  for (long long it = 0; it < (1ll << 24); ++it) {
+    unsigned a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+    if (b == seq && d == seq) {
+      v = __hiloint2double((int)c, (int)a);
+      return true;
+    }
+    if (it > 2000) {
+      if (*reinterpret_cast<volatile unsigned int *>(error)) return false;   // somebody already gave up
+      __nanosleep(100);
+    }
+  }
+  *error = 1u;
+  return false;
+}
+
+// Blocks [0, nb): my first row <-> rank-1; [nb, 2nb): my last row <-> rank+1, one node per thread; block 2nb (if
+// nvals > 0): all-reduce of nvals scalars, folded in rank order on every rank (+ the PCG bookkeeping that follows the
+// (rr, rz) all-reduce).
+struct FusedXchg {
+  double2 *v_lo, *v_hi;
+  const double2 *base_lo, *base_hi;
+  int base_f32, n, nb;
+  char *region, *peer_lo, *peer_hi;
+  size_t off_lo, off_hi, stride;           // flag-in-data row slots: [parity][n] x 2 doubles x 16 B
+  P2PCounters *c;
+  double *vals;
+  int nvals, my_rank, world, finish;       // finish: 0 none, 1 PCG bookkeeping, 2 the same for the initial pass, 3: max instead of sum
+  SolverScalars *sc;
+};
+__device__ __forceinline__ void pcg_bookkeeping(SolverScalars *sc, int init) {
+  if (!init && sc->done) return;
+  const double rr = sc->aux[1], rz = sc->aux[2];
+  sc->rr = rr;
+  if (!init) sc->iters += 1;
+  sc->rz[1] = init ? 0.0 : rz / sc->rz[0];
+  sc->rz[0] = rz;
+  if (rr <= sc->tol2 * sc->bb || !(rr == rr)) sc->done = 1;
+  else if (sc->iters >= sc->maxit) sc->done = 2;
+}
+__global__ void __launch_bounds__(256) k_p2p_fused(const __grid_constant__ FusedXchg a, const __grid_constant__ PeerTable peers) {
+  P2PCounters *c = a.c;
+  const int t = threadIdx.x;
+  if ((int)blockIdx.x == 2 * a.nb) {                       // ---- scalars ----
+    const unsigned long long seq = c->scal_push + 1;
+    const unsigned s32 = (unsigned)seq;
+    double mine[16];
+    if (t < a.world)
+      for (int j = 0; j < a.nvals; ++j) mine[j] = a.vals[j];
+    __syncthreads();                                       // every thread holds my values before anybody overwrites them
+    if (t < a.world) {
+      uint4 *dst = hdr(peers.p[t])->ll_scalar[seq & 1ull][a.my_rank];
+      for (int j = 0; j < a.nvals; ++j) ll_store(dst + j, mine[j], s32);
+    }
+    if (t < a.nvals) {
+      const P2PHeader *H = hdr(a.region);
+      double acc = 0.0;
+      bool ok = true;
+      for (int r = 0; r < a.world && ok; ++r) {
+        double q;
+        ok = ll_load(&H->ll_scalar[seq & 1ull][r][t], s32, q, &c->error);
+        acc = r == 0 ? q : (a.finish == 3 ? ((q > acc || q != q) ? q : acc) : acc + q);
+      }
+      if (ok) a.vals[t] = acc;
+    }
+    __syncthreads();
+    if (t == 0) {
+      if (a.finish == 1 || a.finish == 2) pcg_bookkeeping(a.sc, a.finish == 2);
+      c->scal_push = seq;
+      c->scal_wait = seq;
+    }
+    return;
+  }
+  // ---- rows ----
+  const unsigned long long seq = c->halo_push + 1;
+  const unsigned s32 = (unsigned)seq;
+  const size_t buf = (size_t)(seq & 1ull) * a.stride;
+  const bool lo = (int)blockIdx.x < a.nb;
+  const int i = (lo ? blockIdx.x : blockIdx.x - a.nb) * blockDim.x + t;
+  char *peer = lo ? a.peer_lo : a.peer_hi;
+  if (peer != nullptr && i < a.n) {
+    double2 *v = lo ? a.v_lo : a.v_hi;
+    double2 x = v[i];
+    // my first row lands in the lower neighbour's "from above" slot, my last row in the upper neighbour's "from below" slot
+    uint4 *dst = reinterpret_cast<uint4 *>(peer + (lo ? a.off_hi : a.off_lo) + buf) + 2 * (size_t)i;
+    ll_store(dst, x.x, s32);
+    ll_store(dst + 1, x.y, s32);
+    const double2 *base = lo ? a.base_lo : a.base_hi;
+    double2 q = make_double2(0.0, 0.0);
+    if (base != nullptr) {
+      if (a.base_f32) {
+        const float2 f = reinterpret_cast<const float2 *>(base)[i];
+        q = make_double2((double)f.x, (double)f.y);
+      } else {
+        q = base[i];
+      }
+    }
+    const uint4 *rcv = reinterpret_cast<const uint4 *>(a.region + (lo ? a.off_lo : a.off_hi) + buf) + 2 * (size_t)i;
+    double bx, by;
+    if (ll_load(rcv, s32, bx, &c->error) && ll_load(rcv + 1, s32, by, &c->error)) {
+      if (base != nullptr) { x.x = (x.x + bx) - q.x; x.y = (x.y + by) - q.y; }
+      else { x.x += bx; x.y += by; }
+      v[i] = x;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(&c->fticket[2], 1u) == 2u * (unsigned)a.nb - 1u) {
+      c->fticket[2] = 0u;
+      c->halo_push = seq;
+      c->halo_wait = seq;
+    }
+  }
+}
+
+// level-K pieces to every rank, wait for everybody's, assemble the global right-hand side -- one launch.
+// Blocks [0, world) push first (block r -> rank r); every block then assembles its nodes, polling the values it needs.
+__global__ void __launch_bounds__(256) k_p2p_gather_fused(const double2 *__restrict__ src, long long n, const __grid_constant__ PeerTable peers,
+                                                          int my_rank, int world, char *region, size_t off_gather, size_t stride,
+                                                          P2PCounters *c, double2 *__restrict__ b, int npr, int rows) {
+  const unsigned long long seq = c->gather_push + 1;
+  const unsigned s32 = (unsigned)seq;
+  const int t = threadIdx.x, T = blockDim.x;
+  if ((int)blockIdx.x < world) {
+    uint4 *dst = reinterpret_cast<uint4 *>(peers.p[blockIdx.x] + off_gather + (size_t)(seq & 1ull) * stride) + 2 * (size_t)my_rank * n;
+    for (long long i = t; i < n; i += T) {
+      const double2 x = src[i];
+      ll_store(dst + 2 * i, x.x, s32);
+      ll_store(dst + 2 * i + 1, x.y, s32);
+    }
+  }
+  const uint4 *__restrict__ recv = reinterpret_cast<const uint4 *>(region + off_gather + (size_t)(seq & 1ull) * stride);
+  const int64_t nn = (int64_t)npr * ((int64_t)rows * world + 1);
+  const int64_t per = (int64_t)(rows + 1) * npr;
+  for (int64_t m = (int64_t)blockIdx.x * T + t; m < nn; m += (int64_t)gridDim.x * T) {
+    int J, I;
+    rc_of_host(m, npr, J, I);
+    const int g = J / rows, j = J - g * rows;
+    double2 acc = make_double2(0.0, 0.0);
+    bool ok = true;
+    if (g < world) {
+      const uint4 *w = recv + 2 * ((int64_t)g * per + (int64_t)j * npr + I);
+      ok = ll_load(w, s32, acc.x, &c->error) && ll_load(w + 1, s32, acc.y, &c->error);
+    }
+    if (ok && j == 0 && g > 0) {
+      const uint4 *w = recv + 2 * ((int64_t)(g - 1) * per + (int64_t)rows * npr + I);
+      double qx, qy;
+      ok = ll_load(w, s32, qx, &c->error) && ll_load(w + 1, s32, qy, &c->error);
+      acc.x += qx; acc.y += qy;
+    }
+    if (ok) b[m] = acc;
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(&c->fticket[3], 1u) == gridDim.x - 1u) {
+      c->fticket[3] = 0u;
+      c->gather_push = seq;
+      c->gather_wait = seq;
+    }
+  }
 }
 
 int p2p_check(topo_handle *h) {
@@ -755,6 +942,77 @@ extern "C" int topo_dist_p2p_allreduce(topo_t *h, int phase, int what, int n, in
   }
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
+}
+
+int topo_dist_tail_after_assemble(topo_handle *h);
+
+// one-launch exchange (see k_p2p_fused): interface rows of `what` (+ level), optionally the all-reduce (sum) of the first
+// scal_n doubles of scalar block scal_what (scal_n = 0: none) and the PCG bookkeeping (finish = 1; 2 for the initial pass)
+extern "C" int topo_dist_p2p_fused(topo_t *h, int what, int level, int scal_what, int scal_n, int finish) {
+  TOPO_TRY(p2p_check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  double2 *v = nullptr;
+  const double2 *base = nullptr;
+  int npr = h->nx + 1, ny = h->ny;
+  switch (what) {
+    case -1: npr = 0; break;                                 // scalars only
+    case TOPO_X_AP: v = h->Ap; break;
+    case TOPO_X_R0: v = h->r; break;
+    case TOPO_X_Z: v = h->z; base = h->tmp2; break;
+    case TOPO_X_LEVEL_B:
+    case TOPO_X_LEVEL_X2:
+      if (level < 1 || level >= D.K) return TOPO_EINVAL;
+      v = (what == TOPO_X_LEVEL_B) ? h->levels[level].b : h->levels[level].x2;
+      if (what == TOPO_X_LEVEL_X2) base = h->levels[level].x;
+      npr = h->levels[level].nx + 1; ny = h->levels[level].ny;
+      break;
+    default:
+      topo_set_error("peer-memory exchange: kind %d is not a node-row exchange", what);
+      return TOPO_EINVAL;
+  }
+  if (npr == 0 && scal_n < 1) return TOPO_EINVAL;
+  const size_t last = (size_t)ny * npr;
+  FusedXchg a = {};
+  a.v_lo = v; a.v_hi = v + last;
+  a.base_f32 = (what == TOPO_X_Z) ? 1 : 0;
+  a.base_lo = base;
+  a.base_hi = !base ? nullptr : (a.base_f32 ? reinterpret_cast<const double2 *>(reinterpret_cast<const float2 *>(base) + last) : base + last);
+  a.n = npr;
+  a.nb = (npr + 255) / 256;                              // one node per thread
+  a.region = D.p2p_region;
+  a.peer_lo = D.has_lo ? D.p2p_peer[D.rank - 1] : nullptr;
+  a.peer_hi = D.has_hi ? D.p2p_peer[D.rank + 1] : nullptr;
+  a.off_lo = D.p2p_off_ll_lo; a.off_hi = D.p2p_off_ll_hi; a.stride = 2 * D.p2p_row_stride;
+  a.c = D.p2p_cnt;
+  a.my_rank = D.rank; a.world = D.world; a.finish = finish; a.sc = h->sc;
+  if (scal_n > 0) {
+    void *ptr = nullptr;
+    int nmax = 0;
+    TOPO_TRY(topo_dist_scalar_ptr(h, scal_what, &ptr, &nmax));
+    if (scal_n > nmax || scal_n > 16) return TOPO_EINVAL;
+    a.vals = static_cast<double *>(ptr);
+    a.nvals = scal_n;
+  }
+  const int blocks = 2 * a.nb + (a.nvals > 0 ? 1 : 0);
+  KL(h, "k_p2p_fused", k_p2p_fused<<<blocks, 256, 0, h->stream>>>(a, peer_table(D)));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// one-launch gather of the level-K right-hand side + assembly, then the tail kernel (levels >= K on every rank)
+extern "C" int topo_dist_p2p_gather_tail(topo_t *h) {
+  TOPO_TRY(p2p_check(h));
+  CUDA_TRY(cudaSetDevice(h->device));
+  DistState &D = h->dist;
+  GmgLevel &G = h->levels[D.K];
+  const int rows = (h->ny >> D.K);
+  const int blocks = std::max(D.world, (int)std::min<int64_t>((G.nn + 255) / 256, 64));
+  KL(h, "k_p2p_gather_fused", k_p2p_gather_fused<<<blocks, 256, 0, h->stream>>>(D.bK_send, D.bK_count, peer_table(D), D.rank, D.world,
+                                                                              D.p2p_region, D.p2p_off_ll_gather, 2 * D.p2p_gather_stride,
+                                                                              D.p2p_cnt, G.b, G.nx + 1, rows));
+  CUDA_TRY(cudaGetLastError());
+  return topo_dist_tail_after_assemble(h);
 }
 
 // 1 if a peer wait timed out since the handle was created

@@ -366,7 +366,11 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const
   double ax, ay;
   double2 xc;
   tile_apply<SYM>(L, xs, n, r, c, nn, ax, ay, xc);
-  L.x2[n] = make_double2(fma(omega * dv.x, bv.x - ax, xc.x), fma(omega * dv.y, bv.y - ay, xc.y));
+  // row-slab mode: W b makes the distributed copy of b on interface rows (W = 1 elsewhere: fma(1, b, -ax) == b - ax), and
+  // the exchange that completes an interface row of x2 subtracts x~ there, so those rows of x~ are stored
+  const double wr = row_weight(L, r);
+  if (wr != 1.0) L.x[n] = xc;
+  L.x2[n] = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xc.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xc.y));
 }
 
 // ---- multi-block kernels (large coarse levels): the two-dimensional kernels above + the residual of an iterate ------
@@ -930,6 +934,12 @@ int topo_dist_tail(topo_handle *h, int p2p) {
   return launch_tail(h, D.K, nullptr, 0, 0);
 }
 
+// levels >= K when the global right-hand side is already in place (topo_dist_p2p_gather_tail)
+int topo_dist_tail_after_assemble(topo_handle *h) {
+  if (!h->dist.on) return TOPO_EINVAL;
+  return launch_tail(h, h->dist.K, nullptr, 0, 0);
+}
+
 // this slab's rows of the level-(l+1) result (global levels are indexed with the slab's row offset)
 static const double2 *dist_coarse_result(const topo_handle *h, int l_coarse) {
   const DistState &D = h->dist;
@@ -945,6 +955,12 @@ int topo_dist_level_up(topo_handle *h, int l) {
   GmgLevel &F = h->levels[l];
   const LevelView V = dist_view(h, l);
   const int *done = &h->sc->done;
+  if (h->knobs.lvl_tiled) {
+    // (x = w D^-1 b is recomputed from the accumulated b; the interface rows of x~ are stored for the exchange)
+    KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V,
+                                                  dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], h->omega, done)));
+    return TOPO_OK;
+  }
   KL(h, "k_lvl_prolong", k_lvl_prolong2<<<lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));
   KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_smooth2<true> : k_lvl_smooth2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V,
                                                 h->omega, done)));

@@ -96,12 +96,14 @@ struct P2PHeader {                       // start of the region; written by peer
   unsigned long long flag_gather[TOPO_P2P_MAXW];           // by rank
   unsigned long long flag_scalar[TOPO_P2P_MAXW];
   double scalar_slot[2][TOPO_P2P_MAXW][16];
+  uint4 ll_scalar[2][TOPO_P2P_MAXW][16];                    // one-launch all-reduce: every double travels as (lo, seq, hi, seq)
 };
 struct P2PCounters {                     // local
   unsigned long long halo_push, halo_wait, gather_push, gather_wait, scal_push, scal_wait;
   unsigned int ticket[4];
   unsigned int error;                    // a wait gave up (peer never wrote): results are invalid
   unsigned int pad;
+  unsigned int fticket[4];               // one-launch exchanges: push tickets towards rank-1 / rank+1, end-of-kernel ticket, gather
 };
 
 struct DistState {
@@ -123,6 +125,7 @@ struct DistState {
   bool p2p_on;
   char *p2p_region;                    // P2PHeader | recv_lo[2][npr] | recv_hi[2][npr] | gather_recv[2][world][bK_count]
   size_t p2p_bytes, p2p_off_lo, p2p_off_hi, p2p_off_gather, p2p_row_stride, p2p_gather_stride;
+  size_t p2p_off_ll_lo, p2p_off_ll_hi, p2p_off_ll_gather;   // flag-in-data copies of the three payload areas (32 B per double2)
   char *p2p_peer[TOPO_P2P_MAXW];       // mapped regions by rank (own region at [rank])
   bool p2p_opened[TOPO_P2P_MAXW];      // mapped through cudaIpcOpenMemHandle (must be closed)
   P2PCounters *p2p_cnt;

@@ -8,9 +8,10 @@ interface rows (local elements only); the halo exchange adds the neighbour's par
 ``2*(nx+1)`` doubles each way per matvec, e.g. 131 KB at nx = 8192).  Scalars (dot products) are all-reduced;
 each node row is counted by exactly one rank (the lower slab owns its top interface row).
 
-What is distributed so far: K(rho)u with halo sum, the Jacobi diagonal, and a Jacobi-preconditioned CG on top of
-them (host loop in Python, every vector kernel is the library's own, NCCL only moves halo rows and scalars).  The
-multigrid preconditioner, filter and OC stages are single-GPU only.
+Two layers live here: ``SlabSolver`` (the first building block: K(rho)u with halo sum, the Jacobi diagonal and a
+Jacobi-preconditioned CG on caller-owned tensors, NCCL only moves halo rows and scalars) and ``SlabSimp`` (the WHOLE
+design iteration on row slabs: multigrid-preconditioned CG, sensitivity, filter and OC, with peer-memory or NCCL
+transport and CUDA-graph capture -- DESIGN.md section 6).
 
 The numerical kernels are injected through a small backend object so that the slab / halo / ownership logic is
 testable on CPU with the ``gloo`` backend (``tests/test_distributed_cpu.py``) -- the product backend is
@@ -198,7 +199,7 @@ class SlabSimp:
 
     def __init__(self, nx, ny, ke, cons, loads, volfrac=0.5, penal=3.0, emin=1e-9, emax=1.0, rmin=None, dx=1.0, dy=1.0,
                  move=0.2, rtol=1e-9, maxit=2000, world=None, dist=None, device=0, K=0, use_graph=True,
-                 transport="p2p"):
+                 transport="p2p", fused=True):
         import torch
         from solidspy_opt import _capi
         self.torch, self._capi, self.dist = torch, _capi, dist
@@ -243,6 +244,9 @@ class SlabSimp:
         self.p2p, self.p2p_error = False, None
         if transport == "p2p":
             self._attach_p2p()
+        # one-launch exchanges (push + wait + completion [+ all-reduce + bookkeeping] in ONE kernel): only with one slab per
+        # process -- several slabs of one process share a stream, where a kernel that waits for a peer would wait forever
+        self.fused = bool(fused) and self.p2p and dist is not None and len(self.slabs) == 1
         self._lam_prev = 0.0
         self._last_iters = 0
         self.halo_bytes = 0
@@ -307,6 +311,10 @@ class SlabSimp:
     # ---- movement ----------------------------------------------------------------------------------------------------
     def exchange(self, what, level=0):
         """Interface rows / blocks to both neighbours, then the library's finishing kernel."""
+        if self.fused and what in self._ROW_KINDS:
+            self.slabs[0].dist_call("p2p_fused", what, level, 0, 0, 0)
+            self.collectives += 1
+            return
         if self.p2p and what in self._ROW_KINDS:
             for t in self.slabs:                                           # every push before any wait
                 t.dist_call("p2p_xchg", 0, what, level)
@@ -350,6 +358,10 @@ class SlabSimp:
         self.collectives += 1
 
     def allreduce(self, what, n, op="sum"):
+        if self.fused:                                                     # one launch, flag-in-data protocol
+            self.slabs[0].dist_call("p2p_fused", -1, 0, what, n, 3 if op == "max" else 0)
+            self.collectives += 1
+            return
         if self.p2p:
             self._all("p2p_allreduce", 0, what, n, 1 if op == "max" else 0)
             self._all("p2p_allreduce", 1, what, n, 1 if op == "max" else 0)
@@ -380,6 +392,20 @@ class SlabSimp:
     def _cycle(self, par, init):
         """update + V-cycle + smoothing: everything of an iteration after the K p product."""
         c, K = self._capi, self.K
+        if self.fused:
+            t = self.slabs[0]
+            t.dist_call("pcg_update", par, init)
+            for l in range(1, K):
+                t.dist_call("p2p_fused", c.X_LEVEL_B, l, 0, 0, 0)
+                t.dist_call("vcycle_down", l)
+            t.dist_call("p2p_gather_tail")
+            for l in range(K - 1, 0, -1):
+                t.dist_call("vcycle_up", l)
+                t.dist_call("p2p_fused", c.X_LEVEL_X2, l, 0, 0, 0)
+            t.dist_call("pcg_smooth", par, init)
+            t.dist_call("p2p_fused", c.X_Z, 0, c.S_RR_RZ, 2, 2 if init else 1)
+            self.collectives += 2*K + 1
+            return
         self._all("pcg_update", par, init)
         for l in range(1, K):
             self.exchange(c.X_LEVEL_B, l)
@@ -397,8 +423,12 @@ class SlabSimp:
     def _iteration(self, par):
         c = self._capi
         self._all("pcg_matvec", par)
-        self.exchange(c.X_AP)
-        self.allreduce(c.S_PAP, 1)
+        if self.fused:
+            self.slabs[0].dist_call("p2p_fused", c.X_AP, 0, c.S_PAP, 1, 0)
+            self.collectives += 1
+        else:
+            self.exchange(c.X_AP)
+            self.allreduce(c.S_PAP, 1)
         self._cycle(par, 0)
 
     def _pair(self):

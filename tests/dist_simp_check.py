@@ -45,16 +45,18 @@ def main():
     nx, ny = 384, 64*world
     cons, loads, ke = model(nx, ny)
     steps = 4
-    for transport, use_graph in (("p2p", True), ("nccl", True), ("nccl", False)):
+    # (p2p with and without the one-launch exchanges, graph-captured and eager; NCCL graph-captured and eager)
+    for transport, use_graph, fused in (("p2p", True, True), ("p2p", False, True), ("p2p", True, False), ("nccl", True, False),
+                                        ("nccl", False, False)):
         sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph,
-                       transport=transport)
+                       transport=transport, fused=fused)
         g, hist = 0.0, []
         for _ in range(steps):
             g, res = sim.step(g)
             hist.append((res["compliance"], res["cg_iters"], res["oc_steps"], g))
         rho = gather_rho(sim, world)
-        key = transport + ("_graph" if use_graph else "_eager")
-        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p)}
+        key = transport + ("_fused" if fused else "") + ("_graph" if use_graph else "_eager")
+        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p), "fused": bool(sim.fused)}
         out[key + "_error"] = [sim.graph_error, sim.p2p_error]
         out["K"] = sim.K
         sim.close()
@@ -99,9 +101,9 @@ def main():
     if big:
         nx, ny = (int(v) for v in big.lower().split("x"))
         cons, loads, ke = model(nx, ny)
-        for transport, use_graph in (("p2p", True), ("nccl", True)):
+        for transport, use_graph, fused in (("p2p", True, True), ("p2p", True, False), ("nccl", True, False)):
             sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph,
-                           transport=transport)
+                           transport=transport, fused=fused)
             g = 0.0
             for _ in range(3):
                 g, res = sim.step(g)
@@ -115,10 +117,11 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             dt = (time.perf_counter() - t0)/n
-            key = "big_" + transport
+            key = "big_" + transport + ("_fused" if fused else "")
             out[key] = {"mesh": "%dx%d" % (nx, ny), "ms_per_step": dt*1e3, "it_per_s": 1.0/dt, "cg_iters": its,
                         "graph_used": bool(sim.use_graph), "graph_error": sim.graph_error, "p2p": bool(sim.p2p),
-                        "p2p_error": sim.p2p_error, "K": sim.K}
+                        "p2p_error": sim.p2p_error, "K": sim.K, "fused": bool(sim.fused),
+                        "stage_ms": {k: round(v, 3) for k, v in res["stage_ms"].items()}}
             sim.close()
     if rank == 0:
         print(json.dumps(out))
