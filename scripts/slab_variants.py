@@ -31,7 +31,7 @@ def main():
         transport, fused, K = v.split(",")
         try:
             sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, maxit=100000, transport=transport,
-                           fused=bool(int(fused)), K=int(K))
+                           fused=int(fused), K=int(K))
             g, its, stage, comp = 0.0, [], {}, []
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for k in range(warm + steps):
@@ -51,7 +51,7 @@ def main():
             torch.cuda.synchronize()
             t = torch.tensor([ev0.elapsed_time(ev1)/steps], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out = {"variant": v, "world": world, "ms_per_step": round(float(t.item()), 3), "cg_iters": its, "K": sim.K, "fused": sim.fused,
+            out = {"variant": v, "world": world, "ms_per_step": round(float(t.item()), 3), "cg_iters": its, "K": sim.K, "fused": sim.fused, "inkernel": sim.inkernel,
                    "p2p": sim.p2p, "graph": sim.use_graph, "graph_error": sim.graph_error,
                    "solve_us_per_pcg_iteration": round(1e3*stage["solve"]*steps/(sum(its) + steps), 1),
                    "stage_ms": {k: round(x, 3) for k, x in stage.items()}, "compliance_last": comp[-1]}

@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "topo_internal.cuh"
+#include "p2p_ll.cuh"
 
 int topo_fine_pcg_matvec(topo_handle *h, const double2 *z, const double2 *p_in, double2 *p_out, double2 *Ap);
 int topo_fine_update_resid0(topo_handle *h, const double2 *p, const double2 *Ap, const double2 *u_in,
@@ -641,28 +642,6 @@ __global__ void k_p2p_scalar_reduce(double *__restrict__ vals, int n, char *regi
 // flag and no ticket on the critical path: a thread pushes the values of its node, polls its own slot until both halves
 // show the expected number, and completes its node.  Slots are double-buffered by the parity of the sequence number and
 // a stale slot holds an OLDER number, so equality is the only test needed.
-__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned seq) {
-  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
-}
-// bounded spin (~ seconds): a missing peer must not hang the GPU
-__device__ __forceinline__ bool ll_load(const uint4 *src, unsigned seq, double &v, unsigned int *error) {
-  for (long long it = 0; it < (1ll << 24); ++it) {
-    unsigned a, b, c, d;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
-    if (b == seq && d == seq) {
-      v = __hiloint2double((int)c, (int)a);
-      return true;
-    }
-    if (it > 2000) {
-      if (*reinterpret_cast<volatile unsigned int *>(error)) return false;   // somebody already gave up
-      __nanosleep(100);
-    }
-  }
-  *error = 1u;
-  return false;
-}
-
 // Blocks [0, nb): my first row <-> rank-1; [nb, 2nb): my last row <-> rank+1, one node per thread; block 2nb (if
 // nvals > 0): all-reduce of nvals scalars, folded in rank order on every rank (+ the PCG bookkeeping that follows the
 // (rr, rz) all-reduce).
@@ -721,19 +700,13 @@ __global__ void __launch_bounds__(256) k_p2p_fused(const __grid_constant__ Fused
     return;
   }
   // ---- rows ----
-  const unsigned long long seq = c->halo_push + 1;
-  const unsigned s32 = (unsigned)seq;
-  const size_t buf = (size_t)(seq & 1ull) * a.stride;
+  const RowXchg x = {a.region, a.peer_lo, a.peer_hi, a.off_lo, a.off_hi, a.stride, a.c};
+  const unsigned long long seq = ll_rows_seq(x);
   const bool lo = (int)blockIdx.x < a.nb;
   const int i = (lo ? blockIdx.x : blockIdx.x - a.nb) * blockDim.x + t;
-  char *peer = lo ? a.peer_lo : a.peer_hi;
-  if (peer != nullptr && i < a.n) {
+  if ((lo ? a.peer_lo : a.peer_hi) != nullptr && i < a.n) {
     double2 *v = lo ? a.v_lo : a.v_hi;
-    double2 x = v[i];
-    // my first row lands in the lower neighbour's "from above" slot, my last row in the upper neighbour's "from below" slot
-    uint4 *dst = reinterpret_cast<uint4 *>(peer + (lo ? a.off_hi : a.off_lo) + buf) + 2 * (size_t)i;
-    ll_store(dst, x.x, s32);
-    ll_store(dst + 1, x.y, s32);
+    double2 mine = v[i], theirs;
     const double2 *base = lo ? a.base_lo : a.base_hi;
     double2 q = make_double2(0.0, 0.0);
     if (base != nullptr) {
@@ -744,23 +717,14 @@ __global__ void __launch_bounds__(256) k_p2p_fused(const __grid_constant__ Fused
         q = base[i];
       }
     }
-    const uint4 *rcv = reinterpret_cast<const uint4 *>(a.region + (lo ? a.off_lo : a.off_hi) + buf) + 2 * (size_t)i;
-    double bx, by;
-    if (ll_load(rcv, s32, bx, &c->error) && ll_load(rcv + 1, s32, by, &c->error)) {
-      if (base != nullptr) { x.x = (x.x + bx) - q.x; x.y = (x.y + by) - q.y; }
-      else { x.x += bx; x.y += by; }
-      v[i] = x;
+    if (ll_row_swap(x, lo, i, seq, mine, theirs)) {
+      if (base != nullptr) { mine.x = (mine.x + theirs.x) - q.x; mine.y = (mine.y + theirs.y) - q.y; }
+      else { mine.x += theirs.x; mine.y += theirs.y; }
+      v[i] = mine;
     }
   }
   __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    if (atomicAdd(&c->fticket[2], 1u) == 2u * (unsigned)a.nb - 1u) {
-      c->fticket[2] = 0u;
-      c->halo_push = seq;
-      c->halo_wait = seq;
-    }
-  }
+  if (t == 0) ll_rows_done(x, seq, 2u * (unsigned)a.nb);
 }
 
 // level-K pieces to every rank, wait for everybody's, assemble the global right-hand side -- one launch.
@@ -810,6 +774,20 @@ __global__ void __launch_bounds__(256) k_p2p_gather_fused(const double2 *__restr
     }
   }
 }
+
+}  // namespace
+RowXchg topo_dist_row_xchg(const topo_handle *h) {
+  RowXchg x = {};
+  const DistState &D = h->dist;
+  if (!D.on || !D.p2p_on || !D.p2p_inkernel) return x;
+  x.region = D.p2p_region;
+  x.peer_lo = D.has_lo ? D.p2p_peer[D.rank - 1] : nullptr;
+  x.peer_hi = D.has_hi ? D.p2p_peer[D.rank + 1] : nullptr;
+  x.off_lo = D.p2p_off_ll_lo; x.off_hi = D.p2p_off_ll_hi; x.stride = 2 * D.p2p_row_stride;
+  x.c = D.p2p_cnt;
+  return x;
+}
+namespace {
 
 int p2p_check(topo_handle *h) {
   TOPO_TRY(check(h));
@@ -997,6 +975,15 @@ extern "C" int topo_dist_p2p_fused(topo_t *h, int what, int level, int scal_what
   const int blocks = 2 * a.nb + (a.nvals > 0 ? 1 : 0);
   KL(h, "k_p2p_fused", k_p2p_fused<<<blocks, 256, 0, h->stream>>>(a, peer_table(D)));
   CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// in-kernel exchanges on (1) / off (0): the restriction kernels of topo_dist_pcg_update / topo_dist_vcycle_down and the up
+// kernel of topo_dist_vcycle_up swap their interface rows with the neighbours themselves (flag-in-data slots), so the host
+// issues NO TOPO_X_LEVEL_B / TOPO_X_LEVEL_X2 exchange.  One slab per process only (see topo_dist_p2p_fused).
+extern "C" int topo_dist_p2p_mode(topo_t *h, int inkernel) {
+  TOPO_TRY(p2p_check(h));
+  h->dist.p2p_inkernel = inkernel != 0;
   return TOPO_OK;
 }
 

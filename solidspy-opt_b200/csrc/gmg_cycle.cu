@@ -17,6 +17,7 @@
 
 #include "topo_internal.cuh"
 #include "gmg_common.cuh"
+#include "p2p_ll.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -248,6 +249,26 @@ __global__ void __launch_bounds__(LB_X * LB_Y) k_restrict2(const V2 *__restrict_
   if (I > nxc || J > nyc) return;
   bc[(size_t)J * (nxc + 1) + I] = restrict_node(rf, I, J, nxf, nyf);
 }
+// row-slab mode, in-kernel exchange: the threads of the first / last coarse row swap their partial sums with the
+// neighbouring slabs (flag-in-data slots) and store the ACCUMULATED right-hand side -- no separate exchange kernel
+template <class V2>
+__global__ void __launch_bounds__(LB_X * LB_Y) k_restrict_x(const V2 *__restrict__ rf, double2 *__restrict__ bc, int nxf, int nyf,
+                                                            int nxc, int nyc, const int *done, const __grid_constant__ RowXchg x) {
+  if (done && *done) return;
+  const unsigned long long seq = ll_rows_seq(x);
+  const int I = blockIdx.x * LB_X + threadIdx.x, J = blockIdx.y * LB_Y + threadIdx.y;
+  if (I <= nxc && J <= nyc) {
+    double2 b = restrict_node(rf, I, J, nxf, nyf), q;
+    if (J == 0 && x.peer_lo != nullptr && ll_row_swap(x, true, I, seq, b, q)) { b.x += q.x; b.y += q.y; }
+    if (J == nyc && x.peer_hi != nullptr && ll_row_swap(x, false, I, seq, b, q)) { b.x += q.x; b.y += q.y; }
+    bc[(size_t)J * (nxc + 1) + I] = b;
+  }
+  // only the blocks that hold an interface row take part in the end-of-kernel ticket (one atomic per block of a 30 000-block
+  // grid cost more than the exchange saved)
+  if (blockIdx.y != 0 && blockIdx.y != gridDim.y - 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
+}
 // fine grid: x^ += mask(P x1)   (the fine-grid x^ is a float2 array: see FK<>::F32MASK in fine.cu)
 __global__ void __launch_bounds__(LB_X * LB_Y) k_prolong_add_fine2(const double2 *__restrict__ xc, float2 *__restrict__ xf,
                                                                    const uint8_t *__restrict__ fixed, int nxf, int nyf, int nxc,
@@ -334,8 +355,9 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_down_t(const LevelView L, con
 // up: x~ = w D^-1 b + mask(P xc) ; x2 = x~ + w D^-1 (b - A x~)
 template <bool SYM>
 __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const double2 *__restrict__ xcoarse, int cnx, double omega,
-                                                        const int *done) {
+                                                        const int *done, const __grid_constant__ RowXchg x) {
   if (done && *done) return;
+  const unsigned long long seq = x.c != nullptr ? ll_rows_seq(x) : 0ull;
   __shared__ double2 xs[TLY + 2][TLX + 2];
   const int c0 = blockIdx.x * TLX, r0 = blockIdx.y * TLY;
   const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
@@ -362,15 +384,25 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const
     xs[hy][hx] = xv;
   }
   __syncthreads();
-  if (!own) return;
-  double ax, ay;
-  double2 xc;
-  tile_apply<SYM>(L, xs, n, r, c, nn, ax, ay, xc);
-  // row-slab mode: W b makes the distributed copy of b on interface rows (W = 1 elsewhere: fma(1, b, -ax) == b - ax), and
-  // the exchange that completes an interface row of x2 subtracts x~ there, so those rows of x~ are stored
-  const double wr = row_weight(L, r);
-  if (wr != 1.0) L.x[n] = xc;
-  L.x2[n] = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xc.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xc.y));
+  if (own) {
+    double ax, ay;
+    double2 xc;
+    tile_apply<SYM>(L, xs, n, r, c, nn, ax, ay, xc);
+    // row-slab mode: W b makes the distributed copy of b on interface rows (W = 1 elsewhere: fma(1, b, -ax) == b - ax).
+    // An interface row of x2 is completed by x2 + x2(neighbour) - x~: here, by swapping the node with the neighbour
+    // (in-kernel exchange), or by the host's exchange, for which those rows of x~ are stored
+    const double wr = row_weight(L, r);
+    double2 v = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xc.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xc.y)), q;
+    if (wr != 1.0) {
+      if (x.c == nullptr) L.x[n] = xc;
+      else if (ll_row_swap(x, r == 0, c, seq, v, q)) { v.x = (v.x + q.x) - xc.x; v.y = (v.y + q.y) - xc.y; }
+    }
+    L.x2[n] = v;
+  }
+  if (x.c != nullptr && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {      // (blocks that hold an interface row)
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
+  }
 }
 
 // ---- multi-block kernels (large coarse levels): the two-dimensional kernels above + the residual of an iterate ------
@@ -857,7 +889,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     LevelView V = view_of(h, F);
     const int unfused_min = h->knobs.unfused_min;
     if (tiled(l)) {
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, result_of(l + 1), C.nx, om, done)));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, result_of(l + 1), C.nx, om, done, RowXchg{})));
       continue;
     }
     if (F.nn > unfused_min) {
@@ -899,6 +931,13 @@ static int dist_restrict_from(topo_handle *h, int l, const double2 *r) {
   double2 *dst = (l + 1 < D.K) ? h->levels[l + 1].b : D.bK_send;
   const int nxc = h->lvl_nx[l + 1], nyc = nyf / 2;
   const int nb = blocks_for((int64_t)(nxc + 1) * (nyc + 1));
+  const RowXchg x = topo_dist_row_xchg(h);
+  if (x.c != nullptr && l + 1 < D.K) {                     // the interface rows of b_{l+1} are summed inside the kernel
+    if (l == 0) KL(h, "k_restrict_x", k_restrict_x<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(rf32, dst, nxf, nyf, nxc, nyc, done, x));
+    else KL(h, "k_restrict_x", k_restrict_x<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(r, dst, nxf, nyf, nxc, nyc, done, x));
+    CUDA_TRY(cudaGetLastError());
+    return TOPO_OK;
+  }
   if (l == 0) KL(h, "k_restrict", k_restrict2<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(rf32, dst, nxf, nyf, nxc, nyc, done));
   else KL(h, "k_restrict", k_restrict2<<<lvl_grid(nxc, nyc), dim3(LB_X, LB_Y), 0, h->stream>>>(r, dst, nxf, nyf, nxc, nyc, done));
   CUDA_TRY(cudaGetLastError());
@@ -958,7 +997,7 @@ int topo_dist_level_up(topo_handle *h, int l) {
   if (h->knobs.lvl_tiled) {
     // (x = w D^-1 b is recomputed from the accumulated b; the interface rows of x~ are stored for the exchange)
     KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V,
-                                                  dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], h->omega, done)));
+                                                  dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], h->omega, done, topo_dist_row_xchg(h))));
     return TOPO_OK;
   }
   KL(h, "k_lvl_prolong", k_lvl_prolong2<<<lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, h->stream>>>(V, dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], done));

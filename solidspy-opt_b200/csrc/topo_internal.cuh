@@ -123,6 +123,7 @@ struct DistState {
   int filt_hy;
   // peer-memory transport
   bool p2p_on;
+  bool p2p_inkernel;                   // the restriction / up kernels of slab-local levels swap their interface rows themselves
   char *p2p_region;                    // P2PHeader | recv_lo[2][npr] | recv_hi[2][npr] | gather_recv[2][world][bK_count]
   size_t p2p_bytes, p2p_off_lo, p2p_off_hi, p2p_off_gather, p2p_row_stride, p2p_gather_stride;
   size_t p2p_off_ll_lo, p2p_off_ll_hi, p2p_off_ll_gather;   // flag-in-data copies of the three payload areas (32 B per double2)

@@ -34,7 +34,7 @@ SYMBOLS = [
     "topo_dist_vcycle_up", "topo_dist_pcg_smooth", "topo_dist_pcg_finish", "topo_dist_solve_poll",
     "topo_dist_solve_end", "topo_dist_compliance_partial", "topo_dist_filter_pack", "topo_dist_oc",
     "topo_dist_oc_state", "topo_dist_p2p_export", "topo_dist_p2p_attach", "topo_dist_p2p_xchg", "topo_dist_p2p_gather",
-    "topo_dist_p2p_allreduce", "topo_dist_p2p_error", "topo_dist_p2p_fused", "topo_dist_p2p_gather_tail",
+    "topo_dist_p2p_allreduce", "topo_dist_p2p_error", "topo_dist_p2p_fused", "topo_dist_p2p_gather_tail", "topo_dist_p2p_mode",
 ]
 
 # row-slab mode: exchange kinds, gather kinds, scalar blocks (include/topo_b200.h)
@@ -152,6 +152,7 @@ def load_library():
         "topo_dist_p2p_error": [vp, ip],
         "topo_dist_p2p_fused": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
         "topo_dist_p2p_gather_tail": [vp],
+        "topo_dist_p2p_mode": [vp, C.c_int],
         "topo_dist_vcycle_up": [vp, C.c_int],
         "topo_dist_pcg_smooth": [vp, C.c_int, C.c_int],
         "topo_dist_pcg_finish": [vp, C.c_int],

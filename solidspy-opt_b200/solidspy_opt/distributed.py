@@ -199,7 +199,7 @@ class SlabSimp:
 
     def __init__(self, nx, ny, ke, cons, loads, volfrac=0.5, penal=3.0, emin=1e-9, emax=1.0, rmin=None, dx=1.0, dy=1.0,
                  move=0.2, rtol=1e-9, maxit=2000, world=None, dist=None, device=0, K=0, use_graph=True,
-                 transport="p2p", fused=True):
+                 transport="p2p", fused=2):
         import torch
         from solidspy_opt import _capi
         self.torch, self._capi, self.dist = torch, _capi, dist
@@ -247,6 +247,11 @@ class SlabSimp:
         # one-launch exchanges (push + wait + completion [+ all-reduce + bookkeeping] in ONE kernel): only with one slab per
         # process -- several slabs of one process share a stream, where a kernel that waits for a peer would wait forever
         self.fused = bool(fused) and self.p2p and dist is not None and len(self.slabs) == 1
+        # fused == 2 ("inkernel", default with fused=True): the restriction / up kernels of the slab-local levels swap their
+        # interface rows themselves -- no exchange launch at all for those levels
+        self.inkernel = self.fused and fused is not False and int(fused) != 1
+        if self.fused:
+            self.slabs[0].dist_call("p2p_mode", 1 if self.inkernel else 0)
         self._lam_prev = 0.0
         self._last_iters = 0
         self.halo_bytes = 0
@@ -396,12 +401,14 @@ class SlabSimp:
             t = self.slabs[0]
             t.dist_call("pcg_update", par, init)
             for l in range(1, K):
-                t.dist_call("p2p_fused", c.X_LEVEL_B, l, 0, 0, 0)
+                if not self.inkernel:
+                    t.dist_call("p2p_fused", c.X_LEVEL_B, l, 0, 0, 0)
                 t.dist_call("vcycle_down", l)
             t.dist_call("p2p_gather_tail")
             for l in range(K - 1, 0, -1):
                 t.dist_call("vcycle_up", l)
-                t.dist_call("p2p_fused", c.X_LEVEL_X2, l, 0, 0, 0)
+                if not self.inkernel:
+                    t.dist_call("p2p_fused", c.X_LEVEL_X2, l, 0, 0, 0)
             t.dist_call("pcg_smooth", par, init)
             t.dist_call("p2p_fused", c.X_Z, 0, c.S_RR_RZ, 2, 2 if init else 1)
             self.collectives += 2*K + 1

@@ -46,8 +46,10 @@ def main():
     cons, loads, ke = model(nx, ny)
     steps = 4
     # (p2p with and without the one-launch exchanges, graph-captured and eager; NCCL graph-captured and eager)
-    for transport, use_graph, fused in (("p2p", True, True), ("p2p", False, True), ("p2p", True, False), ("nccl", True, False),
-                                        ("nccl", False, False)):
+    # fused: 2 = one-launch exchanges + in-kernel interface rows on the slab-local levels (default), 1 = one-launch exchanges
+    # only, 0 = two-phase push / finish kernels
+    for transport, use_graph, fused in (("p2p", True, 2), ("p2p", False, 2), ("p2p", True, 1), ("p2p", True, 0), ("nccl", True, 0),
+                                        ("nccl", False, 0)):
         sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph,
                        transport=transport, fused=fused)
         g, hist = 0.0, []
@@ -55,8 +57,8 @@ def main():
             g, res = sim.step(g)
             hist.append((res["compliance"], res["cg_iters"], res["oc_steps"], g))
         rho = gather_rho(sim, world)
-        key = transport + ("_fused" if fused else "") + ("_graph" if use_graph else "_eager")
-        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p), "fused": bool(sim.fused)}
+        key = transport + ("_fused%d" % fused if fused else "") + ("_graph" if use_graph else "_eager")
+        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p), "fused": bool(sim.fused), "inkernel": bool(sim.inkernel)}
         out[key + "_error"] = [sim.graph_error, sim.p2p_error]
         out["K"] = sim.K
         sim.close()
@@ -101,7 +103,7 @@ def main():
     if big:
         nx, ny = (int(v) for v in big.lower().split("x"))
         cons, loads, ke = model(nx, ny)
-        for transport, use_graph, fused in (("p2p", True, True), ("p2p", True, False), ("nccl", True, False)):
+        for transport, use_graph, fused in (("p2p", True, 2), ("p2p", True, 1), ("p2p", True, 0), ("nccl", True, 0)):
             sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph,
                            transport=transport, fused=fused)
             g = 0.0
@@ -117,7 +119,7 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             dt = (time.perf_counter() - t0)/n
-            key = "big_" + transport + ("_fused" if fused else "")
+            key = "big_" + transport + ("_fused%d" % fused if fused else "")
             out[key] = {"mesh": "%dx%d" % (nx, ny), "ms_per_step": dt*1e3, "it_per_s": 1.0/dt, "cg_iters": its,
                         "graph_used": bool(sim.use_graph), "graph_error": sim.graph_error, "p2p": bool(sim.p2p),
                         "p2p_error": sim.p2p_error, "K": sim.K, "fused": bool(sim.fused),
