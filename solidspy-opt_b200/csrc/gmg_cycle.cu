@@ -353,11 +353,12 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_down_t(const LevelView L, con
 }
 
 // up: x~ = w D^-1 b + mask(P xc) ; x2 = x~ + w D^-1 (b - A x~)
-template <bool SYM>
+// XCH: row-slab mode (row weights, interface rows of x~ stored or swapped); false: the single-GPU instantiation carries none of it
+template <bool SYM, bool XCH>
 __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const double2 *__restrict__ xcoarse, int cnx, double omega,
                                                         const int *done, const __grid_constant__ RowXchg x) {
   if (done && *done) return;
-  const unsigned long long seq = x.c != nullptr ? ll_rows_seq(x) : 0ull;
+  const unsigned long long seq = (XCH && x.c != nullptr) ? ll_rows_seq(x) : 0ull;
   __shared__ double2 xs[TLY + 2][TLX + 2];
   const int c0 = blockIdx.x * TLX, r0 = blockIdx.y * TLY;
   const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
@@ -391,15 +392,15 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const
     // row-slab mode: W b makes the distributed copy of b on interface rows (W = 1 elsewhere: fma(1, b, -ax) == b - ax).
     // An interface row of x2 is completed by x2 + x2(neighbour) - x~: here, by swapping the node with the neighbour
     // (in-kernel exchange), or by the host's exchange, for which those rows of x~ are stored
-    const double wr = row_weight(L, r);
+    const double wr = XCH ? row_weight(L, r) : 1.0;
     double2 v = make_double2(fma(omega * dv.x, fma(wr, bv.x, -ax), xc.x), fma(omega * dv.y, fma(wr, bv.y, -ay), xc.y)), q;
-    if (wr != 1.0) {
+    if (XCH && wr != 1.0) {
       if (x.c == nullptr) L.x[n] = xc;
       else if (ll_row_swap(x, r == 0, c, seq, v, q)) { v.x = (v.x + q.x) - xc.x; v.y = (v.y + q.y) - xc.y; }
     }
     L.x2[n] = v;
   }
-  if (x.c != nullptr && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {      // (blocks that hold an interface row)
+  if (XCH && x.c != nullptr && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {      // (blocks that hold an interface row)
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
   }
@@ -889,7 +890,7 @@ int topo_gmg_coarse(topo_handle *h, const double2 *res_fine, double2 *xhat_fine,
     LevelView V = view_of(h, F);
     const int unfused_min = h->knobs.unfused_min;
     if (tiled(l)) {
-      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, result_of(l + 1), C.nx, om, done, RowXchg{})));
+      KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true, false> : k_lvl_up_t<false, false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V, result_of(l + 1), C.nx, om, done, RowXchg{})));
       continue;
     }
     if (F.nn > unfused_min) {
@@ -996,7 +997,7 @@ int topo_dist_level_up(topo_handle *h, int l) {
   const int *done = &h->sc->done;
   if (h->knobs.lvl_tiled) {
     // (x = w D^-1 b is recomputed from the accumulated b; the interface rows of x~ are stored for the exchange)
-    KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true> : k_lvl_up_t<false>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V,
+    KL(h, lvl_name("up", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_up_t<true, true> : k_lvl_up_t<false, true>, tile_grid(F.nx, F.ny), dim3(TLX, TLY), 0, V,
                                                   dist_coarse_result(h, l + 1), h->lvl_nx[l + 1], h->omega, done, topo_dist_row_xchg(h))));
     return TOPO_OK;
   }
