@@ -214,6 +214,8 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  h->rho_out_host = nullptr;
   h->inv_pending = false;
   h->inv_overlap = getenv("TOPO_NO_INV_OVERLAP") ? false : true;
   CUDA_TRY(cudaEventCreate(&h->ev0));
@@ -309,6 +311,7 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaStreamDestroy(h->side);
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_inv);
+  cudaEventDestroy(h->ev_copy);
   cudaGetLastError();
   delete h;
   return TOPO_OK;
@@ -475,6 +478,13 @@ extern "C" int topo_simp_step(topo_t *h, const topo_simp_params *p, double *g_in
   *g_inout = g;
   res->g = g;
   CUDA_TRY(cudaEventRecord(h->evs[5], st));
+  if (h->rho_out_host != nullptr) {              // (topo_simp_step_host) download of the new densities || equilibrium guard
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->rho_out_host, h->rho, sizeof(double) * (size_t)h->ne, cudaMemcpyDeviceToHost, h->side));
+    CUDA_TRY(cudaEventRecord(h->ev_copy, h->side));
+    h->rho_out_host = nullptr;                  // (topo_simp_step_host waits for the side stream)
+  }
   TOPO_TRY(topo_equilibrium_check(h, &res->equilibrium_ok));
   CUDA_TRY(cudaEventRecord(h->evs[6], st));
   CUDA_TRY(cudaEventSynchronize(h->evs[6]));
@@ -493,9 +503,13 @@ extern "C" int topo_simp_step_host(topo_t *h, const topo_simp_params *p, const d
   const size_t ev = sizeof(double) * (size_t)h->ne;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpyAsync(h->rho, rho_in, ev, cudaMemcpyHostToDevice, h->stream));
+  h->rho_out_host = rho_out;                     // downloaded by the step itself, overlapping its equilibrium guard
   int s = topo_simp_step(h, p, g_inout, res);
+  const bool copied = h->rho_out_host == nullptr;
+  h->rho_out_host = nullptr;
   if (s != TOPO_OK && s != TOPO_ENOCONV) return s;
-  CUDA_TRY(cudaMemcpyAsync(rho_out, h->rho, ev, cudaMemcpyDeviceToHost, h->stream));
+  if (!copied) CUDA_TRY(cudaMemcpyAsync(rho_out, h->rho, ev, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->side));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return s;
 }

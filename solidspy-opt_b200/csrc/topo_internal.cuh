@@ -166,6 +166,10 @@ struct topo_handle {
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_inv;
   bool inv_pending, inv_overlap;
+  // topo_simp_step_host: the download of the new densities starts on the side stream as soon as the OC update has
+  // finished and overlaps the equilibrium guard (K u = f check: three passes over the fine grid)
+  double *rho_out_host;
+  cudaEvent_t ev_copy;
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
