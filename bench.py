@@ -542,7 +542,11 @@ def main():
                 row.update(algorithmic_mb=round(alg[nm]/1e6, 2), gbs=round(gbs, 1), frac=round(gbs/peak, 4))
             rows.append(row)
         dom = next((r for r in rows if "gbs" in r), None)
-        traffic = {"k_fine<update_resid0>": (189564160 + 73890560, "profiles/r1_ncu_k_fine_update_resid0.txt")}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of the round's final kernels on this mesh
+        src = "profiles/r2_ncu_cycle_tiled_raw.csv"
+        traffic = {"k_fine<update_resid0>": (189531136 + 72666880, src), "k_fine<smooth_dot>": (92902400 + 11430656, src),
+                   "k_fine<pcg_matvec>": (104573440 + 30194944, src), "k_tail2": (2443008, src),
+                   "k_lvl_down L1": (67291904 + 4879104, src), "k_lvl_up L1": (61012224 + 1015552, src)}
         mv_iso = (32*nn + 8*ne)/(mv_iso_ms*1e-3)/1e9
         timed = res_dev[W:]
         line = {

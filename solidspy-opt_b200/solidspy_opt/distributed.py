@@ -472,6 +472,8 @@ class SlabSimp:
             done, iters, relres = self.slabs[0].dist_solve_poll()
             if done or launched >= self.maxit:
                 break
+            if self.p2p and launched and any(t.dist_p2p_error() for t in self.slabs):
+                break                                                  # a peer never answered: stop queueing work (raised below)
             # consecutive design iterations need almost the same number of PCG iterations: enqueue the expected
             # count (minus one) before the first poll, then poll after every pair
             if self._last_iters > 4:
