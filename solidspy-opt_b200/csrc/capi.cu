@@ -215,6 +215,9 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_edge[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_edge[1], cudaEventDisableTiming));
+  h->edge_pending = false;
   h->rho_out_host = nullptr;
   h->inv_pending = false;
   h->inv_overlap = getenv("TOPO_NO_INV_OVERLAP") ? false : true;
@@ -312,6 +315,8 @@ extern "C" int topo_destroy(topo_t *h) {
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_inv);
   cudaEventDestroy(h->ev_copy);
+  cudaEventDestroy(h->ev_edge[0]);
+  cudaEventDestroy(h->ev_edge[1]);
   cudaGetLastError();
   delete h;
   return TOPO_OK;

@@ -183,32 +183,89 @@ __device__ __forceinline__ void level1_entries(const KeParam &ke, const L1Childr
   }
 }
 
+// ---- branch-free path of the two kernels below ----------------------------------------------------------------------------
+// ncu (profiles/r2_ncu_kernels.txt): k_stencil_level1 and k_cells_level2 execute ~2000 instructions per thread for 256-768
+// FMAs -- the rest is the bookkeeping of cells cut by the mesh edge and of children that touch constrained DOFs (9 flag
+// bytes per level-1 cell, bit packing, run-time interpolation variants: indexed constant loads), at 144-154 registers.
+// Away from the mesh edge and from the supports none of it is needed: every cell has its four children, every variant
+// index is a compile-time constant and the node weights of a child are the constants 1, 1/2, 1/4, 0.  k_interior_flags
+// marks those level-1 nodes / level-2 cells once per set-up; the FAST instantiations handle them with the SAME fma chains
+// in the same order (terms with an exactly zero weight dropped: fma(m, 0, s) == s), so the operators are bit-identical;
+// the general instantiations handle the rest (a strip along the mesh edge and the supports).
+__device__ __forceinline__ void level1_load_fast(const double *__restrict__ scale, int nxf, int I, int J, double (&s)[4]) {
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) s[2 * cy + cx] = __ldg(scale + (size_t)(2 * J + cy) * nxf + (2 * I + cx));
+}
+template <int NE, class Idx>
+__device__ __forceinline__ void level1_entries_fast(const double (&s)[4], Idx idx, double (&acc)[NE]) {
+#pragma unroll
+  for (int q = 0; q < NE; ++q) acc[q] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < NE; ++q) acc[q] = fma(s[c], c_g.g[3 * (c >> 1) + (c & 1)][idx(q)], acc[q]);
+}
+__device__ __forceinline__ bool fixed_block_clear(const uint8_t *__restrict__ fixed, int npr0, int r0, int c0, int rows, int cols) {
+  unsigned any = 0u;
+  for (int j = 0; j < rows; ++j)
+    for (int i = 0; i < cols; ++i) any |= (unsigned)__ldg(fixed + (size_t)(r0 + j) * npr0 + (c0 + i));
+  return (any & 3u) == 0u;
+}
+// fine mesh nx0 x ny0, level 1 nx1 x ny1 cells, level 2 nx2 x ny2 cells
+__global__ void k_interior_flags(const uint8_t *__restrict__ fixed, int nx0, int ny0, int nx1, int ny1, int nx2, int ny2,
+                                 uint8_t *__restrict__ node1, uint8_t *__restrict__ cell2) {
+  const int64_t nn1 = (int64_t)(nx1 + 1) * (ny1 + 1), nc2 = (int64_t)nx2 * ny2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nn1) {
+    const int r = (int)(t / (nx1 + 1)), c = (int)(t - (int64_t)r * (nx1 + 1));
+    // the four cells around the node exist and have 2 x 2 children; no constrained DOF among the 5 x 5 fine nodes around
+    bool ok = r >= 1 && r <= ny1 - 1 && c >= 1 && c <= nx1 - 1 && 2 * c + 2 <= nx0 && 2 * r + 2 <= ny0;
+    if (ok) ok = fixed_block_clear(fixed, nx0 + 1, 2 * r - 2, 2 * c - 2, 5, 5);
+    node1[t] = ok ? 1 : 0;
+  }
+  if (cell2 != nullptr && t < nc2) {
+    const int J = (int)(t / nx2), I = (int)(t - (int64_t)J * nx2);
+    // 2 x 2 children with 2 x 2 children each; no constrained DOF among the cell's 5 x 5 fine nodes
+    bool ok = 2 * I + 2 <= nx1 && 2 * J + 2 <= ny1 && 4 * I + 4 <= nx0 && 4 * J + 4 <= ny0;
+    if (ok) ok = fixed_block_clear(fixed, nx0 + 1, 4 * J, 4 * I, 5, 5);
+    cell2[t] = ok ? 1 : 0;
+  }
+}
+
 // level-1 node stencil (and D^-1) from the element scales: per adjacent cell the two matrix rows of this node
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_stencil_level1(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
                                                         const uint8_t *__restrict__ fixed, stencil_t *__restrict__ st,
-                                                        double2 *__restrict__ dinv, int nxf, int nyf, int nx, int ny) {
+                                                        double2 *__restrict__ dinv, int nxf, int nyf, int nx, int ny,
+                                                        const uint8_t *__restrict__ interior) {
   const int npr = nx + 1;
   const int64_t nn = (int64_t)npr * (ny + 1);
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nn) return;
+  if ((interior[n] != 0) != FAST) return;                // (the other instantiation handles this node)
   const int r = (int)(n / npr), c = (int)(n - (int64_t)r * npr);
   double s[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) s[k] = 0.0;
   const int cro[4] = {0, 0, -1, -1}, cco[4] = {0, -1, -1, 0};
-  L1Children ch[4];
+  L1Children ch[FAST ? 1 : 4];
+  double sc[FAST ? 4 : 1][4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int cr = r + cro[q], cc = c + cco[q];
-    level1_load(scale, fixed, nxf, nyf, cc, cr, !(cr < 0 || cr >= ny || cc < 0 || cc >= nx), ch[q]);
+    if (FAST) level1_load_fast(scale, nxf, cc, cr, sc[FAST ? q : 0]);
+    else level1_load(scale, fixed, nxf, nyf, cc, cr, !(cr < 0 || cr >= ny || cc < 0 || cc >= nx), ch[FAST ? 0 : q]);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int cr = r + cro[q], cc = c + cco[q];
-    if (cr < 0 || cr >= ny || cc < 0 || cc >= nx) continue;
+    if (!FAST && (cr < 0 || cr >= ny || cc < 0 || cc >= nx)) continue;
     const int a = q;                                     // local index of this node in that cell
     double part[16];                                     // rows 2a, 2a+1 of the cell matrix
-    level1_entries<16>(ke, ch[q], [a](int t) { return (2 * a + (t >> 3)) * 8 + (t & 7); }, part);
+    if (FAST) level1_entries_fast<16>(sc[FAST ? q : 0], [a](int t) { return (2 * a + (t >> 3)) * 8 + (t & 7); }, part);
+    else level1_entries<16>(ke, ch[FAST ? 0 : q], [a](int t) { return (2 * a + (t >> 3)) * 8 + (t & 7); }, part);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int dr = cr + ly(b) - r, dc = cc + lx(b) - c;
@@ -228,25 +285,34 @@ __global__ void __launch_bounds__(128) k_stencil_level1(const __grid_constant__ 
 }
 
 // level-2 cells from the element scales: k_cells_coarsen with the child (level-1) cell entries computed on the fly
+// FAST (cells marked by k_interior_flags): the component pair (d, e) is a compile-time parameter (the matrix indices of
+// the Galerkin table become immediates), the child weights are constants and their zero terms are not executed
+template <bool FAST, int DE>
 __global__ void __launch_bounds__(128) k_cells_level2(const __grid_constant__ KeParam ke, const double *__restrict__ scale,
                                                       const uint8_t *__restrict__ fixed, double *__restrict__ ccell, int nx0,
-                                                      int ny0, int nxf, int nyf, int nxc, int nyc) {
+                                                      int ny0, int nxf, int nyf, int nxc, int nyc,
+                                                      const uint8_t *__restrict__ interior) {
   const int64_t ncc = (int64_t)nxc * nyc;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ncc) return;
-  const int d = blockIdx.y >> 1, e = blockIdx.y & 1;
+  if ((interior[t] != 0) != FAST) return;                // (the other instantiation handles this cell)
+  const int d = FAST ? (DE >> 1) : (int)(blockIdx.y >> 1), e = FAST ? (DE & 1) : (int)(blockIdx.y & 1);
   const int J = (int)(t / nxc), I = (int)(t - (int64_t)J * nxc);
-  const int sx = min(2, nxf - 2 * I), sy = min(2, nyf - 2 * J);
+  const int sx = FAST ? 2 : min(2, nxf - 2 * I), sy = FAST ? 2 : min(2, nyf - 2 * J);
   double acc[4][4];
 #pragma unroll
   for (int A = 0; A < 4; ++A)
 #pragma unroll
     for (int B = 0; B < 4; ++B) acc[A][B] = 0.0;
-  L1Children ch[4];
+  L1Children ch[FAST ? 1 : 4];
+  double sc[FAST ? 4 : 1][4];
 #pragma unroll
   for (int cy = 0; cy < 2; ++cy)
 #pragma unroll
-    for (int cx = 0; cx < 2; ++cx) level1_load(scale, fixed, nx0, ny0, 2 * I + cx, 2 * J + cy, cx < sx && cy < sy, ch[2 * cy + cx]);
+    for (int cx = 0; cx < 2; ++cx) {
+      if (FAST) level1_load_fast(scale, nx0, 2 * I + cx, 2 * J + cy, sc[FAST ? 2 * cy + cx : 0]);
+      else level1_load(scale, fixed, nx0, ny0, 2 * I + cx, 2 * J + cy, cx < sx && cy < sy, ch[FAST ? 0 : 2 * cy + cx]);
+    }
 #pragma unroll
   for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
@@ -254,19 +320,21 @@ __global__ void __launch_bounds__(128) k_cells_level2(const __grid_constant__ Ke
       if (cx >= sx || cy >= sy) continue;
       const int v = 3 * (sy == 2 ? cy : 2) + (sx == 2 ? cx : 2);
       double m16[16];                                    // M[a][b] = child cell entry (2a+d, 2b+e)
-      level1_entries<16>(ke, ch[2 * cy + cx], [d, e](int q) { return (2 * (q >> 2) + d) * 8 + 2 * (q & 3) + e; }, m16);
+      if (FAST) level1_entries_fast<16>(sc[FAST ? 2 * cy + cx : 0], [d, e](int q) { return (2 * (q >> 2) + d) * 8 + 2 * (q & 3) + e; }, m16);
+      else level1_entries<16>(ke, ch[FAST ? 0 : 2 * cy + cx], [d, e](int q) { return (2 * (q >> 2) + d) * 8 + 2 * (q & 3) + e; }, m16);
       double W[4][4], T[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int A = 0; A < 4; ++A) W[a][A] = c_pw.w[v][a][A];
+        for (int A = 0; A < 4; ++A) W[a][A] = FAST ? l1d(cx, lx(a), lx(A)) * l1d(cy, ly(a), ly(A)) : c_pw.w[v][a][A];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int B = 0; B < 4; ++B) {
           double s = 0.0;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) s = fma(m16[4 * a + b], W[b][B], s);
+          for (int b = 0; b < 4; ++b)
+            if (!FAST || W[b][B] != 0.0) s = fma(m16[4 * a + b], W[b][B], s);
           T[a][B] = s;
         }
 #pragma unroll
@@ -275,7 +343,8 @@ __global__ void __launch_bounds__(128) k_cells_level2(const __grid_constant__ Ke
         for (int B = 0; B < 4; ++B) {
           double s = acc[A][B];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) s = fma(W[a][A], T[a][B], s);
+          for (int a = 0; a < 4; ++a)
+            if (!FAST || W[a][A] != 0.0) s = fma(W[a][A], T[a][B], s);
           acc[A][B] = s;
         }
     }
@@ -499,6 +568,8 @@ int topo_gmg_plan(topo_handle *h) {
     // level-1 cells are never stored (k_stencil_level1 / k_cells_level2 work from the element scales)
     // (row-slab mode with K == 1: level 1 is the first global level and its gathered cells live here)
     if (l >= 2 || (h->dist.on && h->dist.K == 1)) CUDA_TRY(cudaMalloc(&L.cell, sizeof(double) * 64 * (size_t)L.ncell));
+    if (l == 1) CUDA_TRY(cudaMalloc(&L.interior, (size_t)L.nn));          // per level-1 node
+    if (l == 2) CUDA_TRY(cudaMalloc(&L.interior, (size_t)L.ncell));       // per level-2 cell
   }
   // Per-cycle data of the levels: level 1 gets its own allocation; levels >= 2 (and the coarsest dense
   // inverse) share ONE slab so that a single L2 persisting access-policy window can cover them -- the
@@ -632,6 +703,51 @@ static int invert_coarsest(topo_handle *h) {
   return TOPO_OK;
 }
 
+// level-1 stencil / level-2 cells straight from the element scales of an nx0 x ny0 mesh (the whole mesh, or a slab):
+// interior flags first, then the branch-free instantiations for the marked nodes / cells and the general ones for the rest
+// Order: flags | side stream: level-2 edge cells, level-1 edge nodes | main stream: level-2 cells, level-1 stencil, then
+// the join with the level-2 edge cells (the coarsening chain that follows reads all level-2 cells).  The level-1 edge
+// nodes are joined by join_level1_edge at the end of the set-up.  Profile mode (event brackets on the main stream):
+// everything on the main stream.
+static int launch_level12(topo_handle *h, int nx1, int ny1, double *cell2, int nx2, int ny2) {
+  cudaStream_t st = h->stream;
+  GmgLevel &L1 = h->levels[1];
+  uint8_t *f1 = L1.interior, *f2 = (cell2 != nullptr) ? h->levels[2].interior : nullptr;
+  const int64_t nn1 = (int64_t)(nx1 + 1) * (ny1 + 1), nc2 = (int64_t)nx2 * ny2;
+  KL(h, "k_interior_flags", k_interior_flags<<<blocks_for(std::max<int64_t>(nn1, cell2 ? nc2 : 0), 256), 256, 0, st>>>(h->fixed, h->nx, h->ny, nx1, ny1, nx2, ny2, f1, f2));
+  const bool side = !h->prof_on;
+  cudaStream_t se = side ? h->side : st;
+  if (side) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  }
+  const dim3 g1(blocks_for(nc2), 1), g4(blocks_for(nc2), 4);
+#define TOPO_CL2(FAST, DE, GRID, STREAM) k_cells_level2<FAST, DE><<<GRID, 128, 0, STREAM>>>(h->ke, h->scale, h->fixed, cell2, h->nx, h->ny, nx1, ny1, nx2, ny2, f2)
+#define TOPO_ST1(FAST, STREAM) k_stencil_level1<FAST><<<blocks_for(nn1), 128, 0, STREAM>>>(h->ke, h->scale, h->fixed, L1.st, L1.dinv, h->nx, h->ny, nx1, ny1, f1)
+  if (cell2 != nullptr) KL(h, "k_cells_level2 edge", TOPO_CL2(false, 0, g4, se));
+  if (side) CUDA_TRY(cudaEventRecord(h->ev_edge[0], h->side));
+  KL(h, "k_stencil_level1 edge", TOPO_ST1(false, se));
+  if (side) {
+    CUDA_TRY(cudaEventRecord(h->ev_edge[1], h->side));
+    h->edge_pending = true;
+  }
+  if (cell2 != nullptr)
+    KL(h, "k_cells_level2", (TOPO_CL2(true, 0, g1, st), TOPO_CL2(true, 1, g1, st), TOPO_CL2(true, 2, g1, st), TOPO_CL2(true, 3, g1, st)));
+  KL(h, "k_stencil_level1", TOPO_ST1(true, st));
+#undef TOPO_CL2
+#undef TOPO_ST1
+  if (side) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_edge[0], 0));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+static int join_level1_edge(topo_handle *h) {
+  if (h->edge_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_edge[1], 0));
+    h->edge_pending = false;
+  }
+  return TOPO_OK;
+}
+
 int topo_gmg_setup(topo_handle *h) {
   if (h->n_levels < 2) return TOPO_OK;
   if (h->dist.on) {
@@ -640,10 +756,10 @@ int topo_gmg_setup(topo_handle *h) {
   }
   cudaStream_t st = h->stream;
   TOPO_TRY(upload_gtable(h));
-  if (h->n_levels > 2) {
-    GmgLevel &F = h->levels[1], &C = h->levels[2];
-    dim3 grid(blocks_for(C.ncell), 4);
-    KL(h, "k_cells_level2", k_cells_level2<<<grid, 128, 0, st>>>(h->ke, h->scale, h->fixed, C.cell, h->nx, h->ny, F.nx, F.ny, C.nx, C.ny));
+  {
+    GmgLevel &F = h->levels[1];
+    if (h->n_levels > 2) TOPO_TRY(launch_level12(h, F.nx, F.ny, h->levels[2].cell, h->levels[2].nx, h->levels[2].ny));
+    else TOPO_TRY(launch_level12(h, F.nx, F.ny, nullptr, 0, 0));
   }
   for (int l = 3; l < h->n_levels; ++l) {
     GmgLevel &F = h->levels[l - 1], &C = h->levels[l];
@@ -651,12 +767,16 @@ int topo_gmg_setup(topo_handle *h) {
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
   // coarsest level first: its dense inverse (side stream) then overlaps the stencils of the other levels
-  for (int l = h->n_levels - 1; l >= 1; --l) {
+  for (int l = h->n_levels - 1; l >= 2; --l) {
     GmgLevel &L = h->levels[l];
-    if (l == 1) KL(h, "k_stencil_level1", k_stencil_level1<<<blocks_for(L.nn), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.st, L.dinv, h->nx, h->ny, L.nx, L.ny));
-    else KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
     if (l == h->n_levels - 1) TOPO_TRY(invert_coarsest(h));
   }
+  if (h->n_levels == 2) {                                  // level 1 is the coarsest: its stencil was written above
+    TOPO_TRY(join_level1_edge(h));
+    TOPO_TRY(invert_coarsest(h));
+  }
+  TOPO_TRY(join_level1_edge(h));
   h->gmg_valid = true;
   return TOPO_OK;
 }
@@ -709,9 +829,7 @@ int topo_dist_setup_local(topo_handle *h) {
     KL(h, "k_cells_level1", k_cells_level1<<<blocks_for((int64_t)nxc * nyc), 128, 0, st>>>(h->ke, h->scale, h->fixed, local_cells(1), h->nx, h->ny,
                                                                                             nxc, nyc));
   } else {
-    const int nxf = h->lvl_nx[1], nyf = local_ny(1), nxc = h->lvl_nx[2], nyc = local_ny(2);
-    dim3 grid(blocks_for((int64_t)nxc * nyc), 4);
-    KL(h, "k_cells_level2", k_cells_level2<<<grid, 128, 0, st>>>(h->ke, h->scale, h->fixed, local_cells(2), h->nx, h->ny, nxf, nyf, nxc, nyc));
+    TOPO_TRY(launch_level12(h, h->lvl_nx[1], local_ny(1), local_cells(2), h->lvl_nx[2], local_ny(2)));
   }
   for (int l = 3; l <= K; ++l) {
     const int nxf = h->lvl_nx[l - 1], nyf = local_ny(l - 1), nxc = h->lvl_nx[l], nyc = local_ny(l);
@@ -720,9 +838,9 @@ int topo_dist_setup_local(topo_handle *h) {
   }
   for (int l = 1; l < K; ++l) {
     GmgLevel &L = h->levels[l];
-    if (l == 1) KL(h, "k_stencil_level1", k_stencil_level1<<<blocks_for(L.nn), 128, 0, st>>>(h->ke, h->scale, h->fixed, L.st, L.dinv, h->nx, h->ny, L.nx, L.ny));
-    else KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
+    if (l >= 2) KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
   }
+  TOPO_TRY(join_level1_edge(h));
   long long off = 0;
   for (int l = 0; l < K; ++l) {
     const int npr = h->lvl_nx[l] + 1, ny = local_ny(l);
@@ -777,7 +895,10 @@ void topo_tail2_forget(topo_handle *h);
 
 void topo_gmg_free(topo_handle *h) {
   topo_tail2_forget(h);
-  for (size_t l = 1; l < h->levels.size(); ++l) cudaFree(h->levels[l].cell);
+  for (size_t l = 1; l < h->levels.size(); ++l) {
+    cudaFree(h->levels[l].cell);
+    cudaFree(h->levels[l].interior);
+  }
   h->levels.clear();
   cudaFree(h->lvl1_slab);
   cudaFree(h->coarse_slab);

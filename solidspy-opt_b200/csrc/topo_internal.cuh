@@ -77,6 +77,10 @@ struct GmgLevel {
   double2 *dinv;       // 1/diag (0 at constrained DOFs)
   double2 *x, *x2, *b, *r;
   uint8_t *fixed;
+  // level 1: one byte per NODE, level 2: one byte per CELL -- 1 where the Galerkin set-up may take its branch-free path
+  // (all cells / children around exist in full and no constrained DOF is near); rewritten by every set-up because
+  // ESO / BESO pin nodes as they go
+  uint8_t *interior;
 };
 
 // Row-slab decomposition: this handle is slab `rank` of `world` equal slabs of a mesh with ny_global
@@ -170,6 +174,11 @@ struct topo_handle {
   // finished and overlaps the equilibrium guard (K u = f check: three passes over the fine grid)
   double *rho_out_host;
   cudaEvent_t ev_copy;
+  // multigrid set-up: the general ("edge") instantiations of the level-1 / level-2 Galerkin kernels do a strip of nodes
+  // along the mesh edge and the supports -- a few warps with a long dependent instruction stream (70 us whatever the
+  // mesh) -- and run on the side stream next to the branch-free kernels; joined through these events
+  cudaEvent_t ev_edge[2];
+  bool edge_pending;
 
   // fine-grid fields
   double2 *u, *f, *r, *z, *p, *Ap, *dinv, *tmp, *tmp2, *u2, *r2, *p2;
