@@ -253,8 +253,7 @@ def algorithmic_bytes(levels, tail_max=10000):
         co = [512*nc[l - 1] + 512*nc[l] for l in range(2, L)]
         if co:
             out["k_cells_coarsen"] = sum(co)/(4.0*len(co))                 # four launches (one per component pair) per level
-        cs = [512*nc[l] + 160*nn[l] for l in range(1, L)]
-        out["k_cells_to_stencil"] = sum(cs)/len(cs)
+        out["k_cells_to_stencil"] = sum(512*nc[l] + 160*nn[l] for l in range(2, L))    # all levels >= 2 in one launch
         out["k_coarse_invert"] = 144*nn[L - 1] + 8*(2*nn[L - 1])**2
     return out
 

@@ -416,8 +416,20 @@ __global__ void __launch_bounds__(128) k_cells_coarsen(const double *__restrict_
 
 // ---- cells -> node stencils ---------------------------------------------------------------------------
 // stencil plane index: 4*nb + 2*i + j with nb = 3*(dr+1) + (dc+1)
-__global__ void __launch_bounds__(128) k_cells_to_stencil(const double *__restrict__ cell, stencil_t *__restrict__ st,
-                                                          double2 *__restrict__ dinv, int nx, int ny) {
+// (all levels of a set-up in ONE launch, blockIdx.y = entry: the levels are independent of each other once their cells
+// exist, and seven launches of 11 us each were latency, not work)
+struct ToStencilArgs {
+  const double *cell[TOPO_MAX_LEVELS];
+  stencil_t *st[TOPO_MAX_LEVELS];
+  double2 *dinv[TOPO_MAX_LEVELS];
+  int nx[TOPO_MAX_LEVELS], ny[TOPO_MAX_LEVELS];
+};
+__global__ void __launch_bounds__(128) k_cells_to_stencil(const __grid_constant__ ToStencilArgs args) {
+  const int lv = blockIdx.y;
+  const double *__restrict__ cell = args.cell[lv];
+  stencil_t *__restrict__ st = args.st[lv];
+  double2 *__restrict__ dinv = args.dinv[lv];
+  const int nx = args.nx[lv], ny = args.ny[lv];
   const int npr = nx + 1;
   const int64_t nn = (int64_t)npr * (ny + 1), ncell = (int64_t)nx * ny;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -705,6 +717,21 @@ static int invert_coarsest(topo_handle *h) {
 
 // level-1 stencil / level-2 cells straight from the element scales of an nx0 x ny0 mesh (the whole mesh, or a slab):
 // interior flags first, then the branch-free instantiations for the marked nodes / cells and the general ones for the rest
+// node stencils + D^-1 of levels [l0, l1) from their cells, one launch
+static int launch_to_stencil(topo_handle *h, int l0, int l1) {
+  if (l1 <= l0) return TOPO_OK;
+  ToStencilArgs a = {};
+  int64_t nmax = 0;
+  for (int l = l0; l < l1; ++l) {
+    const GmgLevel &L = h->levels[l];
+    a.cell[l - l0] = L.cell; a.st[l - l0] = L.st; a.dinv[l - l0] = L.dinv; a.nx[l - l0] = L.nx; a.ny[l - l0] = L.ny;
+    nmax = std::max<int64_t>(nmax, L.nn);
+  }
+  KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<dim3(blocks_for(nmax), l1 - l0), 128, 0, h->stream>>>(a));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
 // Order: flags | side stream: level-2 edge cells, level-1 edge nodes | main stream: level-2 cells, level-1 stencil, then
 // the join with the level-2 edge cells (the coarsening chain that follows reads all level-2 cells).  The level-1 edge
 // nodes are joined by join_level1_edge at the end of the set-up.  Profile mode (event brackets on the main stream):
@@ -766,12 +793,8 @@ int topo_gmg_setup(topo_handle *h) {
     dim3 grid(blocks_for(C.ncell), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
-  // coarsest level first: its dense inverse (side stream) then overlaps the stencils of the other levels
-  for (int l = h->n_levels - 1; l >= 2; --l) {
-    GmgLevel &L = h->levels[l];
-    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
-    if (l == h->n_levels - 1) TOPO_TRY(invert_coarsest(h));
-  }
+  TOPO_TRY(launch_to_stencil(h, 2, h->n_levels));
+  if (h->n_levels > 2) TOPO_TRY(invert_coarsest(h));       // (side stream: overlaps the start of the solve)
   if (h->n_levels == 2) {                                  // level 1 is the coarsest: its stencil was written above
     TOPO_TRY(join_level1_edge(h));
     TOPO_TRY(invert_coarsest(h));
@@ -836,10 +859,7 @@ int topo_dist_setup_local(topo_handle *h) {
     dim3 grid(blocks_for((int64_t)nxc * nyc), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(local_cells(l - 1), local_cells(l), nxf, nyf, nxc, nyc));
   }
-  for (int l = 1; l < K; ++l) {
-    GmgLevel &L = h->levels[l];
-    if (l >= 2) KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
-  }
+  TOPO_TRY(launch_to_stencil(h, 2, K));
   TOPO_TRY(join_level1_edge(h));
   long long off = 0;
   for (int l = 0; l < K; ++l) {
@@ -882,10 +902,7 @@ int topo_dist_setup_global(topo_handle *h) {
     dim3 grid(blocks_for(C.ncell), 4);
     KL(h, "k_cells_coarsen", k_cells_coarsen<<<grid, 128, 0, st>>>(F.cell, C.cell, F.nx, F.ny, C.nx, C.ny));
   }
-  for (int l = K; l < h->n_levels; ++l) {
-    GmgLevel &L = h->levels[l];
-    KL(h, "k_cells_to_stencil", k_cells_to_stencil<<<blocks_for(L.nn), 128, 0, st>>>(L.cell, L.st, L.dinv, L.nx, L.ny));
-  }
+  TOPO_TRY(launch_to_stencil(h, K, h->n_levels));
   TOPO_TRY(invert_coarsest(h));
   h->gmg_valid = true;
   return TOPO_OK;
