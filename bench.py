@@ -452,6 +452,23 @@ def main():
                 single_ms = big.timer_stop()/n_timed
                 mv_after = big.matvec_device(20)             # the same launch on the state the design iterations left behind
                 mv_ms = mv_fresh
+                # per-kernel roofline on THIS mesh (every operand streams from HBM): two more design iterations with every
+                # launch bracketed by CUDA events (graph replay off), same accounting as roofline.kernels
+                big.profile_matvec(True)
+                for _ in range(2):
+                    g, r = big.simp_step(pb, g)
+                rep_big = big.profile_report()
+                big.profile_matvec(False)
+                alg_big = algorithmic_bytes(big.gmg_levels())
+                peak_big = measured_peak()[0]
+                kern_big = []
+                for nm, n, ms in rep_big[:14]:
+                    row = {"kernel": nm, "avg_us": round(ms*1e3/n, 1), "ms_per_step": round(ms/2, 3)}
+                    if alg_big.get(nm):
+                        gbs = alg_big[nm]/(ms*1e-3/n)/1e9
+                        row.update(gbs=round(gbs, 1), frac=round(gbs/peak_big, 3))
+                    kern_big.append(row)
+                out["single_gpu_kernels"] = kern_big
             mv_bytes = 32*(bx + 1)*(by + 1) + 8*bx*by
             out.update(single_gpu_ms_per_step=single_ms, single_gpu_it_per_s=1e3/single_ms, single_gpu_cg_iters=its1,
                        single_gpu_matvec={"avg_launch_us": mv_ms*1e3, "algorithmic_bytes": mv_bytes,
