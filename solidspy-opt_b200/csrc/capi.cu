@@ -185,6 +185,7 @@ extern "C" int topo_create(topo_t **out, int nx, int ny, const double ke[64], in
     k.tail_kind = (int)env_i("TOPO_TAIL_KIND", 2);
     k.extrap = getenv("TOPO_EXTRAP") ? atof(getenv("TOPO_EXTRAP")) : 0.0;
     k.lvl_tiled = (int)env_i("TOPO_LVL_TILED", 1);
+    k.setup_fast = (int)env_i("TOPO_SETUP_FAST", 1);
   }
   h->omega = getenv("TOPO_OMEGA") ? atof(getenv("TOPO_OMEGA")) : 0.7;
   h->nu_pre = 1;

@@ -215,20 +215,20 @@ __device__ __forceinline__ bool fixed_block_clear(const uint8_t *__restrict__ fi
 }
 // fine mesh nx0 x ny0, level 1 nx1 x ny1 cells, level 2 nx2 x ny2 cells
 __global__ void k_interior_flags(const uint8_t *__restrict__ fixed, int nx0, int ny0, int nx1, int ny1, int nx2, int ny2,
-                                 uint8_t *__restrict__ node1, uint8_t *__restrict__ cell2) {
+                                 uint8_t *__restrict__ node1, uint8_t *__restrict__ cell2, int enable) {
   const int64_t nn1 = (int64_t)(nx1 + 1) * (ny1 + 1), nc2 = (int64_t)nx2 * ny2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < nn1) {
     const int r = (int)(t / (nx1 + 1)), c = (int)(t - (int64_t)r * (nx1 + 1));
     // the four cells around the node exist and have 2 x 2 children; no constrained DOF among the 5 x 5 fine nodes around
-    bool ok = r >= 1 && r <= ny1 - 1 && c >= 1 && c <= nx1 - 1 && 2 * c + 2 <= nx0 && 2 * r + 2 <= ny0;
+    bool ok = enable && r >= 1 && r <= ny1 - 1 && c >= 1 && c <= nx1 - 1 && 2 * c + 2 <= nx0 && 2 * r + 2 <= ny0;
     if (ok) ok = fixed_block_clear(fixed, nx0 + 1, 2 * r - 2, 2 * c - 2, 5, 5);
     node1[t] = ok ? 1 : 0;
   }
   if (cell2 != nullptr && t < nc2) {
     const int J = (int)(t / nx2), I = (int)(t - (int64_t)J * nx2);
     // 2 x 2 children with 2 x 2 children each; no constrained DOF among the cell's 5 x 5 fine nodes
-    bool ok = 2 * I + 2 <= nx1 && 2 * J + 2 <= ny1 && 4 * I + 4 <= nx0 && 4 * J + 4 <= ny0;
+    bool ok = enable && 2 * I + 2 <= nx1 && 2 * J + 2 <= ny1 && 4 * I + 4 <= nx0 && 4 * J + 4 <= ny0;
     if (ok) ok = fixed_block_clear(fixed, nx0 + 1, 4 * J, 4 * I, 5, 5);
     cell2[t] = ok ? 1 : 0;
   }
@@ -741,7 +741,7 @@ static int launch_level12(topo_handle *h, int nx1, int ny1, double *cell2, int n
   GmgLevel &L1 = h->levels[1];
   uint8_t *f1 = L1.interior, *f2 = (cell2 != nullptr) ? h->levels[2].interior : nullptr;
   const int64_t nn1 = (int64_t)(nx1 + 1) * (ny1 + 1), nc2 = (int64_t)nx2 * ny2;
-  KL(h, "k_interior_flags", k_interior_flags<<<blocks_for(std::max<int64_t>(nn1, cell2 ? nc2 : 0), 256), 256, 0, st>>>(h->fixed, h->nx, h->ny, nx1, ny1, nx2, ny2, f1, f2));
+  KL(h, "k_interior_flags", k_interior_flags<<<blocks_for(std::max<int64_t>(nn1, cell2 ? nc2 : 0), 256), 256, 0, st>>>(h->fixed, h->nx, h->ny, nx1, ny1, nx2, ny2, f1, f2, h->knobs.setup_fast));
   const bool side = !h->prof_on;
   cudaStream_t se = side ? h->side : st;
   if (side) {

@@ -152,6 +152,8 @@ struct TopoKnobs {
   int no_l2persist;         // TOPO_NO_L2PERSIST
   double extrap;            // TOPO_EXTRAP          initial guess of a warm solve: u + extrap*(u - u_previous_design) (0: off)
   int tail_kind;            // TOPO_TAIL_KIND       2: shared-memory tail k_tail2 where its plan fits (default), 0: generic k_tail
+  int setup_fast;           // TOPO_SETUP_FAST      1 (default): branch-free level-1 / level-2 Galerkin kernels where k_interior_flags
+                            //                      allows; 0: every node / cell takes the general instantiation
   int lvl_tiled;            // TOPO_LVL_TILED       1 (default): tile kernels for levels 1..tail-1 (restriction inside the down
                             //                      kernel, prolongation inside the up kernel); 0: separate transfer kernels
 };

@@ -508,6 +508,53 @@ def test_slab_simp_on_two_gpus(capi):
     assert json.loads(line)["ok"]
 
 
+@pytest.mark.parametrize("knob", ["TOPO_LVL_TILED", "TOPO_SETUP_FAST"])
+def test_round2_kernel_variants_are_bit_identical(capi, monkeypatch, knob):
+    """The tile level kernels (transfers inside) against the separate transfer kernels, and the branch-free Galerkin
+    set-up kernels against the general ones: same operations in the same order, so the trajectories must agree BIT FOR
+    BIT -- compliance history, PCG iteration counts and the final densities (mesh with odd level sizes on purpose)."""
+    nx, ny = 300, 140
+    d, p = np.array([[0, -1]]), np.array([[35, 1]])
+    runs = []
+    for value in ("1", "0"):
+        monkeypatch.setenv(knob, value)                 # read once per handle in topo_create
+        from solidspy_opt.optimize import SIMP
+        hist = {}
+        rho = SIMP(float(nx), float(ny), nx, ny, d, p, 6, 3, history=hist, verbose=False)
+        runs.append((hist["compliance"], hist["cg_iters"], rho))
+    assert runs[0][1] == runs[1][1]
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][2], runs[1][2])
+
+
+def test_simp_step_with_host_buffers_equals_device_resident_path(capi):
+    """topo_simp_step_host (the e2e path of the bench: density upload, step, download overlapping the equilibrium guard on
+    the side stream) against the device-resident step: identical results, and the downloaded densities are the device's."""
+    nx, ny = 200, 96
+    ke = t1.kloc_closed_form(E0, NU)
+    pr = capi.SimpParams(penal=3.0, emin=1e-9, emax=1.0, rmin=2.5, dx=1.0, dy=1.0, move=0.2, rtol=1e-10,
+                         precond=capi.PRECOND_GMG, maxit=2000, warm=1)
+    out = []
+    for host in (False, True):
+        with capi.Topo(nx, ny, ke) as t:
+            t.set_cons(_cons(nx, ny, "cantilever"))
+            t.set_loads(np.array([[(nx + 1)*(ny//4) - 1, 0.0, -1.0]]))
+            t.fill(capi.F_RHO, 0.5)
+            a, b = np.full(nx*ny, 0.5), np.empty(nx*ny)
+            g, hist = 0.0, []
+            for _ in range(4):
+                if host:
+                    g, r = t.simp_step(pr, g, rho_in=a, rho_out=b)
+                    assert np.array_equal(b, t.get(capi.F_RHO))
+                    a, b = b, a
+                else:
+                    g, r = t.simp_step(pr, g)
+                hist.append((r.compliance, r.cg_iters, r.oc_steps, r.change))
+            out.append((hist, t.get(capi.F_RHO)))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1], out[1][1])
+
+
 def test_handle_lifecycle_and_errors(capi):
     """Repeated create/destroy does not leak device memory; bad arguments return error codes, not crashes."""
     import ctypes as C
