@@ -272,10 +272,11 @@ int topo_dist_p2p_allreduce(topo_t *h, int phase, int what, int n, int is_max);
  * level-K pieces pushed, awaited, assembled, then the tail kernel (replaces topo_dist_p2p_gather x2 + topo_dist_vcycle_tail). */
 int topo_dist_p2p_fused(topo_t *h, int what, int level, int scal_what, int scal_n, int finish);
 int topo_dist_p2p_gather_tail(topo_t *h);
-/* inkernel != 0: the restriction kernels (topo_dist_pcg_update, topo_dist_vcycle_down) and the up kernel
+/* mode bit 0: the restriction kernels (topo_dist_pcg_update, topo_dist_vcycle_down) and the up kernel
  * (topo_dist_vcycle_up) swap their interface rows with the neighbours themselves; the host then issues no
  * TOPO_X_LEVEL_B / TOPO_X_LEVEL_X2 exchange.  One slab per process only. */
-int topo_dist_p2p_mode(topo_t *h, int inkernel);
+int topo_dist_p2p_mode(topo_t *h, int mode);   /* bit 0: in-kernel row swaps; bit 1 (with bit 0): the small slab-local levels
+                                                 * and the level-K gather inside one persistent kernel per direction */
 int topo_dist_p2p_error(topo_t *h, int *error);              /* 1: a wait gave up (peer missing) */
 
 /* ---- instrumentation ----------------------------------------------------------------------- */

@@ -86,6 +86,29 @@ def main():
         if rank == 0:
             print(json.dumps(out), flush=True)
         dist.barrier()
+    if os.environ.get("SLAB_PROFILE"):
+        # where does a PCG iteration go on THIS world size: eager launches, every launch bracketed by CUDA events (kernels
+        # that wait for a neighbour include the wait)
+        transport, fused, K = variants[0].split(",")
+        sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, maxit=100000, transport=transport,
+                       fused=int(fused), K=int(K), use_graph=False)
+        g, its = 0.0, 0
+        t0 = sim.slabs[0]
+        for k in range(warm + 2):
+            if k == warm:
+                t0.profile_matvec(True)
+            g, r = sim.step(g)
+            if k >= warm:
+                its += r["cg_iters"] + 1
+        rep = sorted(t0.profile_report(), key=lambda x: -x[2])
+        t0.profile_matvec(False)
+        tot = sum(x[2] for x in rep)
+        if rank == 0:
+            print("# rank 0, eager + event brackets, %d PCG iterations (incl. initial passes): %.1f us of kernel time per iteration" % (its, tot*1e3/its))
+            for nm, n, ms in rep[:28]:
+                print("#   %-28s n %5d  avg %8.2f us  per PCG it %8.2f us" % (nm, n, ms*1e3/n, ms*1e3/its), flush=True)
+        sim.close()
+        dist.barrier()
     dist.destroy_process_group()
 
 

@@ -121,6 +121,7 @@ void free_dist(DistState &D) {
     if (D.p2p_opened[r]) cudaIpcCloseMemHandle(D.p2p_peer[r]);
   cudaFree(D.p2p_region);
   cudaFree(D.p2p_cnt);
+  cudaFree(D.mid_bar);
   cudaGetLastError();
   D = DistState{};
 }
@@ -205,6 +206,9 @@ extern "C" int topo_dist_init(topo_t *h, int rank, int world, int K_request) {
     CUDA_TRY(cudaMemset(D.p2p_region, 0, D.p2p_bytes));
     CUDA_TRY(cudaMalloc(&D.p2p_cnt, sizeof(P2PCounters)));
     CUDA_TRY(cudaMemset(D.p2p_cnt, 0, sizeof(P2PCounters)));
+    CUDA_TRY(cudaMalloc(&D.mid_bar, 2 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(D.mid_bar, 0, 2 * sizeof(unsigned int)));
+    D.mid_from = 0;
     D.p2p_on = false;
   }
   h->diag_valid = h->gmg_valid = false;
@@ -479,6 +483,7 @@ extern "C" int topo_dist_compliance_partial(topo_t *h) {
 // =====================================================================================================================
 namespace {
 
+PeerTable peer_table(const DistState &D);
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -498,9 +503,6 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
   return false;
 }
 
-struct PeerTable {
-  char *p[TOPO_P2P_MAXW];
-};
 __device__ __forceinline__ P2PHeader *hdr(char *region) { return reinterpret_cast<P2PHeader *>(region); }
 __device__ __forceinline__ void rc_of_host(int64_t n, int npr, int &r, int &c) {
   const unsigned un = (unsigned)n, q = un / (unsigned)npr;
@@ -776,6 +778,7 @@ __global__ void __launch_bounds__(256) k_p2p_gather_fused(const double2 *__restr
 }
 
 }  // namespace
+PeerTable topo_dist_peer_table(const topo_handle *h) { return peer_table(h->dist); }
 RowXchg topo_dist_row_xchg(const topo_handle *h) {
   RowXchg x = {};
   const DistState &D = h->dist;
@@ -981,10 +984,12 @@ extern "C" int topo_dist_p2p_fused(topo_t *h, int what, int level, int scal_what
 // in-kernel exchanges on (1) / off (0): the restriction kernels of topo_dist_pcg_update / topo_dist_vcycle_down and the up
 // kernel of topo_dist_vcycle_up swap their interface rows with the neighbours themselves (flag-in-data slots), so the host
 // issues NO TOPO_X_LEVEL_B / TOPO_X_LEVEL_X2 exchange.  One slab per process only (see topo_dist_p2p_fused).
-extern "C" int topo_dist_p2p_mode(topo_t *h, int inkernel) {
+int topo_dist_mid_plan(topo_handle *h, int enable);
+extern "C" int topo_dist_p2p_mode(topo_t *h, int mode) {
   TOPO_TRY(p2p_check(h));
-  h->dist.p2p_inkernel = inkernel != 0;
-  return TOPO_OK;
+  h->dist.p2p_inkernel = (mode & 1) != 0;
+  // bit 1: the small slab-local levels (+ the level-K gather) in one persistent kernel per direction
+  return topo_dist_mid_plan(h, (mode & 3) == 3);
 }
 
 // one-launch gather of the level-K right-hand side + assembly, then the tail kernel (levels >= K on every rank)
@@ -992,6 +997,7 @@ extern "C" int topo_dist_p2p_gather_tail(topo_t *h) {
   TOPO_TRY(p2p_check(h));
   CUDA_TRY(cudaSetDevice(h->device));
   DistState &D = h->dist;
+  if (D.mid_from > 0) return topo_dist_tail_after_assemble(h);      // (k_slab_mid_down pushed, gathered and assembled)
   GmgLevel &G = h->levels[D.K];
   const int rows = (h->ny >> D.K);
   const int blocks = std::max(D.world, (int)std::min<int64_t>((G.nn + 255) / 256, 64));

@@ -24,6 +24,9 @@ namespace cg = cooperative_groups;
 bool topo_tail2_applicable(const topo_handle *h, int tail);
 int topo_tail2_launch(topo_handle *h, int tail, const double2 *r_parent, int pnx, int pny, int parent_f32);
 
+int topo_dist_mid_down(topo_handle *h);
+int topo_dist_mid_up(topo_handle *h);
+
 namespace {
 
 inline int blocks_for(int64_t n, int threads = 128) { return (int)((n + threads - 1) / threads); }
@@ -354,13 +357,11 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_down_t(const LevelView L, con
 
 // up: x~ = w D^-1 b + mask(P xc) ; x2 = x~ + w D^-1 (b - A x~)
 // XCH: row-slab mode (row weights, interface rows of x~ stored or swapped); false: the single-GPU instantiation carries none of it
+// (bx, by) = tile; xs = the block's (TLY + 2) x (TLX + 2) shared tile.  Ends WITHOUT a block barrier.
 template <bool SYM, bool XCH>
-__global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const double2 *__restrict__ xcoarse, int cnx, double omega,
-                                                        const int *done, const __grid_constant__ RowXchg x) {
-  if (done && *done) return;
-  const unsigned long long seq = (XCH && x.c != nullptr) ? ll_rows_seq(x) : 0ull;
-  __shared__ double2 xs[TLY + 2][TLX + 2];
-  const int c0 = blockIdx.x * TLX, r0 = blockIdx.y * TLY;
+__device__ __forceinline__ void lvl_up_tile(const LevelView &L, const double2 *__restrict__ xcoarse, int cnx, double omega,
+                                            const RowXchg &x, unsigned long long seq, int bx, int by, double2 (*xs)[TLX + 2]) {
+  const int c0 = bx * TLX, r0 = by * TLY;
   const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
   const int npr = L.nx + 1, nn = npr * (L.ny + 1), n = r * npr + c;
   const bool own = c <= L.nx && r <= L.ny;
@@ -400,9 +401,160 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const
     }
     L.x2[n] = v;
   }
+}
+template <bool SYM, bool XCH>
+__global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const double2 *__restrict__ xcoarse, int cnx, double omega,
+                                                        const int *done, const __grid_constant__ RowXchg x) {
+  if (done && *done) return;
+  const unsigned long long seq = (XCH && x.c != nullptr) ? ll_rows_seq(x) : 0ull;
+  __shared__ double2 xs[TLY + 2][TLX + 2];
+  lvl_up_tile<SYM, XCH>(L, xcoarse, cnx, omega, x, seq, blockIdx.x, blockIdx.y, xs);
   if (XCH && x.c != nullptr && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {      // (blocks that hold an interface row)
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
+  }
+}
+
+// ---- row-slab mode: the SMALL slab-local levels in one launch per direction ------------------------------------------------
+// On 8 GPUs the slab-local levels 3..5 of an 8192 x 4096 mesh have 66 000, 17 000 and 4 400 nodes; each of their kernels
+// (restriction, sweep, up) takes 6-10 us whatever its size, ten launches and six in-kernel row swaps per V-cycle.  Here one
+// persistent grid (one block per SM, all resident) walks through the phases with a grid barrier between them:
+//   down:  for l = Lm..K-1:  b_l = P^T r_{l-1} (+ row swap)  |  r_l = W b_l - A_loc (w D^-1 b_l)  ;  then the level-K piece
+//          P^T r_{K-1} is pushed to every rank (flag-in-data) and the global level-K right-hand side is assembled
+//   up:    for l = K-1..Lm:  x2_l = tile up-kernel body (+ row swap)
+// Row swaps of consecutive phases use consecutive sequence numbers (alternating slot parity); a rank cannot be two swaps
+// ahead of its neighbour because every swap is followed by a grid barrier on both sides.
+struct MidArgs {
+  LevelView lv[8];
+  int n;                                   // levels Lm .. K-1
+  const double2 *r_parent;                 // residual of level Lm-1 (down) / result of level K on this slab's rows (up)
+  int pnx, pny;                            // its size (down) ; pnx = cells per row of level K (up)
+  double omega;
+  const int *done;
+  RowXchg x;
+  unsigned int *bar;                       // [0] arrivals, [1] generation
+  // level-K piece and gather (down only)
+  int nxK, nyK;                            // local level-K piece: nxK x nyK cells
+  PeerTable peers;
+  int my_rank, world;
+  char *region;
+  size_t off_gather, gstride;
+  double2 *bK;                             // assembled global right-hand side of level K
+};
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    const unsigned int gen = *reinterpret_cast<volatile unsigned int *>(bar + 1);
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned int *>(bar + 1) == gen) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(TLX * TLY) k_slab_mid_down(const __grid_constant__ MidArgs a) {
+  if (a.done && *a.done) return;
+  P2PCounters *c = a.x.c;
+  const int T = TLX * TLY, tid = threadIdx.y * TLX + threadIdx.x;
+  const int gt = blockIdx.x * T + tid, GT = gridDim.x * T;
+  const unsigned long long seq0 = ll_rows_seq(a.x), gseq = c->gather_push + 1;
+  const double2 *rp = a.r_parent;
+  int pnx = a.pnx, pny = a.pny;
+  for (int k = 0; k < a.n; ++k) {
+    const LevelView &L = a.lv[k];
+    const int npr = L.nx + 1, nn = npr * (L.ny + 1);
+    for (int n = gt; n < nn; n += GT) {
+      int J, I;
+      rc_of(n, npr, J, I);
+      double2 b = restrict_node(rp, I, J, pnx, pny), q;
+      if (J == 0 && a.x.peer_lo != nullptr && ll_row_swap(a.x, true, I, seq0 + k, b, q)) { b.x += q.x; b.y += q.y; }
+      if (J == L.ny && a.x.peer_hi != nullptr && ll_row_swap(a.x, false, I, seq0 + k, b, q)) { b.x += q.x; b.y += q.y; }
+      L.b[n] = b;
+    }
+    grid_barrier(a.bar, gridDim.x);
+    if (L.sym) { for (int n = gt; n < nn; n += GT) node_down<true>(L, n, a.omega); }
+    else { for (int n = gt; n < nn; n += GT) node_down<false>(L, n, a.omega); }
+    grid_barrier(a.bar, gridDim.x);
+    rp = L.r; pnx = L.nx; pny = L.ny;
+  }
+  // level-K piece: restricted, pushed to every rank's gather slot [my rank] (partial sums on the interface rows stay partial)
+  {
+    const unsigned s32 = (unsigned)gseq;
+    const int nprK = a.nxK + 1;
+    const long long npiece = (long long)nprK * (a.nyK + 1);
+    for (long long i = gt; i < npiece; i += GT) {
+      int J, I;
+      rc_of(i, nprK, J, I);
+      const double2 v = restrict_node(rp, I, J, pnx, pny);
+      for (int r = 0; r < a.world; ++r) {
+        uint4 *dst = reinterpret_cast<uint4 *>(a.peers.p[r] + a.off_gather + (size_t)(gseq & 1ull) * a.gstride) + 2 * ((size_t)a.my_rank * npiece + i);
+        ll_store(dst, v.x, s32);
+        ll_store(dst + 1, v.y, s32);
+      }
+    }
+    // assemble the global right-hand side (every rank, identically): rank g holds coarse rows [g nyK, (g+1) nyK]
+    const uint4 *__restrict__ recv = reinterpret_cast<const uint4 *>(a.region + a.off_gather + (size_t)(gseq & 1ull) * a.gstride);
+    const long long nn = (long long)nprK * ((long long)a.nyK * a.world + 1);
+    for (long long m = gt; m < nn; m += GT) {
+      int J, I;
+      rc_of(m, nprK, J, I);
+      const int g = J / a.nyK, j = J - g * a.nyK;
+      double2 acc = make_double2(0.0, 0.0);
+      bool ok = true;
+      if (g < a.world) {
+        const uint4 *w = recv + 2 * ((long long)g * npiece + (long long)j * nprK + I);
+        ok = ll_load(w, s32, acc.x, &c->error) && ll_load(w + 1, s32, acc.y, &c->error);
+      }
+      if (ok && j == 0 && g > 0) {
+        const uint4 *w = recv + 2 * ((long long)(g - 1) * npiece + (long long)a.nyK * nprK + I);
+        double qx, qy;
+        ok = ll_load(w, s32, qx, &c->error) && ll_load(w + 1, s32, qy, &c->error);
+        acc.x += qx; acc.y += qy;
+      }
+      if (ok) a.bK[m] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&c->fticket[3], 1u) == gridDim.x - 1u) {
+      c->fticket[3] = 0u;
+      if (a.n > 0) { c->halo_push = seq0 + a.n - 1; c->halo_wait = seq0 + a.n - 1; }
+      c->gather_push = gseq;
+      c->gather_wait = gseq;
+    }
+  }
+}
+__global__ void __launch_bounds__(TLX * TLY) k_slab_mid_up(const __grid_constant__ MidArgs a) {
+  if (a.done && *a.done) return;
+  P2PCounters *c = a.x.c;
+  __shared__ double2 xs[TLY + 2][TLX + 2];
+  const unsigned long long seq0 = ll_rows_seq(a.x);
+  const double2 *xc = a.r_parent;
+  int cnx = a.pnx;
+  for (int k = a.n - 1, ph = 0; k >= 0; --k, ++ph) {
+    const LevelView &L = a.lv[k];
+    const int tx = (L.nx + TLX) / TLX, ty = (L.ny + TLY) / TLY;
+    for (int t = blockIdx.x; t < tx * ty; t += gridDim.x) {
+      if (L.sym) lvl_up_tile<true, true>(L, xc, cnx, a.omega, a.x, seq0 + ph, t % tx, t / tx, xs);
+      else lvl_up_tile<false, true>(L, xc, cnx, a.omega, a.x, seq0 + ph, t % tx, t / tx, xs);
+      __syncthreads();
+    }
+    if (k > 0) grid_barrier(a.bar, gridDim.x);
+    xc = L.x2; cnx = L.nx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    if (atomicAdd(&c->fticket[2], 1u) == gridDim.x - 1u) {
+      c->fticket[2] = 0u;
+      if (a.n > 0) { c->halo_push = seq0 + a.n - 1; c->halo_wait = seq0 + a.n - 1; }
+    }
   }
 }
 
@@ -950,10 +1102,13 @@ int topo_dist_restrict_fine(topo_handle *h, const double2 *res_fine) { return di
 // requires b_l accumulated: x = w D^-1 b ; r = W b - A_loc x (distributed) ; restrict
 int topo_dist_level_down(topo_handle *h, int l) {
   if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
+  const DistState &D = h->dist;
+  if (D.mid_from > 0 && l >= D.mid_from) return l == D.mid_from ? topo_dist_mid_down(h) : TOPO_OK;
   GmgLevel &F = h->levels[l];
   const LevelView V = dist_view(h, l);
   KL(h, lvl_name("down", l), CUDA_TRY(topo_launch(h, V.sym ? k_lvl_down2<true> : k_lvl_down2<false>, lvl_grid(F.nx, F.ny), dim3(LB_X, LB_Y), 0, V,
                                                   h->omega, &h->sc->done)));
+  if (D.mid_from > 0 && l + 1 == D.mid_from) return TOPO_OK;        // (the persistent kernel restricts this residual itself)
   return dist_restrict_from(h, l, F.r);
 }
 
@@ -992,6 +1147,7 @@ static const double2 *dist_coarse_result(const topo_handle *h, int l_coarse) {
 // (the host adds the neighbour's x2 row and subtracts x there: topo_dist_xchg_finish)
 int topo_dist_level_up(topo_handle *h, int l) {
   if (!h->dist.on || l < 1 || l >= h->dist.K) return TOPO_EINVAL;
+  if (h->dist.mid_from > 0 && l >= h->dist.mid_from) return l == h->dist.K - 1 ? topo_dist_mid_up(h) : TOPO_OK;
   GmgLevel &F = h->levels[l];
   const LevelView V = dist_view(h, l);
   const int *done = &h->sc->done;
@@ -1012,6 +1168,69 @@ int topo_dist_prolong_fine(topo_handle *h, double2 *xhat_fine) {
   if (!h->dist.on) return TOPO_EINVAL;
   KL(h, "k_prolong_add_fine", k_prolong_add_fine2<<<lvl_grid(h->nx, h->ny), dim3(LB_X, LB_Y), 0, h->stream>>>(dist_coarse_result(h, 1), reinterpret_cast<float2 *>(xhat_fine), h->fixed, h->nx,
                                                                                            h->ny, h->lvl_nx[1], &h->sc->done));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+
+// ---- row-slab mode: the small slab-local levels in one persistent kernel per direction (k_slab_mid_down / _up) ------------
+// plan: mid_from = first level l >= 2 (l < K) whose tiles AND nodes fit one wave of resident blocks -- every block then
+// owns at most one tile / every thread at most one node per phase, so a thread waiting for a neighbour's row never holds
+// back work the other neighbour waits for
+int topo_dist_mid_plan(topo_handle *h, int enable) {
+  DistState &D = h->dist;
+  D.mid_from = 0;
+  if (!enable || !D.on || !D.p2p_on || !D.p2p_inkernel || !(h->knobs.lvl_tiled & 1) || D.K < 3) return TOPO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int sms = 0, occ_d = 0, occ_u = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, k_slab_mid_down, TLX * TLY, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_slab_mid_up, TLX * TLY, 0));
+  const int cap = sms * std::max(1, std::min(std::min(occ_d, occ_u), 3));
+  for (int l = 2; l < D.K; ++l) {
+    const GmgLevel &L = h->levels[l];
+    const int tiles = div_up(L.nx + 1, TLX) * div_up(L.ny + 1, TLY);
+    if (tiles <= cap && (int64_t)L.nn <= (int64_t)cap * TLX * TLY && D.K - l <= 8) {
+      D.mid_from = l;
+      D.mid_grid = std::max(tiles, std::min(cap, div_up(L.nn, TLX * TLY)));
+      break;
+    }
+  }
+  return TOPO_OK;
+}
+static void mid_args(topo_handle *h, MidArgs &a) {
+  const DistState &D = h->dist;
+  a = MidArgs{};
+  a.n = D.K - D.mid_from;
+  for (int l = D.mid_from; l < D.K; ++l) a.lv[l - D.mid_from] = dist_view(h, l);
+  a.omega = h->omega;
+  a.done = &h->sc->done;
+  a.x = topo_dist_row_xchg(h);
+  a.bar = D.mid_bar;
+}
+int topo_dist_mid_down(topo_handle *h) {
+  const DistState &D = h->dist;
+  if (!D.on || D.mid_from < 2) return TOPO_EINVAL;
+  MidArgs a;
+  mid_args(h, a);
+  const GmgLevel &P = h->levels[D.mid_from - 1];
+  a.r_parent = P.r; a.pnx = P.nx; a.pny = P.ny;
+  a.nxK = h->lvl_nx[D.K]; a.nyK = h->ny >> D.K;
+  a.peers = topo_dist_peer_table(h);
+  a.my_rank = D.rank; a.world = D.world;
+  a.region = D.p2p_region; a.off_gather = D.p2p_off_ll_gather; a.gstride = 2 * D.p2p_gather_stride;
+  a.bK = h->levels[D.K].b;
+  KL(h, "k_slab_mid_down", k_slab_mid_down<<<D.mid_grid, dim3(TLX, TLY), 0, h->stream>>>(a));
+  CUDA_TRY(cudaGetLastError());
+  return TOPO_OK;
+}
+int topo_dist_mid_up(topo_handle *h) {
+  const DistState &D = h->dist;
+  if (!D.on || D.mid_from < 2) return TOPO_EINVAL;
+  MidArgs a;
+  mid_args(h, a);
+  a.r_parent = dist_coarse_result(h, D.K);
+  a.pnx = h->lvl_nx[D.K];
+  KL(h, "k_slab_mid_up", k_slab_mid_up<<<D.mid_grid, dim3(TLX, TLY), 0, h->stream>>>(a));
   CUDA_TRY(cudaGetLastError());
   return TOPO_OK;
 }

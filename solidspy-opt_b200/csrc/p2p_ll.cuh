@@ -61,4 +61,9 @@ __device__ __forceinline__ void ll_rows_done(const RowXchg &x, unsigned long lon
 
 }  // namespace
 
-RowXchg topo_dist_row_xchg(const topo_handle *h);   // dist.cu: the handle's slots if in-kernel exchanges are on, else zeros
+struct PeerTable {
+  char *p[TOPO_P2P_MAXW];                  // mapped regions by rank (own region at [rank])
+};
+
+RowXchg topo_dist_row_xchg(const topo_handle *h);
+PeerTable topo_dist_peer_table(const topo_handle *h);   // dist.cu: the handle's slots if in-kernel exchanges are on, else zeros

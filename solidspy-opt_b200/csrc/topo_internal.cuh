@@ -128,6 +128,9 @@ struct DistState {
   // peer-memory transport
   bool p2p_on;
   bool p2p_inkernel;                   // the restriction / up kernels of slab-local levels swap their interface rows themselves
+  int mid_from;                        // > 0: slab-local levels mid_from..K-1 run inside k_slab_mid_down / k_slab_mid_up
+  int mid_grid;                        // blocks of those persistent kernels (all resident; >= tiles of level mid_from)
+  unsigned int *mid_bar;               // their grid barrier: [0] arrivals, [1] generation
   char *p2p_region;                    // P2PHeader | recv_lo[2][npr] | recv_hi[2][npr] | gather_recv[2][world][bK_count]
   size_t p2p_bytes, p2p_off_lo, p2p_off_hi, p2p_off_gather, p2p_row_stride, p2p_gather_stride;
   size_t p2p_off_ll_lo, p2p_off_ll_hi, p2p_off_ll_gather;   // flag-in-data copies of the three payload areas (32 B per double2)

@@ -250,8 +250,11 @@ class SlabSimp:
         # fused == 2 ("inkernel", default with fused=True): the restriction / up kernels of the slab-local levels swap their
         # interface rows themselves -- no exchange launch at all for those levels
         self.inkernel = self.fused and fused is not False and int(fused) != 1
+        # fused == 3: additionally the SMALL slab-local levels and the level-K gather run inside one persistent kernel per
+        # direction (k_slab_mid_down / k_slab_mid_up); the segment calls of those levels become no-ops inside the library
+        self.mid = self.inkernel and int(fused) == 3
         if self.fused:
-            self.slabs[0].dist_call("p2p_mode", 1 if self.inkernel else 0)
+            self.slabs[0].dist_call("p2p_mode", (1 if self.inkernel else 0) | (2 if self.mid else 0))
         self._lam_prev = 0.0
         self._last_iters = 0
         self.halo_bytes = 0

@@ -42,14 +42,17 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {"world": world, "ok": True}
     # ---- correctness against the single-GPU path -----------------------------------------------------------------
-    nx, ny = 384, 64*world
-    cons, loads, ke = model(nx, ny)
     steps = 4
     # (p2p with and without the one-launch exchanges, graph-captured and eager; NCCL graph-captured and eager)
     # fused: 2 = one-launch exchanges + in-kernel interface rows on the slab-local levels (default), 1 = one-launch exchanges
     # only, 0 = two-phase push / finish kernels
-    for transport, use_graph, fused in (("p2p", True, 2), ("p2p", False, 2), ("p2p", True, 1), ("p2p", True, 0), ("nccl", True, 0),
-                                        ("nccl", False, 0)):
+    # fused = 3 adds the persistent kernels for the small slab-local levels: they need a hierarchy with >= 3 slab-local levels,
+    # so the second mesh (K = 4 on two slabs) is there for them
+    cases = [(384, 64*world, t, g_, f) for t, g_, f in (("p2p", True, 2), ("p2p", False, 2), ("p2p", True, 1), ("p2p", True, 0),
+                                                         ("nccl", True, 0), ("nccl", False, 0))]
+    cases += [(1536, 384*world, t, g_, f) for t, g_, f in (("p2p", True, 3), ("p2p", False, 3), ("p2p", True, 2))]
+    for nx, ny, transport, use_graph, fused in cases:
+        cons, loads, ke = model(nx, ny)
         sim = SlabSimp(nx, ny, ke, cons, loads, rmin=2.5, dist=dist, device=local, rtol=1e-10, use_graph=use_graph,
                        transport=transport, fused=fused)
         g, hist = 0.0, []
@@ -57,8 +60,9 @@ def main():
             g, res = sim.step(g)
             hist.append((res["compliance"], res["cg_iters"], res["oc_steps"], g))
         rho = gather_rho(sim, world)
-        key = transport + ("_fused%d" % fused if fused else "") + ("_graph" if use_graph else "_eager")
-        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p), "fused": bool(sim.fused), "inkernel": bool(sim.inkernel)}
+        key = "%dx%d_" % (nx, ny) + transport + ("_fused%d" % fused if fused else "") + ("_graph" if use_graph else "_eager")
+        out[key + "_used"] = {"graph": bool(sim.use_graph), "p2p": bool(sim.p2p), "fused": bool(sim.fused), "inkernel": bool(sim.inkernel),
+                              "mid": bool(sim.mid), "K": sim.K}
         out[key + "_error"] = [sim.graph_error, sim.p2p_error]
         out["K"] = sim.K
         sim.close()
@@ -103,7 +107,7 @@ def main():
     if big:
         nx, ny = (int(v) for v in big.lower().split("x"))
         cons, loads, ke = model(nx, ny)
-        for transport, use_graph, fused in (("p2p", True, 2), ("p2p", True, 1), ("p2p", True, 0), ("nccl", True, 0)):
+        for transport, use_graph, fused in (("p2p", True, 3), ("p2p", True, 2), ("p2p", True, 1), ("p2p", True, 0), ("nccl", True, 0)):
             sim = SlabSimp(nx, ny, ke, cons, loads, rmin=4.0, dist=dist, device=local, rtol=1e-9, use_graph=use_graph,
                            transport=transport, fused=fused)
             g = 0.0
