@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(LB_X * LB_Y) k_restrict_x(const V2 *__restrict
                                                             int nxc, int nyc, const int *done, const __grid_constant__ RowXchg x) {
   if (done && *done) return;
   const unsigned long long seq = ll_rows_seq(x);
-  const int I = blockIdx.x * LB_X + threadIdx.x, J = blockIdx.y * LB_Y + threadIdx.y;
+  // the blocks of the LAST row are scheduled right after those of the first: both interface rows are pushed at the start of
+  // the kernel, so a neighbour that started later is waited for behind the interior work, not on top of it
+  const int nby = gridDim.y, by = nby < 3 ? (int)blockIdx.y : (blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? nby - 1 : (int)blockIdx.y - 1));
+  const int I = blockIdx.x * LB_X + threadIdx.x, J = by * LB_Y + threadIdx.y;
   if (I <= nxc && J <= nyc) {
     double2 b = restrict_node(rf, I, J, nxf, nyf), q;
     if (J == 0 && x.peer_lo != nullptr && ll_row_swap(x, true, I, seq, b, q)) { b.x += q.x; b.y += q.y; }
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(LB_X * LB_Y) k_restrict_x(const V2 *__restrict
   }
   // only the blocks that hold an interface row take part in the end-of-kernel ticket (one atomic per block of a 30 000-block
   // grid cost more than the exchange saved)
-  if (blockIdx.y != 0 && blockIdx.y != gridDim.y - 1) return;
+  if (by != 0 && by != nby - 1) return;
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
 }
@@ -408,8 +411,11 @@ __global__ void __launch_bounds__(TLX * TLY) k_lvl_up_t(const LevelView L, const
   if (done && *done) return;
   const unsigned long long seq = (XCH && x.c != nullptr) ? ll_rows_seq(x) : 0ull;
   __shared__ double2 xs[TLY + 2][TLX + 2];
-  lvl_up_tile<SYM, XCH>(L, xcoarse, cnx, omega, x, seq, blockIdx.x, blockIdx.y, xs);
-  if (XCH && x.c != nullptr && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {      // (blocks that hold an interface row)
+  // row-slab mode: the tiles of the last tile row right after those of the first (see k_restrict_x)
+  const int nby = gridDim.y;
+  const int by = (!XCH || nby < 3) ? (int)blockIdx.y : (blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? nby - 1 : (int)blockIdx.y - 1));
+  lvl_up_tile<SYM, XCH>(L, xcoarse, cnx, omega, x, seq, blockIdx.x, by, xs);
+  if (XCH && x.c != nullptr && (by == 0 || by == nby - 1)) {      // (blocks that hold an interface row)
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) ll_rows_done(x, seq, gridDim.x * (gridDim.y > 1 ? 2u : 1u));
   }
